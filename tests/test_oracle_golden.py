@@ -1,0 +1,143 @@
+"""Pin the CPU oracle (oracle/onet_oracle.py) against golden vectors produced by the UNMODIFIED
+reference module (tests/golden/make_golden.py) and, when /root/reference is present, against the
+live reference.  CPU only."""
+import os
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import onet_oracle as orc
+from oracle.ref_import import reference_available
+
+CASES = ["c1_b2_32x32", "c3_b1_48x32", "c1_b2_32x32_noshare", "c1_b2_40x56_pad"]
+SAMPLE_STRIDE = 9973
+
+
+def _states(meta):
+    cin, b, h, w, bshare, seed = (int(v) for v in meta)
+    st = orc.perturb_bn_affine(orc.init_state(cin, seed=seed), seed=seed + 100)
+    st_d = None if bshare else orc.perturb_bn_affine(orc.init_state(cin, seed=seed + 50), seed=seed + 150)
+    return st, st_d
+
+
+def _check_summary(name, t, g, rtol):
+    a = t.detach().numpy().astype(np.float64)
+    norm = np.sqrt((a ** 2).sum())
+    assert abs(norm - g[f"{name}.norm"]) <= rtol * max(g[f"{name}.norm"], 1e-12), name
+    if f"{name}.full" in g:
+        ref = g[f"{name}.full"].astype(np.float64)
+        assert np.linalg.norm(a - ref) <= rtol * max(np.linalg.norm(ref), 1e-12), name
+    else:
+        ref = g[f"{name}.sample"].astype(np.float64)
+        got = a.reshape(-1)[::SAMPLE_STRIDE]
+        assert np.linalg.norm(got - ref) <= rtol * max(np.linalg.norm(ref), 1e-12), name
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_matches_reference_golden(case, golden_dir):
+    g = np.load(os.path.join(golden_dir, case + ".npz"))
+    st, st_d = _states(g["meta"])
+    x = torch.from_numpy(g["x"])
+    # the input generator itself is part of the fixture contract
+    cin, b, h, w, _, seed = (int(v) for v in g["meta"])
+    assert torch.equal(orc.rayleigh_frames(b, cin, h, w, seed=seed), x)
+    res = orc.train_step_outputs(st, x, st_d)
+    out, grads, new_state = res[0], res[1], res[2]
+    # same ATen CPU kernels underneath -> tight tolerance (summation order may differ slightly)
+    assert abs(out["loss"].item() - float(g["loss"])) <= 2e-6 * abs(float(g["loss"]))
+    for k in ("Vt", "Vd", "S"):
+        ref = torch.from_numpy(g[k])
+        assert torch.linalg.norm(out[k] - ref) <= 2e-5 * torch.linalg.norm(ref), k
+    _check_summary("Lt", out["Lt"], g, 2e-5)
+    _check_summary("Ld", out["Ld"], g, 2e-5)
+    for k, gr in grads.items():
+        _check_summary("grad.topu." + k, gr, g, 5e-3)   # fp32 noise floor: 18 BN layers, deepest BN sees only B*2*2 values
+    if st_d is not None:
+        for k, gr in res[3].items():
+            _check_summary("grad.dwnu." + k, gr, g, 5e-3)
+    for k, v in new_state.items():
+        if "running" in k:
+            ref = g["buf.topu." + k]
+            assert np.allclose(v.numpy(), ref, rtol=2e-5, atol=1e-6), k
+        if "num_batches" in k:
+            assert int(v) == int(g["buf.topu." + k]), k   # shared twin: += 2 per step
+    # eval-mode forward with the updated running statistics, and labels
+    st_eval = new_state
+    sd_eval = res[4] if st_d is not None else None
+    with torch.no_grad():
+        Lt, Vt, Ld, Vd, S = orc.onet_forward(st_eval, x, training=False, st_dwn=sd_eval)
+    for k, t in (("eval.Vt", Vt), ("eval.Vd", Vd), ("eval.S", S)):
+        ref = torch.from_numpy(g[k])
+        assert torch.linalg.norm(t - ref) <= 2e-5 * torch.linalg.norm(ref), k
+    lab = orc.predict_label(S).numpy().astype(np.uint8)
+    assert (lab == g["eval.label"]).mean() >= 0.9995
+
+
+def test_log1pexp_known_answers(golden_dir):
+    g = np.load(os.path.join(golden_dir, "log1pexp_kat.npz"))
+    x = torch.from_numpy(g["x"]).requires_grad_(True)
+    y = orc.log1pexp(x)
+    y.sum().backward()
+    assert np.array_equal(y.detach().numpy(), g["y"])          # bit-exact, incl. ln2 below -37
+    assert np.allclose(x.grad.numpy(), g["dy"], rtol=1e-6, atol=1e-12)
+    # numpy restatement (value + closed-form derivative)
+    v, d = orc._sp_np(g["x"])
+    assert np.allclose(v, g["y"], rtol=1e-6, atol=1e-12)
+    assert np.allclose(d, g["dy"], rtol=1e-5, atol=1e-12)
+
+
+def test_numpy_head_matches_autograd():
+    torch.manual_seed(3)
+    B, C, H, W = 2, 64, 8, 12
+    # scale so that a*S spans all softplus branches (a up to ~70 as at random init)
+    Lt, Ht, Ld, Hd = [(torch.rand(B, C, H, W) * s).requires_grad_(True) for s in (1.5, 0.05, 1.2, 0.05)]
+    Vt = (Lt * Ht).sum(1, keepdim=True)
+    Vd = (Ld * Hd).sum(1, keepdim=True)
+    S = torch.softmax(torch.cat([Vt, Vd], 1), 1)
+    loss = orc.compute_loss(Lt, S[:, 0:1], Ld, S[:, 1:2])
+    loss.backward()
+    r = orc.head_loss_numpy(Lt.detach().numpy(), Ht.detach().numpy(), Ld.detach().numpy(), Hd.detach().numpy())
+    assert abs(r["loss"] - loss.item()) <= 2e-6 * abs(loss.item())
+    for k, t in (("dLt", Lt), ("dHt", Ht), ("dLd", Ld), ("dHd", Hd)):
+        ref = t.grad.numpy()
+        assert np.linalg.norm(r[k] - ref) <= 2e-5 * np.linalg.norm(ref), k
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree only exists in the build container")
+def test_oracle_matches_live_reference():
+    from oracle.ref_import import import_reference
+    ref = import_reference()
+    st = orc.perturb_bn_affine(orc.init_state(1, seed=21), seed=22)
+    x = orc.rayleigh_frames(2, 1, 32, 48, seed=23)
+    onet = ref.Onet(1, True, True)
+    sd = OrderedDict()
+    for k, v in st.items():
+        sd["topu." + k] = v.clone()
+        sd["dwnu." + k] = v.clone()
+    onet.load_state_dict(sd)
+    onet.train()
+    Lt, Vt, Ld, Vd, S = onet(x)
+    loss = onet.compute_loss(Lt, S[:, 0:1], Ld, S[:, 1:2])
+    loss.backward()
+    out, grads, _ = orc.train_step_outputs(st, x)
+    assert abs(out["loss"].item() - loss.item()) <= 2e-6 * abs(loss.item())
+    for k, p in onet.named_parameters():
+        gk = grads[k[len("topu."):]]
+        assert torch.linalg.norm(gk - p.grad) <= 5e-3 * torch.linalg.norm(p.grad) + 1e-12, k
+
+
+def test_adam_matches_torch():
+    torch.manual_seed(0)
+    p = torch.randn(100)
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=5e-6, betas=(0.9, 0.999), eps=1e-8)
+    m = torch.zeros(100)
+    v = torch.zeros(100)
+    for step in range(1, 4):
+        g = torch.randn(100)
+        ref.grad = g.clone()
+        opt.step()
+        p, m, v = orc.adam_step(p, g, m, v, step, 5e-6)
+    assert torch.allclose(p, ref.detach(), rtol=1e-6, atol=1e-9)
