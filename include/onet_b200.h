@@ -1,0 +1,120 @@
+/* onet_b200 — C ABI of the B200-native Onet hot path (libonet_b200.so).
+ *
+ * The reference (joeyee/Onet) is pure Python/PyTorch and has no FFI of its own: its hot path is the ATen
+ * operator sequence dispatched by `source_code/Onet_vanilla_20240606.py`.  Each entry point below replaces
+ * one group of those ATen calls; the file:line it replaces is cited next to it.  The host-side mirror of the
+ * reference interface (class `Onet` with forward / compute_loss / predict_label and identical state_dict
+ * keys) lives in `onet_b200/model.py` and binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch); no allocation happens inside.
+ *   - activations are NHWC; `ld*` is the number of channels per pixel of the underlying buffer and `*off`
+ *     the first channel used, so a view into a wider (skip-concat) buffer needs no copy.
+ *   - the twin batch holds the top branch in images [0,B) and the down branch in [B,2B); `group_images` = B
+ *     is the BatchNorm statistics group size (statistics are per branch, Onet_vanilla_20240606.py:175,181).
+ *   - dtype: ONET_F32 (FP32 verification mode, CUDA-core FMA) or ONET_BF16 (bf16 storage, fp32 accumulate).
+ *   - engine: ONET_ENGINE_SIMT (CUDA cores) or ONET_ENGINE_TC (tcgen05 + TMEM + TMA; bf16 only,
+ *     channel counts multiples of 64).
+ *   - `stream` is a cudaStream_t passed as void*.
+ *   - return value 0 = ok; non-zero = error, message via onet_last_error().  No exceptions, no global state
+ *     except the last-error string (thread-local) and the cached driver entry point for tensor-map encoding.
+ */
+#ifndef ONET_B200_H
+#define ONET_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ONET_F32 0
+#define ONET_BF16 1
+#define ONET_ENGINE_SIMT 0
+#define ONET_ENGINE_TC 1
+
+int onet_version(void);
+const char* onet_last_error(void);
+int onet_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* X (B,Cin,H,W) fp32 NCHW -> twin NHWC batch [2B,H,W,Cin] = (X, clip(1-X+bias,0,1)).
+ * Replaces Onet.forward's input handling, Onet_vanilla_20240606.py:175,180-181. */
+int onet_prep_input(const float* x, int B, int Cin, int H, int W, float bias, void* out, int dtype, void* stream);
+
+/* Pack fp32 master weights into kernel operand layouts (once per optimizer step).
+ * conv  w[Co][Ci][3][3] -> wf[Co][tap][Ci], wd[Ci][8-tap][Co] (wd may be NULL);
+ * convT w[Ci][Co][2][2] -> wf[(tap,co)][ci], wd[ci][(tap,co)]. */
+int onet_pack_conv_weights(const float* w, int Cout, int Cin, void* wf, void* wd, int dtype, void* stream);
+int onet_pack_convT_weights(const float* w, int Cin, int Cout, void* wf, void* wd, int dtype, void* stream);
+
+/* 3x3 / pad 1 / no-bias convolution on packed weights wp[Cout][9][Cin]; writes the RAW output and, when
+ * stat_sum != NULL, accumulates per-group per-channel sum / sum-of-squares (doubles, [groups][Cout]) for the
+ * training-mode BatchNorm that follows.  Used for forward (nn.Conv2d, Onet_vanilla_20240606.py:47,51) and,
+ * with wd, for the data gradient (autograd of the same lines). */
+int onet_conv3x3_fwd(const void* in, int64_t ldi, int ci_off, int N, int H, int W, int Cin, const void* wp, int Cout,
+                     void* out, int64_t ldo, int co_off, double* stat_sum, double* stat_sq, int group_images,
+                     int dtype, int engine, void* stream);
+
+/* Weight gradient of the same convolution, accumulated (atomics) into dw fp32 [Cout][Cin][3][3]. */
+int onet_conv3x3_wgrad(const void* g, int64_t ldg, int g_off, const void* in, int64_t ldi, int ci_off, int N, int H,
+                       int W, int Cin, int Cout, float* dw, int dtype, int engine, void* stream);
+
+/* BatchNorm2d training statistics -> mean / invstd / scale / shift ([G][C] floats) + running-buffer update
+ * (momentum, unbiased variance), groups folded sequentially (nn.BatchNorm2d, Onet_vanilla_20240606.py:48,52).
+ * Per-group parameter pointers; for the weight-shared twin both groups pass the same pointers. */
+int onet_bn_finalize(const double* stat_sum, const double* stat_sq, int G, int C, double count,
+                     const float* gamma0, const float* beta0, float* running_mean0, float* running_var0,
+                     const float* gamma1, const float* beta1, float* running_mean1, float* running_var1,
+                     float momentum, float* mean, float* invstd, float* scale, float* shift, void* stream);
+/* eval mode: scale / shift from the running statistics */
+int onet_bn_eval_prepare(int G, int C, const float* gamma0, const float* beta0, const float* running_mean0,
+                         const float* running_var0, const float* gamma1, const float* beta1,
+                         const float* running_mean1, const float* running_var1, float* scale, float* shift,
+                         void* stream);
+
+/* y -> relu(y*scale+shift) written to out (+ooff, ld ldo; e.g. the skip half of a concat buffer) and, when
+ * pool != NULL, the 2x2 max-pooled map [N,H/2,W/2,C] in the same pass (nn.ReLU :49,53 + nn.MaxPool2d(2) :67
+ * + the skip half of torch.cat :100). */
+int onet_bn_relu_apply(const void* y, int N, int H, int W, int C, const float* scale, const float* shift,
+                       int group_images, void* out, int64_t ldo, int ooff, void* pool, int dtype, void* stream);
+
+/* Backward of BN -> ReLU (-> skip / max-pool): gradient sources g1 (+ optional g2, optional pooled gp routed to
+ * the first maximum of each 2x2 window), produces dy [N,H,W,C] and accumulates dgamma/dbeta.  `sums` is a
+ * zero-initialised [G][2][C] double workspace. */
+int onet_bn_relu_bwd(const void* y, int N, int H, int W, int C, const float* scale, const float* shift,
+                     const float* mean, const float* invstd, int group_images, const void* g1, int64_t ld1, int off1,
+                     const void* g2, int64_t ld2, int off2, const void* gp, double* sums, double count, void* dy,
+                     float* dgamma0, float* dbeta0, float* dgamma1, float* dbeta1, int dtype, void* stream);
+
+/* ConvTranspose2d(Cin, Co, 2, 2) + bias written directly into channels [ooff, ooff+Co) of the concat buffer
+ * (nn.ConvTranspose2d :86 + F.pad :92-96 (no-op when sizes divide) + the up half of torch.cat :100).
+ * SIMT engine takes the fp32 master weight w[Cin][Co][2][2]; TC engine takes the packed wf / wd. */
+int onet_convT2x2_fwd(const void* x, int64_t ldx, int xoff, int N, int H, int W, int Cin, const void* w,
+                      const float* bias, int Co, void* out, int64_t ldo, int ooff, int dtype, int engine, void* stream);
+int onet_convT2x2_dgrad(const void* go, int64_t ldg, int goff, int N, int H, int W, int Cin, const void* w, int Co,
+                        void* dx, int64_t ldd, int doff, int dtype, int engine, void* stream);
+int onet_convT2x2_wgrad(const void* x, int64_t ldx, int xoff, const void* go, int64_t ldg, int goff, int N, int H,
+                        int W, int Cin, int Co, float* dw, float* dbias, int dtype, int engine, void* stream);
+
+/* Head + loss (Onet.forward :176-189 and compute_loss/jensen_shannon_divergence/log1pexp :221-267) in one
+ * bandwidth-bound pass: Vt, Vd, S=softmax([Vt,Vd]), a=sum_p Lt_p, b=sum_p Ld_p, and the sum over pixels of the
+ * four piecewise-softplus terms added to *loss_acc (loss = *loss_acc / (2*B*H*W)). */
+int onet_head_fwd(const void* L, int64_t ldl, int offl, const void* Hf, int64_t ldh, int offh, int B, int H, int W,
+                  float* Vt, float* Vd, float* S, float* a, float* b, double* loss_acc, int dtype, void* stream);
+/* Backward: closed-form JSD gradient scaled by *gscale (NULL = none) plus optional external gradients w.r.t.
+ * Vt, Vd, S; writes dL and dH as dense [2B,H,W,64]. */
+int onet_head_bwd(const void* L, int64_t ldl, int offl, const void* Hf, int64_t ldh, int offh, int B, int H, int W,
+                  const float* Vt, const float* Vd, const float* a, const float* b, const float* gscale,
+                  const float* gVt, const float* gVd, const float* gS, void* dL, void* dH, int dtype, void* stream);
+
+/* argmax of the 2-way softmax: 1 iff Vd > Vt (Onet.predict_label :193-202) */
+int onet_predict_label(const float* Vt, const float* Vd, int64_t n, int64_t* out, void* stream);
+
+/* torch.optim.Adam step (no weight decay, amsgrad=False; Train_Onet_on_simclutter_20250407.py:181-182) over a
+ * flat fp32 arena; `step` is the 1-based step count, gradients are multiplied by grad_scale first. */
+int onet_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                   float eps, int step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ONET_B200_H */

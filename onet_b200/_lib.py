@@ -1,0 +1,101 @@
+"""ctypes binding of the C-ABI library `libonet_b200.so` (include/onet_b200.h).
+
+The library is built in-tree by `__graft_entry__.build()` (nvcc, sm_100a).  There is NO fallback: if the
+shared object is missing or a call fails, an exception is raised."""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libonet_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+F32, BF16 = 0, 1
+ENGINE_SIMT, ENGINE_TC = 0, 1
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
+              "-Xcompiler", "-fPIC"]
+
+
+def _sources():
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))] + \
+        [os.path.join(os.path.dirname(_HERE), "include", "onet_b200.h")]
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/capi.cu -> libonet_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    if not force and os.path.isfile(LIB_PATH):
+        newest = max(os.path.getmtime(s) for s in _sources())
+        if os.path.getmtime(LIB_PATH) >= newest:
+            return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "capi.cu"), "-lcudart"]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+class OnetLibError(RuntimeError):
+    pass
+
+
+_p, _i, _i64, _f, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double
+
+# name -> argtypes, exactly the prototypes of include/onet_b200.h
+SIGNATURES = {
+    "onet_version": [],
+    "onet_device_info": [_p, _p, _p],
+    "onet_prep_input": [_p, _i, _i, _i, _i, _f, _p, _i, _p],
+    "onet_pack_conv_weights": [_p, _i, _i, _p, _p, _i, _p],
+    "onet_pack_convT_weights": [_p, _i, _i, _p, _p, _i, _p],
+    "onet_conv3x3_fwd": [_p, _i64, _i, _i, _i, _i, _i, _p, _i, _p, _i64, _i, _p, _p, _i, _i, _i, _p],
+    "onet_conv3x3_wgrad": [_p, _i64, _i, _p, _i64, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p],
+    "onet_bn_finalize": [_p, _p, _i, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p],
+    "onet_bn_eval_prepare": [_i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "onet_bn_relu_apply": [_p, _i, _i, _i, _i, _p, _p, _i, _p, _i64, _i, _p, _i, _p],
+    "onet_bn_relu_bwd": [_p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _i64, _i, _p, _i64, _i, _p, _p, _d, _p,
+                         _p, _p, _p, _p, _i, _p],
+    "onet_convT2x2_fwd": [_p, _i64, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i64, _i, _i, _i, _p],
+    "onet_convT2x2_dgrad": [_p, _i64, _i, _i, _i, _i, _i, _p, _i, _p, _i64, _i, _i, _i, _p],
+    "onet_convT2x2_wgrad": [_p, _i64, _i, _p, _i64, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p],
+    "onet_head_fwd": [_p, _i64, _i, _p, _i64, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p],
+    "onet_head_bwd": [_p, _i64, _i, _p, _i64, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
+    "onet_predict_label": [_p, _p, _i64, _p, _p],
+    "onet_adam_step": [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i, _f, _p],
+}
+
+_lib = None
+LAUNCHES = 0   # number of kernel-launching C-ABI calls made by this process (bench.py reports it)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise OnetLibError(f"{LIB_PATH} not built — run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                               "there is no CPU / PyTorch fallback for the Onet hot path")
+        _lib = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(_lib, name)
+            fn.argtypes = argtypes
+            fn.restype = ctypes.c_int
+        _lib.onet_last_error.restype = ctypes.c_char_p
+        _lib.onet_last_error.argtypes = []
+    return _lib
+
+
+def call(name, *args):
+    """Invoke a C-ABI entry point; raise with the library's message on a non-zero status."""
+    global LAUNCHES
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        raise OnetLibError(f"{name} failed: {lib().onet_last_error().decode()}")
+    LAUNCHES += 1
+
+
+def ptr(t, elem_offset=0):
+    """Device pointer of a torch tensor (+ element offset), or None."""
+    if t is None:
+        return None
+    return t.data_ptr() + elem_offset * t.element_size()

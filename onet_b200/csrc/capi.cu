@@ -1,0 +1,637 @@
+// C ABI of libonet_b200.so: host-side launchers for the kernels in this directory (see include/onet_b200.h).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "../../include/onet_b200.h"
+#include "elementwise.cuh"
+#include "simt_conv.cuh"
+#include "tapgemm_tc.cuh"
+
+using namespace onet;
+typedef __nv_bfloat16 bf16;
+
+static thread_local char g_err[512] = "";
+
+static int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+static int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("%s: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+static inline int grid_for(long long items, int block, int cap = 148 * 16) {
+    long long g = (items + block - 1) / block;
+    return static_cast<int>(std::max(1LL, std::min<long long>(g, cap)));
+}
+static inline int p2floor(int v) {
+    int p = 1;
+    while (p * 2 <= v) p *= 2;
+    return p;
+}
+static inline int ilog2(int v) {
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return l;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tensor maps
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 5-D bf16 view (c, w, q, h, n) with 128-byte swizzle; strides in ELEMENTS for dims 1..4
+static int make_map5(CUtensorMap* m, const void* base, const uint64_t dims[5], const uint64_t strides_el[4],
+                     const uint32_t box[5]) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gd[5], gs[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < 5; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i < 4; ++i) gs[i] = strides_el[i] * 2;
+    if (reinterpret_cast<uintptr_t>(base) % 16) return fail("tensor map base not 16-byte aligned");
+    for (int i = 0; i < 4; ++i)
+        if (gs[i] % 16) return fail("tensor map stride %d (%llu B) not a multiple of 16", i, (unsigned long long)gs[i]);
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gd, gs, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(5d) failed with %d", static_cast<int>(r));
+    return 0;
+}
+static int make_map2(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
+                     uint32_t box_outer) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gd[2] = {inner, outer}, gs[1] = {inner * 2};
+    cuuint32_t bx[2] = {box_inner, box_outer}, es[2] = {1, 1};
+    if (reinterpret_cast<uintptr_t>(base) % 16 || gs[0] % 16) return fail("weight tensor map misaligned");
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gd, gs, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(2d) failed with %d", static_cast<int>(r));
+    return 0;
+}
+// plain NHWC activation view: (C, W, 1, H, N)
+static int make_act_map(CUtensorMap* m, const bf16* base, int C, int N, int H, int W, long long ld, const uint32_t box[5]) {
+    const uint64_t dims[5] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), 1, static_cast<uint64_t>(H),
+                              static_cast<uint64_t>(N)};
+    const uint64_t st[4] = {static_cast<uint64_t>(ld), static_cast<uint64_t>(ld) * W, static_cast<uint64_t>(ld) * W,
+                            static_cast<uint64_t>(ld) * W * H};
+    return make_map5(m, base, dims, st, box);
+}
+// 2x-upsampled grid [N,2H,2W,ld] seen from the coarse grid: (c' = dx*ld + c, w, q = dy, h, n)
+static int make_up_map(CUtensorMap* m, const bf16* base, int C, int N, int H, int W, long long ld, const uint32_t box[5]) {
+    const uint64_t dims[5] = {static_cast<uint64_t>(ld + C), static_cast<uint64_t>(W), 2, static_cast<uint64_t>(H),
+                              static_cast<uint64_t>(N)};
+    const uint64_t st[4] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(ld) * 2 * W,
+                            static_cast<uint64_t>(ld) * 4 * W, static_cast<uint64_t>(ld) * 4 * W * H};
+    return make_map5(m, base, dims, st, box);
+}
+
+static int g_sm_count = 0;
+static int sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sm_count <= 0) g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pixel-major tcgen05 launcher
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+static int launch_px(const CUtensorMap& tA, const CUtensorMap& tB, const PxParams& p, cudaStream_t st) {
+    using Cfg = PxCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_px_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (e != cudaSuccess) return fail("cudaFuncSetAttribute(px<%d>): %s", BN, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    const int grid = std::min(tiles, sm_count());
+    tapgemm_px_kernel<BN><<<grid, 192, Cfg::kSmemBytes, st>>>(tA, tB, p);
+    return check_launch("tapgemm_px_kernel");
+}
+
+// Fill the pixel tiling of PxParams; TN is restricted to divide `group_images` so that a tile never straddles
+// the two BatchNorm statistics groups.
+static void px_tiling(PxParams& p, int N, int H, int W, int group_images) {
+    p.N = N; p.H = H; p.W = W;
+    p.TW = std::min(p2floor(W), 16);
+    p.TH = std::min(p2floor(H), 128 / p.TW);
+    int tn = 128 / (p.TW * p.TH);
+    tn = std::min(tn, p2floor(N));
+    if (group_images > 0)
+        while (tn > 1 && (group_images % tn) != 0) tn >>= 1;
+    p.TN = tn;
+    p.log_tw = ilog2(p.TW);
+    p.log_th = ilog2(p.TH);
+    p.tiles_w = (W + p.TW - 1) / p.TW;
+    p.tiles_h = (H + p.TH - 1) / p.TH;
+    p.tiles_n = (N + p.TN - 1) / p.TN;
+    p.num_m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    p.valid_rows = p.TW * p.TH * p.TN;
+}
+
+static int pick_bn(int cout) { return (cout % 256 == 0) ? 256 : (cout % 128 == 0 ? 128 : 64); }
+
+static int conv3x3_tc(const bf16* in, long long ldi, int ci_off, int N, int H, int W, int Cin, const bf16* wp, int Cout,
+                      bf16* out, long long ldo, int co_off, double* ssum, double* ssq, int group_images, cudaStream_t st) {
+    if (Cin % 64 || Cout % 64) return fail("tc conv needs Cin, Cout multiples of 64 (got %d, %d)", Cin, Cout);
+    if (ldo % 8 || co_off % 8) return fail("tc conv output channel stride/offset must be multiples of 8");
+    PxParams p;
+    memset(&p, 0, sizeof(p));
+    px_tiling(p, N, H, W, ssum ? group_images : 0);
+    const int BN = pick_bn(Cout);
+    p.num_n_tiles = Cout / BN;
+    p.ntaps = 9; p.k_chunks = Cin / 64; p.cin = Cin;
+    for (int t = 0; t < 9; ++t) p.taps[t] = make_int4(0, t % 3 - 1, 0, t / 3 - 1);
+    p.epi_mode = EPI_STORE;
+    p.out = out; p.ldo = ldo; p.out_coff = co_off;
+    p.stat_sum = ssum; p.stat_sq = ssq; p.cout_total = Cout; p.group_images = group_images > 0 ? group_images : N;
+    CUtensorMap tA, tB;
+    const uint32_t box[5] = {64, static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
+    if (make_act_map(&tA, in + ci_off, Cin, N, H, W, ldi, box)) return 1;
+    if (make_map2(&tB, wp, 9ULL * Cin, Cout, 64, BN)) return 1;
+    if (BN == 256) return launch_px<256>(tA, tB, p, st);
+    if (BN == 128) return launch_px<128>(tA, tB, p, st);
+    return launch_px<64>(tA, tB, p, st);
+}
+
+// convT fwd on tensor cores: D[px][(tap,co)] = X[px][:] . wf[(tap,co)][:], scatter epilogue
+static int convT_fwd_tc(const bf16* x, long long ldx, int xoff, int N, int H, int W, int Cin, const bf16* wf,
+                        const float* bias, int Co, bf16* out, long long ldo, int ooff, cudaStream_t st) {
+    if (Cin % 64 || Co % 64) return fail("tc convT needs Cin, Co multiples of 64 (got %d, %d)", Cin, Co);
+    if (ldo % 8 || ooff % 8) return fail("tc convT output channel stride/offset must be multiples of 8");
+    PxParams p;
+    memset(&p, 0, sizeof(p));
+    px_tiling(p, N, H, W, 0);
+    const int BN = pick_bn(Co);
+    p.num_n_tiles = 4 * Co / BN;
+    p.ntaps = 1; p.k_chunks = Cin / 64; p.cin = Cin;
+    p.taps[0] = make_int4(0, 0, 0, 0);
+    p.epi_mode = EPI_CONVT;
+    p.out = out; p.ldo = ldo; p.out_coff = ooff;
+    p.bias = bias; p.co_per_tap = Co; p.cout_total = 4 * Co; p.group_images = N;
+    CUtensorMap tA, tB;
+    const uint32_t box[5] = {64, static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
+    if (make_act_map(&tA, x + xoff, Cin, N, H, W, ldx, box)) return 1;
+    if (make_map2(&tB, wf, Cin, 4ULL * Co, 64, BN)) return 1;
+    if (BN == 256) return launch_px<256>(tA, tB, p, st);
+    if (BN == 128) return launch_px<128>(tA, tB, p, st);
+    return launch_px<64>(tA, tB, p, st);
+}
+
+// convT dgrad on tensor cores: dX[px][ci] = sum_{tap,co} dO[2px+tap][co] * wd[ci][(tap,co)]
+static int convT_dgrad_tc(const bf16* go, long long ldg, int goff, int N, int H, int W, int Cin, const bf16* wd, int Co,
+                          bf16* dx, long long ldd, int doff, cudaStream_t st) {
+    if (Cin % 64 || Co % 64) return fail("tc convT dgrad needs Cin, Co multiples of 64 (got %d, %d)", Cin, Co);
+    if (ldd % 8 || doff % 8) return fail("tc convT dgrad output channel stride/offset must be multiples of 8");
+    PxParams p;
+    memset(&p, 0, sizeof(p));
+    px_tiling(p, N, H, W, 0);
+    const int BN = pick_bn(Cin);
+    p.num_n_tiles = Cin / BN;
+    p.ntaps = 4; p.k_chunks = Co / 64; p.cin = Co;
+    for (int t = 0; t < 4; ++t) p.taps[t] = make_int4((t & 1) * static_cast<int>(ldg), 0, t >> 1, 0);
+    p.epi_mode = EPI_STORE;
+    p.out = dx; p.ldo = ldd; p.out_coff = doff;
+    p.cout_total = Cin; p.group_images = N;
+    CUtensorMap tA, tB;
+    const uint32_t box[5] = {64, static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
+    if (make_up_map(&tA, go + goff, Co, N, H, W, ldg, box)) return 1;
+    if (make_map2(&tB, wd, 4ULL * Co, Cin, 64, BN)) return 1;
+    if (BN == 256) return launch_px<256>(tA, tB, p, st);
+    if (BN == 128) return launch_px<128>(tA, tB, p, st);
+    return launch_px<64>(tA, tB, p, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight-gradient tcgen05 launcher
+//   dW[m][n][t] (or transposed) = sum_px G[px (-) t][m] * In[px][n]
+//   g_is_up: the M-side operand lives on the 2x upsampled grid (transposed conv), taps = 2x2 positions.
+// ------------------------------------------------------------------------------------------------
+template <int BNW>
+static int launch_wg(const CUtensorMap& tG, const CUtensorMap& tI, const WgParams& p, cudaStream_t st) {
+    using Cfg = WgCfg<BNW>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_wg_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (e != cudaSuccess) return fail("cudaFuncSetAttribute(wg<%d>): %s", BNW, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int units = p.ngroups * p.num_m_tiles * p.num_n_tiles * p.ksplit;
+    const int grid = std::min(units, sm_count());
+    tapgemm_wg_kernel<BNW><<<grid, 192, Cfg::kSmemBytes, st>>>(tG, tI, p);
+    return check_launch("tapgemm_wg_kernel");
+}
+
+static int wgrad_tc(const bf16* g, long long ldg, int goff, int Mc, bool g_is_up, const bf16* in, long long ldi, int ioff,
+                    int Nc, int N, int H, int W, int ntaps, float* dw, bool transposed, cudaStream_t st) {
+    if (Mc % 64 || Nc % 64) return fail("tc wgrad needs channel counts multiples of 64 (got %d, %d)", Mc, Nc);
+    WgParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = N; p.H = H; p.W = W;
+    p.TW = std::min(p2floor(W), 8);
+    p.TH = std::min(p2floor(H), 64 / p.TW);
+    p.TN = 64 / (p.TW * p.TH);
+    p.tiles_w = (W + p.TW - 1) / p.TW;
+    p.tiles_h = (H + p.TH - 1) / p.TH;
+    p.tiles_n = (N + p.TN - 1) / p.TN;
+    p.num_px_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    p.ntaps = ntaps;
+    for (int t = 0; t < ntaps; ++t) {
+        if (g_is_up) p.taps[t] = make_int4((t & 1) * static_cast<int>(ldg), 0, t >> 1, 0);
+        else p.taps[t] = make_int4(0, -(t % 3 - 1), 0, -(t / 3 - 1));
+    }
+    // accumulator groups
+    int ng = 0;
+    if (Mc >= 128) {
+        if (Mc % 128) return fail("tc wgrad: M channels %d not a multiple of 128", Mc);
+        p.m_tile_channels = 128;
+        p.num_m_tiles = Mc / 128;
+        for (int t0 = 0; t0 < ntaps; t0 += kWgMaxAcc) {
+            WgGroup& gr = p.groups[ng++];
+            gr.nacc = std::min(kWgMaxAcc, ntaps - t0);
+            for (int a = 0; a < gr.nacc; ++a) { gr.tapA[a] = gr.tapB[a] = t0 + a; gr.offA[a] = 0; gr.offB[a] = 64; }
+        }
+    } else {
+        p.m_tile_channels = 64;
+        p.num_m_tiles = 1;
+        const int npairs = (ntaps + 1) / 2;
+        for (int p0 = 0; p0 < npairs; p0 += kWgMaxAcc) {
+            WgGroup& gr = p.groups[ng++];
+            gr.nacc = std::min(kWgMaxAcc, npairs - p0);
+            for (int a = 0; a < gr.nacc; ++a) {
+                const int ta = 2 * (p0 + a), tb = ta + 1;
+                gr.tapA[a] = ta; gr.offA[a] = 0;
+                gr.tapB[a] = tb < ntaps ? tb : -1; gr.offB[a] = 0;
+            }
+        }
+    }
+    p.ngroups = ng;
+    const int BNW = (Nc % 128 == 0) ? 128 : 64;
+    p.num_n_tiles = Nc / BNW;
+    const int base_units = p.ngroups * p.num_m_tiles * p.num_n_tiles;
+    int ks = std::max(1, (2 * sm_count() + base_units - 1) / base_units);
+    ks = std::min(ks, std::max(1, p.num_px_tiles / 4));
+    p.px_tiles_per_split = (p.num_px_tiles + ks - 1) / ks;
+    p.ksplit = (p.num_px_tiles + p.px_tiles_per_split - 1) / p.px_tiles_per_split;
+    p.out = dw;
+    p.m_total = Mc; p.n_total = Nc; p.out_transposed = transposed ? 1 : 0;
+    CUtensorMap tG, tI;
+    const uint32_t box[5] = {64, static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
+    if (g_is_up) { if (make_up_map(&tG, g + goff, Mc, N, H, W, ldg, box)) return 1; }
+    else { if (make_act_map(&tG, g + goff, Mc, N, H, W, ldg, box)) return 1; }
+    if (make_act_map(&tI, in + ioff, Nc, N, H, W, ldi, box)) return 1;
+    if (BNW == 128) return launch_wg<128>(tG, tI, p, st);
+    return launch_wg<64>(tG, tI, p, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// exported entry points
+// ------------------------------------------------------------------------------------------------
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int onet_version(void) { return 100; }
+const char* onet_last_error(void) { return g_err; }
+
+int onet_device_info(int* smc, int* major, int* minor) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail("no CUDA device");
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, dev) != cudaSuccess) return fail("cudaGetDeviceProperties failed");
+    if (smc) *smc = pr.multiProcessorCount;
+    if (major) *major = pr.major;
+    if (minor) *minor = pr.minor;
+    return 0;
+}
+
+int onet_prep_input(const float* x, int B, int Cin, int H, int W, float bias, void* out, int dtype, void* stream) {
+    const long long total = static_cast<long long>(B) * H * W * Cin;
+    if (dtype == ONET_F32)
+        prep_input_kernel<float><<<grid_for(total, 256), 256, 0, ST(stream)>>>(x, B, Cin, static_cast<long long>(H) * W, bias, static_cast<float*>(out));
+    else
+        prep_input_kernel<bf16><<<grid_for(total, 256), 256, 0, ST(stream)>>>(x, B, Cin, static_cast<long long>(H) * W, bias, static_cast<bf16*>(out));
+    return check_launch("prep_input");
+}
+
+int onet_pack_conv_weights(const float* w, int Cout, int Cin, void* wf, void* wd, int dtype, void* stream) {
+    const long long total = 9LL * Cout * Cin;
+    if (dtype == ONET_F32)
+        pack_conv_w_kernel<float><<<grid_for(total, 256), 256, 0, ST(stream)>>>(w, Cout, Cin, static_cast<float*>(wf), static_cast<float*>(wd));
+    else
+        pack_conv_w_kernel<bf16><<<grid_for(total, 256), 256, 0, ST(stream)>>>(w, Cout, Cin, static_cast<bf16*>(wf), static_cast<bf16*>(wd));
+    return check_launch("pack_conv_weights");
+}
+
+int onet_pack_convT_weights(const float* w, int Cin, int Cout, void* wf, void* wd, int dtype, void* stream) {
+    const long long total = 4LL * Cout * Cin;
+    if (dtype == ONET_F32)
+        pack_convT_w_kernel<float><<<grid_for(total, 256), 256, 0, ST(stream)>>>(w, Cin, Cout, static_cast<float*>(wf), static_cast<float*>(wd));
+    else
+        pack_convT_w_kernel<bf16><<<grid_for(total, 256), 256, 0, ST(stream)>>>(w, Cin, Cout, static_cast<bf16*>(wf), static_cast<bf16*>(wd));
+    return check_launch("pack_convT_weights");
+}
+
+int onet_conv3x3_fwd(const void* in, int64_t ldi, int ci_off, int N, int H, int W, int Cin, const void* wp, int Cout,
+                     void* out, int64_t ldo, int co_off, double* stat_sum, double* stat_sq, int group_images,
+                     int dtype, int engine, void* stream) {
+    if (N <= 0 || H <= 0 || W <= 0) return fail("conv3x3_fwd: empty tensor");
+    if (engine == ONET_ENGINE_TC) {
+        if (dtype != ONET_BF16) return fail("tc engine is bf16 only");
+        return conv3x3_tc(static_cast<const bf16*>(in), ldi, ci_off, N, H, W, Cin, static_cast<const bf16*>(wp), Cout,
+                          static_cast<bf16*>(out), ldo, co_off, stat_sum, stat_sq, group_images, ST(stream));
+    }
+    const long long M = static_cast<long long>(N) * H * W;
+    dim3 grid(static_cast<unsigned>((M + 63) / 64), (Cout + 63) / 64);
+    const int gi = group_images > 0 ? group_images : N;
+    if (dtype == ONET_F32)
+        conv3x3_simt_kernel<float><<<grid, 256, 0, ST(stream)>>>(static_cast<const float*>(in), ldi, ci_off, N, H, W, Cin,
+                                                                 static_cast<const float*>(wp), Cout, static_cast<float*>(out),
+                                                                 ldo, co_off, stat_sum, stat_sq, gi);
+    else
+        conv3x3_simt_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(static_cast<const bf16*>(in), ldi, ci_off, N, H, W, Cin,
+                                                                static_cast<const bf16*>(wp), Cout, static_cast<bf16*>(out), ldo,
+                                                                co_off, stat_sum, stat_sq, gi);
+    return check_launch("conv3x3_simt");
+}
+
+int onet_conv3x3_wgrad(const void* g, int64_t ldg, int g_off, const void* in, int64_t ldi, int ci_off, int N, int H,
+                       int W, int Cin, int Cout, float* dw, int dtype, int engine, void* stream) {
+    if (engine == ONET_ENGINE_TC) {
+        if (dtype != ONET_BF16) return fail("tc engine is bf16 only");
+        return wgrad_tc(static_cast<const bf16*>(g), ldg, g_off, Cout, false, static_cast<const bf16*>(in), ldi, ci_off, Cin,
+                        N, H, W, 9, dw, false, ST(stream));
+    }
+    const long long M = static_cast<long long>(N) * H * W;
+    const int K = 9 * Cin;
+    const int bx = (Cout + 63) / 64, by = (K + 63) / 64;
+    int splits = std::max(1, (4 * sm_count()) / (bx * by));
+    long long per = (M + splits - 1) / splits;
+    per = std::max<long long>(16, (per + 15) / 16 * 16);
+    splits = static_cast<int>((M + per - 1) / per);
+    dim3 grid(bx, by, splits);
+    if (dtype == ONET_F32)
+        conv3x3_wgrad_simt_kernel<float><<<grid, 256, 0, ST(stream)>>>(static_cast<const float*>(g), ldg, g_off,
+                                                                       static_cast<const float*>(in), ldi, ci_off, N, H, W, Cin, Cout, dw, per);
+    else
+        conv3x3_wgrad_simt_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(static_cast<const bf16*>(g), ldg, g_off,
+                                                                      static_cast<const bf16*>(in), ldi, ci_off, N, H, W, Cin, Cout, dw, per);
+    return check_launch("conv3x3_wgrad_simt");
+}
+
+int onet_bn_finalize(const double* stat_sum, const double* stat_sq, int G, int C, double count, const float* gamma0,
+                     const float* beta0, float* running_mean0, float* running_var0, const float* gamma1,
+                     const float* beta1, float* running_mean1, float* running_var1, float momentum, float* mean,
+                     float* invstd, float* scale, float* shift, void* stream) {
+    if (G < 1 || G > 2) return fail("bn_finalize: G must be 1 or 2");
+    BnGroupPtrs p;
+    p.gamma[0] = gamma0; p.beta[0] = beta0; p.running_mean[0] = running_mean0; p.running_var[0] = running_var0;
+    p.gamma[1] = gamma1; p.beta[1] = beta1; p.running_mean[1] = running_mean1; p.running_var[1] = running_var1;
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(stat_sum, stat_sq, G, C, count, p, momentum, mean, invstd, scale, shift);
+    return check_launch("bn_finalize");
+}
+
+int onet_bn_eval_prepare(int G, int C, const float* gamma0, const float* beta0, const float* running_mean0,
+                         const float* running_var0, const float* gamma1, const float* beta1,
+                         const float* running_mean1, const float* running_var1, float* scale, float* shift,
+                         void* stream) {
+    if (G < 1 || G > 2) return fail("bn_eval_prepare: G must be 1 or 2");
+    BnGroupPtrs p;
+    p.gamma[0] = gamma0; p.beta[0] = beta0;
+    p.running_mean[0] = const_cast<float*>(running_mean0); p.running_var[0] = const_cast<float*>(running_var0);
+    p.gamma[1] = gamma1; p.beta[1] = beta1;
+    p.running_mean[1] = const_cast<float*>(running_mean1); p.running_var[1] = const_cast<float*>(running_var1);
+    bn_eval_prepare_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(G, C, p, scale, shift);
+    return check_launch("bn_eval_prepare");
+}
+
+int onet_bn_relu_apply(const void* y, int N, int H, int W, int C, const float* scale, const float* shift,
+                       int group_images, void* out, int64_t ldo, int ooff, void* pool, int dtype, void* stream) {
+    if (C % 8 || ldo % 8 || ooff % 8) return fail("bn_relu_apply: channel counts/offsets must be multiples of 8");
+    const long long total = static_cast<long long>(N) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+    const int gi = group_images > 0 ? group_images : N;
+    if (dtype == ONET_F32)
+        bn_relu_apply_kernel<float><<<grid_for(total, 256, 148 * 32), 256, 0, ST(stream)>>>(
+            static_cast<const float*>(y), N, H, W, C, scale, shift, gi, static_cast<float*>(out), ldo, ooff, static_cast<float*>(pool));
+    else
+        bn_relu_apply_kernel<bf16><<<grid_for(total, 256, 148 * 32), 256, 0, ST(stream)>>>(
+            static_cast<const bf16*>(y), N, H, W, C, scale, shift, gi, static_cast<bf16*>(out), ldo, ooff, static_cast<bf16*>(pool));
+    return check_launch("bn_relu_apply");
+}
+
+}  // extern "C"
+
+template <typename T>
+static int bn_bwd_impl(const void* y, int N, int H, int W, int C, const float* scale, const float* shift, const float* mean,
+                       const float* invstd, int group_images, const void* g1, int64_t ld1, int off1, const void* g2,
+                       int64_t ld2, int off2, const void* gp, double* sums, double count, void* dy, float* dgamma0,
+                       float* dbeta0, float* dgamma1, float* dbeta1, cudaStream_t st) {
+    BnBwdArgs<T> a;
+    a.y = static_cast<const T*>(y); a.N = N; a.H = H; a.W = W; a.C = C;
+    a.scale = scale; a.shift = shift; a.mean = mean; a.invstd = invstd;
+    a.group_images = group_images > 0 ? group_images : N;
+    a.g1 = static_cast<const T*>(g1); a.ld1 = ld1; a.off1 = off1;
+    a.g2 = static_cast<const T*>(g2); a.ld2 = ld2; a.off2 = off2;
+    a.gp = static_cast<const T*>(gp);
+    a.sums = sums; a.count = count; a.dy = static_cast<T*>(dy);
+    const int G = (N + a.group_images - 1) / a.group_images;
+    const int OC = C / 8, lanes = 256 / OC;
+    const long long quads = static_cast<long long>(a.group_images) * ((H + 1) / 2) * ((W + 1) / 2);
+    const int gx = static_cast<int>(std::max(1LL, std::min<long long>((quads + lanes - 1) / lanes, 148 * 8 / G)));
+    bn_bwd_reduce_kernel<T><<<dim3(gx, G), 256, 0, st>>>(a);
+    if (check_launch("bn_bwd_reduce")) return 1;
+    const long long total = static_cast<long long>(N) * ((H + 1) / 2) * ((W + 1) / 2) * OC;
+    bn_bwd_apply_kernel<T><<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(a);
+    if (check_launch("bn_bwd_apply")) return 1;
+    if (dgamma0 != nullptr) {
+        bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, G, C, dgamma0, dbeta0, dgamma1 ? dgamma1 : dgamma0,
+                                                              dbeta1 ? dbeta1 : dbeta0);
+        if (check_launch("bn_param_grad")) return 1;
+    }
+    return 0;
+}
+
+extern "C" {
+
+int onet_bn_relu_bwd(const void* y, int N, int H, int W, int C, const float* scale, const float* shift,
+                     const float* mean, const float* invstd, int group_images, const void* g1, int64_t ld1, int off1,
+                     const void* g2, int64_t ld2, int off2, const void* gp, double* sums, double count, void* dy,
+                     float* dgamma0, float* dbeta0, float* dgamma1, float* dbeta1, int dtype, void* stream) {
+    if (C % 8 || C > 2048) return fail("bn_relu_bwd: C must be a multiple of 8 and <= 2048");
+    if (256 % (C / 8) != 0 && (C / 8) < 256) return fail("bn_relu_bwd: C/8 must divide 256");
+    if (g1 == nullptr) return fail("bn_relu_bwd: g1 is required");
+    if (dtype == ONET_F32)
+        return bn_bwd_impl<float>(y, N, H, W, C, scale, shift, mean, invstd, group_images, g1, ld1, off1, g2, ld2, off2, gp,
+                                  sums, count, dy, dgamma0, dbeta0, dgamma1, dbeta1, ST(stream));
+    return bn_bwd_impl<bf16>(y, N, H, W, C, scale, shift, mean, invstd, group_images, g1, ld1, off1, g2, ld2, off2, gp, sums,
+                             count, dy, dgamma0, dbeta0, dgamma1, dbeta1, ST(stream));
+}
+
+int onet_convT2x2_fwd(const void* x, int64_t ldx, int xoff, int N, int H, int W, int Cin, const void* w,
+                      const float* bias, int Co, void* out, int64_t ldo, int ooff, int dtype, int engine, void* stream) {
+    if (engine == ONET_ENGINE_TC) {
+        if (dtype != ONET_BF16) return fail("tc engine is bf16 only");
+        return convT_fwd_tc(static_cast<const bf16*>(x), ldx, xoff, N, H, W, Cin, static_cast<const bf16*>(w), bias, Co,
+                            static_cast<bf16*>(out), ldo, ooff, ST(stream));
+    }
+    const long long total = 4LL * N * H * W * Co;
+    if (dtype == ONET_F32)
+        convT2x2_fwd_simt_kernel<float><<<grid_for(total, 256, 148 * 64), 256, 0, ST(stream)>>>(
+            static_cast<const float*>(x), ldx, xoff, N, H, W, Cin, static_cast<const float*>(w), bias, Co, static_cast<float*>(out), ldo, ooff, 0);
+    else
+        convT2x2_fwd_simt_kernel<bf16><<<grid_for(total, 256, 148 * 64), 256, 0, ST(stream)>>>(
+            static_cast<const bf16*>(x), ldx, xoff, N, H, W, Cin, static_cast<const float*>(w), bias, Co, static_cast<bf16*>(out), ldo, ooff, 1);
+    return check_launch("convT2x2_fwd_simt");
+}
+
+int onet_convT2x2_dgrad(const void* go, int64_t ldg, int goff, int N, int H, int W, int Cin, const void* w, int Co,
+                        void* dx, int64_t ldd, int doff, int dtype, int engine, void* stream) {
+    if (engine == ONET_ENGINE_TC) {
+        if (dtype != ONET_BF16) return fail("tc engine is bf16 only");
+        return convT_dgrad_tc(static_cast<const bf16*>(go), ldg, goff, N, H, W, Cin, static_cast<const bf16*>(w), Co,
+                              static_cast<bf16*>(dx), ldd, doff, ST(stream));
+    }
+    const long long total = static_cast<long long>(N) * H * W * Cin;
+    if (dtype == ONET_F32)
+        convT2x2_dgrad_simt_kernel<float><<<grid_for(total, 256, 148 * 64), 256, 0, ST(stream)>>>(
+            static_cast<const float*>(go), ldg, goff, N, H, W, Cin, static_cast<const float*>(w), Co, static_cast<float*>(dx), ldd, doff);
+    else
+        convT2x2_dgrad_simt_kernel<bf16><<<grid_for(total, 256, 148 * 64), 256, 0, ST(stream)>>>(
+            static_cast<const bf16*>(go), ldg, goff, N, H, W, Cin, static_cast<const float*>(w), Co, static_cast<bf16*>(dx), ldd, doff);
+    return check_launch("convT2x2_dgrad_simt");
+}
+
+int onet_convT2x2_wgrad(const void* x, int64_t ldx, int xoff, const void* go, int64_t ldg, int goff, int N, int H,
+                        int W, int Cin, int Co, float* dw, float* dbias, int dtype, int engine, void* stream) {
+    const long long M = static_cast<long long>(N) * H * W;
+    if (dbias != nullptr) {
+        // bias gradient = column sums of dO over the whole upsampled grid
+        const int cpb = std::min(Co, 64);
+        dim3 grid(static_cast<unsigned>(std::min<long long>(148 * 4, (4 * M + (256 / cpb) - 1) / (256 / cpb))), (Co + cpb - 1) / cpb);
+        if (dtype == ONET_F32)
+            colsum_kernel<float><<<grid, 256, 0, ST(stream)>>>(static_cast<const float*>(go), ldg, goff, 4 * M, Co, dbias);
+        else
+            colsum_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(static_cast<const bf16*>(go), ldg, goff, 4 * M, Co, dbias);
+        if (check_launch("colsum")) return 1;
+    }
+    if (engine == ONET_ENGINE_TC) {
+        if (dtype != ONET_BF16) return fail("tc engine is bf16 only");
+        // M-side = dO on the upsampled grid (m = co), N-side = X (n = ci); dW[ci][co][tap] -> transposed output
+        return wgrad_tc(static_cast<const bf16*>(go), ldg, goff, Co, true, static_cast<const bf16*>(x), ldx, xoff, Cin, N, H, W,
+                        4, dw, true, ST(stream));
+    }
+    const long long nthreads = 4LL * Cin * Co;
+    int splits = static_cast<int>(std::max<long long>(1, std::min<long long>(M, (148LL * 2048) / std::max<long long>(1, nthreads))));
+    const long long per = (M + splits - 1) / splits;
+    splits = static_cast<int>((M + per - 1) / per);
+    dim3 grid(static_cast<unsigned>((nthreads + 255) / 256), splits);
+    if (dtype == ONET_F32)
+        convT2x2_wgrad_simt_kernel<float><<<grid, 256, 0, ST(stream)>>>(static_cast<const float*>(x), ldx, xoff,
+                                                                        static_cast<const float*>(go), ldg, goff, N, H, W, Cin, Co, dw, per);
+    else
+        convT2x2_wgrad_simt_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), ldx, xoff,
+                                                                       static_cast<const bf16*>(go), ldg, goff, N, H, W, Cin, Co, dw, per);
+    return check_launch("convT2x2_wgrad_simt");
+}
+
+}  // extern "C"
+
+template <typename T>
+static void fill_head(HeadArgs<T>& a, const void* L, int64_t ldl, int offl, const void* Hf, int64_t ldh, int offh, int B,
+                      int H, int W) {
+    memset(&a, 0, sizeof(a));
+    a.L = static_cast<const T*>(L); a.ldl = ldl; a.offl = offl;
+    a.Hf = static_cast<const T*>(Hf); a.ldh = ldh; a.offh = offh;
+    a.B = B; a.HW = static_cast<long long>(H) * W;
+}
+
+extern "C" {
+
+int onet_head_fwd(const void* L, int64_t ldl, int offl, const void* Hf, int64_t ldh, int offh, int B, int H, int W,
+                  float* Vt, float* Vd, float* S, float* a_out, float* b_out, double* loss_acc, int dtype, void* stream) {
+    if (ldl % 8 || offl % 8 || ldh % 8 || offh % 8) return fail("head: channel strides/offsets must be multiples of 8");
+    const long long npx = static_cast<long long>(B) * H * W;
+    const int grid = grid_for(npx * 8, 256, 148 * 8);
+    if (dtype == ONET_F32) {
+        HeadArgs<float> a;
+        fill_head(a, L, ldl, offl, Hf, ldh, offh, B, H, W);
+        a.Vt = Vt; a.Vd = Vd; a.S = S; a.a = a_out; a.b = b_out; a.loss_acc = loss_acc;
+        head_fwd_kernel<float><<<grid, 256, 0, ST(stream)>>>(a);
+    } else {
+        HeadArgs<bf16> a;
+        fill_head(a, L, ldl, offl, Hf, ldh, offh, B, H, W);
+        a.Vt = Vt; a.Vd = Vd; a.S = S; a.a = a_out; a.b = b_out; a.loss_acc = loss_acc;
+        head_fwd_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(a);
+    }
+    return check_launch("head_fwd");
+}
+
+int onet_head_bwd(const void* L, int64_t ldl, int offl, const void* Hf, int64_t ldh, int offh, int B, int H, int W,
+                  const float* Vt, const float* Vd, const float* a_in, const float* b_in, const float* gscale,
+                  const float* gVt, const float* gVd, const float* gS, void* dL, void* dH, int dtype, void* stream) {
+    const long long npx = static_cast<long long>(B) * H * W;
+    const int grid = grid_for(npx * 8, 256, 148 * 8);
+    if (dtype == ONET_F32) {
+        HeadArgs<float> a;
+        fill_head(a, L, ldl, offl, Hf, ldh, offh, B, H, W);
+        a.Vt = const_cast<float*>(Vt); a.Vd = const_cast<float*>(Vd); a.a = const_cast<float*>(a_in); a.b = const_cast<float*>(b_in);
+        a.gscale = gscale; a.gVt = gVt; a.gVd = gVd; a.gS = gS;
+        a.dL = static_cast<float*>(dL); a.dH = static_cast<float*>(dH);
+        head_bwd_kernel<float><<<grid, 256, 0, ST(stream)>>>(a);
+    } else {
+        HeadArgs<bf16> a;
+        fill_head(a, L, ldl, offl, Hf, ldh, offh, B, H, W);
+        a.Vt = const_cast<float*>(Vt); a.Vd = const_cast<float*>(Vd); a.a = const_cast<float*>(a_in); a.b = const_cast<float*>(b_in);
+        a.gscale = gscale; a.gVt = gVt; a.gVd = gVd; a.gS = gS;
+        a.dL = static_cast<bf16*>(dL); a.dH = static_cast<bf16*>(dH);
+        head_bwd_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(a);
+    }
+    return check_launch("head_bwd");
+}
+
+int onet_predict_label(const float* Vt, const float* Vd, int64_t n, int64_t* out, void* stream) {
+    predict_label_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(Vt, Vd, n, reinterpret_cast<long long*>(out));
+    return check_launch("predict_label");
+}
+
+int onet_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                   float eps, int step, float grad_scale, void* stream) {
+    if (step < 1) return fail("adam: step must be >= 1");
+    const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+    const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
+    adam_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale);
+    return check_launch("adam");
+}
+
+}  // extern "C"

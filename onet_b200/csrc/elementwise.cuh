@@ -1,0 +1,542 @@
+// HBM-bound kernels of the Onet path: BatchNorm statistics finalisation, BN+ReLU(+2x2 max-pool) apply that
+// writes straight into the skip-concat buffer, the matching backward passes (ReLU mask, max-pool routing and
+// BatchNorm backward fused), the dot-product head + sigmoid + JSD loss forward/backward, input preparation,
+// weight packing and Adam.  All activations NHWC; 8 channels (16 B of bf16 / 32 B of fp32) per thread access.
+#pragma once
+#include "simt_conv.cuh"
+
+namespace onet {
+
+template <typename T> __device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <> __device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+template <typename T> __device__ __forceinline__ void store8(T* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 u;
+    __nv_bfloat162 t;
+    t = __floats2bfloat162_rn(v[0], v[1]); u.x = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(v[2], v[3]); u.y = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(v[4], v[5]); u.z = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(v[6], v[7]); u.w = *reinterpret_cast<uint32_t*>(&t);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+template <typename T> __device__ __forceinline__ float round_to(float v) { return to_f<T>(from_f<T>(v)); }
+
+constexpr float kBnEps = 1e-5f;
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm statistics -> per-group (mean, invstd, scale, shift) and the running-buffer update.
+// stats layout: [G][C] doubles for sum and sumsq; outputs [G][C] floats.  One thread per channel; the
+// groups (twin branches) are folded into the running buffers SEQUENTIALLY, group 0 first, which is what
+// two successive calls of the same nn.BatchNorm2d do in the reference (Onet_vanilla_20240606.py:175,181).
+// For the non-shared twin the per-group pointers differ.
+// ------------------------------------------------------------------------------------------------
+struct BnGroupPtrs {
+    const float* gamma[2];
+    const float* beta[2];
+    float* running_mean[2];
+    float* running_var[2];
+};
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sq, int G, int C,
+                                   double count, BnGroupPtrs ptrs, float momentum, float* __restrict__ mean,
+                                   float* __restrict__ invstd, float* __restrict__ scale, float* __restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    for (int g = 0; g < G; ++g) {
+        const double m = sum[g * C + c] / count;
+        double var = sq[g * C + c] / count - m * m;
+        var = var > 0.0 ? var : 0.0;
+        const float mf = static_cast<float>(m);
+        const float is = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kBnEps)));
+        const float sc = ptrs.gamma[g][c] * is;
+        mean[g * C + c] = mf;
+        invstd[g * C + c] = is;
+        scale[g * C + c] = sc;
+        shift[g * C + c] = ptrs.beta[g][c] - mf * sc;
+        if (ptrs.running_mean[g] != nullptr) {
+            const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+            ptrs.running_mean[g][c] = (1.f - momentum) * ptrs.running_mean[g][c] + momentum * mf;
+            ptrs.running_var[g][c] = (1.f - momentum) * ptrs.running_var[g][c] + momentum * static_cast<float>(unb);
+        }
+    }
+}
+
+// eval mode: scale/shift from the running statistics
+__global__ void bn_eval_prepare_kernel(int G, int C, BnGroupPtrs ptrs, float* __restrict__ scale, float* __restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    for (int g = 0; g < G; ++g) {
+        const float sc = ptrs.gamma[g][c] / sqrtf(ptrs.running_var[g][c] + kBnEps);
+        scale[g * C + c] = sc;
+        shift[g * C + c] = ptrs.beta[g][c] - ptrs.running_mean[g][c] * sc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN + ReLU apply, optional fused 2x2 max-pool.  One thread = one 2x2 pixel quad x 8 channels.
+//   y   : raw conv output [N,H,W,C]
+//   out : [N,H,W,ldo] (+ooff)  (e.g. the skip half of a concat buffer)
+//   pool: [N,H/2,W/2,C] or nullptr (floor semantics of nn.MaxPool2d(2))
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_relu_apply_kernel(const T* __restrict__ y, int N, int H, int W, int C, const float* __restrict__ scale,
+                     const float* __restrict__ shift, int group_images, T* __restrict__ out, long long ldo, int ooff,
+                     T* __restrict__ pool) {
+    const int OC = C >> 3, H2 = (H + 1) >> 1, W2 = (W + 1) >> 1, HP = H >> 1, WP = W >> 1;
+    const long long total = static_cast<long long>(N) * H2 * W2 * OC;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int oc = static_cast<int>(idx % OC);
+        long long q = idx / OC;
+        const int w2 = static_cast<int>(q % W2); q /= W2;
+        const int h2 = static_cast<int>(q % H2);
+        const int n = static_cast<int>(q / H2);
+        const int g = min(n / group_images, 1);
+        float sc[8], sh[8], mx[8];
+        load8<float>(scale + g * C + oc * 8, sc);
+        load8<float>(shift + g * C + oc * 8, sh);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mx[i] = 0.f;   // post-ReLU values are >= 0
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const int h = 2 * h2 + dy, w = 2 * w2 + dx;
+                if (h < H && w < W) {
+                    const long long px = (static_cast<long long>(n) * H + h) * W + w;
+                    float v[8];
+                    load8<T>(y + px * C + oc * 8, v);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        v[i] = round_to<T>(fmaxf(fmaf(v[i], sc[i], sh[i]), 0.f));
+                        mx[i] = fmaxf(mx[i], v[i]);
+                    }
+                    store8<T>(out + px * ldo + ooff + oc * 8, v);
+                }
+            }
+        if (pool != nullptr && h2 < HP && w2 < WP)
+            store8<T>(pool + ((static_cast<long long>(n) * HP + h2) * WP + w2) * C + oc * 8, mx);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward of (BN -> ReLU [-> skip / 2x2 max-pool]).  The gradient w.r.t. the post-ReLU activation is the
+// sum of up to two dense sources (g1, g2: e.g. the skip half of d(concat) and the head's dL) and a pooled
+// source gp (gradient of the max-pool output, routed to the first maximum of each 2x2 window exactly as
+// ATen's max_pool2d backward does).  Pass 1 (reduce): s1 = sum dZ, s2 = sum dZ * xhat per group/channel.
+// Pass 2 (apply): dY = gamma * invstd * (dZ - s1/n - xhat * s2/n).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct BnBwdArgs {
+    const T* y; int N, H, W, C;
+    const float* scale; const float* shift; const float* mean; const float* invstd;   // [G][C]
+    int group_images;
+    const T* g1; long long ld1; int off1;
+    const T* g2; long long ld2; int off2;
+    const T* gp;                                 // [N,H/2,W/2,C] or nullptr
+    double* sums;                                // [G][2][C]
+    double count;                                // elements per channel per group
+    T* dy;                                       // [N,H,W,C]
+};
+
+template <typename T>
+__device__ __forceinline__ void bn_bwd_quad(const BnBwdArgs<T>& a, int n, int h2, int w2, int oc, const float (&sc)[8],
+                                            const float (&sh)[8], const float (&mu)[8], const float (&is)[8],
+                                            float (&dz)[4][8], float (&xh)[4][8], bool (&ok)[4]) {
+    const int HP = a.H >> 1, WP = a.W >> 1;
+    float act[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int h = 2 * h2 + (k >> 1), w = 2 * w2 + (k & 1);
+        ok[k] = (h < a.H) && (w < a.W);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { dz[k][i] = 0.f; xh[k][i] = 0.f; act[k][i] = 0.f; }
+        if (!ok[k]) continue;
+        const long long px = (static_cast<long long>(n) * a.H + h) * a.W + w;
+        float yv[8], gv[8];
+        load8<T>(a.y + px * a.C + oc * 8, yv);
+        load8<T>(a.g1 + px * a.ld1 + a.off1 + oc * 8, gv);
+        if (a.g2 != nullptr) {
+            float g2v[8];
+            load8<T>(a.g2 + px * a.ld2 + a.off2 + oc * 8, g2v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) gv[i] += g2v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            act[k][i] = round_to<T>(fmaxf(fmaf(yv[i], sc[i], sh[i]), 0.f));
+            xh[k][i] = (yv[i] - mu[i]) * is[i];
+            dz[k][i] = gv[i];
+        }
+    }
+    if (a.gp != nullptr && h2 < HP && w2 < WP) {
+        float pv[8];
+        load8<T>(a.gp + ((static_cast<long long>(n) * HP + h2) * WP + w2) * a.C + oc * 8, pv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int best = 0;
+            float bv = act[0][i];
+#pragma unroll
+            for (int k = 1; k < 4; ++k)
+                if (act[k][i] > bv) { bv = act[k][i]; best = k; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k == best) dz[k][i] += pv[i];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (!(act[k][i] > 0.f)) dz[k][i] = 0.f;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const BnBwdArgs<T> a) {
+    __shared__ float s_red[16][256];
+    const int OC = a.C >> 3, LANES = 256 / OC;
+    const int oc = threadIdx.x % OC, ln = threadIdx.x / OC;
+    const int g = blockIdx.y;
+    const int H2 = (a.H + 1) >> 1, W2 = (a.W + 1) >> 1;
+    const int n_begin = g * a.group_images, n_end = min(a.N, (g + 1) * a.group_images);
+    const long long quads = static_cast<long long>(n_end - n_begin) * H2 * W2;
+    float acc1[8] = {}, acc2[8] = {};
+    if (ln < LANES) {
+        float sc[8], sh[8], mu[8], is[8];
+        load8<float>(a.scale + g * a.C + oc * 8, sc);
+        load8<float>(a.shift + g * a.C + oc * 8, sh);
+        load8<float>(a.mean + g * a.C + oc * 8, mu);
+        load8<float>(a.invstd + g * a.C + oc * 8, is);
+        for (long long q = blockIdx.x * static_cast<long long>(LANES) + ln; q < quads;
+             q += static_cast<long long>(gridDim.x) * LANES) {
+            const int w2 = static_cast<int>(q % W2), h2 = static_cast<int>((q / W2) % H2),
+                      n = n_begin + static_cast<int>(q / (static_cast<long long>(W2) * H2));
+            float dz[4][8], xh[4][8];
+            bool ok[4];
+            bn_bwd_quad<T>(a, n, h2, w2, oc, sc, sh, mu, is, dz, xh, ok);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    acc1[i] += dz[k][i];
+                    acc2[i] = fmaf(dz[k][i], xh[k][i], acc2[i]);
+                }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        s_red[i][threadIdx.x] = acc1[i];
+        s_red[8 + i][threadIdx.x] = acc2[i];
+    }
+    __syncthreads();
+    // thread t < 16*OC: (which = t / OC in 0..15, oc = t % OC) sums over lanes
+    for (int t = threadIdx.x; t < 16 * OC; t += 256) {
+        const int which = t / OC, o = t % OC;
+        float s = 0.f;
+        for (int l = 0; l < LANES; ++l) s += s_red[which][l * OC + o];
+        const int stat = which >> 3, i = which & 7;
+        atomicAdd(a.sums + (static_cast<long long>(g) * 2 + stat) * a.C + o * 8 + i, static_cast<double>(s));
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const BnBwdArgs<T> a) {
+    const int OC = a.C >> 3, H2 = (a.H + 1) >> 1, W2 = (a.W + 1) >> 1;
+    const long long total = static_cast<long long>(a.N) * H2 * W2 * OC;
+    const float inv_n = static_cast<float>(1.0 / a.count);
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int oc = static_cast<int>(idx % OC);
+        long long q = idx / OC;
+        const int w2 = static_cast<int>(q % W2); q /= W2;
+        const int h2 = static_cast<int>(q % H2);
+        const int n = static_cast<int>(q / H2);
+        const int g = min(n / a.group_images, 1);
+        float sc[8], sh[8], mu[8], is[8], m1[8], m2[8];
+        load8<float>(a.scale + g * a.C + oc * 8, sc);
+        load8<float>(a.shift + g * a.C + oc * 8, sh);
+        load8<float>(a.mean + g * a.C + oc * 8, mu);
+        load8<float>(a.invstd + g * a.C + oc * 8, is);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            m1[i] = static_cast<float>(a.sums[(static_cast<long long>(g) * 2 + 0) * a.C + oc * 8 + i]) * inv_n;
+            m2[i] = static_cast<float>(a.sums[(static_cast<long long>(g) * 2 + 1) * a.C + oc * 8 + i]) * inv_n;
+        }
+        float dz[4][8], xh[4][8];
+        bool ok[4];
+        bn_bwd_quad<T>(a, n, h2, w2, oc, sc, sh, mu, is, dz, xh, ok);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!ok[k]) continue;
+            const int h = 2 * h2 + (k >> 1), w = 2 * w2 + (k & 1);
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = sc[i] * (dz[k][i] - m1[i] - xh[k][i] * m2[i]);
+            store8<T>(a.dy + ((static_cast<long long>(n) * a.H + h) * a.W + w) * a.C + oc * 8, o);
+        }
+    }
+}
+
+// dgamma[c] (+)= sum_g s2[g][c], dbeta[c] (+)= sum_g s1[g][c]; per-group targets may alias (shared twin)
+__global__ void bn_param_grad_kernel(const double* __restrict__ sums, int G, int C, float* dgamma0, float* dbeta0,
+                                     float* dgamma1, float* dbeta1) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    for (int g = 0; g < G; ++g) {
+        float* dg = g == 0 ? dgamma0 : dgamma1;
+        float* db = g == 0 ? dbeta0 : dbeta1;
+        db[c] += static_cast<float>(sums[(static_cast<long long>(g) * 2 + 0) * C + c]);
+        dg[c] += static_cast<float>(sums[(static_cast<long long>(g) * 2 + 1) * C + c]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Head: V = sum_p L_p*H_p per branch, S = softmax([Vt,Vd]), a = sum_p Lt_p, b = sum_p Ld_p, and the JSD
+// loss  (1/2N) sum [ sp(-a St) + sp(a Sd) + sp(-b Sd) + sp(b St) ]  with the reference's piecewise
+// softplus `sp` (Onet_vanilla_20240606.py:237-251, including its ln2 plateau below -37).
+// 8 threads per pixel, 8 channels each (C = 64).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sp_ref(float x, float& val, float& der) {
+    if (x <= -37.f) {            // exp(x) ~ 0+ is re-matched by the (-37,18] branch -> log(1+exp(exp(x)))
+        const float e = expf(x), ee = expf(e);
+        val = logf(1.f + ee);
+        der = ee / (1.f + ee) * e;
+    } else if (x <= 18.f) {
+        const float e = expf(x);
+        val = logf(1.f + e);
+        der = e / (1.f + e);
+    } else if (x < 33.3f) {
+        const float e = expf(-x);
+        val = x + e;
+        der = 1.f - e;
+    } else {
+        val = x;
+        der = 1.f;
+    }
+}
+
+template <typename T>
+struct HeadArgs {
+    const T* L; long long ldl; int offl;     // twin local features  [2B,H,W,ldl]
+    const T* Hf; long long ldh; int offh;    // twin global features [2B,H,W,ldh]
+    int B; long long HW;                     // images per branch, pixels per image
+    float* Vt; float* Vd; float* S;          // (B,1,H,W), (B,1,H,W), (B,2,H,W) fp32
+    float* a; float* b;                      // (B,H,W) fp32 channel sums of Lt / Ld
+    double* loss_acc;                        // sum of the four softplus terms over all pixels
+    // backward only
+    const float* gscale;                     // upstream d(loss) scalar (device) or nullptr (=> no fused loss grad)
+    const float* gVt; const float* gVd; const float* gS;   // optional external gradients, fp32
+    T* dL; T* dH;                            // [2B,H,W,64] dense
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(const HeadArgs<T> a) {
+    const long long npx = static_cast<long long>(a.B) * a.HW;
+    const int sub = threadIdx.x & 7;
+    float lsum = 0.f;
+    for (long long p = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 3; p < npx;
+         p += (static_cast<long long>(gridDim.x) * blockDim.x) >> 3) {
+        const long long pd = p + npx;   // same pixel of the down-branch image
+        float lt[8], ht[8], ld[8], hd[8];
+        load8<T>(a.L + p * a.ldl + a.offl + sub * 8, lt);
+        load8<T>(a.Hf + p * a.ldh + a.offh + sub * 8, ht);
+        load8<T>(a.L + pd * a.ldl + a.offl + sub * 8, ld);
+        load8<T>(a.Hf + pd * a.ldh + a.offh + sub * 8, hd);
+        float vt = 0.f, vd = 0.f, sa = 0.f, sb = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            vt = fmaf(lt[i], ht[i], vt);
+            vd = fmaf(ld[i], hd[i], vd);
+            sa += lt[i];
+            sb += ld[i];
+        }
+#pragma unroll
+        for (int o = 4; o >= 1; o >>= 1) {
+            vt += __shfl_xor_sync(0xffffffffu, vt, o);
+            vd += __shfl_xor_sync(0xffffffffu, vd, o);
+            sa += __shfl_xor_sync(0xffffffffu, sa, o);
+            sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        }
+        if (sub == 0) {
+            const float mx = fmaxf(vt, vd);
+            const float et = expf(vt - mx), ed = expf(vd - mx);
+            const float inv = 1.f / (et + ed);
+            const float st = et * inv, sd = ed * inv;
+            const long long n = p / a.HW, hw = p % a.HW;
+            a.Vt[p] = vt;
+            a.Vd[p] = vd;
+            a.S[(n * 2 + 0) * a.HW + hw] = st;
+            a.S[(n * 2 + 1) * a.HW + hw] = sd;
+            a.a[p] = sa;
+            a.b[p] = sb;
+            float v1, v2, v3, v4, d;
+            sp_ref(-sa * st, v1, d);
+            sp_ref(sa * sd, v2, d);
+            sp_ref(-sb * sd, v3, d);
+            sp_ref(sb * st, v4, d);
+            lsum += (v1 + v2) + (v3 + v4);
+        }
+    }
+    __shared__ float s_l[256];
+    s_l[threadIdx.x] = lsum;
+    __syncthreads();
+    for (int s = 128; s >= 1; s >>= 1) {
+        if (threadIdx.x < s) s_l[threadIdx.x] += s_l[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && a.loss_acc != nullptr) atomicAdd(a.loss_acc, static_cast<double>(s_l[0]));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(const HeadArgs<T> a) {
+    const long long npx = static_cast<long long>(a.B) * a.HW;
+    const int sub = threadIdx.x & 7;
+    const float gs = a.gscale != nullptr ? *a.gscale : 0.f;
+    const float cc = gs / (2.f * static_cast<float>(npx));
+    for (long long p = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 3; p < npx;
+         p += (static_cast<long long>(gridDim.x) * blockDim.x) >> 3) {
+        const long long pd = p + npx;
+        const float vt = a.Vt[p], vd = a.Vd[p], sa = a.a[p], sb = a.b[p];
+        const float mx = fmaxf(vt, vd);
+        const float et = expf(vt - mx), ed = expf(vd - mx);
+        const float inv = 1.f / (et + ed);
+        const float st = et * inv, sd = ed * inv;
+        float g_a = 0.f, g_b = 0.f, g_st = 0.f, g_sd = 0.f;
+        if (a.gscale != nullptr) {
+            float v, d1, d2, d3, d4;
+            sp_ref(-sa * st, v, d1);
+            sp_ref(sa * sd, v, d2);
+            sp_ref(-sb * sd, v, d3);
+            sp_ref(sb * st, v, d4);
+            g_a = (-st * d1 + sd * d2) * cc;
+            g_b = (-sd * d3 + st * d4) * cc;
+            g_st = (-sa * d1 + sb * d4) * cc;
+            g_sd = (sa * d2 - sb * d3) * cc;
+        }
+        if (a.gS != nullptr) {
+            const long long n = p / a.HW, hw = p % a.HW;
+            g_st += a.gS[(n * 2 + 0) * a.HW + hw];
+            g_sd += a.gS[(n * 2 + 1) * a.HW + hw];
+        }
+        const float gsm = st * sd * (g_st - g_sd);          // softmax backward
+        float g_vt = gsm, g_vd = -gsm;
+        if (a.gVt != nullptr) g_vt += a.gVt[p];
+        if (a.gVd != nullptr) g_vd += a.gVd[p];
+        float lt[8], ht[8], ld[8], hd[8], o[8];
+        load8<T>(a.L + p * a.ldl + a.offl + sub * 8, lt);
+        load8<T>(a.Hf + p * a.ldh + a.offh + sub * 8, ht);
+        load8<T>(a.L + pd * a.ldl + a.offl + sub * 8, ld);
+        load8<T>(a.Hf + pd * a.ldh + a.offh + sub * 8, hd);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaf(g_vt, ht[i], g_a);
+        store8<T>(a.dL + p * 64 + sub * 8, o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = g_vt * lt[i];
+        store8<T>(a.dH + p * 64 + sub * 8, o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaf(g_vd, hd[i], g_b);
+        store8<T>(a.dL + pd * 64 + sub * 8, o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = g_vd * ld[i];
+        store8<T>(a.dH + pd * 64 + sub * 8, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// input preparation: X (B,Cin,H,W) fp32 NCHW  ->  twin batch [2B,H,W,Cin] NHWC with the complementary pair
+// (X, clip(1 - X + bias, 0, 1))  (Onet_vanilla_20240606.py:175,180-181)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void prep_input_kernel(const float* __restrict__ x, int B, int Cin, long long HW, float bias, T* __restrict__ out) {
+    const long long total = static_cast<long long>(B) * HW * Cin;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % Cin);
+        const long long px = i / Cin;          // n*HW + hw
+        const long long n = px / HW, hw = px % HW;
+        const float v = x[(n * Cin + c) * HW + hw];
+        out[i] = from_f<T>(v);
+        out[i + total] = from_f<T>(fminf(fmaxf(1.f - v + bias, 0.f), 1.f));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing (once per optimizer step)
+//   conv  w [Co][Ci][3][3] fp32 -> wf [Co][tap][Ci] (fwd B operand) and wd [Ci][8-tap][Co] (dgrad B operand)
+//   convT w [Ci][Co][2][2] fp32 -> wf [(tap,co)][ci] (fwd B operand) and wd [ci][(tap,co)] (dgrad B operand)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_conv_w_kernel(const float* __restrict__ w, int Co, int Ci, T* __restrict__ wf, T* __restrict__ wd) {
+    const long long total = static_cast<long long>(Co) * Ci * 9;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int tap = static_cast<int>(i % 9);
+        const int ci = static_cast<int>((i / 9) % Ci);
+        const int co = static_cast<int>(i / (9LL * Ci));
+        const T v = from_f<T>(w[i]);
+        wf[(static_cast<long long>(co) * 9 + tap) * Ci + ci] = v;
+        if (wd != nullptr) wd[(static_cast<long long>(ci) * 9 + (8 - tap)) * Co + co] = v;
+    }
+}
+template <typename T>
+__global__ void pack_convT_w_kernel(const float* __restrict__ w, int Ci, int Co, T* __restrict__ wf, T* __restrict__ wd) {
+    const long long total = static_cast<long long>(Ci) * Co * 4;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int tap = static_cast<int>(i & 3);
+        const int co = static_cast<int>((i >> 2) % Co);
+        const int ci = static_cast<int>((i >> 2) / Co);
+        const T v = from_f<T>(w[i]);
+        wf[(static_cast<long long>(tap) * Co + co) * Ci + ci] = v;
+        wd[static_cast<long long>(ci) * 4 * Co + tap * Co + co] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam semantics, no weight decay / amsgrad) over one flat fp32 parameter arena
+// ------------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr, float beta1, float beta2, float eps, float bc1, float bc2_sqrt,
+                            float grad_scale) {
+    const float step = lr / bc1;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float gi = g[i] * grad_scale;
+        const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+        const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        p[i] -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    }
+}
+
+// label = 1 iff Vd > Vt (argmax of the 2-way softmax, ties -> 0), Onet_vanilla_20240606.py:193-202
+__global__ void predict_label_kernel(const float* __restrict__ Vt, const float* __restrict__ Vd, long long n,
+                                     long long* __restrict__ out) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        out[i] = Vd[i] > Vt[i] ? 1 : 0;
+}
+
+}  // namespace onet

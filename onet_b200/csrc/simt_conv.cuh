@@ -1,0 +1,303 @@
+// CUDA-core (FP32 FMA) implicit-GEMM kernels, templated on the storage type T (float = FP32 verification
+// mode, __nv_bfloat16 = throughput mode).  They serve three purposes: the FP32 verification mode of the whole
+// path, the first convolution (K = 9*in_chns = 9 or 27 is not a tensor-core shape), and the ground truth the
+// tcgen05 kernels are unit-tested against.  Activations NHWC, weights in PyTorch layouts.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace onet {
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 / pad 1 convolution, forward (also used for dgrad with flipped+transposed packed weights).
+//   in  : [N,H,W,ldi] (+ci_off), Cin channels used
+//   wp  : packed [Cout][9][Cin]  (K index = tap*Cin + ci), type T
+//   out : [N,H,W,ldo] (+co_off), raw conv output, type T
+//   stat_sum / stat_sq : double [groups][Cout] partial sums of the STORED values, or nullptr
+// Tile: 64 pixels x 64 couts per 256-thread block, 4x4 outputs per thread, K chunks of 16.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv3x3_simt_kernel(const T* __restrict__ in, long long ldi, int ci_off, int N, int H, int W, int Cin,
+                    const T* __restrict__ wp, int Cout, T* __restrict__ out, long long ldo, int co_off,
+                    double* __restrict__ stat_sum, double* __restrict__ stat_sq, int group_images) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Bs[16][64 + 4];
+    __shared__ float s_stat[2][2][64];   // [group][sum|sq][channel]
+    const int tid = threadIdx.x;
+    const long long M = static_cast<long long>(N) * H * W;
+    const long long m0 = static_cast<long long>(blockIdx.x) * 64;
+    const int co0 = blockIdx.y * 64;
+    const int K = 9 * Cin;
+
+    // A-loader role: thread loads k = tid%16, pixels tid/16 + 16*e
+    const int a_kk = tid & 15;
+    int a_n[4], a_h[4], a_w[4];
+    bool a_ok[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const long long m = m0 + (tid >> 4) + 16 * e;
+        a_ok[e] = m < M;
+        const long long mm = a_ok[e] ? m : 0;
+        a_w[e] = static_cast<int>(mm % W);
+        a_h[e] = static_cast<int>((mm / W) % H);
+        a_n[e] = static_cast<int>(mm / (static_cast<long long>(W) * H));
+    }
+    // B-loader role: thread loads k = tid%16, couts tid/16 + 16*e
+    const int ty = tid >> 4, tx = tid & 15;   // compute role: pixels ty*4.., couts tx*4..
+    float acc[4][4] = {};
+
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        const int k = k0 + a_kk;
+        int tap = k / Cin, ci = k - tap * Cin;
+        const int kh = tap / 3 - 1, kw = tap % 3 - 1;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float v = 0.f;
+            if (k < K && a_ok[e]) {
+                const int hh = a_h[e] + kh, ww = a_w[e] + kw;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                    v = to_f<T>(in[((static_cast<long long>(a_n[e]) * H + hh) * W + ww) * ldi + ci_off + ci]);
+            }
+            As[a_kk][(tid >> 4) + 16 * e] = v;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int co = co0 + (tid >> 4) + 16 * e;
+            float v = 0.f;
+            if (k < K && co < Cout) v = to_f<T>(wp[static_cast<long long>(co) * K + k]);
+            Bs[a_kk][(tid >> 4) + 16 * e] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    const bool do_stats = stat_sum != nullptr;
+    if (do_stats) {
+        for (int i = tid; i < 2 * 2 * 64; i += 256) (&s_stat[0][0][0])[i] = 0.f;
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+        const int n = static_cast<int>(m / (static_cast<long long>(W) * H));
+        const int grp = do_stats ? min(n / group_images, 1) : 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int co = co0 + tx * 4 + j;
+            if (co >= Cout) continue;
+            const T sv = from_f<T>(acc[i][j]);
+            out[m * ldo + co_off + co] = sv;
+            if (do_stats) {
+                const float f = to_f<T>(sv);
+                atomicAdd(&s_stat[grp][0][tx * 4 + j], f);
+                atomicAdd(&s_stat[grp][1][tx * 4 + j], f * f);
+            }
+        }
+    }
+    if (do_stats) {
+        __syncthreads();
+        for (int i = tid; i < 2 * 64; i += 256) {
+            const int g = i >> 6, c = i & 63;
+            if (co0 + c < Cout && (s_stat[g][1][c] != 0.f || s_stat[g][0][c] != 0.f)) {
+                atomicAdd(stat_sum + static_cast<long long>(g) * Cout + co0 + c, static_cast<double>(s_stat[g][0][c]));
+                atomicAdd(stat_sq + static_cast<long long>(g) * Cout + co0 + c, static_cast<double>(s_stat[g][1][c]));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 convolution weight gradient:  dW[co][ci][kh][kw] += sum_pixels G[p][co] * In[p + (kh-1,kw-1)][ci]
+//   g : [N,H,W,ldg] (+co_off) ; in : [N,H,W,ldi] (+ci_off) ; dw : fp32 PyTorch OIHW, atomically accumulated.
+// Tile: 64 couts x 64 k (k = tap*Cin + ci) per block, pixel range split over blockIdx.z.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv3x3_wgrad_simt_kernel(const T* __restrict__ g, long long ldg, int co_off, const T* __restrict__ in, long long ldi,
+                          int ci_off, int N, int H, int W, int Cin, int Cout, float* __restrict__ dw,
+                          long long px_per_split) {
+    __shared__ float Gs[16][64 + 4];
+    __shared__ float Is[16][64 + 4];
+    const int tid = threadIdx.x;
+    const long long M = static_cast<long long>(N) * H * W;
+    const int co0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+    const int K = 9 * Cin;
+    const long long p_begin = static_cast<long long>(blockIdx.z) * px_per_split;
+    const long long p_end = min(p_begin + px_per_split, M);
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[4][4] = {};
+
+    // I-loader role: thread loads pixel pp = tid/16 of the chunk, k = k0 + tid%16 + 16*e
+    int l_tap[4], l_ci[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int k = k0 + (tid & 15) + 16 * e;
+        l_tap[e] = (k < K) ? k / Cin : -1;
+        l_ci[e] = (k < K) ? k % Cin : 0;
+    }
+    for (long long pc = p_begin; pc < p_end; pc += 16) {
+        const long long pm = pc + (tid >> 4);
+        const bool ok = pm < p_end;
+        const long long mm = ok ? pm : 0;
+        const int w = static_cast<int>(mm % W), h = static_cast<int>((mm / W) % H),
+                  n = static_cast<int>(mm / (static_cast<long long>(W) * H));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int co = co0 + (tid & 15) + 16 * e;
+            Gs[tid >> 4][(tid & 15) + 16 * e] = (ok && co < Cout) ? to_f<T>(g[mm * ldg + co_off + co]) : 0.f;
+            float v = 0.f;
+            if (ok && l_tap[e] >= 0) {
+                const int hh = h + l_tap[e] / 3 - 1, ww = w + l_tap[e] % 3 - 1;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                    v = to_f<T>(in[((static_cast<long long>(n) * H + hh) * W + ww) * ldi + ci_off + l_ci[e]]);
+            }
+            Is[tid >> 4][(tid & 15) + 16 * e] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = Gs[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Is[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int co = co0 + ty * 4 + i;
+        if (co >= Cout) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + tx * 4 + j;
+            if (k >= K) continue;
+            const int tap = k / Cin, ci = k % Cin;
+            atomicAdd(dw + (static_cast<long long>(co) * Cin + ci) * 9 + tap, acc[i][j]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2x2 / stride-2 transposed convolution (ConvTranspose2d(Cin, Co, 2, 2) with bias), direct kernels.
+//   x : [N,H,W,ldx] (+xoff), w : fp32 PyTorch layout [Cin][Co][2][2], out : [N,2H,2W,ldo] (+ooff)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void convT2x2_fwd_simt_kernel(const T* __restrict__ x, long long ldx, int xoff, int N, int H, int W, int Cin,
+                                         const float* __restrict__ w, const float* __restrict__ bias, int Co,
+                                         T* __restrict__ out, long long ldo, int ooff, int round_w_bf16) {
+    const long long total = static_cast<long long>(N) * 2 * H * 2 * W * Co;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int co = static_cast<int>(i % Co);
+        long long r = i / Co;
+        const int ow = static_cast<int>(r % (2 * W)); r /= 2 * W;
+        const int oh = static_cast<int>(r % (2 * H));
+        const int n = static_cast<int>(r / (2 * H));
+        const int tap = (oh & 1) * 2 + (ow & 1);
+        const T* xp = x + ((static_cast<long long>(n) * H + (oh >> 1)) * W + (ow >> 1)) * ldx + xoff;
+        float acc = 0.f;
+        for (int ci = 0; ci < Cin; ++ci) {
+            float wv = w[(static_cast<long long>(ci) * Co + co) * 4 + tap];
+            if (round_w_bf16) wv = __bfloat162float(__float2bfloat16_rn(wv));
+            acc = fmaf(to_f<T>(xp[ci]), wv, acc);
+        }
+        out[((static_cast<long long>(n) * 2 * H + oh) * 2 * W + ow) * ldo + ooff + co] = from_f<T>(acc + bias[co]);
+    }
+}
+
+// dX[n,h,w,ci] = sum_{tap,co} dO[n,2h+dy,2w+dx,co] * W[ci][co][tap]
+template <typename T>
+__global__ void convT2x2_dgrad_simt_kernel(const T* __restrict__ go, long long ldg, int goff, int N, int H, int W, int Cin,
+                                           const float* __restrict__ w, int Co, T* __restrict__ dx, long long ldd, int doff) {
+    const long long total = static_cast<long long>(N) * H * W * Cin;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ci = static_cast<int>(i % Cin);
+        long long r = i / Cin;
+        const int ww = static_cast<int>(r % W); r /= W;
+        const int hh = static_cast<int>(r % H);
+        const int n = static_cast<int>(r / H);
+        float acc = 0.f;
+        for (int tap = 0; tap < 4; ++tap) {
+            const T* gp = go + ((static_cast<long long>(n) * 2 * H + 2 * hh + (tap >> 1)) * 2 * W + 2 * ww + (tap & 1)) * ldg + goff;
+            const float* wr = w + static_cast<long long>(ci) * Co * 4 + tap;
+            for (int co = 0; co < Co; ++co) acc = fmaf(to_f<T>(gp[co]), wr[co * 4], acc);
+        }
+        dx[((static_cast<long long>(n) * H + hh) * W + ww) * ldd + doff + ci] = from_f<T>(acc);
+    }
+}
+
+// dW[ci][co][tap] += sum_px X[px][ci] * dO[2px+tap][co]; one thread per (ci,co,tap), pixel range split over blockIdx.y
+template <typename T>
+__global__ void convT2x2_wgrad_simt_kernel(const T* __restrict__ x, long long ldx, int xoff, const T* __restrict__ go,
+                                           long long ldg, int goff, int N, int H, int W, int Cin, int Co,
+                                           float* __restrict__ dw, long long px_per_split) {
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (idx >= static_cast<long long>(Cin) * Co * 4) return;
+    const int tap = static_cast<int>(idx & 3);
+    const int co = static_cast<int>((idx >> 2) % Co);
+    const int ci = static_cast<int>((idx >> 2) / Co);
+    const long long M = static_cast<long long>(N) * H * W;
+    const long long p0 = blockIdx.y * px_per_split, p1 = min(p0 + px_per_split, M);
+    float acc = 0.f;
+    for (long long pm = p0; pm < p1; ++pm) {
+        const int ww = static_cast<int>(pm % W), hh = static_cast<int>((pm / W) % H),
+                  n = static_cast<int>(pm / (static_cast<long long>(W) * H));
+        const float xv = to_f<T>(x[pm * ldx + xoff + ci]);
+        const float gv = to_f<T>(
+            go[((static_cast<long long>(n) * 2 * H + 2 * hh + (tap >> 1)) * 2 * W + 2 * ww + (tap & 1)) * ldg + goff + co]);
+        acc = fmaf(xv, gv, acc);
+    }
+    atomicAdd(dw + idx, acc);
+}
+
+// column sums: out[c] += sum over rows of v[row*ld + off + c]  (bias gradient of the transposed conv)
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ v, long long ld, int off, long long rows, int C, float* __restrict__ out) {
+    // blockDim.x = 256: thread -> channel c = tid % cpb, row lane = tid / cpb
+    const int cpb = min(C, 64);
+    const int lanes = 256 / cpb;
+    const int c = blockIdx.y * cpb + threadIdx.x % cpb;
+    const int rl = threadIdx.x / cpb;
+    float acc = 0.f;
+    if (c < C && rl < lanes)
+        for (long long r = blockIdx.x * static_cast<long long>(lanes) + rl; r < rows; r += static_cast<long long>(gridDim.x) * lanes)
+            acc += to_f<T>(v[r * ld + off + c]);
+    __shared__ float s[256];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    if (rl == 0 && c < C) {
+        float t = 0.f;
+        for (int l = 0; l < lanes; ++l) t += s[l * cpb + threadIdx.x % cpb];
+        atomicAdd(out + c, t);
+    }
+}
+
+}  // namespace onet

@@ -1,0 +1,470 @@
+// tcgen05 / TMEM / TMA "tap-GEMM" kernels for sm_100a: the tensor-core engine behind the 3x3 convolutions
+// (fwd, dgrad, wgrad) and the 2x2/stride-2 transposed convolutions (fwd, dgrad, wgrad) of the Onet U-Nets.
+//
+// Activations are NHWC bf16.  Every operand tile is fetched by TMA from a 5-D view (c, w, q, h, n) of an
+// activation tensor with the 128-byte swizzle, so a "tap" (a filter offset) is nothing but a coordinate
+// offset of the box; out-of-bounds rows are zero-filled by the TMA unit, which implements the conv padding.
+//
+//   pixel-major kernel (tapgemm_px_kernel):   D[pixel][cout] = sum_taps sum_cin In[pixel (+) tap][cin] * Wt[cout][tap][cin]
+//       A = 128 pixels x 64 channels (K-major), B = BN couts x 64 channels (K-major), fp32 accumulators in TMEM.
+//       Epilogues: raw conv output (bf16) + per-channel BatchNorm partial sums, or the 2x2 pixel-shuffle
+//       scatter (+bias) of the transposed convolution straight into the skip-concat buffer.
+//   weight-gradient kernel (tapgemm_wg_kernel): dW[m][n][tap] = sum_pixels G[pixel (-) tap][m] * In[pixel][n]
+//       both operands MN-major (pixels are the K dimension), split-K over pixel slabs, fp32 atomics.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+// warps 2..5 = epilogue (one TMEM lane quarter each).  Persistent CTAs, static round-robin tile schedule,
+// smem ring of STAGES operand stages, double-buffered TMEM accumulators (pixel-major kernel).
+#pragma once
+#include "tc_common.cuh"
+
+namespace onet {
+
+constexpr int kMaxTaps = 9;
+
+enum EpiMode : int { EPI_STORE = 0, EPI_CONVT = 1 };
+
+struct PxParams {
+    // output pixel grid and its tiling (all tile dims are powers of two, TW*TH*TN <= 128)
+    int N, H, W;
+    int TW, TH, TN, log_tw, log_th;
+    int tiles_w, tiles_h, tiles_n;
+    int num_m_tiles, num_n_tiles;
+    int valid_rows;            // TW*TH*TN
+    int ntaps, k_chunks, cin;  // K = ntaps * cin, cin = 64 * k_chunks
+    int4 taps[kMaxTaps];       // coordinate offsets (dc, dw, dq, dh) of each tap in the 5-D input view
+    // epilogue
+    int epi_mode;
+    __nv_bfloat16* out;        // EPI_STORE: [N,H,W,ldo]; EPI_CONVT: [N,2H,2W,ldo]
+    long long ldo;             // channels per pixel of the output buffer
+    int out_coff;              // first output channel inside the buffer
+    double* stat_sum;          // [groups][cout_total] or nullptr
+    double* stat_sq;
+    int cout_total;
+    int group_images;          // images per BatchNorm statistics group (twin branch)
+    const float* bias;         // EPI_CONVT: [co_per_tap]
+    int co_per_tap;            // EPI_CONVT: output channels per 2x2 position
+};
+
+template <int BN>
+struct PxCfg {
+    static constexpr int kABytes = 128 * 128;
+    static constexpr int kBBytes = BN * 128;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : 2 * BN;   // two accumulators
+    static constexpr int kAuxBytes = 1024 + 4 * 2 * BN * 4;           // barriers + per-warp stat partials
+    static constexpr int kSmemBytes = kStages * kStageBytes + kAuxBytes + 1024;  // + alignment slack
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PxParams p) {
+    using Cfg = PxCfg<BN>;
+    constexpr int STAGES = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (base - raw);
+    const uint32_t aux = base + STAGES * Cfg::kStageBytes;
+    uint8_t* gen_aux = gen_base + STAGES * Cfg::kStageBytes;
+    // aux layout: full[STAGES] | empty[STAGES] | tfull[2] | tempty[2] | tmem_ptr | ... | stat partials @1024
+    const uint32_t bar_full = aux, bar_empty = aux + 8 * STAGES, bar_tfull = aux + 16 * STAGES,
+                   bar_tempty = bar_tfull + 16;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gen_aux + 16 * STAGES + 32);
+    float* s_part = reinterpret_cast<float*>(gen_aux + 1024);   // [4 warps][2][BN]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1);
+            mbar_init(bar_tempty + 8 * a, 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::kTmemCols>(smem_u32(tmem_ptr_smem));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int k_iters = p.ntaps * p.k_chunks;
+    const uint32_t a_tx = static_cast<uint32_t>(p.valid_rows) * 128u;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
+                const int wt = m_tile % p.tiles_w, ht = (m_tile / p.tiles_w) % p.tiles_h,
+                          nt = m_tile / (p.tiles_w * p.tiles_h);
+                const int w0 = wt * p.TW, h0 = ht * p.TH, n0 = nt * p.TN, co0 = n_tile * BN;
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    for (int t = 0; t < p.ntaps; ++t) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        const uint32_t sA = base + stage * Cfg::kStageBytes, sB = sA + Cfg::kABytes;
+                        const uint32_t fb = bar_full + 8 * stage;
+                        mbar_expect_tx(fb, a_tx + Cfg::kBBytes);
+                        const int4 tp = p.taps[t];
+                        tma_load_5d(sA, &tmA, fb, tp.x + kc * 64, w0 + tp.y, tp.z, h0 + tp.w, n0);
+                        tma_load_2d(sB, &tmB, fb, t * p.cin + kc * 64, co0);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int k = 0; k < k_iters; ++k) {
+                mbar_wait(bar_full + 8 * stage, phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sA = base + stage * Cfg::kStageBytes, sB = sA + Cfg::kABytes;
+                    const uint64_t da = umma_smem_desc(sA, 16, 1024), db = umma_smem_desc(sB, 16, 1024);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)   // 4 x (K = 16 bf16 = 32 B) inside the 128-B swizzle row
+                        umma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0);
+                    umma_commit(bar_empty + 8 * stage);
+                    if (k == k_iters - 1) umma_commit(bar_tfull + 8 * acc);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (4 warps)
+        const int q = warp & 3;            // TMEM lane quarter this warp may access
+        const int ew = warp - 2;           // 0..3
+        const int row = q * 32 + lane;
+        const int w_l = row & (p.TW - 1), h_l = (row >> p.log_tw) & (p.TH - 1), n_l = row >> (p.log_tw + p.log_th);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
+            const int wt = m_tile % p.tiles_w, ht = (m_tile / p.tiles_w) % p.tiles_h,
+                      nt = m_tile / (p.tiles_w * p.tiles_h);
+            const int w = wt * p.TW + w_l, h = ht * p.TH + h_l, n = nt * p.TN + n_l, co0 = n_tile * BN;
+            const bool valid = (row < p.valid_rows) && (w < p.W) && (h < p.H) && (n < p.N);
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+
+            if (p.epi_mode == EPI_STORE) {
+                __nv_bfloat16* orow =
+                    p.out + ((static_cast<long long>(n) * p.H + h) * p.W + w) * p.ldo + p.out_coff + co0;
+                const bool do_stats = p.stat_sum != nullptr;
+#pragma unroll 1
+                for (int ch = 0; ch < BN / 32; ++ch) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_addr + ch * 32, r);
+                    tmem_ld_wait();
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                    if (valid) {
+                        uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    }
+                    if (do_stats) {
+                        // statistics of the STORED (bf16-rounded) values; transposing butterfly so that
+                        // lane j ends with the sum over this warp's 32 rows of column j
+                        float v[32], s2[32];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
+                            const float lo = valid ? __low2float(b) : 0.f, hi = valid ? __high2float(b) : 0.f;
+                            v[2 * j] = lo; v[2 * j + 1] = hi;
+                            s2[2 * j] = lo * lo; s2[2 * j + 1] = hi * hi;
+                        }
+#pragma unroll
+                        for (int off = 16; off >= 1; off >>= 1) {
+                            const bool up = (lane & off) != 0;
+#pragma unroll
+                            for (int i = 0; i < off; ++i) {
+                                const float send = up ? v[i] : v[i + off];
+                                const float keep = up ? v[i + off] : v[i];
+                                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                                const float send2 = up ? s2[i] : s2[i + off];
+                                const float keep2 = up ? s2[i + off] : s2[i];
+                                s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+                            }
+                        }
+                        s_part[(ew * 2 + 0) * BN + ch * 32 + lane] = v[0];
+                        s_part[(ew * 2 + 1) * BN + ch * 32 + lane] = s2[0];
+                    }
+                }
+                // accumulator drained -> hand the TMEM buffer back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                if (do_stats) {
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    const int grp = (nt * p.TN) / p.group_images;
+                    for (int c = ew * 32 + lane; c < BN; c += 128) {
+                        float s = 0.f, sq = 0.f;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            s += s_part[(e * 2 + 0) * BN + c];
+                            sq += s_part[(e * 2 + 1) * BN + c];
+                        }
+                        atomicAdd(p.stat_sum + static_cast<long long>(grp) * p.cout_total + co0 + c, static_cast<double>(s));
+                        atomicAdd(p.stat_sq + static_cast<long long>(grp) * p.cout_total + co0 + c, static_cast<double>(sq));
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+            } else {
+                // EPI_CONVT: column = (tap, co); scatter to the 2x upsampled grid, add bias
+                const int tap = co0 / p.co_per_tap, cbase = co0 % p.co_per_tap;
+                const int dy = tap >> 1, dx = tap & 1;
+                __nv_bfloat16* orow = p.out +
+                                      ((static_cast<long long>(n) * (2 * p.H) + (2 * h + dy)) * (2 * p.W) + (2 * w + dx)) * p.ldo +
+                                      p.out_coff + cbase;
+#pragma unroll 1
+                for (int ch = 0; ch < BN / 32; ++ch) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_addr + ch * 32, r);
+                    tmem_ld_wait();
+                    if (valid) {
+                        uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int c = ch * 32 + j * 8 + i * 2;
+                                pk[i] = pack_bf16x2(__uint_as_float(r[j * 8 + i * 2]) + __ldg(p.bias + cbase + c),
+                                                    __uint_as_float(r[j * 8 + i * 2 + 1]) + __ldg(p.bias + cbase + c + 1));
+                            }
+                            dst[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+// =====================================================================================================
+// weight-gradient kernel
+// =====================================================================================================
+constexpr int kWgMaxAcc = 3;
+constexpr int kWgMaxGroups = 4;
+
+struct WgGroup {          // one work-unit type: up to 3 accumulators, each M=128 made of two 64-channel blocks
+    int nacc;
+    int tapA[kWgMaxAcc], offA[kWgMaxAcc];   // tap index, channel offset (relative to the m-tile base) of rows 0..63
+    int tapB[kWgMaxAcc], offB[kWgMaxAcc];   // ... of rows 64..127; tapB < 0 -> unused (rows ignored)
+};
+
+struct WgParams {
+    int N, H, W;                         // pixel grid that is reduced over
+    int TW, TH, TN;                      // pixel slab = TW*TH*TN = 64 pixels
+    int tiles_w, tiles_h, tiles_n, num_px_tiles;
+    int ksplit, px_tiles_per_split;
+    int ngroups, num_m_tiles, num_n_tiles;
+    int m_tile_channels;                 // 128 (two adjacent blocks) or 64 (two taps)
+    int4 taps[kMaxTaps];                 // coordinate offsets (dc, dw, dq, dh) applied to the M-side (G) operand
+    int ntaps;
+    WgGroup groups[kWgMaxGroups];
+    float* out;                          // dW, PyTorch layout, accumulated with atomics
+    int m_total, n_total;                // out index = (m*n_total + n)*ntaps + t, or (n*m_total + m)*ntaps + t
+    int out_transposed;
+};
+
+template <int BNW>
+struct WgCfg {
+    static constexpr int kNBytes = (BNW / 64) * 8192;            // N-side (unshifted) operand per stage
+    static constexpr int kMBytes = kWgMaxAcc * 2 * 8192;          // M-side: up to 3 acc x 2 blocks
+    static constexpr int kStageBytes = kNBytes + kMBytes;
+    static constexpr int kStages = (BNW == 128) ? 3 : 3;
+    static constexpr int kTmemCols = 512;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 1024;
+};
+
+template <int BNW>
+__global__ void __launch_bounds__(192, 1)
+tapgemm_wg_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmI, const WgParams p) {
+    using Cfg = WgCfg<BNW>;
+    constexpr int STAGES = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (base - raw);
+    const uint32_t aux = base + STAGES * Cfg::kStageBytes;
+    uint8_t* gen_aux = gen_base + STAGES * Cfg::kStageBytes;
+    const uint32_t bar_full = aux, bar_empty = aux + 8 * STAGES, bar_tfull = aux + 16 * STAGES,
+                   bar_tempty = bar_tfull + 8;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gen_aux + 16 * STAGES + 32);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmG);
+        tma_prefetch_desc(&tmI);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tempty, 4);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::kTmemCols>(smem_u32(tmem_ptr_smem));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    // unit = ((g * num_m_tiles + mt) * num_n_tiles + nt) * ksplit + ks
+    const int num_units = p.ngroups * p.num_m_tiles * p.num_n_tiles * p.ksplit;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+                const int ks = unit % p.ksplit;
+                const int nt = (unit / p.ksplit) % p.num_n_tiles;
+                const int mt = (unit / (p.ksplit * p.num_n_tiles)) % p.num_m_tiles;
+                const int g = unit / (p.ksplit * p.num_n_tiles * p.num_m_tiles);
+                const WgGroup& grp = p.groups[g];
+                const int m0 = mt * p.m_tile_channels, n0 = nt * BNW;
+                const int px_begin = ks * p.px_tiles_per_split;
+                const int px_end = min(px_begin + p.px_tiles_per_split, p.num_px_tiles);
+                int nboxes = 0;
+                for (int a = 0; a < grp.nacc; ++a) nboxes += (grp.tapB[a] >= 0) ? 2 : 1;
+                const uint32_t tx = static_cast<uint32_t>(nboxes) * 8192u + Cfg::kNBytes;
+                for (int pt = px_begin; pt < px_end; ++pt) {
+                    const int wt = pt % p.tiles_w, ht = (pt / p.tiles_w) % p.tiles_h, nn = pt / (p.tiles_w * p.tiles_h);
+                    const int w0 = wt * p.TW, h0 = ht * p.TH, nimg0 = nn * p.TN;
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t sN = base + stage * Cfg::kStageBytes, sM = sN + Cfg::kNBytes;
+                    const uint32_t fb = bar_full + 8 * stage;
+                    mbar_expect_tx(fb, tx);
+#pragma unroll
+                    for (int b = 0; b < BNW / 64; ++b) tma_load_5d(sN + b * 8192, &tmI, fb, n0 + b * 64, w0, 0, h0, nimg0);
+                    for (int a = 0; a < grp.nacc; ++a) {
+                        const int4 ta = p.taps[grp.tapA[a]];
+                        tma_load_5d(sM + (2 * a) * 8192, &tmG, fb, m0 + grp.offA[a] + ta.x, w0 + ta.y, ta.z, h0 + ta.w, nimg0);
+                        if (grp.tapB[a] >= 0) {
+                            const int4 tb = p.taps[grp.tapB[a]];
+                            tma_load_5d(sM + (2 * a + 1) * 8192, &tmG, fb, m0 + grp.offB[a] + tb.x, w0 + tb.y, tb.z,
+                                        h0 + tb.w, nimg0);
+                        }
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = umma_idesc_bf16(128, BNW, 1, 1);   // both operands MN-major
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+            const int ks = unit % p.ksplit;
+            const int g = unit / (p.ksplit * p.num_n_tiles * p.num_m_tiles);
+            const int nacc = p.groups[g].nacc;
+            const int px_begin = ks * p.px_tiles_per_split;
+            const int px_end = min(px_begin + p.px_tiles_per_split, p.num_px_tiles);
+            mbar_wait(bar_tempty, (it & 1) ^ 1);
+            tc_fence_after();
+            for (int pt = px_begin; pt < px_end; ++pt) {
+                mbar_wait(bar_full + 8 * stage, phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sN = base + stage * Cfg::kStageBytes, sM = sN + Cfg::kNBytes;
+                    const uint64_t db = umma_smem_desc(sN, 8192, 1024);
+                    for (int a = 0; a < nacc; ++a) {
+                        const uint64_t da = umma_smem_desc(sM + a * 16384, 8192, 1024);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)   // 4 x 16 pixels; 16 pixel rows = 2048 B
+                            umma_bf16(tmem_base + a * BNW, da + 128 * kk, db + 128 * kk, idesc, (pt > px_begin) || kk);
+                    }
+                    umma_commit(bar_empty + 8 * stage);
+                    if (pt == px_end - 1) umma_commit(bar_tfull);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int it = 0;
+        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+            const int nt = (unit / p.ksplit) % p.num_n_tiles;
+            const int mt = (unit / (p.ksplit * p.num_n_tiles)) % p.num_m_tiles;
+            const int g = unit / (p.ksplit * p.num_n_tiles * p.num_m_tiles);
+            const WgGroup& grp = p.groups[g];
+            const int m0 = mt * p.m_tile_channels, n0 = nt * BNW;
+            mbar_wait(bar_tfull, it & 1);
+            tc_fence_after();
+            for (int a = 0; a < grp.nacc; ++a) {
+                const int tap = (row < 64) ? grp.tapA[a] : grp.tapB[a];
+                const int m = m0 + ((row < 64) ? grp.offA[a] + row : grp.offB[a] + row - 64);
+                const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BNW;
+#pragma unroll 1
+                for (int ch = 0; ch < BNW / 32; ++ch) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_addr + ch * 32, r);
+                    tmem_ld_wait();
+                    if (tap >= 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = n0 + ch * 32 + j;
+                            const long long idx = p.out_transposed
+                                                      ? (static_cast<long long>(n) * p.m_total + m) * p.ntaps + tap
+                                                      : (static_cast<long long>(m) * p.n_total + n) * p.ntaps + tap;
+                            atomicAdd(p.out + idx, __uint_as_float(r[j]));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+}  // namespace onet

@@ -1,0 +1,272 @@
+"""Per-kernel parity tests on the GPU (-m gpu): every C-ABI kernel against the matching torch op evaluated in
+FP32 (TF32 off) on the same inputs.  The tcgen05 kernels are additionally compared with the CUDA-core kernels."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _imports():
+    from tests import gpu_util as U
+    return U
+
+
+def _bf16r(t):
+    return t.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 1, 64), (3, 12, 20, 3, 64), (2, 8, 8, 64, 128), (1, 5, 7, 16, 32)])
+def test_conv3x3_simt_fp32(n, h, w, cin, cout):
+    U = _imports()
+    torch.manual_seed(0)
+    x = torch.randn(n, cin, h, w, device="cuda")
+    wt = torch.randn(cout, cin, 3, 3, device="cuda") * 0.1
+    wf, wd = U.pack_conv(wt, U.F32)
+    y, st = U.conv3x3(U.to_nhwc(x, torch.float32), wf, cout, U.F32, U.ENGINE_SIMT, group_images=max(n // 2, 1), stats=True)
+    ref = F.conv2d(x, wt, padding=1)
+    assert U.rel_l2(U.from_nhwc(y), ref) < 1e-6
+    # statistics: group 0 = first group_images images
+    g = max(n // 2, 1)
+    s0 = ref[:g].double().sum(dim=(0, 2, 3))
+    q0 = (ref[:g].double() ** 2).sum(dim=(0, 2, 3))
+    assert torch.allclose(st[0, 0], s0, rtol=1e-5, atol=1e-4)
+    assert torch.allclose(st[1, 0], q0, rtol=1e-5, atol=1e-4)
+    if n > g:
+        s1 = ref[g:2 * g].double().sum(dim=(0, 2, 3))
+        assert torch.allclose(st[0, 1], s1 + (ref[2 * g:].double().sum(dim=(0, 2, 3)) if n > 2 * g else 0), rtol=1e-5, atol=1e-4)
+    # dgrad = conv with flipped/transposed weights
+    gy = torch.randn_like(ref)
+    dx, _ = U.conv3x3(U.to_nhwc(gy, torch.float32), wd, cin, U.F32, U.ENGINE_SIMT)
+    dref = torch.nn.grad.conv2d_input(x.shape, wt, gy, padding=1)
+    assert U.rel_l2(U.from_nhwc(dx), dref) < 1e-6
+    dw = U.conv3x3_wgrad(U.to_nhwc(gy, torch.float32), U.to_nhwc(x, torch.float32), U.F32, U.ENGINE_SIMT)
+    wref = torch.nn.grad.conv2d_weight(x, wt.shape, gy, padding=1)
+    assert U.rel_l2(dw, wref) < 1e-5
+
+
+TC_SHAPES = [(2, 16, 16, 64, 64), (4, 16, 16, 128, 256), (2, 32, 32, 64, 128), (8, 4, 4, 256, 256), (4, 2, 2, 128, 64),
+             (2, 24, 40, 128, 64), (6, 8, 8, 192, 320)]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", TC_SHAPES)
+def test_conv3x3_tc_fwd(n, h, w, cin, cout):
+    U = _imports()
+    torch.manual_seed(1)
+    x = _bf16r(torch.randn(n, cin, h, w, device="cuda"))
+    wt = _bf16r(torch.randn(cout, cin, 3, 3, device="cuda") * (2.0 / (9 * cin)) ** 0.5)
+    wf, wd = U.pack_conv(wt, U.BF16)
+    xb = U.to_nhwc(x, torch.bfloat16)
+    g = n // 2
+    y, st = U.conv3x3(xb, wf, cout, U.BF16, U.ENGINE_TC, group_images=g, stats=True)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x, wt, padding=1)
+    err = U.rel_l2(U.from_nhwc(y), ref)
+    assert err < 4e-3, err                       # bf16 output rounding only (inputs are bf16-exact)
+    yf = U.from_nhwc(y).double()
+    assert torch.allclose(st[0, 0], yf[:g].sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(st[1, 0], (yf[:g] ** 2).sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(st[0, 1], yf[g:].sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-2)
+    # same kernel as dgrad
+    gy = _bf16r(torch.randn(n, cout, h, w, device="cuda"))
+    dx, _ = U.conv3x3(U.to_nhwc(gy, torch.bfloat16), wd, cin, U.BF16, U.ENGINE_TC)
+    dref = torch.nn.grad.conv2d_input(x.shape, wt, gy, padding=1)
+    err = U.rel_l2(U.from_nhwc(dx), dref)
+    assert err < 4e-3, err
+
+
+def test_conv3x3_tc_strided_input():
+    """input taken from channels [64,128) of a wider (concat-like) buffer"""
+    U = _imports()
+    torch.manual_seed(2)
+    n, h, w, cin, cout = 2, 16, 16, 64, 64
+    buf = _bf16r(torch.randn(n, h, w, 192, device="cuda")).to(torch.bfloat16)
+    wt = _bf16r(torch.randn(cout, cin, 3, 3, device="cuda") * 0.05)
+    wf, _ = U.pack_conv(wt, U.BF16)
+    y, _ = U.conv3x3(buf, wf, cout, U.BF16, U.ENGINE_TC, ld_in=192, off_in=64, cin=64)
+    ref = F.conv2d(buf[..., 64:128].float().permute(0, 3, 1, 2), wt, padding=1)
+    assert U.rel_l2(U.from_nhwc(y), ref) < 4e-3
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", TC_SHAPES)
+def test_conv3x3_tc_wgrad(n, h, w, cin, cout):
+    U = _imports()
+    torch.manual_seed(3)
+    x = _bf16r(torch.randn(n, cin, h, w, device="cuda"))
+    gy = _bf16r(torch.randn(n, cout, h, w, device="cuda"))
+    dw = U.conv3x3_wgrad(U.to_nhwc(gy, torch.bfloat16), U.to_nhwc(x, torch.bfloat16), U.BF16, U.ENGINE_TC)
+    torch.cuda.synchronize()
+    wref = torch.nn.grad.conv2d_weight(x, (cout, cin, 3, 3), gy, padding=1)
+    err = U.rel_l2(dw, wref)
+    assert err < 1e-4, err                       # bf16-exact inputs, fp32 accumulate
+
+
+@pytest.mark.parametrize("engine_name", ["simt_fp32", "simt_bf16", "tc"])
+@pytest.mark.parametrize("n,h,w,cin", [(2, 4, 4, 128), (3, 8, 8, 256), (2, 16, 16, 128), (4, 2, 2, 1024)])
+def test_convT2x2(engine_name, n, h, w, cin):
+    U = _imports()
+    call, ptr = U.call, U.ptr
+    dt = U.F32 if engine_name == "simt_fp32" else U.BF16
+    eng = U.ENGINE_TC if engine_name == "tc" else U.ENGINE_SIMT
+    tdt = U.TDT[dt]
+    rnd = (lambda t: t) if dt == U.F32 else _bf16r
+    co = cin // 2
+    torch.manual_seed(4)
+    x = rnd(torch.randn(n, cin, h, w, device="cuda"))
+    wt = rnd(torch.randn(cin, co, 2, 2, device="cuda") * (1.0 / cin) ** 0.5)
+    b = torch.randn(co, device="cuda") * 0.1
+    # forward into the upper half of a concat buffer
+    cat = torch.zeros(n, 2 * h, 2 * w, 2 * co, dtype=tdt, device="cuda")
+    xn = U.to_nhwc(x, tdt)
+    wf, wd = U.pack_convT(wt, dt)
+    call("onet_convT2x2_fwd", ptr(xn), cin, 0, n, h, w, cin, ptr(wf) if eng == U.ENGINE_TC else ptr(wt), ptr(b), co,
+         ptr(cat, co), 2 * co, 0, dt, eng, U.stream())
+    ref = F.conv_transpose2d(x, wt, b, stride=2)
+    tol = 1e-6 if dt == U.F32 else 4e-3
+    assert U.rel_l2(cat[..., co:].float().permute(0, 3, 1, 2), ref) < tol
+    assert float(cat[..., :co].float().abs().max()) == 0.0
+    # backward: go lives in the upper half of a [n,2h,2w,2co] gradient buffer
+    go = rnd(torch.randn(n, co, 2 * h, 2 * w, device="cuda"))
+    gbuf = torch.zeros(n, 2 * h, 2 * w, 2 * co, dtype=tdt, device="cuda")
+    gbuf[..., co:] = go.permute(0, 2, 3, 1).to(tdt)
+    dx = torch.empty(n, h, w, cin, dtype=tdt, device="cuda")
+    call("onet_convT2x2_dgrad", ptr(gbuf, co), 2 * co, 0, n, h, w, cin, ptr(wd) if eng == U.ENGINE_TC else ptr(wt), co,
+         ptr(dx), cin, 0, dt, eng, U.stream())
+    dref = F.conv2d(go, wt, stride=2)            # adjoint of conv_transpose2d
+    assert U.rel_l2(U.from_nhwc(dx), dref) < tol
+    dw = torch.zeros(cin, co, 2, 2, device="cuda")
+    db = torch.zeros(co, device="cuda")
+    call("onet_convT2x2_wgrad", ptr(xn), cin, 0, ptr(gbuf, co), 2 * co, 0, n, h, w, cin, co, ptr(dw), ptr(db), dt, eng,
+         U.stream())
+    xr = x.clone().requires_grad_(True)
+    wr = wt.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    F.conv_transpose2d(xr, wr, br, stride=2).backward(go)
+    assert U.rel_l2(dw, wr.grad) < (1e-5 if dt == U.F32 else 1e-4)
+    assert U.rel_l2(db, br.grad) < 1e-5
+
+
+@pytest.mark.parametrize("dt_name", ["fp32", "bf16"])
+@pytest.mark.parametrize("n,h,w,c,pool", [(4, 8, 8, 64, True), (2, 6, 10, 128, True), (2, 4, 4, 1024, False), (4, 16, 16, 64, False)])
+def test_bn_relu_fwd_bwd(dt_name, n, h, w, c, pool):
+    """conv-output statistics -> finalize -> apply(+pool) and the fused backward, against torch autograd through
+    batch_norm(training) -> relu -> (identity skip + max_pool2d)."""
+    U = _imports()
+    call, ptr = U.call, U.ptr
+    dt = U.F32 if dt_name == "fp32" else U.BF16
+    tdt = U.TDT[dt]
+    rnd = (lambda t: t) if dt == U.F32 else _bf16r
+    torch.manual_seed(5)
+    g = n // 2
+    y = rnd(torch.randn(n, c, h, w, device="cuda") * 1.5 + 0.3)
+    gamma = (1 + 0.2 * torch.randn(c, device="cuda"))
+    beta = 0.2 * torch.randn(c, device="cuda")
+    rm = torch.zeros(c, device="cuda")
+    rv = torch.ones(c, device="cuda")
+    yn = U.to_nhwc(y, tdt)
+    yd = y.double()
+    ssum = torch.stack([yd[:g].sum(dim=(0, 2, 3)), yd[g:].sum(dim=(0, 2, 3))])
+    ssq = torch.stack([(yd[:g] ** 2).sum(dim=(0, 2, 3)), (yd[g:] ** 2).sum(dim=(0, 2, 3))])
+    aff = torch.empty(4, 2, c, device="cuda")
+    count = float(g * h * w)
+    call("onet_bn_finalize", ptr(ssum), ptr(ssq), 2, c, count, ptr(gamma), ptr(beta), ptr(rm), ptr(rv), ptr(gamma), ptr(beta),
+         ptr(rm), ptr(rv), 0.1, ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]), U.stream())
+    out = torch.zeros(n, h, w, 2 * c, dtype=tdt, device="cuda")         # skip half of a concat buffer
+    pl = torch.empty(n, h // 2, w // 2, c, dtype=tdt, device="cuda") if pool else None
+    call("onet_bn_relu_apply", ptr(yn), n, h, w, c, ptr(aff[2]), ptr(aff[3]), g, ptr(out), 2 * c, 0, ptr(pl), dt, U.stream())
+    # torch reference, branch by branch (shared BN module called twice)
+    bn = torch.nn.BatchNorm2d(c).cuda()
+    with torch.no_grad():
+        bn.weight.copy_(gamma)
+        bn.bias.copy_(beta)
+    bn.train()
+    yr = y.clone().requires_grad_(True)
+    a0 = torch.relu(bn(yr[:g]))
+    a1 = torch.relu(bn(yr[g:]))
+    act = torch.cat([a0, a1])
+    tol = 2e-6 if dt == U.F32 else 4e-3
+    assert U.rel_l2(out[..., :c].float().permute(0, 3, 1, 2), act) < tol
+    assert torch.allclose(rm, bn.running_mean, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(rv, bn.running_var, rtol=1e-5, atol=1e-6)
+    g1 = rnd(torch.randn(n, c, h, w, device="cuda"))
+    g2 = rnd(torch.randn(n, c, h, w, device="cuda"))
+    loss = (act * g1).sum() + (act * g2).sum()
+    gp = None
+    if pool:
+        pr = F.max_pool2d(act, 2)
+        assert U.rel_l2(pl.float().permute(0, 3, 1, 2), pr) < tol
+        gp = rnd(torch.randn_like(pr))
+        loss = loss + (pr * gp).sum()
+    loss.backward()
+    sums = torch.zeros(2, 2, c, dtype=torch.float64, device="cuda")
+    dy = torch.empty(n, h, w, c, dtype=tdt, device="cuda")
+    dgam = torch.zeros(c, device="cuda")
+    dbet = torch.zeros(c, device="cuda")
+    g1n, g2n = U.to_nhwc(g1, tdt), U.to_nhwc(g2, tdt)
+    gpn = U.to_nhwc(gp, tdt) if pool else None
+    call("onet_bn_relu_bwd", ptr(yn), n, h, w, c, ptr(aff[2]), ptr(aff[3]), ptr(aff[0]), ptr(aff[1]), g, ptr(g1n), c, 0,
+         ptr(g2n), c, 0, ptr(gpn), ptr(sums), count, ptr(dy), ptr(dgam), ptr(dbet), ptr(dgam), ptr(dbet), dt, U.stream())
+    btol = 2e-5 if dt == U.F32 else 8e-3
+    assert U.rel_l2(U.from_nhwc(dy), yr.grad) < btol
+    assert U.rel_l2(dgam, bn.weight.grad) < btol
+    assert U.rel_l2(dbet, bn.bias.grad) < btol
+
+
+@pytest.mark.parametrize("dt_name", ["fp32", "bf16"])
+def test_head_fwd_bwd_vs_numpy_oracle(dt_name):
+    U = _imports()
+    from oracle import onet_oracle as orc
+    call, ptr = U.call, U.ptr
+    dt = U.F32 if dt_name == "fp32" else U.BF16
+    tdt = U.TDT[dt]
+    rnd = (lambda t: t) if dt == U.F32 else _bf16r
+    torch.manual_seed(6)
+    B, H, W = 2, 8, 12
+    # local features up to ~1.5 so that a = sum_p L_p reaches the |x| > 37 and > 18 softplus branches
+    Lt, Ht, Ld, Hd = [rnd(torch.rand(B, 64, H, W, device="cuda") * s) for s in (1.5, 0.05, 1.2, 0.05)]
+    cat0 = torch.zeros(2 * B, H, W, 128, dtype=tdt, device="cuda")
+    cat0[:B, ..., :64] = Lt.permute(0, 2, 3, 1).to(tdt)
+    cat0[B:, ..., :64] = Ld.permute(0, 2, 3, 1).to(tdt)
+    Hf = torch.cat([Ht, Hd]).permute(0, 2, 3, 1).contiguous().to(tdt)
+    f32 = dict(dtype=torch.float32, device="cuda")
+    Vt, Vd, S = torch.empty(B, 1, H, W, **f32), torch.empty(B, 1, H, W, **f32), torch.empty(B, 2, H, W, **f32)
+    a, b = torch.empty(B, H, W, **f32), torch.empty(B, H, W, **f32)
+    acc = torch.zeros((), dtype=torch.float64, device="cuda")
+    call("onet_head_fwd", ptr(cat0), 128, 0, ptr(Hf), 64, 0, B, H, W, ptr(Vt), ptr(Vd), ptr(S), ptr(a), ptr(b), ptr(acc), dt,
+         U.stream())
+    r = orc.head_loss_numpy(Lt.cpu().numpy(), Ht.cpu().numpy(), Ld.cpu().numpy(), Hd.cpu().numpy())
+    n = B * H * W
+    loss = float(acc.item()) / (2 * n)
+    assert abs(loss - float(r["loss"])) <= 1e-5 * abs(float(r["loss"]))
+    assert U.rel_l2(Vt[:, 0].cpu(), torch.from_numpy(r["Vt"])) < 1e-6
+    assert U.rel_l2(S[:, 0].cpu(), torch.from_numpy(r["St"])) < 1e-5
+    assert U.rel_l2(S[:, 1].cpu(), torch.from_numpy(r["Sd"])) < 1e-5
+    gscale = torch.ones((), **f32)
+    dL = torch.empty(2 * B, H, W, 64, dtype=tdt, device="cuda")
+    dH = torch.empty(2 * B, H, W, 64, dtype=tdt, device="cuda")
+    call("onet_head_bwd", ptr(cat0), 128, 0, ptr(Hf), 64, 0, B, H, W, ptr(Vt), ptr(Vd), ptr(a), ptr(b), ptr(gscale), None,
+         None, None, ptr(dL), ptr(dH), dt, U.stream())
+    tol = 2e-5 if dt == U.F32 else 4e-3
+    for got, key in ((dL[:B], "dLt"), (dH[:B], "dHt"), (dL[B:], "dLd"), (dH[B:], "dHd")):
+        assert U.rel_l2(got.float().permute(0, 3, 1, 2).cpu(), torch.from_numpy(r[key])) < tol, key
+
+
+def test_adam_kernel_matches_torch():
+    U = _imports()
+    call, ptr = U.call, U.ptr
+    torch.manual_seed(7)
+    n = 100003
+    p = torch.randn(n, device="cuda")
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=5e-6, betas=(0.9, 0.999), eps=1e-8)
+    m = torch.zeros(n, device="cuda")
+    v = torch.zeros(n, device="cuda")
+    for step in range(1, 4):
+        g = torch.randn(n, device="cuda")
+        ref.grad = g.clone()
+        opt.step()
+        call("onet_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), n, 5e-6, 0.9, 0.999, 1e-8, step, 1.0, U.stream())
+    assert torch.allclose(p, ref.detach(), rtol=1e-6, atol=1e-8)

@@ -1,0 +1,153 @@
+"""Whole-path parity on the GPU (-m gpu): onet_b200.Onet through its public surface (forward, compute_loss,
+backward, eval forward, predict_label) against (a) the golden vectors produced by the unmodified reference and
+(b) the CPU oracle on larger seeded inputs.  Tolerances are the north-star ones: FP32 verification mode —
+activations / loss 1e-5 relative (2e-5 on rel-L2 of maps), gradients 2e-2; BF16 mode — activations / loss 1e-2,
+gradients reported against 2e-2 per tensor-norm, masks >= 99.9 % outside the |Vt-Vd| rounding band."""
+import os
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = ["c1_b2_32x32", "c3_b1_48x32", "c1_b2_32x32_noshare"]
+SAMPLE_STRIDE = 9973
+
+
+def _build(case_meta, mode, use_tc=True):
+    import onet_b200
+    from oracle import onet_oracle as orc
+    cin, b, h, w, bshare, seed = (int(v) for v in case_meta)
+    st = orc.perturb_bn_affine(orc.init_state(cin, seed=seed), seed=seed + 100)
+    st_d = None if bshare else orc.perturb_bn_affine(orc.init_state(cin, seed=seed + 50), seed=seed + 150)
+    net = onet_b200.Onet(cin, True, bool(bshare), mode=mode, use_tc=use_tc)
+    sd = OrderedDict()
+    for k, v in st.items():
+        sd["topu." + k] = v.clone()
+    for k, v in (st if st_d is None else st_d).items():
+        sd["dwnu." + k] = v.clone()
+    net.load_state_dict(sd)
+    return net.cuda(), st, st_d
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _step(net, x):
+    net.train()
+    net.zero_grad()
+    Lt, Vt, Ld, Vd, S = net(x)
+    St = S[:, 0, :, :].unsqueeze(dim=1)
+    Sd = S[:, 1, :, :].unsqueeze(dim=1)
+    loss = net.compute_loss(Lt, St, Ld, Sd)
+    loss.backward()
+    torch.cuda.synchronize()
+    return Lt, Vt, Ld, Vd, S, loss
+
+
+@pytest.mark.parametrize("case", GOLDEN)
+def test_fp32_mode_matches_reference_golden(case, golden_dir):
+    g = np.load(os.path.join(golden_dir, case + ".npz"))
+    net, _, _ = _build(g["meta"], "fp32")
+    x = torch.from_numpy(g["x"]).cuda()
+    Lt, Vt, Ld, Vd, S, loss = _step(net, x)
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    for name, t in (("Vt", Vt), ("Vd", Vd), ("S", S)):
+        assert _rel(t, g[name]) < 2e-5, (name, _rel(t, g[name]))
+    assert abs(float(Lt.float().double().norm()) - float(g["Lt.norm"])) <= 2e-5 * float(g["Lt.norm"])
+    worst = 0.0
+    for k, p in net.named_parameters():
+        gk = "grad." + k
+        if gk + ".full" in g:
+            e = _rel(p.grad, g[gk + ".full"])
+        else:
+            e = _rel(p.grad.reshape(-1)[::SAMPLE_STRIDE], g[gk + ".sample"])
+        worst = max(worst, e)
+        assert e < 2e-2, (k, e)
+    print(f"{case}: worst gradient rel-L2 {worst:.2e}")
+    for k, v in net.state_dict().items():
+        if "running" in k:
+            assert np.allclose(v.cpu().numpy(), g["buf." + k], rtol=1e-4, atol=1e-6), k
+        if "num_batches" in k:
+            assert int(v) == int(g["buf." + k]), k
+    net.eval()
+    with torch.no_grad():
+        Lt2, Vt2, Ld2, Vd2, S2 = net(x)
+        lab = net.predict_label(S2)
+    assert _rel(Vt2, g["eval.Vt"]) < 2e-5 and _rel(Vd2, g["eval.Vd"]) < 2e-5 and _rel(S2, g["eval.S"]) < 2e-5
+    assert (lab.cpu().numpy().astype(np.uint8) == g["eval.label"]).mean() >= 0.999
+
+
+@pytest.mark.parametrize("use_tc", [False, True])
+@pytest.mark.parametrize("case", GOLDEN)
+def test_bf16_mode_against_reference_golden(case, use_tc, golden_dir):
+    g = np.load(os.path.join(golden_dir, case + ".npz"))
+    net, _, _ = _build(g["meta"], "bf16", use_tc=use_tc)
+    x = torch.from_numpy(g["x"]).cuda()
+    Lt, Vt, Ld, Vd, S, loss = _step(net, x)
+    rl = abs(loss.item() - float(g["loss"])) / abs(float(g["loss"]))
+    ev = {n: _rel(t, g[n]) for n, t in (("Vt", Vt), ("Vd", Vd), ("S", S))}
+    gerr = []
+    for k, p in net.named_parameters():
+        gk = "grad." + k
+        ref = g[gk + ".full"] if gk + ".full" in g else g[gk + ".sample"]
+        got = p.grad if gk + ".full" in g else p.grad.reshape(-1)[::SAMPLE_STRIDE]
+        gerr.append(_rel(got, ref))
+    print(f"{case} tc={use_tc}: loss rel {rl:.2e}, act {ev}, grad rel-L2 median {np.median(gerr):.2e} max {max(gerr):.2e}")
+    assert rl < 1e-2
+    assert ev["Vt"] < 2e-2 and ev["Vd"] < 2e-2 and ev["S"] < 5e-2     # tiny 32x32 maps: deepest BN sees B*2*2 values
+    assert np.median(gerr) < 1e-1
+
+
+@pytest.mark.parametrize("mode,use_tc", [("fp32", False), ("bf16", False), ("bf16", True)])
+def test_against_oracle_128(mode, use_tc):
+    """B=4, 128x128 Rayleigh frames with targets, weight-shared twin: CUDA path vs CPU oracle."""
+    from oracle import onet_oracle as orc
+    meta = (1, 4, 128, 128, 1, 31)
+    net, st, _ = _build(meta, mode, use_tc)
+    x = orc.rayleigh_frames(4, 1, 128, 128, seed=31)
+    out, grads, new_state = orc.train_step_outputs(st, x)
+    Lt, Vt, Ld, Vd, S, loss = _step(net, x.cuda())
+    rl = abs(loss.item() - out["loss"].item()) / abs(out["loss"].item())
+    ev = {n: _rel(t, out[n]) for n, t in (("Lt", Lt), ("Vt", Vt), ("Vd", Vd), ("S", S))}
+    gerr = {k: _rel(p.grad, grads[k[len("topu."):]]) for k, p in net.named_parameters()}
+    worst = max(gerr, key=gerr.get)
+    lab_ref = orc.predict_label(out["S"])
+    lab = net.predict_label(S).cpu()
+    agree = float((lab == lab_ref).float().mean())
+    band = (out["Vt"] - out["Vd"]).abs()[:, 0] > 1e-2 * out["Vt"].abs()[:, 0]
+    agree_band = float((lab == lab_ref)[band].float().mean())
+    print(f"mode={mode} tc={use_tc}: loss rel {rl:.2e}; act {ev}; grad rel-L2 median {np.median(list(gerr.values())):.2e} "
+          f"worst {worst} {gerr[worst]:.2e}; mask agreement {agree:.5f} (outside 1% band {agree_band:.5f})")
+    if mode == "fp32":
+        assert rl < 1e-5
+        assert max(ev.values()) < 2e-5
+        assert max(gerr.values()) < 2e-2
+        assert agree >= 0.999
+    else:
+        assert rl < 1e-2
+        assert ev["Lt"] < 1e-2 and ev["Vt"] < 2e-2 and ev["Vd"] < 2e-2
+        assert np.median(list(gerr.values())) < 5e-2
+        assert agree_band >= 0.999
+
+
+def test_generic_autograd_path_matches_fused():
+    """A caller-defined loss on the returned tensors (not compute_loss) goes through the generic backward."""
+    from oracle import onet_oracle as orc
+    meta = (1, 2, 32, 32, 1, 41)
+    net, st, _ = _build(meta, "fp32")
+    x = orc.rayleigh_frames(2, 1, 32, 32, seed=41).cuda()
+    _step(net, x)
+    fused = {k: p.grad.clone() for k, p in net.named_parameters()}
+    net2, _, _ = _build(meta, "fp32")
+    net2.train()
+    Lt, Vt, Ld, Vd, S = net2(x)
+    St, Sd = S[:, 0:1].clone(), S[:, 1:2].clone()      # clones defeat the fused fast path
+    loss = net2.compute_loss(Lt, St, Ld, Sd)
+    loss.backward()
+    for k, p in net2.named_parameters():
+        assert _rel(p.grad, fused[k]) < 1e-3, k
