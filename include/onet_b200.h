@@ -33,6 +33,8 @@ extern "C" {
 #define ONET_ENGINE_TC 1
 
 int onet_version(void);
+/* number of kernels this process has launched through the library so far */
+int64_t onet_launch_count(void);
 const char* onet_last_error(void);
 int onet_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

@@ -82,16 +82,33 @@ def lib():
             fn.restype = ctypes.c_int
         _lib.onet_last_error.restype = ctypes.c_char_p
         _lib.onet_last_error.argtypes = []
+        _lib.onet_launch_count.restype = ctypes.c_int64
+        _lib.onet_launch_count.argtypes = []
     return _lib
+
+
+PROFILE = None   # set to a list to record (name, int args, start event, end event) of every call (bench.py)
 
 
 def call(name, *args):
     """Invoke a C-ABI entry point; raise with the library's message on a non-zero status."""
     global LAUNCHES
+    if PROFILE is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(lib(), name)(*args)
     if rc != 0:
         raise OnetLibError(f"{name} failed: {lib().onet_last_error().decode()}")
     LAUNCHES += 1
+    if PROFILE is not None:
+        e1.record()
+        PROFILE.append((name, args, e0, e1))
+
+
+def launch_count():
+    """Kernels launched through the library by this process."""
+    return int(lib().onet_launch_count())
 
 
 def ptr(t, elem_offset=0):

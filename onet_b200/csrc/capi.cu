@@ -24,7 +24,9 @@ static int fail(const char* fmt, ...) {
     va_end(ap);
     return 1;
 }
+static long long g_launches = 0;
 static int check_launch(const char* what) {
+    ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("%s: %s", what, cudaGetErrorString(e));
     return 0;
@@ -323,6 +325,7 @@ static int wgrad_tc(const bf16* g, long long ldg, int goff, int Mc, bool g_is_up
 extern "C" {
 
 int onet_version(void) { return 100; }
+int64_t onet_launch_count(void) { return g_launches; }
 const char* onet_last_error(void) { return g_err; }
 
 int onet_device_info(int* smc, int* major, int* minor) {

@@ -352,7 +352,7 @@ class _Engine:
              ptr(rec.a), ptr(rec.b), ptr(rec.loss_acc), self.dt, self.stream)
 
     # -------------------------------------------------------------------------------- backward
-    def backward(self, rec, gscale, gVt, gVd, gS, gLt, gLd, grad_of):
+    def backward(self, rec, gscale, gVt, gVd, gS, gLt, gLd, grad_of, after_block=None):
         """Full backward of head + both U-Nets.  `grad_of(param)` returns the fp32 tensor the parameter's
         gradient must be ACCUMULATED into."""
         B, H, W, N2 = rec.B, rec.H, rec.W, rec.N2
@@ -390,9 +390,13 @@ class _Engine:
                 up = ups[j]
                 below = rec.x5 if k == 3 else rec.mid[("dec_out", k + 1)]
                 g_out = self._upconv_bwd(seg, up, below, 2 * c, n0, n, hs[k + 1], ws[k + 1], dcat[k], 2 * c, c, grad_of)
+                if after_block is not None:
+                    after_block(seg.unet, _DEC[j][0])
             # encoder, bottom (level 4) to top
             d_mid = bwd(9, g_out, 1024, 0)
             d_pool = bwd(8, d_mid, 1024, 0)                             # grad wrt pool[3]
+            if after_block is not None:
+                after_block(seg.unet, "down4")
             for k in (3, 2, 1, 0):
                 c = cs[k]
                 li = 2 * k
@@ -402,6 +406,8 @@ class _Engine:
                 else:
                     d_mid = bwd(li + 1, dcat[k], 2 * c, 0, gp=d_pool)
                     d_pool = bwd(li, d_mid, c, 0)
+                if after_block is not None:
+                    after_block(seg.unet, "inc" if k == 0 else _ENC[k - 1][0])
 
     def _conv_bn_relu_bwd(self, rec, si, seg, li, conv, bn, n0, n, g1, ld1, off1, g2, ld2, off2, gp, need_dgrad, grad_of):
         """g1/g2/gp are SEGMENT-LOCAL tensors (first image = image n0 of the batch)."""
@@ -472,7 +478,8 @@ class _OnetFn(torch.autograd.Function):
         f32 = lambda t: None if t is None else t.contiguous().float()
         with torch.no_grad(), torch.cuda.device(eng.dev):
             grad_of = onet._grad_targets()
-            eng.backward(rec, f32(g_anchor), f32(gVt), f32(gVd), f32(gS), gLt, gLd, grad_of)
+            eng.backward(rec, f32(g_anchor), f32(gVt), f32(gVd), f32(gS), gLt, gLd, grad_of,
+                         after_block=getattr(onet, "_after_block", None))
         ctx.rec = None
         return (None, None) + (None,) * (len(ctx.needs_input_grad) - 2)
 
@@ -507,6 +514,7 @@ class Onet(nn.Module):
         self._last = None
         self._fwd_rec = None
         self._arena = None
+        self._after_block = None
 
     # ------------------------------------------------------------------ parameters / gradients
     def _unets(self):

