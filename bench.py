@@ -162,6 +162,15 @@ def profile_steps(trainer, x, nsteps):
         trainer.step(x)
     torch.cuda.synchronize()
     prof, _lib.PROFILE = _lib.PROFILE, None
+    detail = os.environ.get("ONET_BENCH_DETAIL")
+    if detail:      # per-call dump of the LAST profiled step: name, integer args, ms, TFLOP/s
+        per = len(prof) // nsteps
+        with open(detail, "w") as f:
+            for name, a, e0, e1 in prof[-per:]:
+                fam_name, fl = _family(name, a)
+                ms = e0.elapsed_time(e1)
+                ints = [v for v in a if isinstance(v, int) and not isinstance(v, bool) and abs(v) < (1 << 40)]
+                f.write(f"{name}\t{fam_name}\t{ms:.4f}\t{(fl / (ms * 1e-3) / 1e12) if fl else 0:.1f}\t{ints}\n")
     fam = {}
     for name, a, e0, e1 in prof:
         f, fl = _family(name, a)

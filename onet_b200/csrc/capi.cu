@@ -378,6 +378,20 @@ int onet_conv3x3_fwd(const void* in, int64_t ldi, int ci_off, int N, int H, int 
     const long long M = static_cast<long long>(N) * H * W;
     dim3 grid(static_cast<unsigned>((M + 63) / 64), (Cout + 63) / 64);
     const int gi = group_images > 0 ? group_images : N;
+    if ((Cin == 1 || Cin == 3) && Cout == 64 && ldi == Cin && ci_off == 0 && ldo == 64 && co_off == 0) {
+        // first layer of the U-Net: direct bandwidth-bound kernel
+        const int G = std::min(2, (N + gi - 1) / gi);
+        const long long px = static_cast<long long>(gi) * H * W;
+        dim3 fg(static_cast<unsigned>(std::max(1LL, std::min<long long>((px + 31) / 32, 148 * 16 / G))), G);
+#define ONET_FIRST(TT, CC)                                                                                          \
+    conv_first_fwd_kernel<TT, CC><<<fg, 256, 0, ST(stream)>>>(static_cast<const TT*>(in), N, H, W,                  \
+                                                              static_cast<const TT*>(wp), static_cast<TT*>(out),   \
+                                                              stat_sum, stat_sq, gi)
+        if (dtype == ONET_F32) { if (Cin == 1) ONET_FIRST(float, 1); else ONET_FIRST(float, 3); }
+        else { if (Cin == 1) ONET_FIRST(bf16, 1); else ONET_FIRST(bf16, 3); }
+#undef ONET_FIRST
+        return check_launch("conv_first_fwd");
+    }
     if (dtype == ONET_F32)
         conv3x3_simt_kernel<float><<<grid, 256, 0, ST(stream)>>>(static_cast<const float*>(in), ldi, ci_off, N, H, W, Cin,
                                                                  static_cast<const float*>(wp), Cout, static_cast<float*>(out),
@@ -397,6 +411,18 @@ int onet_conv3x3_wgrad(const void* g, int64_t ldg, int g_off, const void* in, in
                         N, H, W, 9, dw, false, ST(stream));
     }
     const long long M = static_cast<long long>(N) * H * W;
+    if ((Cin == 1 || Cin == 3) && Cout == 64 && ldi == Cin && ci_off == 0 && ldg == 64 && g_off == 0) {
+        const int lanes = Cin == 1 ? 32 : 8;
+        const int gx = static_cast<int>(std::max(1LL, std::min<long long>((M + lanes - 1) / lanes, 148 * 4)));
+        if (dtype == ONET_F32) {
+            if (Cin == 1) conv_first_wgrad_kernel<float, 1, 8><<<gx, 256, 0, ST(stream)>>>(static_cast<const float*>(g), static_cast<const float*>(in), N, H, W, dw);
+            else conv_first_wgrad_kernel<float, 3, 2><<<gx, 256, 0, ST(stream)>>>(static_cast<const float*>(g), static_cast<const float*>(in), N, H, W, dw);
+        } else {
+            if (Cin == 1) conv_first_wgrad_kernel<bf16, 1, 8><<<gx, 256, 0, ST(stream)>>>(static_cast<const bf16*>(g), static_cast<const bf16*>(in), N, H, W, dw);
+            else conv_first_wgrad_kernel<bf16, 3, 2><<<gx, 256, 0, ST(stream)>>>(static_cast<const bf16*>(g), static_cast<const bf16*>(in), N, H, W, dw);
+        }
+        return check_launch("conv_first_wgrad");
+    }
     const int K = 9 * Cin;
     const int bx = (Cout + 63) / 64, by = (K + 63) / 64;
     int splits = std::max(1, (4 * sm_count()) / (bx * by));
@@ -468,15 +494,24 @@ static int bn_bwd_impl(const void* y, int N, int H, int W, int C, const float* s
     a.g2 = static_cast<const T*>(g2); a.ld2 = ld2; a.off2 = off2;
     a.gp = static_cast<const T*>(gp);
     a.sums = sums; a.count = count; a.dy = static_cast<T*>(dy);
-    const int G = (N + a.group_images - 1) / a.group_images;
+    const int G = std::min(2, (N + a.group_images - 1) / a.group_images);
     const int OC = C / 8, lanes = 256 / OC;
-    const long long quads = static_cast<long long>(a.group_images) * ((H + 1) / 2) * ((W + 1) / 2);
-    const int gx = static_cast<int>(std::max(1LL, std::min<long long>((quads + lanes - 1) / lanes, 148 * 8 / G)));
-    bn_bwd_reduce_kernel<T><<<dim3(gx, G), 256, 0, st>>>(a);
-    if (check_launch("bn_bwd_reduce")) return 1;
-    const long long total = static_cast<long long>(N) * ((H + 1) / 2) * ((W + 1) / 2) * OC;
-    bn_bwd_apply_kernel<T><<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(a);
-    if (check_launch("bn_bwd_apply")) return 1;
+    if (gp != nullptr) {
+        const long long quads = static_cast<long long>(a.group_images) * ((H + 1) / 2) * ((W + 1) / 2);
+        const int gx = static_cast<int>(std::max(1LL, std::min<long long>((quads + lanes - 1) / lanes, 148 * 8 / G)));
+        bn_bwd_pool_kernel<T, false><<<dim3(gx, G), 256, 0, st>>>(a);
+        if (check_launch("bn_bwd_pool_reduce")) return 1;
+        bn_bwd_pool_kernel<T, true><<<dim3(gx, G), 256, 0, st>>>(a);
+        if (check_launch("bn_bwd_pool_apply")) return 1;
+    } else {
+        constexpr int UNR = 4;
+        const long long px = static_cast<long long>(a.group_images) * H * W;
+        const int gx = static_cast<int>(std::max(1LL, std::min<long long>((px + lanes * UNR - 1) / (lanes * UNR), 148 * 8 / G)));
+        bn_bwd_reduce_px_kernel<T, UNR><<<dim3(gx, G), 256, 0, st>>>(a);
+        if (check_launch("bn_bwd_reduce")) return 1;
+        bn_bwd_apply_px_kernel<T, UNR><<<dim3(gx, G), 256, 0, st>>>(a);
+        if (check_launch("bn_bwd_apply")) return 1;
+    }
     if (dgamma0 != nullptr) {
         bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, G, C, dgamma0, dbeta0, dgamma1 ? dgamma1 : dgamma0,
                                                               dbeta1 ? dbeta1 : dbeta0);

@@ -156,98 +156,105 @@ struct BnBwdArgs {
     T* dy;                                       // [N,H,W,C]
 };
 
+// raw 8-channel vector (16 B of bf16 / 32 B of fp32) kept packed so that all loads of a work item can be issued
+// before any of them is consumed
+template <typename T> struct Raw8;
+template <> struct Raw8<float> { float4 a, b; };
+template <> struct Raw8<__nv_bfloat16> { uint4 u; };
+template <typename T> __device__ __forceinline__ Raw8<T> ldraw(const T* p);
+template <> __device__ __forceinline__ Raw8<float> ldraw<float>(const float* p) {
+    Raw8<float> r;
+    r.a = __ldg(reinterpret_cast<const float4*>(p));
+    r.b = __ldg(reinterpret_cast<const float4*>(p + 4));
+    return r;
+}
+template <> __device__ __forceinline__ Raw8<__nv_bfloat16> ldraw<__nv_bfloat16>(const __nv_bfloat16* p) {
+    Raw8<__nv_bfloat16> r;
+    r.u = __ldg(reinterpret_cast<const uint4*>(p));
+    return r;
+}
+template <typename T> __device__ __forceinline__ Raw8<T> zero_raw();
+template <> __device__ __forceinline__ Raw8<float> zero_raw<float>() {
+    Raw8<float> r; r.a = make_float4(0.f, 0.f, 0.f, 0.f); r.b = r.a; return r;
+}
+template <> __device__ __forceinline__ Raw8<__nv_bfloat16> zero_raw<__nv_bfloat16>() {
+    Raw8<__nv_bfloat16> r; r.u = make_uint4(0u, 0u, 0u, 0u); return r;
+}
+__device__ __forceinline__ void unpack(const Raw8<float>& r, float (&v)[8]) {
+    v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+}
+__device__ __forceinline__ void unpack(const Raw8<__nv_bfloat16>& r, float (&v)[8]) {
+    const uint32_t w[4] = {r.u.x, r.u.y, r.u.z, r.u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+
+// Gradient w.r.t. the BN output (dz) and xhat of one pixel x 8 channels.
 template <typename T>
-__device__ __forceinline__ void bn_bwd_quad(const BnBwdArgs<T>& a, int n, int h2, int w2, int oc, const float (&sc)[8],
-                                            const float (&sh)[8], const float (&mu)[8], const float (&is)[8],
-                                            float (&dz)[4][8], float (&xh)[4][8], bool (&ok)[4]) {
-    const int HP = a.H >> 1, WP = a.W >> 1;
-    float act[4][8];
+__device__ __forceinline__ void bn_bwd_pixel(const Raw8<T>& ry, const Raw8<T>& rg1, const Raw8<T>& rg2, bool has_g2,
+                                             const float (&sc)[8], const float (&sh)[8], const float (&mu)[8],
+                                             const float (&is)[8], const float (&extra)[8], float (&dz)[8], float (&xh)[8]) {
+    float y[8], g[8];
+    unpack(ry, y);
+    unpack(rg1, g);
+    if (has_g2) {
+        float g2[8];
+        unpack(rg2, g2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] += g2[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float z = fmaf(y[i], sc[i], sh[i]);
+        xh[i] = (y[i] - mu[i]) * is[i];
+        dz[i] = (round_to<T>(fmaxf(z, 0.f)) > 0.f) ? g[i] + extra[i] : 0.f;
+    }
+}
+
+// For a 2x2 window: per channel, which of the 4 pixels holds the first maximum of the (stored) activation.
+template <typename T>
+__device__ __forceinline__ void pool_argmax(const Raw8<T> (&ry)[4], const float (&sc)[8], const float (&sh)[8],
+                                            int (&best)[8]) {
+    float bv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { best[i] = 0; bv[i] = -1.f; }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int h = 2 * h2 + (k >> 1), w = 2 * w2 + (k & 1);
-        ok[k] = (h < a.H) && (w < a.W);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { dz[k][i] = 0.f; xh[k][i] = 0.f; act[k][i] = 0.f; }
-        if (!ok[k]) continue;
-        const long long px = (static_cast<long long>(n) * a.H + h) * a.W + w;
-        float yv[8], gv[8];
-        load8<T>(a.y + px * a.C + oc * 8, yv);
-        load8<T>(a.g1 + px * a.ld1 + a.off1 + oc * 8, gv);
-        if (a.g2 != nullptr) {
-            float g2v[8];
-            load8<T>(a.g2 + px * a.ld2 + a.off2 + oc * 8, g2v);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) gv[i] += g2v[i];
-        }
+        float y[8];
+        unpack(ry[k], y);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            act[k][i] = round_to<T>(fmaxf(fmaf(yv[i], sc[i], sh[i]), 0.f));
-            xh[k][i] = (yv[i] - mu[i]) * is[i];
-            dz[k][i] = gv[i];
+            const float a = round_to<T>(fmaxf(fmaf(y[i], sc[i], sh[i]), 0.f));
+            if (a > bv[i]) { bv[i] = a; best[i] = k; }
         }
     }
-    if (a.gp != nullptr && h2 < HP && w2 < WP) {
-        float pv[8];
-        load8<T>(a.gp + ((static_cast<long long>(n) * HP + h2) * WP + w2) * a.C + oc * 8, pv);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            int best = 0;
-            float bv = act[0][i];
-#pragma unroll
-            for (int k = 1; k < 4; ++k)
-                if (act[k][i] > bv) { bv = act[k][i]; best = k; }
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (k == best) dz[k][i] += pv[i];
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (!(act[k][i] > 0.f)) dz[k][i] = 0.f;
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256)
-bn_bwd_reduce_kernel(const BnBwdArgs<T> a) {
-    __shared__ float s_red[16][256];
-    const int OC = a.C >> 3, LANES = 256 / OC;
-    const int oc = threadIdx.x % OC, ln = threadIdx.x / OC;
-    const int g = blockIdx.y;
-    const int H2 = (a.H + 1) >> 1, W2 = (a.W + 1) >> 1;
-    const int n_begin = g * a.group_images, n_end = min(a.N, (g + 1) * a.group_images);
-    const long long quads = static_cast<long long>(n_end - n_begin) * H2 * W2;
-    float acc1[8] = {}, acc2[8] = {};
-    if (ln < LANES) {
-        float sc[8], sh[8], mu[8], is[8];
+struct BnBwdCtx {      // per-thread channel constants
+    float sc[8], sh[8], mu[8], is[8];
+    __device__ __forceinline__ void load(const BnBwdArgs<T>& a, int g, int oc) {
         load8<float>(a.scale + g * a.C + oc * 8, sc);
         load8<float>(a.shift + g * a.C + oc * 8, sh);
         load8<float>(a.mean + g * a.C + oc * 8, mu);
         load8<float>(a.invstd + g * a.C + oc * 8, is);
-        for (long long q = blockIdx.x * static_cast<long long>(LANES) + ln; q < quads;
-             q += static_cast<long long>(gridDim.x) * LANES) {
-            const int w2 = static_cast<int>(q % W2), h2 = static_cast<int>((q / W2) % H2),
-                      n = n_begin + static_cast<int>(q / (static_cast<long long>(W2) * H2));
-            float dz[4][8], xh[4][8];
-            bool ok[4];
-            bn_bwd_quad<T>(a, n, h2, w2, oc, sc, sh, mu, is, dz, xh, ok);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    acc1[i] += dz[k][i];
-                    acc2[i] = fmaf(dz[k][i], xh[k][i], acc2[i]);
-                }
-        }
     }
+};
+
+// block-wide reduction of the per-thread (acc1, acc2) over the pixel lanes and one double atomic per channel
+template <typename T>
+__device__ __forceinline__ void bn_bwd_block_reduce(const BnBwdArgs<T>& a, int g, const float (&acc1)[8],
+                                                    const float (&acc2)[8], float (*s_red)[256]) {
+    const int OC = a.C >> 3, LANES = 256 / OC;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         s_red[i][threadIdx.x] = acc1[i];
         s_red[8 + i][threadIdx.x] = acc2[i];
     }
     __syncthreads();
-    // thread t < 16*OC: (which = t / OC in 0..15, oc = t % OC) sums over lanes
     for (int t = threadIdx.x; t < 16 * OC; t += 256) {
         const int which = t / OC, o = t % OC;
         float s = 0.f;
@@ -257,43 +264,166 @@ bn_bwd_reduce_kernel(const BnBwdArgs<T> a) {
     }
 }
 
-template <typename T>
+// ---- variant without a pooled source: one thread = one pixel x 8 channels, UNROLL pixels in flight
+template <typename T, int UNROLL>
 __global__ void __launch_bounds__(256)
-bn_bwd_apply_kernel(const BnBwdArgs<T> a) {
-    const int OC = a.C >> 3, H2 = (a.H + 1) >> 1, W2 = (a.W + 1) >> 1;
-    const long long total = static_cast<long long>(a.N) * H2 * W2 * OC;
-    const float inv_n = static_cast<float>(1.0 / a.count);
-    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int oc = static_cast<int>(idx % OC);
-        long long q = idx / OC;
-        const int w2 = static_cast<int>(q % W2); q /= W2;
-        const int h2 = static_cast<int>(q % H2);
-        const int n = static_cast<int>(q / H2);
-        const int g = min(n / a.group_images, 1);
-        float sc[8], sh[8], mu[8], is[8], m1[8], m2[8];
-        load8<float>(a.scale + g * a.C + oc * 8, sc);
-        load8<float>(a.shift + g * a.C + oc * 8, sh);
-        load8<float>(a.mean + g * a.C + oc * 8, mu);
-        load8<float>(a.invstd + g * a.C + oc * 8, is);
+bn_bwd_reduce_px_kernel(const BnBwdArgs<T> a) {
+    __shared__ float s_red[16][256];
+    const int OC = a.C >> 3, LANES = 256 / OC;
+    const int oc = threadIdx.x % OC, ln = threadIdx.x / OC;
+    const int g = blockIdx.y;
+    const long long HW = static_cast<long long>(a.H) * a.W;
+    const long long p_begin = static_cast<long long>(g) * a.group_images * HW;
+    const long long p_end = static_cast<long long>(g == static_cast<int>(gridDim.y) - 1 ? a.N : (g + 1) * a.group_images) * HW;
+    const bool has_g2 = a.g2 != nullptr;
+    float acc1[8] = {}, acc2[8] = {};
+    if (ln < LANES) {
+        BnBwdCtx<T> c;
+        c.load(a, g, oc);
+        const float zero8[8] = {};
+        const long long stride = static_cast<long long>(gridDim.x) * LANES;
+        for (long long p = p_begin + blockIdx.x * static_cast<long long>(LANES) + ln; p < p_end; p += stride * UNROLL) {
+            Raw8<T> ry[UNROLL], rg1[UNROLL], rg2[UNROLL];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            m1[i] = static_cast<float>(a.sums[(static_cast<long long>(g) * 2 + 0) * a.C + oc * 8 + i]) * inv_n;
-            m2[i] = static_cast<float>(a.sums[(static_cast<long long>(g) * 2 + 1) * a.C + oc * 8 + i]) * inv_n;
-        }
-        float dz[4][8], xh[4][8];
-        bool ok[4];
-        bn_bwd_quad<T>(a, n, h2, w2, oc, sc, sh, mu, is, dz, xh, ok);
+            for (int u = 0; u < UNROLL; ++u) {
+                const long long q = p + u * stride;
+                const bool ok = q < p_end;
+                ry[u] = ok ? ldraw<T>(a.y + q * a.C + oc * 8) : zero_raw<T>();
+                rg1[u] = ok ? ldraw<T>(a.g1 + q * a.ld1 + a.off1 + oc * 8) : zero_raw<T>();
+                rg2[u] = (ok && has_g2) ? ldraw<T>(a.g2 + q * a.ld2 + a.off2 + oc * 8) : zero_raw<T>();
+            }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (!ok[k]) continue;
-            const int h = 2 * h2 + (k >> 1), w = 2 * w2 + (k & 1);
-            float o[8];
+            for (int u = 0; u < UNROLL; ++u) {
+                float dz[8], xh[8];
+                bn_bwd_pixel<T>(ry[u], rg1[u], rg2[u], has_g2, c.sc, c.sh, c.mu, c.is, zero8, dz, xh);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = sc[i] * (dz[k][i] - m1[i] - xh[k][i] * m2[i]);
-            store8<T>(a.dy + ((static_cast<long long>(n) * a.H + h) * a.W + w) * a.C + oc * 8, o);
+                for (int i = 0; i < 8; ++i) {
+                    acc1[i] += dz[i];
+                    acc2[i] = fmaf(dz[i], xh[i], acc2[i]);
+                }
+            }
         }
     }
+    bn_bwd_block_reduce<T>(a, g, acc1, acc2, s_red);
+}
+
+template <typename T, int UNROLL>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_px_kernel(const BnBwdArgs<T> a) {
+    const int OC = a.C >> 3, LANES = 256 / OC;
+    const int oc = threadIdx.x % OC, ln = threadIdx.x / OC;
+    const int g = blockIdx.y;
+    if (ln >= LANES) return;
+    const long long HW = static_cast<long long>(a.H) * a.W;
+    const long long p_begin = static_cast<long long>(g) * a.group_images * HW;
+    const long long p_end = static_cast<long long>(g == static_cast<int>(gridDim.y) - 1 ? a.N : (g + 1) * a.group_images) * HW;
+    const bool has_g2 = a.g2 != nullptr;
+    const float inv_n = static_cast<float>(1.0 / a.count);
+    BnBwdCtx<T> c;
+    c.load(a, g, oc);
+    float m1[8], m2[8];
+    const float zero8[8] = {};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        m1[i] = static_cast<float>(a.sums[(static_cast<long long>(g) * 2 + 0) * a.C + oc * 8 + i]) * inv_n;
+        m2[i] = static_cast<float>(a.sums[(static_cast<long long>(g) * 2 + 1) * a.C + oc * 8 + i]) * inv_n;
+    }
+    const long long stride = static_cast<long long>(gridDim.x) * LANES;
+    for (long long p = p_begin + blockIdx.x * static_cast<long long>(LANES) + ln; p < p_end; p += stride * UNROLL) {
+        Raw8<T> ry[UNROLL], rg1[UNROLL], rg2[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const long long q = p + u * stride;
+            const bool ok = q < p_end;
+            ry[u] = ok ? ldraw<T>(a.y + q * a.C + oc * 8) : zero_raw<T>();
+            rg1[u] = ok ? ldraw<T>(a.g1 + q * a.ld1 + a.off1 + oc * 8) : zero_raw<T>();
+            rg2[u] = (ok && has_g2) ? ldraw<T>(a.g2 + q * a.ld2 + a.off2 + oc * 8) : zero_raw<T>();
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const long long q = p + u * stride;
+            if (q >= p_end) break;
+            float dz[8], xh[8], o[8];
+            bn_bwd_pixel<T>(ry[u], rg1[u], rg2[u], has_g2, c.sc, c.sh, c.mu, c.is, zero8, dz, xh);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = c.sc[i] * (dz[i] - m1[i] - xh[i] * m2[i]);
+            store8<T>(a.dy + q * a.C + oc * 8, o);
+        }
+    }
+}
+
+// ---- variant with a pooled gradient source: one thread = one 2x2 window x 8 channels (H, W even is NOT required:
+// windows hanging over the border take part as plain pixels, exactly like floor-mode MaxPool2d leaves them out)
+template <typename T, bool APPLY>
+__global__ void __launch_bounds__(256)
+bn_bwd_pool_kernel(const BnBwdArgs<T> a) {
+    __shared__ float s_red[APPLY ? 1 : 16][256];
+    const int OC = a.C >> 3, LANES = 256 / OC;
+    const int oc = threadIdx.x % OC, ln = threadIdx.x / OC;
+    const int g = blockIdx.y;
+    const int H2 = (a.H + 1) >> 1, W2 = (a.W + 1) >> 1, HP = a.H >> 1, WP = a.W >> 1;
+    const int n_begin = g * a.group_images, n_end = (g == static_cast<int>(gridDim.y) - 1) ? a.N : (g + 1) * a.group_images;
+    const int quads_per_img = H2 * W2;
+    const int quads = (n_end - n_begin) * quads_per_img;
+    const bool has_g2 = a.g2 != nullptr;
+    const float inv_n = static_cast<float>(1.0 / a.count);
+    float acc1[8] = {}, acc2[8] = {};
+    if (ln < LANES) {
+        BnBwdCtx<T> c;
+        c.load(a, g, oc);
+        float m1[8], m2[8];
+        if (APPLY) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                m1[i] = static_cast<float>(a.sums[(static_cast<long long>(g) * 2 + 0) * a.C + oc * 8 + i]) * inv_n;
+                m2[i] = static_cast<float>(a.sums[(static_cast<long long>(g) * 2 + 1) * a.C + oc * 8 + i]) * inv_n;
+            }
+        }
+        for (int q = blockIdx.x * LANES + ln; q < quads; q += gridDim.x * LANES) {
+            const int n = n_begin + q / quads_per_img;
+            const int r = q % quads_per_img;
+            const int h2 = r / W2, w2 = r % W2;
+            Raw8<T> ry[4], rg1[4], rg2[4], rp;
+            long long px[4];
+            bool ok[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int h = 2 * h2 + (k >> 1), w = 2 * w2 + (k & 1);
+                ok[k] = (h < a.H) && (w < a.W);
+                px[k] = (static_cast<long long>(n) * a.H + h) * a.W + w;
+                ry[k] = ok[k] ? ldraw<T>(a.y + px[k] * a.C + oc * 8) : zero_raw<T>();
+                rg1[k] = ok[k] ? ldraw<T>(a.g1 + px[k] * a.ld1 + a.off1 + oc * 8) : zero_raw<T>();
+                rg2[k] = (ok[k] && has_g2) ? ldraw<T>(a.g2 + px[k] * a.ld2 + a.off2 + oc * 8) : zero_raw<T>();
+            }
+            const bool pooled = (h2 < HP) && (w2 < WP);
+            rp = pooled ? ldraw<T>(a.gp + ((static_cast<long long>(n) * HP + h2) * WP + w2) * a.C + oc * 8) : zero_raw<T>();
+            int best[8];
+            pool_argmax<T>(ry, c.sc, c.sh, best);
+            float gpv[8];
+            unpack(rp, gpv);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!ok[k]) continue;
+                float extra[8], dz[8], xh[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) extra[i] = (pooled && best[i] == k) ? gpv[i] : 0.f;
+                bn_bwd_pixel<T>(ry[k], rg1[k], rg2[k], has_g2, c.sc, c.sh, c.mu, c.is, extra, dz, xh);
+                if (APPLY) {
+                    float o[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = c.sc[i] * (dz[i] - m1[i] - xh[i] * m2[i]);
+                    store8<T>(a.dy + px[k] * a.C + oc * 8, o);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        acc1[i] += dz[i];
+                        acc2[i] = fmaf(dz[i], xh[i], acc2[i]);
+                    }
+                }
+            }
+        }
+    }
+    if (!APPLY) bn_bwd_block_reduce<T>(a, g, acc1, acc2, s_red);
 }
 
 // dgamma[c] (+)= sum_g s2[g][c], dbeta[c] (+)= sum_g s1[g][c]; per-group targets may alias (shared twin)

@@ -129,6 +129,133 @@ conv3x3_simt_kernel(const T* __restrict__ in, long long ldi, int ci_off, int N, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// First convolution of the U-Net (in_chns = CIN <= 4, Cout = 64): K = 9*CIN is not a tensor-core shape and the
+// layer is purely bandwidth-bound (writes 128 B per pixel, reads 2*CIN B), so it gets a direct kernel:
+// one thread = one pixel x 8 output channels, weights in shared memory, BatchNorm partial sums fused.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int CIN>
+__global__ void __launch_bounds__(256)
+conv_first_fwd_kernel(const T* __restrict__ in, int N, int H, int W, const T* __restrict__ wp, T* __restrict__ out,
+                      double* __restrict__ stat_sum, double* __restrict__ stat_sq, int group_images) {
+    constexpr int K = 9 * CIN;
+    __shared__ float ws[K][64];
+    __shared__ float s_red[16][256];
+    for (int i = threadIdx.x; i < K * 64; i += 256) ws[i % K][i / K] = to_f<T>(wp[i]);   // wp is [64][K]
+    __syncthreads();
+    const int oc = threadIdx.x & 7, ln = threadIdx.x >> 3;
+    const int g = blockIdx.y;
+    const long long HW = static_cast<long long>(H) * W;
+    const long long p_begin = static_cast<long long>(g) * group_images * HW;
+    const long long p_end = static_cast<long long>(g == static_cast<int>(gridDim.y) - 1 ? N : (g + 1) * group_images) * HW;
+    float a1[8] = {}, a2[8] = {};
+    for (long long p = p_begin + blockIdx.x * 32LL + ln; p < p_end; p += gridDim.x * 32LL) {
+        const int w = static_cast<int>(p % W), h = static_cast<int>((p / W) % H);
+        const long long nb = p - static_cast<long long>(h) * W - w;      // n*H*W
+        float x[K];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int hh = h + t / 3 - 1, ww = w + t % 3 - 1;
+            const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
+#pragma unroll
+            for (int c = 0; c < CIN; ++c)
+                x[t * CIN + c] = ok ? to_f<T>(in[(nb + static_cast<long long>(hh) * W + ww) * CIN + c]) : 0.f;
+        }
+        float acc[8] = {};
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(x[k], ws[k][oc * 8 + i], acc[i]);
+        T o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            o[i] = from_f<T>(acc[i]);
+            const float f = to_f<T>(o[i]);
+            a1[i] += f;
+            a2[i] = fmaf(f, f, a2[i]);
+        }
+        if (sizeof(T) == 2) {
+            *reinterpret_cast<uint4*>(out + p * 64 + oc * 8) = *reinterpret_cast<const uint4*>(o);
+        } else {
+            *reinterpret_cast<float4*>(out + p * 64 + oc * 8) = *reinterpret_cast<const float4*>(o);
+            *reinterpret_cast<float4*>(out + p * 64 + oc * 8 + 4) = *reinterpret_cast<const float4*>(o + 4);
+        }
+    }
+    if (stat_sum != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            s_red[i][threadIdx.x] = a1[i];
+            s_red[8 + i][threadIdx.x] = a2[i];
+        }
+        __syncthreads();
+        if (threadIdx.x < 128) {
+            const int which = threadIdx.x >> 3, o8 = threadIdx.x & 7;   // which in 0..15, octet o8
+            float sacc = 0.f;
+            for (int l = 0; l < 32; ++l) sacc += s_red[which][l * 8 + o8];
+            const int c = o8 * 8 + (which & 7);
+            double* dst = (which < 8 ? stat_sum : stat_sq) + static_cast<long long>(g) * 64 + c;
+            atomicAdd(dst, static_cast<double>(sacc));
+        }
+    }
+}
+
+// dW[co][ci][tap] += sum_px G[px][co] * In[px + tap][ci] for the first convolution (CIN <= 4, Cout = 64).
+// One thread = CPT output channels x all 9*CIN taps, pixels strided over lanes/blocks; warp-shuffle + atomics.
+template <typename T, int CIN, int CPT>
+__global__ void __launch_bounds__(256)
+conv_first_wgrad_kernel(const T* __restrict__ g, const T* __restrict__ in, int N, int H, int W, float* __restrict__ dw) {
+    constexpr int K = 9 * CIN;
+    constexpr int NG = 64 / CPT;            // channel groups
+    constexpr int LANES = 256 / NG;         // pixel lanes per block
+    const int cg = threadIdx.x % NG, ln = threadIdx.x / NG;
+    const long long M = static_cast<long long>(N) * H * W;
+    float acc[CPT][K];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i)
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[i][k] = 0.f;
+    for (long long p = blockIdx.x * static_cast<long long>(LANES) + ln; p < M; p += static_cast<long long>(gridDim.x) * LANES) {
+        const int w = static_cast<int>(p % W), h = static_cast<int>((p / W) % H);
+        const long long nb = p - static_cast<long long>(h) * W - w;
+        float gv[CPT];
+        if (CPT == 8 && sizeof(T) == 2) {
+            const uint4 u = *reinterpret_cast<const uint4*>(g + p * 64 + cg * 8);
+            const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                gv[(2 * i) % CPT] = __uint_as_float(wv[i] << 16);
+                gv[(2 * i + 1) % CPT] = __uint_as_float(wv[i] & 0xffff0000u);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) gv[i] = to_f<T>(g[p * 64 + cg * CPT + i]);
+        }
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int hh = h + t / 3 - 1, ww = w + t % 3 - 1;
+            const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) {
+                const float xv = ok ? to_f<T>(in[(nb + static_cast<long long>(hh) * W + ww) * CIN + c]) : 0.f;
+#pragma unroll
+                for (int i = 0; i < CPT; ++i) acc[i][t * CIN + c] = fmaf(gv[i], xv, acc[i][t * CIN + c]);
+            }
+        }
+    }
+    // lanes of the same channel group inside a warp sit NG threads apart
+#pragma unroll
+    for (int i = 0; i < CPT; ++i)
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float v = acc[i][k];
+            for (int off = NG; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if ((threadIdx.x & 31) < NG) {
+                const int co = cg * CPT + i, tap = k / CIN, ci = k % CIN;
+                atomicAdd(dw + (static_cast<long long>(co) * CIN + ci) * 9 + tap, v);
+            }
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
 // 3x3 convolution weight gradient:  dW[co][ci][kh][kw] += sum_pixels G[p][co] * In[p + (kh-1,kw-1)][ci]
 //   g : [N,H,W,ldg] (+co_off) ; in : [N,H,W,ldi] (+ci_off) ; dw : fp32 PyTorch OIHW, atomically accumulated.
 // Tile: 64 couts x 64 k (k = tap*Cin + ci) per block, pixel range split over blockIdx.z.
