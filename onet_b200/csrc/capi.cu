@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -11,6 +12,7 @@
 #include "elementwise.cuh"
 #include "simt_conv.cuh"
 #include "tapgemm_tc.cuh"
+#include "conv3x3_halo_tc.cuh"
 
 using namespace onet;
 typedef __nv_bfloat16 bf16;
@@ -162,6 +164,38 @@ static void px_tiling(PxParams& p, int N, int H, int W, int group_images) {
     p.valid_rows = p.TW * p.TH * p.TN;
 }
 
+template <int BN>
+static int launch_halo_px(const CUtensorMap& tA, const CUtensorMap& tB, const PxParams& p, cudaStream_t st) {
+    using Cfg = HaloCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_px_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (e != cudaSuccess) return fail("cudaFuncSetAttribute(halo_px<%d>): %s", BN, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    conv3x3_halo_px_kernel<BN><<<std::min(tiles, sm_count()), 192, Cfg::kSmemBytes, st>>>(tA, tB, p);
+    return check_launch("conv3x3_halo_px_kernel");
+}
+
+// Split-K factor for the weight-gradient kernels: minimise (waves x K-steps per unit + fixed per-unit epilogue cost).
+static void pick_ksplit(int base_units, int num_px_tiles, int* ksplit, int* per_split) {
+    const int sms = sm_count();
+    long long best_cost = -1;
+    int best_per = num_px_tiles;
+    const int max_ks = std::min(num_px_tiles, 8 * sms);
+    for (int ks = 1; ks <= max_ks; ++ks) {
+        const int per = (num_px_tiles + ks - 1) / ks;
+        const int ks_eff = (num_px_tiles + per - 1) / per;
+        const long long units = static_cast<long long>(base_units) * ks_eff;
+        const long long waves = (units + sms - 1) / sms;
+        const long long cost = waves * (per + 6);           // ~6 K-steps worth of epilogue / pipeline fill per unit
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_per = per; }
+    }
+    *per_split = best_per;
+    *ksplit = (num_px_tiles + best_per - 1) / best_per;
+}
+
 static int pick_bn(int cout) { return (cout % 256 == 0) ? 256 : (cout % 128 == 0 ? 128 : 64); }
 
 static int conv3x3_tc(const bf16* in, long long ldi, int ci_off, int N, int H, int W, int Cin, const bf16* wp, int Cout,
@@ -170,8 +204,28 @@ static int conv3x3_tc(const bf16* in, long long ldi, int ci_off, int N, int H, i
     if (ldo % 8 || co_off % 8) return fail("tc conv output channel stride/offset must be multiples of 8");
     PxParams p;
     memset(&p, 0, sizeof(p));
-    px_tiling(p, N, H, W, ssum ? group_images : 0);
     const int BN = pick_bn(Cout);
+    if (H >= 16 && W >= 8 && !getenv("ONET_NO_HALO")) {
+        // H-halo kernel: 16 x 8 pixel tiles, activation boxes shared by the three vertical taps
+        p.N = N; p.H = H; p.W = W;
+        p.TW = 8; p.TH = 16; p.TN = 1; p.log_tw = 3; p.log_th = 4;
+        p.tiles_w = (W + 7) / 8; p.tiles_h = (H + 15) / 16; p.tiles_n = N;
+        p.num_m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+        p.valid_rows = 128;
+        p.num_n_tiles = Cout / BN;
+        p.ntaps = 9; p.k_chunks = Cin / 64; p.cin = Cin;
+        p.epi_mode = EPI_STORE;
+        p.out = out; p.ldo = ldo; p.out_coff = co_off;
+        p.stat_sum = ssum; p.stat_sq = ssq; p.cout_total = Cout; p.group_images = group_images > 0 ? group_images : N;
+        CUtensorMap tA, tB;
+        const uint32_t hbox[5] = {64, 8, 1, 18, 1};
+        if (make_act_map(&tA, in + ci_off, Cin, N, H, W, ldi, hbox)) return 1;
+        if (make_map2(&tB, wp, 9ULL * Cin, Cout, 64, BN)) return 1;
+        if (BN == 256) return launch_halo_px<256>(tA, tB, p, st);
+        if (BN == 128) return launch_halo_px<128>(tA, tB, p, st);
+        return launch_halo_px<64>(tA, tB, p, st);
+    }
+    px_tiling(p, N, H, W, ssum ? group_images : 0);
     p.num_n_tiles = Cout / BN;
     p.ntaps = 9; p.k_chunks = Cin / 64; p.cin = Cin;
     for (int t = 0; t < 9; ++t) p.taps[t] = make_int4(0, t % 3 - 1, 0, t / 3 - 1);
@@ -255,9 +309,77 @@ static int launch_wg(const CUtensorMap& tG, const CUtensorMap& tI, const WgParam
     return check_launch("tapgemm_wg_kernel");
 }
 
+template <int BNW>
+static int launch_wh(const CUtensorMap& tG, const CUtensorMap& tI, const WhParams& p, cudaStream_t st) {
+    using Cfg = WhCfg<BNW>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad3x3_halo_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (e != cudaSuccess) return fail("cudaFuncSetAttribute(wh<%d>): %s", BNW, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int units = p.ntypes * p.num_m_tiles * p.num_n_tiles * p.ksplit;
+    wgrad3x3_halo_kernel<BNW><<<std::min(units, sm_count()), 192, Cfg::kSmemBytes, st>>>(tG, tI, p);
+    return check_launch("wgrad3x3_halo_kernel");
+}
+
+// 3x3 weight gradient, H-halo variant: dW[co][ci][kh][kw] += sum_px G[px - (kh-1,kw-1)][co] * In[px][ci]
+static int wgrad3x3_halo_tc(const bf16* g, long long ldg, int goff, int Mc, const bf16* in, long long ldi, int ioff, int Nc,
+                            int N, int H, int W, float* dw, cudaStream_t st) {
+    WhParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = N; p.H = H; p.W = W;
+    p.tiles_w = (W + 7) / 8; p.tiles_h = (H + 7) / 8;
+    p.num_px_tiles = p.tiles_w * p.tiles_h * N;
+    int BNW;
+    if (Mc >= 128) {
+        if (Mc % 128) return fail("tc wgrad: M channels %d not a multiple of 128", Mc);
+        BNW = (Nc % 128 == 0) ? 128 : 64;
+        p.m_tile_channels = 128; p.num_m_tiles = Mc / 128; p.ntypes = 3;
+        for (int kw = 0; kw < 3; ++kw) {
+            WhUnit& u = p.types[kw];
+            u.nbox = 2;
+            u.box_kw[0] = u.box_kw[1] = kw; u.box_ch[0] = 0; u.box_ch[1] = 64;
+            u.nacc = 3;
+            for (int kh = 0; kh < 3; ++kh) {
+                WhAcc& a = u.acc[kh];
+                a.start_off = (2 - kh) * 1024; a.lbo = kWhBoxBytes;
+                a.tapA = a.tapB = kh * 3 + kw; a.chA = 0; a.chB = 64;
+            }
+        }
+    } else {
+        BNW = 64;
+        p.m_tile_channels = 64; p.num_m_tiles = 1; p.ntypes = 1;
+        WhUnit& u = p.types[0];
+        u.nbox = 3;
+        for (int kw = 0; kw < 3; ++kw) { u.box_kw[kw] = kw; u.box_ch[kw] = 0; }
+        u.nacc = 5;
+        for (int kw = 0; kw < 3; ++kw) {       // rows 0..63 = tap (kh=2,kw), rows 64..127 = tap (kh=1,kw): 8 box rows apart
+            WhAcc& a = u.acc[kw];
+            a.start_off = kw * kWhBoxBytes; a.lbo = 1024;
+            a.tapA = 6 + kw; a.tapB = 3 + kw; a.chA = a.chB = 0;
+        }
+        u.acc[3].start_off = 2048; u.acc[3].lbo = kWhBoxBytes;            // (kh=0,kw=0) | (kh=0,kw=1)
+        u.acc[3].tapA = 0; u.acc[3].tapB = 1; u.acc[3].chA = u.acc[3].chB = 0;
+        u.acc[4].start_off = 2 * kWhBoxBytes + 2048; u.acc[4].lbo = 1024;  // (kh=0,kw=2) | unused
+        u.acc[4].tapA = 2; u.acc[4].tapB = -1; u.acc[4].chA = u.acc[4].chB = 0;
+    }
+    p.num_n_tiles = Nc / BNW;
+    pick_ksplit(p.ntypes * p.num_m_tiles * p.num_n_tiles, p.num_px_tiles, &p.ksplit, &p.px_tiles_per_split);
+    p.out = dw; p.m_total = Mc; p.n_total = Nc;
+    CUtensorMap tG, tI;
+    const uint32_t gbox[5] = {64, 8, 1, 10, 1}, ibox[5] = {64, 8, 1, 8, 1};
+    if (make_act_map(&tG, g + goff, Mc, N, H, W, ldg, gbox)) return 1;
+    if (make_act_map(&tI, in + ioff, Nc, N, H, W, ldi, ibox)) return 1;
+    if (BNW == 128) return launch_wh<128>(tG, tI, p, st);
+    return launch_wh<64>(tG, tI, p, st);
+}
+
 static int wgrad_tc(const bf16* g, long long ldg, int goff, int Mc, bool g_is_up, const bf16* in, long long ldi, int ioff,
                     int Nc, int N, int H, int W, int ntaps, float* dw, bool transposed, cudaStream_t st) {
     if (Mc % 64 || Nc % 64) return fail("tc wgrad needs channel counts multiples of 64 (got %d, %d)", Mc, Nc);
+    if (!g_is_up && ntaps == 9 && !transposed && H >= 8 && W >= 8 && !getenv("ONET_NO_HALO"))
+        return wgrad3x3_halo_tc(g, ldg, goff, Mc, in, ldi, ioff, Nc, N, H, W, dw, st);
     WgParams p;
     memset(&p, 0, sizeof(p));
     p.N = N; p.H = H; p.W = W;
@@ -301,11 +423,7 @@ static int wgrad_tc(const bf16* g, long long ldg, int goff, int Mc, bool g_is_up
     p.ngroups = ng;
     const int BNW = (Nc % 128 == 0) ? 128 : 64;
     p.num_n_tiles = Nc / BNW;
-    const int base_units = p.ngroups * p.num_m_tiles * p.num_n_tiles;
-    int ks = std::max(1, (2 * sm_count() + base_units - 1) / base_units);
-    ks = std::min(ks, std::max(1, p.num_px_tiles / 4));
-    p.px_tiles_per_split = (p.num_px_tiles + ks - 1) / ks;
-    p.ksplit = (p.num_px_tiles + p.px_tiles_per_split - 1) / p.px_tiles_per_split;
+    pick_ksplit(p.ngroups * p.num_m_tiles * p.num_n_tiles, p.num_px_tiles, &p.ksplit, &p.px_tiles_per_split);
     p.out = dw;
     p.m_total = Mc; p.n_total = Nc; p.out_transposed = transposed ? 1 : 0;
     CUtensorMap tG, tI;

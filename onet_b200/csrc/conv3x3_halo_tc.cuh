@@ -1,0 +1,385 @@
+// 3x3-convolution specialisations of the tap-GEMM kernels that cut the L2 -> SM operand traffic.
+//
+// With a pixel tile that is exactly 8 pixels wide, one row of the tile is one 1024-byte swizzle atom (8 rows x
+// 128 B) in shared memory.  A box fetched with a one-row halo above and below therefore serves the three vertical
+// taps (kh = 0,1,2) of a filter column by moving the UMMA descriptor start address in steps of 1024 B — always
+// atom-aligned, so the canonical 128-byte-swizzle layout stays valid.  Only the three horizontal shifts (kw) need
+// their own TMA load:  3 loads of (TH+2) x 8 pixels instead of 9 loads of TH x 8 pixels.
+//
+//   conv3x3_halo_px_kernel : forward / data-gradient, tile = 16 x 8 pixels (M = 128), separate smem rings for the
+//                            activation boxes (18 KB each) and the per-tap weight tiles.
+//   wgrad3x3_halo_kernel   : weight gradient, pixel slab = 8 x 8 (K = 64), the shifted operand is the output
+//                            gradient G; accumulator rows 0..63 / 64..127 may come from two different taps
+//                            (Cout = 64) or two adjacent 64-channel blocks (Cout >= 128).
+#pragma once
+#include "tapgemm_tc.cuh"
+
+namespace onet {
+
+template <int BN>
+struct HaloCfg {
+    static constexpr int kABytes = 144 * 128;                 // (16 + 2) rows x 8 pixels x 64 channels bf16
+    static constexpr int kBBytes = BN * 128;
+    static constexpr int kSA = (BN == 256) ? 3 : 4;
+    static constexpr int kSB = (BN == 256) ? 4 : (BN == 128 ? 6 : 9);
+    static constexpr int kTmemCols = 2 * BN;
+    static constexpr int kAuxBytes = 1024 + 4 * 2 * BN * 4;
+    static constexpr int kSmemBytes = kSA * kABytes + kSB * kBBytes + kAuxBytes + 1024;
+};
+
+// Epilogue shared with tapgemm_px_kernel's EPI_STORE path: raw bf16 output + BatchNorm partial sums.
+template <int BN>
+__device__ __forceinline__ void px_store_epilogue(const PxParams& p, int tile, int acc, uint32_t tmem_base, int q, int ew,
+                                                  int lane, float* s_part, uint32_t bar_tempty) {
+    const int row = q * 32 + lane;
+    const int w_l = row & (p.TW - 1), h_l = (row >> p.log_tw) & (p.TH - 1), n_l = row >> (p.log_tw + p.log_th);
+    const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
+    const int wt = m_tile % p.tiles_w, ht = (m_tile / p.tiles_w) % p.tiles_h, nt = m_tile / (p.tiles_w * p.tiles_h);
+    const int w = wt * p.TW + w_l, h = ht * p.TH + h_l, n = nt * p.TN + n_l, co0 = n_tile * BN;
+    const bool valid = (row < p.valid_rows) && (w < p.W) && (h < p.H) && (n < p.N);
+    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+    __nv_bfloat16* orow = p.out + ((static_cast<long long>(n) * p.H + h) * p.W + w) * p.ldo + p.out_coff + co0;
+    const bool do_stats = p.stat_sum != nullptr;
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_addr + ch * 32, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+        if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        }
+        if (do_stats) {
+            float v[32], s2[32];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
+                const float lo = valid ? __low2float(b) : 0.f, hi = valid ? __high2float(b) : 0.f;
+                v[2 * j] = lo; v[2 * j + 1] = hi;
+                s2[2 * j] = lo * lo; s2[2 * j + 1] = hi * hi;
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int i = 0; i < off; ++i) {
+                    const float send = up ? v[i] : v[i + off];
+                    const float keep = up ? v[i + off] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    const float send2 = up ? s2[i] : s2[i + off];
+                    const float keep2 = up ? s2[i + off] : s2[i];
+                    s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+                }
+            }
+            s_part[(ew * 2 + 0) * BN + ch * 32 + lane] = v[0];
+            s_part[(ew * 2 + 1) * BN + ch * 32 + lane] = s2[0];
+        }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+    if (do_stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int grp = (nt * p.TN) / p.group_images;
+        for (int c = ew * 32 + lane; c < BN; c += 128) {
+            float s = 0.f, sq = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                s += s_part[(e * 2 + 0) * BN + c];
+                sq += s_part[(e * 2 + 1) * BN + c];
+            }
+            atomicAdd(p.stat_sum + static_cast<long long>(grp) * p.cout_total + co0 + c, static_cast<double>(s));
+            atomicAdd(p.stat_sq + static_cast<long long>(grp) * p.cout_total + co0 + c, static_cast<double>(sq));
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+conv3x3_halo_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PxParams p) {
+    using Cfg = HaloCfg<BN>;
+    constexpr int SA = Cfg::kSA, SB = Cfg::kSB;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (base - raw);
+    const uint32_t ringA = base, ringB = base + SA * Cfg::kABytes;
+    const uint32_t aux = ringB + SB * Cfg::kBBytes;
+    uint8_t* gen_aux = gen_base + SA * Cfg::kABytes + SB * Cfg::kBBytes;
+    const uint32_t bar_fullA = aux, bar_emptyA = aux + 8 * SA, bar_fullB = aux + 16 * SA, bar_emptyB = bar_fullB + 8 * SB,
+                   bar_tfull = bar_emptyB + 8 * SB, bar_tempty = bar_tfull + 16;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gen_aux + 16 * SA + 16 * SB + 32);
+    float* s_part = reinterpret_cast<float*>(gen_aux + 1024);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < SA; ++s) { mbar_init(bar_fullA + 8 * s, 1); mbar_init(bar_emptyA + 8 * s, 1); }
+        for (int s = 0; s < SB; ++s) { mbar_init(bar_fullB + 8 * s, 1); mbar_init(bar_emptyB + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::kTmemCols>(smem_u32(tmem_ptr_smem));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
+                const int wt = m_tile % p.tiles_w, ht = (m_tile / p.tiles_w) % p.tiles_h, nt = m_tile / (p.tiles_w * p.tiles_h);
+                const int w0 = wt * 8, h0 = ht * 16, co0 = n_tile * BN;
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    for (int kw = 0; kw < 3; ++kw) {
+                        mbar_wait(bar_emptyA + 8 * sa, pa ^ 1);
+                        mbar_expect_tx(bar_fullA + 8 * sa, Cfg::kABytes);
+                        tma_load_5d(ringA + sa * Cfg::kABytes, &tmA, bar_fullA + 8 * sa, kc * 64, w0 + kw - 1, 0, h0 - 1, nt);
+                        if (++sa == SA) { sa = 0; pa ^= 1; }
+                        for (int kh = 0; kh < 3; ++kh) {
+                            mbar_wait(bar_emptyB + 8 * sb, pb ^ 1);
+                            mbar_expect_tx(bar_fullB + 8 * sb, Cfg::kBBytes);
+                            tma_load_2d(ringB + sb * Cfg::kBBytes, &tmB, bar_fullB + 8 * sb, (kh * 3 + kw) * p.cin + kc * 64, co0);
+                            if (++sb == SB) { sb = 0; pb ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+        int sa = 0, sb = 0;
+        uint32_t pa = 0, pb = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            uint32_t accumulate = 0;
+            for (int kc = 0; kc < p.k_chunks; ++kc) {
+                for (int kw = 0; kw < 3; ++kw) {
+                    mbar_wait(bar_fullA + 8 * sa, pa);
+                    const uint32_t sA = ringA + sa * Cfg::kABytes;
+                    for (int kh = 0; kh < 3; ++kh) {
+                        mbar_wait(bar_fullB + 8 * sb, pb);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t da = umma_smem_desc(sA + kh * 1024, 16, 1024);
+                            const uint64_t db = umma_smem_desc(ringB + sb * Cfg::kBBytes, 16, 1024);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                umma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, accumulate);
+                                accumulate = 1;
+                            }
+                            umma_commit(bar_emptyB + 8 * sb);
+                            if (kh == 2) umma_commit(bar_emptyA + 8 * sa);
+                            if (kh == 2 && kw == 2 && kc == p.k_chunks - 1) umma_commit(bar_tfull + 8 * acc);
+                        }
+                        __syncwarp();
+                        if (++sb == SB) { sb = 0; pb ^= 1; }
+                    }
+                    if (++sa == SA) { sa = 0; pa ^= 1; }
+                }
+            }
+        }
+    } else {
+        const int q = warp & 3, ew = warp - 2;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+            px_store_epilogue<BN>(p, tile, acc, tmem_base, q, ew, lane, s_part, bar_tempty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+// =====================================================================================================
+// weight gradient with H-halo boxes on the shifted (G) operand
+// =====================================================================================================
+constexpr int kWhMaxBox = 4;
+constexpr int kWhMaxAcc = 5;
+constexpr int kWhBoxBytes = 80 * 128;        // (8 + 2) rows x 8 pixels x 64 channels bf16
+
+struct WhAcc {
+    int start_off;            // byte offset of rows 0..63 of the accumulator's M operand inside the stage's M region
+    int lbo;                  // byte distance to rows 64..127
+    int tapA, chA, tapB, chB; // (tap, channel offset inside the m-tile) of the two row blocks; tapB < 0: unused
+};
+struct WhUnit {
+    int nbox;
+    int box_kw[kWhMaxBox], box_ch[kWhMaxBox];
+    int nacc;
+    WhAcc acc[kWhMaxAcc];
+};
+struct WhParams {
+    int N, H, W;
+    int tiles_w, tiles_h, num_px_tiles;       // 8x8 pixel slabs
+    int ksplit, px_tiles_per_split;
+    int ntypes, num_m_tiles, num_n_tiles, m_tile_channels;
+    WhUnit types[3];
+    float* out;                               // dW [m_total][n_total][9], accumulated with atomics
+    int m_total, n_total;
+};
+
+template <int BNW>
+struct WhCfg {
+    static constexpr int kNBytes = (BNW / 64) * 8192;
+    static constexpr int kMBytes = kWhMaxBox * kWhBoxBytes;     // 40 KB
+    static constexpr int kStageBytes = kNBytes + kMBytes;
+    static constexpr int kStages = 3;
+    static constexpr int kTmemCols = 512;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 1024;
+};
+
+template <int BNW>
+__global__ void __launch_bounds__(192, 1)
+wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmI, const WhParams p) {
+    using Cfg = WhCfg<BNW>;
+    constexpr int STAGES = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (base - raw);
+    const uint32_t aux = base + STAGES * Cfg::kStageBytes;
+    uint8_t* gen_aux = gen_base + STAGES * Cfg::kStageBytes;
+    const uint32_t bar_full = aux, bar_empty = aux + 8 * STAGES, bar_tfull = aux + 16 * STAGES, bar_tempty = bar_tfull + 8;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gen_aux + 16 * STAGES + 32);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmG);
+        tma_prefetch_desc(&tmI);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tempty, 4);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::kTmemCols>(smem_u32(tmem_ptr_smem));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    // unit = ((type * num_m_tiles + mt) * num_n_tiles + nt) * ksplit + ks
+    const int num_units = p.ntypes * p.num_m_tiles * p.num_n_tiles * p.ksplit;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+                const int ks = unit % p.ksplit;
+                const int nt = (unit / p.ksplit) % p.num_n_tiles;
+                const int mt = (unit / (p.ksplit * p.num_n_tiles)) % p.num_m_tiles;
+                const WhUnit& u = p.types[unit / (p.ksplit * p.num_n_tiles * p.num_m_tiles)];
+                const int m0 = mt * p.m_tile_channels, n0 = nt * BNW;
+                const int px_begin = ks * p.px_tiles_per_split;
+                const int px_end = min(px_begin + p.px_tiles_per_split, p.num_px_tiles);
+                const uint32_t tx = static_cast<uint32_t>(u.nbox) * kWhBoxBytes + Cfg::kNBytes;
+                for (int pt = px_begin; pt < px_end; ++pt) {
+                    const int wt = pt % p.tiles_w, ht = (pt / p.tiles_w) % p.tiles_h, n = pt / (p.tiles_w * p.tiles_h);
+                    const int w0 = wt * 8, h0 = ht * 8;
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t sN = base + stage * Cfg::kStageBytes, sM = sN + Cfg::kNBytes;
+                    const uint32_t fb = bar_full + 8 * stage;
+                    mbar_expect_tx(fb, tx);
+#pragma unroll
+                    for (int b = 0; b < BNW / 64; ++b) tma_load_5d(sN + b * 8192, &tmI, fb, n0 + b * 64, w0, 0, h0, n);
+                    for (int b = 0; b < u.nbox; ++b)     // G shifted by -(kw-1) in w, one-row halo in h
+                        tma_load_5d(sM + b * kWhBoxBytes, &tmG, fb, m0 + u.box_ch[b], w0 - (u.box_kw[b] - 1), 0, h0 - 1, n);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = umma_idesc_bf16(128, BNW, 1, 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+            const int ks = unit % p.ksplit;
+            const WhUnit& u = p.types[unit / (p.ksplit * p.num_n_tiles * p.num_m_tiles)];
+            const int px_begin = ks * p.px_tiles_per_split;
+            const int px_end = min(px_begin + p.px_tiles_per_split, p.num_px_tiles);
+            mbar_wait(bar_tempty, (it & 1) ^ 1);
+            tc_fence_after();
+            for (int pt = px_begin; pt < px_end; ++pt) {
+                mbar_wait(bar_full + 8 * stage, phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sN = base + stage * Cfg::kStageBytes, sM = sN + Cfg::kNBytes;
+                    const uint64_t db = umma_smem_desc(sN, 8192, 1024);
+                    for (int a = 0; a < u.nacc; ++a) {
+                        const uint64_t da = umma_smem_desc(sM + u.acc[a].start_off, u.acc[a].lbo, 1024);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_bf16(tmem_base + a * BNW, da + 128 * kk, db + 128 * kk, idesc, (pt > px_begin) || kk);
+                    }
+                    umma_commit(bar_empty + 8 * stage);
+                    if (pt == px_end - 1) umma_commit(bar_tfull);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int it = 0;
+        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+            const int nt = (unit / p.ksplit) % p.num_n_tiles;
+            const int mt = (unit / (p.ksplit * p.num_n_tiles)) % p.num_m_tiles;
+            const WhUnit& u = p.types[unit / (p.ksplit * p.num_n_tiles * p.num_m_tiles)];
+            const int m0 = mt * p.m_tile_channels, n0 = nt * BNW;
+            mbar_wait(bar_tfull, it & 1);
+            tc_fence_after();
+            for (int a = 0; a < u.nacc; ++a) {
+                const int tap = (row < 64) ? u.acc[a].tapA : u.acc[a].tapB;
+                const int m = m0 + ((row < 64) ? u.acc[a].chA + row : u.acc[a].chB + row - 64);
+                const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BNW;
+#pragma unroll 1
+                for (int ch = 0; ch < BNW / 32; ++ch) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_addr + ch * 32, r);
+                    tmem_ld_wait();
+                    if (tap >= 0) {
+                        float* dst = p.out + (static_cast<long long>(m) * p.n_total + n0 + ch * 32) * 9 + tap;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) atomicAdd(dst + j * 9, __uint_as_float(r[j]));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+}  // namespace onet

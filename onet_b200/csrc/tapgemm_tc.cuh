@@ -101,7 +101,7 @@ tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -138,7 +138,7 @@ tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int k = 0; k < k_iters; ++k) {
                 mbar_wait(bar_full + 8 * stage, phase);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint32_t sA = base + stage * Cfg::kStageBytes, sB = sA + Cfg::kABytes;
                     const uint64_t da = umma_smem_desc(sA, 16, 1024), db = umma_smem_desc(sB, 16, 1024);
 #pragma unroll
@@ -351,7 +351,7 @@ tapgemm_wg_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     const int num_units = p.ngroups * p.num_m_tiles * p.num_n_tiles * p.ksplit;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
@@ -404,7 +404,7 @@ tapgemm_wg_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
             for (int pt = px_begin; pt < px_end; ++pt) {
                 mbar_wait(bar_full + 8 * stage, phase);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint32_t sN = base + stage * Cfg::kStageBytes, sM = sN + Cfg::kNBytes;
                     const uint64_t db = umma_smem_desc(sN, 8192, 1024);
                     for (int a = 0; a < nacc; ++a) {

@@ -49,7 +49,7 @@ def test_conv3x3_simt_fp32(n, h, w, cin, cout):
 
 
 TC_SHAPES = [(2, 16, 16, 64, 64), (4, 16, 16, 128, 256), (2, 32, 32, 64, 128), (8, 4, 4, 256, 256), (4, 2, 2, 128, 64),
-             (2, 24, 40, 128, 64), (6, 8, 8, 192, 384)]
+             (2, 24, 40, 128, 64), (6, 8, 8, 192, 384), (1, 19, 21, 64, 128)]
 
 
 @pytest.mark.parametrize("n,h,w,cin,cout", TC_SHAPES)
@@ -60,7 +60,7 @@ def test_conv3x3_tc_fwd(n, h, w, cin, cout):
     wt = _bf16r(torch.randn(cout, cin, 3, 3, device="cuda") * (2.0 / (9 * cin)) ** 0.5)
     wf, wd = U.pack_conv(wt, U.BF16)
     xb = U.to_nhwc(x, torch.bfloat16)
-    g = n // 2
+    g = max(n // 2, 1)
     y, st = U.conv3x3(xb, wf, cout, U.BF16, U.ENGINE_TC, group_images=g, stats=True)
     torch.cuda.synchronize()
     ref = F.conv2d(x, wt, padding=1)
@@ -69,7 +69,8 @@ def test_conv3x3_tc_fwd(n, h, w, cin, cout):
     yf = U.from_nhwc(y).double()
     assert torch.allclose(st[0, 0], yf[:g].sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-2)
     assert torch.allclose(st[1, 0], (yf[:g] ** 2).sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-2)
-    assert torch.allclose(st[0, 1], yf[g:].sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-2)
+    if n > g:
+        assert torch.allclose(st[0, 1], yf[g:].sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-2)
     # same kernel as dgrad
     gy = _bf16r(torch.randn(n, cout, h, w, device="cuda"))
     dx, _ = U.conv3x3(U.to_nhwc(gy, torch.bfloat16), wd, cin, U.BF16, U.ENGINE_TC)

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Runs every -m gpu test in its own process (a trapped kernel poisons only its own context) and collects a summary
-# under gpurun_out/.  Usage: bash tools_run_gpu_tests.sh [pytest -k expression]
+# under gpurun_out/.  Usage: bash tools/run_gpu_tests.sh [pytest -k expression]
 mkdir -p gpurun_out
 OUT=gpurun_out/gpu_tests.log
 : > $OUT
