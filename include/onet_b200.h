@@ -75,17 +75,19 @@ int onet_bn_eval_prepare(int G, int C, const float* gamma0, const float* beta0, 
 
 /* y -> relu(y*scale+shift) written to out (+ooff, ld ldo; e.g. the skip half of a concat buffer) and, when
  * pool != NULL, the 2x2 max-pooled map [N,H/2,W/2,C] in the same pass (nn.ReLU :49,53 + nn.MaxPool2d(2) :67
- * + the skip half of torch.cat :100). */
+ * + the skip half of torch.cat :100).  amax (optional, uint8 [N,H/2,W/2,C]) receives the position 0..3 of the first
+ * maximum of every window, which is what the backward pass routes the pooled gradient to. */
 int onet_bn_relu_apply(const void* y, int N, int H, int W, int C, const float* scale, const float* shift,
-                       int group_images, void* out, int64_t ldo, int ooff, void* pool, int dtype, void* stream);
+                       int group_images, void* out, int64_t ldo, int ooff, void* pool, void* amax, int dtype,
+                       void* stream);
 
 /* Backward of BN -> ReLU (-> skip / max-pool): gradient sources g1 (+ optional g2, optional pooled gp routed to
- * the first maximum of each 2x2 window), produces dy [N,H,W,C] and accumulates dgamma/dbeta.  `sums` is a
+ * the window maximum recorded in amax), produces dy [N,H,W,C] and accumulates dgamma/dbeta.  `sums` is a
  * zero-initialised [G][2][C] double workspace. */
 int onet_bn_relu_bwd(const void* y, int N, int H, int W, int C, const float* scale, const float* shift,
                      const float* mean, const float* invstd, int group_images, const void* g1, int64_t ld1, int off1,
-                     const void* g2, int64_t ld2, int off2, const void* gp, double* sums, double count, void* dy,
-                     float* dgamma0, float* dbeta0, float* dgamma1, float* dbeta1, int dtype, void* stream);
+                     const void* g2, int64_t ld2, int off2, const void* gp, const void* amax, double* sums, double count,
+                     void* dy, float* dgamma0, float* dbeta0, float* dgamma1, float* dbeta1, int dtype, void* stream);
 
 /* ConvTranspose2d(Cin, Co, 2, 2) + bias written directly into channels [ooff, ooff+Co) of the concat buffer
  * (nn.ConvTranspose2d :86 + F.pad :92-96 (no-op when sizes divide) + the up half of torch.cat :100).

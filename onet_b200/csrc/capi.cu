@@ -249,7 +249,7 @@ static int convT_fwd_tc(const bf16* x, long long ldx, int xoff, int N, int H, in
     PxParams p;
     memset(&p, 0, sizeof(p));
     px_tiling(p, N, H, W, 0);
-    const int BN = pick_bn(Co);
+    const int BN = 256;                       // 4*Co is a multiple of 256; a tile spans one or more of the 2x2 positions
     p.num_n_tiles = 4 * Co / BN;
     p.ntaps = 1; p.k_chunks = Cin / 64; p.cin = Cin;
     p.taps[0] = make_int4(0, 0, 0, 0);
@@ -496,11 +496,11 @@ int onet_conv3x3_fwd(const void* in, int64_t ldi, int ci_off, int N, int H, int 
     const long long M = static_cast<long long>(N) * H * W;
     dim3 grid(static_cast<unsigned>((M + 63) / 64), (Cout + 63) / 64);
     const int gi = group_images > 0 ? group_images : N;
-    if ((Cin == 1 || Cin == 3) && Cout == 64 && ldi == Cin && ci_off == 0 && ldo == 64 && co_off == 0) {
+    if ((Cin == 1 || Cin == 3) && Cout == 64 && ldi == Cin && ci_off == 0 && ldo == 64 && co_off == 0 && W % 4 == 0) {
         // first layer of the U-Net: direct bandwidth-bound kernel
         const int G = std::min(2, (N + gi - 1) / gi);
-        const long long px = static_cast<long long>(gi) * H * W;
-        dim3 fg(static_cast<unsigned>(std::max(1LL, std::min<long long>((px + 31) / 32, 148 * 16 / G))), G);
+        const long long quads = static_cast<long long>(gi) * H * (W / 4);
+        dim3 fg(static_cast<unsigned>(std::max(1LL, std::min<long long>((quads + 31) / 32, 148 * 8 / G))), G);
 #define ONET_FIRST(TT, CC)                                                                                          \
     conv_first_fwd_kernel<TT, CC><<<fg, 256, 0, ST(stream)>>>(static_cast<const TT*>(in), N, H, W,                  \
                                                               static_cast<const TT*>(wp), static_cast<TT*>(out),   \
@@ -529,9 +529,9 @@ int onet_conv3x3_wgrad(const void* g, int64_t ldg, int g_off, const void* in, in
                         N, H, W, 9, dw, false, ST(stream));
     }
     const long long M = static_cast<long long>(N) * H * W;
-    if ((Cin == 1 || Cin == 3) && Cout == 64 && ldi == Cin && ci_off == 0 && ldg == 64 && g_off == 0) {
+    if ((Cin == 1 || Cin == 3) && Cout == 64 && ldi == Cin && ci_off == 0 && ldg == 64 && g_off == 0 && W % 4 == 0) {
         const int lanes = Cin == 1 ? 32 : 8;
-        const int gx = static_cast<int>(std::max(1LL, std::min<long long>((M + lanes - 1) / lanes, 148 * 4)));
+        const int gx = static_cast<int>(std::max(1LL, std::min<long long>((M / 4 + lanes - 1) / lanes, 148 * 4)));
         if (dtype == ONET_F32) {
             if (Cin == 1) conv_first_wgrad_kernel<float, 1, 8><<<gx, 256, 0, ST(stream)>>>(static_cast<const float*>(g), static_cast<const float*>(in), N, H, W, dw);
             else conv_first_wgrad_kernel<float, 3, 2><<<gx, 256, 0, ST(stream)>>>(static_cast<const float*>(g), static_cast<const float*>(in), N, H, W, dw);
@@ -584,16 +584,18 @@ int onet_bn_eval_prepare(int G, int C, const float* gamma0, const float* beta0, 
 }
 
 int onet_bn_relu_apply(const void* y, int N, int H, int W, int C, const float* scale, const float* shift,
-                       int group_images, void* out, int64_t ldo, int ooff, void* pool, int dtype, void* stream) {
+                       int group_images, void* out, int64_t ldo, int ooff, void* pool, void* amax, int dtype, void* stream) {
     if (C % 8 || ldo % 8 || ooff % 8) return fail("bn_relu_apply: channel counts/offsets must be multiples of 8");
     const long long total = static_cast<long long>(N) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
     const int gi = group_images > 0 ? group_images : N;
     if (dtype == ONET_F32)
         bn_relu_apply_kernel<float><<<grid_for(total, 256, 148 * 32), 256, 0, ST(stream)>>>(
-            static_cast<const float*>(y), N, H, W, C, scale, shift, gi, static_cast<float*>(out), ldo, ooff, static_cast<float*>(pool));
+            static_cast<const float*>(y), N, H, W, C, scale, shift, gi, static_cast<float*>(out), ldo, ooff, static_cast<float*>(pool),
+            static_cast<uint8_t*>(amax));
     else
         bn_relu_apply_kernel<bf16><<<grid_for(total, 256, 148 * 32), 256, 0, ST(stream)>>>(
-            static_cast<const bf16*>(y), N, H, W, C, scale, shift, gi, static_cast<bf16*>(out), ldo, ooff, static_cast<bf16*>(pool));
+            static_cast<const bf16*>(y), N, H, W, C, scale, shift, gi, static_cast<bf16*>(out), ldo, ooff, static_cast<bf16*>(pool),
+            static_cast<uint8_t*>(amax));
     return check_launch("bn_relu_apply");
 }
 
@@ -602,8 +604,8 @@ int onet_bn_relu_apply(const void* y, int N, int H, int W, int C, const float* s
 template <typename T>
 static int bn_bwd_impl(const void* y, int N, int H, int W, int C, const float* scale, const float* shift, const float* mean,
                        const float* invstd, int group_images, const void* g1, int64_t ld1, int off1, const void* g2,
-                       int64_t ld2, int off2, const void* gp, double* sums, double count, void* dy, float* dgamma0,
-                       float* dbeta0, float* dgamma1, float* dbeta1, cudaStream_t st) {
+                       int64_t ld2, int off2, const void* gp, const void* amax, double* sums, double count, void* dy,
+                       float* dgamma0, float* dbeta0, float* dgamma1, float* dbeta1, cudaStream_t st) {
     BnBwdArgs<T> a;
     a.y = static_cast<const T*>(y); a.N = N; a.H = H; a.W = W; a.C = C;
     a.scale = scale; a.shift = shift; a.mean = mean; a.invstd = invstd;
@@ -611,23 +613,24 @@ static int bn_bwd_impl(const void* y, int N, int H, int W, int C, const float* s
     a.g1 = static_cast<const T*>(g1); a.ld1 = ld1; a.off1 = off1;
     a.g2 = static_cast<const T*>(g2); a.ld2 = ld2; a.off2 = off2;
     a.gp = static_cast<const T*>(gp);
+    a.amax = static_cast<const uint8_t*>(amax);
     a.sums = sums; a.count = count; a.dy = static_cast<T*>(dy);
     const int G = std::min(2, (N + a.group_images - 1) / a.group_images);
     const int OC = C / 8, lanes = 256 / OC;
-    if (gp != nullptr) {
-        const long long quads = static_cast<long long>(a.group_images) * ((H + 1) / 2) * ((W + 1) / 2);
-        const int gx = static_cast<int>(std::max(1LL, std::min<long long>((quads + lanes - 1) / lanes, 148 * 8 / G)));
-        bn_bwd_pool_kernel<T, false><<<dim3(gx, G), 256, 0, st>>>(a);
-        if (check_launch("bn_bwd_pool_reduce")) return 1;
-        bn_bwd_pool_kernel<T, true><<<dim3(gx, G), 256, 0, st>>>(a);
-        if (check_launch("bn_bwd_pool_apply")) return 1;
-    } else {
-        constexpr int UNR = 4;
+    {
+        constexpr int UNR = 4, UNRP = 2;     // the pooled variant keeps fewer pixels in flight to stay at 2 blocks / SM
         const long long px = static_cast<long long>(a.group_images) * H * W;
-        const int gx = static_cast<int>(std::max(1LL, std::min<long long>((px + lanes * UNR - 1) / (lanes * UNR), 148 * 8 / G)));
-        bn_bwd_reduce_px_kernel<T, UNR><<<dim3(gx, G), 256, 0, st>>>(a);
-        if (check_launch("bn_bwd_reduce")) return 1;
-        bn_bwd_apply_px_kernel<T, UNR><<<dim3(gx, G), 256, 0, st>>>(a);
+        const int unr = gp != nullptr ? UNRP : UNR;
+        const int gx = static_cast<int>(std::max(1LL, std::min<long long>((px + lanes * unr - 1) / (lanes * unr), 148 * 8 / G)));
+        if (gp != nullptr) {
+            bn_bwd_reduce_px_kernel<T, UNRP, true><<<dim3(gx, G), 256, 0, st>>>(a);
+            if (check_launch("bn_bwd_reduce")) return 1;
+            bn_bwd_apply_px_kernel<T, UNRP, true><<<dim3(gx, G), 256, 0, st>>>(a);
+        } else {
+            bn_bwd_reduce_px_kernel<T, UNR, false><<<dim3(gx, G), 256, 0, st>>>(a);
+            if (check_launch("bn_bwd_reduce")) return 1;
+            bn_bwd_apply_px_kernel<T, UNR, false><<<dim3(gx, G), 256, 0, st>>>(a);
+        }
         if (check_launch("bn_bwd_apply")) return 1;
     }
     if (dgamma0 != nullptr) {
@@ -642,16 +645,18 @@ extern "C" {
 
 int onet_bn_relu_bwd(const void* y, int N, int H, int W, int C, const float* scale, const float* shift,
                      const float* mean, const float* invstd, int group_images, const void* g1, int64_t ld1, int off1,
-                     const void* g2, int64_t ld2, int off2, const void* gp, double* sums, double count, void* dy,
-                     float* dgamma0, float* dbeta0, float* dgamma1, float* dbeta1, int dtype, void* stream) {
+                     const void* g2, int64_t ld2, int off2, const void* gp, const void* amax, double* sums, double count,
+                     void* dy, float* dgamma0, float* dbeta0, float* dgamma1, float* dbeta1, int dtype, void* stream) {
+    if ((gp == nullptr) != (amax == nullptr)) return fail("bn_relu_bwd: gp and amax must be given together");
+    if (static_cast<long long>(N) * H * W >= (1LL << 31)) return fail("bn_relu_bwd: more than 2^31 pixels");
     if (C % 8 || C > 2048) return fail("bn_relu_bwd: C must be a multiple of 8 and <= 2048");
     if (256 % (C / 8) != 0 && (C / 8) < 256) return fail("bn_relu_bwd: C/8 must divide 256");
     if (g1 == nullptr) return fail("bn_relu_bwd: g1 is required");
     if (dtype == ONET_F32)
         return bn_bwd_impl<float>(y, N, H, W, C, scale, shift, mean, invstd, group_images, g1, ld1, off1, g2, ld2, off2, gp,
-                                  sums, count, dy, dgamma0, dbeta0, dgamma1, dbeta1, ST(stream));
-    return bn_bwd_impl<bf16>(y, N, H, W, C, scale, shift, mean, invstd, group_images, g1, ld1, off1, g2, ld2, off2, gp, sums,
-                             count, dy, dgamma0, dbeta0, dgamma1, dbeta1, ST(stream));
+                                  amax, sums, count, dy, dgamma0, dbeta0, dgamma1, dbeta1, ST(stream));
+    return bn_bwd_impl<bf16>(y, N, H, W, C, scale, shift, mean, invstd, group_images, g1, ld1, off1, g2, ld2, off2, gp, amax,
+                             sums, count, dy, dgamma0, dbeta0, dgamma1, dbeta1, ST(stream));
 }
 
 int onet_convT2x2_fwd(const void* x, int64_t ldx, int xoff, int N, int H, int W, int Cin, const void* w,

@@ -20,11 +20,13 @@ template <int BN>
 struct HaloCfg {
     static constexpr int kABytes = 144 * 128;                 // (16 + 2) rows x 8 pixels x 64 channels bf16
     static constexpr int kBBytes = BN * 128;
-    static constexpr int kSA = (BN == 256) ? 3 : 4;
-    static constexpr int kSB = (BN == 256) ? 4 : (BN == 128 ? 6 : 9);
+    static constexpr int kTapsPerB = (BN == 256) ? 1 : 3;     // vertical taps fetched per weight stage
+    static constexpr int kSA = (BN == 64) ? 4 : 3;
+    static constexpr int kSB = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
+    static constexpr int kBStageBytes = kTapsPerB * kBBytes;
     static constexpr int kTmemCols = 2 * BN;
     static constexpr int kAuxBytes = 1024 + 4 * 2 * BN * 4;
-    static constexpr int kSmemBytes = kSA * kABytes + kSB * kBBytes + kAuxBytes + 1024;
+    static constexpr int kSmemBytes = kSA * kABytes + kSB * kBStageBytes + kAuxBytes + 1024;
 };
 
 // Epilogue shared with tapgemm_px_kernel's EPI_STORE path: raw bf16 output + BatchNorm partial sums.
@@ -109,8 +111,9 @@ conv3x3_halo_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* gen_base = smem_raw + (base - raw);
     const uint32_t ringA = base, ringB = base + SA * Cfg::kABytes;
-    const uint32_t aux = ringB + SB * Cfg::kBBytes;
-    uint8_t* gen_aux = gen_base + SA * Cfg::kABytes + SB * Cfg::kBBytes;
+    constexpr int TPB = Cfg::kTapsPerB;
+    const uint32_t aux = ringB + SB * Cfg::kBStageBytes;
+    uint8_t* gen_aux = gen_base + SA * Cfg::kABytes + SB * Cfg::kBStageBytes;
     const uint32_t bar_fullA = aux, bar_emptyA = aux + 8 * SA, bar_fullB = aux + 16 * SA, bar_emptyB = bar_fullB + 8 * SB,
                    bar_tfull = bar_emptyB + 8 * SB, bar_tempty = bar_tfull + 16;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gen_aux + 16 * SA + 16 * SB + 32);
@@ -146,10 +149,13 @@ conv3x3_halo_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                         mbar_expect_tx(bar_fullA + 8 * sa, Cfg::kABytes);
                         tma_load_5d(ringA + sa * Cfg::kABytes, &tmA, bar_fullA + 8 * sa, kc * 64, w0 + kw - 1, 0, h0 - 1, nt);
                         if (++sa == SA) { sa = 0; pa ^= 1; }
-                        for (int kh = 0; kh < 3; ++kh) {
+                        for (int kh = 0; kh < 3; kh += TPB) {
                             mbar_wait(bar_emptyB + 8 * sb, pb ^ 1);
-                            mbar_expect_tx(bar_fullB + 8 * sb, Cfg::kBBytes);
-                            tma_load_2d(ringB + sb * Cfg::kBBytes, &tmB, bar_fullB + 8 * sb, (kh * 3 + kw) * p.cin + kc * 64, co0);
+                            mbar_expect_tx(bar_fullB + 8 * sb, Cfg::kBStageBytes);
+#pragma unroll
+                            for (int j = 0; j < TPB; ++j)
+                                tma_load_2d(ringB + sb * Cfg::kBStageBytes + j * Cfg::kBBytes, &tmB, bar_fullB + 8 * sb,
+                                            ((kh + j) * 3 + kw) * p.cin + kc * 64, co0);
                             if (++sb == SB) { sb = 0; pb ^= 1; }
                         }
                     }
@@ -157,43 +163,47 @@ conv3x3_halo_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
-        int sa = 0, sb = 0;
-        uint32_t pa = 0, pb = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
-            mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * BN;
-            uint32_t accumulate = 0;
-            for (int kc = 0; kc < p.k_chunks; ++kc) {
-                for (int kw = 0; kw < 3; ++kw) {
-                    mbar_wait(bar_fullA + 8 * sa, pa);
-                    const uint32_t sA = ringA + sa * Cfg::kABytes;
-                    for (int kh = 0; kh < 3; ++kh) {
-                        mbar_wait(bar_fullB + 8 * sb, pb);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            const uint64_t da = umma_smem_desc(sA + kh * 1024, 16, 1024);
-                            const uint64_t db = umma_smem_desc(ringB + sb * Cfg::kBBytes, 16, 1024);
+        // one elected thread runs the whole issue loop (no per-iteration warp convergence, no uniform-datapath loops)
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                uint32_t accumulate = 0;
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    for (int kw = 0; kw < 3; ++kw) {
+                        mbar_wait(bar_fullA + 8 * sa, pa);
+                        const uint32_t sA = ringA + sa * Cfg::kABytes;
+                        for (int kh = 0; kh < 3; kh += TPB) {
+                            mbar_wait(bar_fullB + 8 * sb, pb);
+                            tc_fence_after();
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {
-                                umma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, accumulate);
-                                accumulate = 1;
+                            for (int j = 0; j < TPB; ++j) {
+                                const uint64_t da = umma_smem_desc(sA + (kh + j) * 1024, 16, 1024);
+                                const uint64_t db = umma_smem_desc(ringB + sb * Cfg::kBStageBytes + j * Cfg::kBBytes, 16, 1024);
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk) {
+                                    umma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, accumulate);
+                                    accumulate = 1;
+                                }
                             }
                             umma_commit(bar_emptyB + 8 * sb);
-                            if (kh == 2) umma_commit(bar_emptyA + 8 * sa);
-                            if (kh == 2 && kw == 2 && kc == p.k_chunks - 1) umma_commit(bar_tfull + 8 * acc);
+                            if (++sb == SB) { sb = 0; pb ^= 1; }
                         }
-                        __syncwarp();
-                        if (++sb == SB) { sb = 0; pb ^= 1; }
+                        umma_commit(bar_emptyA + 8 * sa);
+                        if (++sa == SA) { sa = 0; pa ^= 1; }
                     }
-                    if (++sa == SA) { sa = 0; pa ^= 1; }
                 }
+                umma_commit(bar_tfull + 8 * acc);
             }
         }
+        __syncwarp();
     } else {
         const int q = warp & 3, ew = warp - 2;
         int it = 0;
@@ -312,21 +322,21 @@ wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_const
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = umma_idesc_bf16(128, BNW, 1, 1);
-        int stage = 0;
-        uint32_t phase = 0;
-        int it = 0;
-        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
-            const int ks = unit % p.ksplit;
-            const WhUnit& u = p.types[unit / (p.ksplit * p.num_n_tiles * p.num_m_tiles)];
-            const int px_begin = ks * p.px_tiles_per_split;
-            const int px_end = min(px_begin + p.px_tiles_per_split, p.num_px_tiles);
-            mbar_wait(bar_tempty, (it & 1) ^ 1);
-            tc_fence_after();
-            for (int pt = px_begin; pt < px_end; ++pt) {
-                mbar_wait(bar_full + 8 * stage, phase);
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, BNW, 1, 1);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+                const int ks = unit % p.ksplit;
+                const WhUnit& u = p.types[unit / (p.ksplit * p.num_n_tiles * p.num_m_tiles)];
+                const int px_begin = ks * p.px_tiles_per_split;
+                const int px_end = min(px_begin + p.px_tiles_per_split, p.num_px_tiles);
+                mbar_wait(bar_tempty, (it & 1) ^ 1);
                 tc_fence_after();
-                if (elect_one()) {
+                for (int pt = px_begin; pt < px_end; ++pt) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
                     const uint32_t sN = base + stage * Cfg::kStageBytes, sM = sN + Cfg::kNBytes;
                     const uint64_t db = umma_smem_desc(sN, 8192, 1024);
                     for (int a = 0; a < u.nacc; ++a) {
@@ -336,12 +346,12 @@ wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_const
                             umma_bf16(tmem_base + a * BNW, da + 128 * kk, db + 128 * kk, idesc, (pt > px_begin) || kk);
                     }
                     umma_commit(bar_empty + 8 * stage);
-                    if (pt == px_end - 1) umma_commit(bar_tfull);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                umma_commit(bar_tfull);
             }
         }
+        __syncwarp();
     } else {
         const int q = warp & 3;
         const int row = q * 32 + lane;

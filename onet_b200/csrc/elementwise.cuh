@@ -98,7 +98,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 bn_relu_apply_kernel(const T* __restrict__ y, int N, int H, int W, int C, const float* __restrict__ scale,
                      const float* __restrict__ shift, int group_images, T* __restrict__ out, long long ldo, int ooff,
-                     T* __restrict__ pool) {
+                     T* __restrict__ pool, uint8_t* __restrict__ amax) {
     const int OC = C >> 3, H2 = (H + 1) >> 1, W2 = (W + 1) >> 1, HP = H >> 1, WP = W >> 1;
     const long long total = static_cast<long long>(N) * H2 * W2 * OC;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -110,10 +110,11 @@ bn_relu_apply_kernel(const T* __restrict__ y, int N, int H, int W, int C, const 
         const int n = static_cast<int>(q / H2);
         const int g = min(n / group_images, 1);
         float sc[8], sh[8], mx[8];
+        uint32_t best[8];
         load8<float>(scale + g * C + oc * 8, sc);
         load8<float>(shift + g * C + oc * 8, sh);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) mx[i] = 0.f;   // post-ReLU values are >= 0
+        for (int i = 0; i < 8; ++i) { mx[i] = -1.f; best[i] = 0; }   // post-ReLU values are >= 0 -> first pixel always wins first
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
@@ -126,13 +127,18 @@ bn_relu_apply_kernel(const T* __restrict__ y, int N, int H, int W, int C, const 
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         v[i] = round_to<T>(fmaxf(fmaf(v[i], sc[i], sh[i]), 0.f));
-                        mx[i] = fmaxf(mx[i], v[i]);
+                        if (v[i] > mx[i]) { mx[i] = v[i]; best[i] = dy * 2 + dx; }   // first maximum, like ATen
                     }
                     store8<T>(out + px * ldo + ooff + oc * 8, v);
                 }
             }
-        if (pool != nullptr && h2 < HP && w2 < WP)
-            store8<T>(pool + ((static_cast<long long>(n) * HP + h2) * WP + w2) * C + oc * 8, mx);
+        if (pool != nullptr && h2 < HP && w2 < WP) {
+            const long long po = ((static_cast<long long>(n) * HP + h2) * WP + w2) * C + oc * 8;
+            store8<T>(pool + po, mx);
+            if (amax != nullptr)
+                *reinterpret_cast<uint2*>(amax + po) = make_uint2(best[0] | (best[1] << 8) | (best[2] << 16) | (best[3] << 24),
+                                                                  best[4] | (best[5] << 8) | (best[6] << 16) | (best[7] << 24));
+        }
     }
 }
 
@@ -151,6 +157,7 @@ struct BnBwdArgs {
     const T* g1; long long ld1; int off1;
     const T* g2; long long ld2; int off2;
     const T* gp;                                 // [N,H/2,W/2,C] or nullptr
+    const uint8_t* amax;                         // [N,H/2,W/2,C] position (0..3) of the window maximum, with gp
     double* sums;                                // [G][2][C]
     double count;                                // elements per channel per group
     T* dy;                                       // [N,H,W,C]
@@ -214,25 +221,6 @@ __device__ __forceinline__ void bn_bwd_pixel(const Raw8<T>& ry, const Raw8<T>& r
     }
 }
 
-// For a 2x2 window: per channel, which of the 4 pixels holds the first maximum of the (stored) activation.
-template <typename T>
-__device__ __forceinline__ void pool_argmax(const Raw8<T> (&ry)[4], const float (&sc)[8], const float (&sh)[8],
-                                            int (&best)[8]) {
-    float bv[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { best[i] = 0; bv[i] = -1.f; }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        float y[8];
-        unpack(ry[k], y);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float a = round_to<T>(fmaxf(fmaf(y[i], sc[i], sh[i]), 0.f));
-            if (a > bv[i]) { bv[i] = a; best[i] = k; }
-        }
-    }
-}
-
 template <typename T>
 struct BnBwdCtx {      // per-thread channel constants
     float sc[8], sh[8], mu[8], is[8];
@@ -264,8 +252,35 @@ __device__ __forceinline__ void bn_bwd_block_reduce(const BnBwdArgs<T>& a, int g
     }
 }
 
-// ---- variant without a pooled source: one thread = one pixel x 8 channels, UNROLL pixels in flight
-template <typename T, int UNROLL>
+// Pooled-gradient contribution for pixel q: gp[n,h/2,w/2,c] where this pixel is the window maximum.
+template <typename T>
+__device__ __forceinline__ void pooled_extra(const BnBwdArgs<T>& a, long long q, int oc, Raw8<T>& rp, uint2& am, int& pos) {
+    const unsigned W = a.W, H = a.H;
+    const unsigned qq = static_cast<unsigned>(q);
+    const unsigned w = qq % W, t = qq / W;
+    const unsigned h = t % H, n = t / H;
+    const unsigned HP = H >> 1, WP = W >> 1;
+    const unsigned h2 = h >> 1, w2 = w >> 1;
+    pos = (h & 1) * 2 + (w & 1);
+    if (h2 < HP && w2 < WP) {
+        const long long po = ((static_cast<long long>(n) * HP + h2) * WP + w2) * a.C + oc * 8;
+        rp = ldraw<T>(a.gp + po);
+        am = __ldg(reinterpret_cast<const uint2*>(a.amax + po));
+    } else {
+        rp = zero_raw<T>();
+        am = make_uint2(0xffffffffu, 0xffffffffu);
+    }
+}
+__device__ __forceinline__ void select_extra(const float (&gpv)[8], uint2 am, int pos, float (&extra)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const unsigned b = ((i < 4 ? am.x : am.y) >> (8 * (i & 3))) & 0xffu;
+        extra[i] = (b == static_cast<unsigned>(pos)) ? gpv[i] : 0.f;
+    }
+}
+
+// ---- one thread = one pixel x 8 channels, UNROLL pixels in flight
+template <typename T, int UNROLL, bool POOL>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_px_kernel(const BnBwdArgs<T> a) {
     __shared__ float s_red[16][256];
@@ -276,14 +291,16 @@ bn_bwd_reduce_px_kernel(const BnBwdArgs<T> a) {
     const long long p_begin = static_cast<long long>(g) * a.group_images * HW;
     const long long p_end = static_cast<long long>(g == static_cast<int>(gridDim.y) - 1 ? a.N : (g + 1) * a.group_images) * HW;
     const bool has_g2 = a.g2 != nullptr;
+    constexpr bool has_gp = POOL;
     float acc1[8] = {}, acc2[8] = {};
     if (ln < LANES) {
         BnBwdCtx<T> c;
         c.load(a, g, oc);
-        const float zero8[8] = {};
         const long long stride = static_cast<long long>(gridDim.x) * LANES;
         for (long long p = p_begin + blockIdx.x * static_cast<long long>(LANES) + ln; p < p_end; p += stride * UNROLL) {
-            Raw8<T> ry[UNROLL], rg1[UNROLL], rg2[UNROLL];
+            Raw8<T> ry[UNROLL], rg1[UNROLL], rg2[UNROLL], rp[UNROLL];
+            uint2 am[UNROLL];
+            int pos[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const long long q = p + u * stride;
@@ -291,11 +308,17 @@ bn_bwd_reduce_px_kernel(const BnBwdArgs<T> a) {
                 ry[u] = ok ? ldraw<T>(a.y + q * a.C + oc * 8) : zero_raw<T>();
                 rg1[u] = ok ? ldraw<T>(a.g1 + q * a.ld1 + a.off1 + oc * 8) : zero_raw<T>();
                 rg2[u] = (ok && has_g2) ? ldraw<T>(a.g2 + q * a.ld2 + a.off2 + oc * 8) : zero_raw<T>();
+                if (ok && has_gp) pooled_extra<T>(a, q, oc, rp[u], am[u], pos[u]);
+                else { rp[u] = zero_raw<T>(); am[u] = make_uint2(0xffffffffu, 0xffffffffu); pos[u] = 0; }
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
-                float dz[8], xh[8];
-                bn_bwd_pixel<T>(ry[u], rg1[u], rg2[u], has_g2, c.sc, c.sh, c.mu, c.is, zero8, dz, xh);
+                float dz[8], xh[8], gpv[8], extra[8] = {};
+                if (has_gp) {
+                    unpack(rp[u], gpv);
+                    select_extra(gpv, am[u], pos[u], extra);
+                }
+                bn_bwd_pixel<T>(ry[u], rg1[u], rg2[u], has_g2, c.sc, c.sh, c.mu, c.is, extra, dz, xh);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     acc1[i] += dz[i];
@@ -307,7 +330,7 @@ bn_bwd_reduce_px_kernel(const BnBwdArgs<T> a) {
     bn_bwd_block_reduce<T>(a, g, acc1, acc2, s_red);
 }
 
-template <typename T, int UNROLL>
+template <typename T, int UNROLL, bool POOL>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_px_kernel(const BnBwdArgs<T> a) {
     const int OC = a.C >> 3, LANES = 256 / OC;
@@ -318,11 +341,11 @@ bn_bwd_apply_px_kernel(const BnBwdArgs<T> a) {
     const long long p_begin = static_cast<long long>(g) * a.group_images * HW;
     const long long p_end = static_cast<long long>(g == static_cast<int>(gridDim.y) - 1 ? a.N : (g + 1) * a.group_images) * HW;
     const bool has_g2 = a.g2 != nullptr;
+    constexpr bool has_gp = POOL;
     const float inv_n = static_cast<float>(1.0 / a.count);
     BnBwdCtx<T> c;
     c.load(a, g, oc);
     float m1[8], m2[8];
-    const float zero8[8] = {};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         m1[i] = static_cast<float>(a.sums[(static_cast<long long>(g) * 2 + 0) * a.C + oc * 8 + i]) * inv_n;
@@ -330,7 +353,9 @@ bn_bwd_apply_px_kernel(const BnBwdArgs<T> a) {
     }
     const long long stride = static_cast<long long>(gridDim.x) * LANES;
     for (long long p = p_begin + blockIdx.x * static_cast<long long>(LANES) + ln; p < p_end; p += stride * UNROLL) {
-        Raw8<T> ry[UNROLL], rg1[UNROLL], rg2[UNROLL];
+        Raw8<T> ry[UNROLL], rg1[UNROLL], rg2[UNROLL], rp[UNROLL];
+        uint2 am[UNROLL];
+        int pos[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const long long q = p + u * stride;
@@ -338,92 +363,24 @@ bn_bwd_apply_px_kernel(const BnBwdArgs<T> a) {
             ry[u] = ok ? ldraw<T>(a.y + q * a.C + oc * 8) : zero_raw<T>();
             rg1[u] = ok ? ldraw<T>(a.g1 + q * a.ld1 + a.off1 + oc * 8) : zero_raw<T>();
             rg2[u] = (ok && has_g2) ? ldraw<T>(a.g2 + q * a.ld2 + a.off2 + oc * 8) : zero_raw<T>();
+            if (ok && has_gp) pooled_extra<T>(a, q, oc, rp[u], am[u], pos[u]);
+            else { rp[u] = zero_raw<T>(); am[u] = make_uint2(0xffffffffu, 0xffffffffu); pos[u] = 0; }
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const long long q = p + u * stride;
             if (q >= p_end) break;
-            float dz[8], xh[8], o[8];
-            bn_bwd_pixel<T>(ry[u], rg1[u], rg2[u], has_g2, c.sc, c.sh, c.mu, c.is, zero8, dz, xh);
+            float dz[8], xh[8], o[8], gpv[8], extra[8] = {};
+            if (has_gp) {
+                unpack(rp[u], gpv);
+                select_extra(gpv, am[u], pos[u], extra);
+            }
+            bn_bwd_pixel<T>(ry[u], rg1[u], rg2[u], has_g2, c.sc, c.sh, c.mu, c.is, extra, dz, xh);
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] = c.sc[i] * (dz[i] - m1[i] - xh[i] * m2[i]);
             store8<T>(a.dy + q * a.C + oc * 8, o);
         }
     }
-}
-
-// ---- variant with a pooled gradient source: one thread = one 2x2 window x 8 channels (H, W even is NOT required:
-// windows hanging over the border take part as plain pixels, exactly like floor-mode MaxPool2d leaves them out)
-template <typename T, bool APPLY>
-__global__ void __launch_bounds__(256)
-bn_bwd_pool_kernel(const BnBwdArgs<T> a) {
-    __shared__ float s_red[APPLY ? 1 : 16][256];
-    const int OC = a.C >> 3, LANES = 256 / OC;
-    const int oc = threadIdx.x % OC, ln = threadIdx.x / OC;
-    const int g = blockIdx.y;
-    const int H2 = (a.H + 1) >> 1, W2 = (a.W + 1) >> 1, HP = a.H >> 1, WP = a.W >> 1;
-    const int n_begin = g * a.group_images, n_end = (g == static_cast<int>(gridDim.y) - 1) ? a.N : (g + 1) * a.group_images;
-    const int quads_per_img = H2 * W2;
-    const int quads = (n_end - n_begin) * quads_per_img;
-    const bool has_g2 = a.g2 != nullptr;
-    const float inv_n = static_cast<float>(1.0 / a.count);
-    float acc1[8] = {}, acc2[8] = {};
-    if (ln < LANES) {
-        BnBwdCtx<T> c;
-        c.load(a, g, oc);
-        float m1[8], m2[8];
-        if (APPLY) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                m1[i] = static_cast<float>(a.sums[(static_cast<long long>(g) * 2 + 0) * a.C + oc * 8 + i]) * inv_n;
-                m2[i] = static_cast<float>(a.sums[(static_cast<long long>(g) * 2 + 1) * a.C + oc * 8 + i]) * inv_n;
-            }
-        }
-        for (int q = blockIdx.x * LANES + ln; q < quads; q += gridDim.x * LANES) {
-            const int n = n_begin + q / quads_per_img;
-            const int r = q % quads_per_img;
-            const int h2 = r / W2, w2 = r % W2;
-            Raw8<T> ry[4], rg1[4], rg2[4], rp;
-            long long px[4];
-            bool ok[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int h = 2 * h2 + (k >> 1), w = 2 * w2 + (k & 1);
-                ok[k] = (h < a.H) && (w < a.W);
-                px[k] = (static_cast<long long>(n) * a.H + h) * a.W + w;
-                ry[k] = ok[k] ? ldraw<T>(a.y + px[k] * a.C + oc * 8) : zero_raw<T>();
-                rg1[k] = ok[k] ? ldraw<T>(a.g1 + px[k] * a.ld1 + a.off1 + oc * 8) : zero_raw<T>();
-                rg2[k] = (ok[k] && has_g2) ? ldraw<T>(a.g2 + px[k] * a.ld2 + a.off2 + oc * 8) : zero_raw<T>();
-            }
-            const bool pooled = (h2 < HP) && (w2 < WP);
-            rp = pooled ? ldraw<T>(a.gp + ((static_cast<long long>(n) * HP + h2) * WP + w2) * a.C + oc * 8) : zero_raw<T>();
-            int best[8];
-            pool_argmax<T>(ry, c.sc, c.sh, best);
-            float gpv[8];
-            unpack(rp, gpv);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (!ok[k]) continue;
-                float extra[8], dz[8], xh[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) extra[i] = (pooled && best[i] == k) ? gpv[i] : 0.f;
-                bn_bwd_pixel<T>(ry[k], rg1[k], rg2[k], has_g2, c.sc, c.sh, c.mu, c.is, extra, dz, xh);
-                if (APPLY) {
-                    float o[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) o[i] = c.sc[i] * (dz[i] - m1[i] - xh[i] * m2[i]);
-                    store8<T>(a.dy + px[k] * a.C + oc * 8, o);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        acc1[i] += dz[i];
-                        acc2[i] = fmaf(dz[i], xh[i], acc2[i]);
-                    }
-                }
-            }
-        }
-    }
-    if (!APPLY) bn_bwd_block_reduce<T>(a, g, acc1, acc2, s_red);
 }
 
 // dgamma[c] (+)= sum_g s2[g][c], dbeta[c] (+)= sum_g s1[g][c]; per-group targets may alias (shared twin)

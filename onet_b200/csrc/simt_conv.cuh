@@ -129,10 +129,28 @@ conv3x3_simt_kernel(const T* __restrict__ in, long long ldi, int ci_off, int N, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// First convolution of the U-Net (in_chns = CIN <= 4, Cout = 64): K = 9*CIN is not a tensor-core shape and the
-// layer is purely bandwidth-bound (writes 128 B per pixel, reads 2*CIN B), so it gets a direct kernel:
-// one thread = one pixel x 8 output channels, weights in shared memory, BatchNorm partial sums fused.
+// First convolution of the U-Net (in_chns = CIN <= 4, Cout = 64, W % 4 == 0): K = 9*CIN is not a tensor-core
+// shape and the layer is purely bandwidth-bound (writes 128 B per pixel, reads 2*CIN B), so it gets a direct
+// kernel: one thread = 4 horizontally adjacent pixels x 8 output channels (the 3 x 6 input patch is shared by the
+// four pixels), weights in shared memory, BatchNorm partial sums fused.
 // ------------------------------------------------------------------------------------------------
+template <typename T, int CIN>
+__device__ __forceinline__ void load_patch(const T* __restrict__ in, long long nb, int h, int w0, int H, int W,
+                                           float (&x)[3][6][CIN]) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int hh = h + r - 1;
+#pragma unroll
+        for (int cidx = 0; cidx < 6; ++cidx) {
+            const int ww = w0 + cidx - 1;
+            const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
+#pragma unroll
+            for (int c = 0; c < CIN; ++c)
+                x[r][cidx][c] = ok ? to_f<T>(in[(nb + static_cast<long long>(hh) * W + ww) * CIN + c]) : 0.f;
+        }
+    }
+}
+
 template <typename T, int CIN>
 __global__ void __launch_bounds__(256)
 conv_first_fwd_kernel(const T* __restrict__ in, int N, int H, int W, const T* __restrict__ wp, T* __restrict__ out,
@@ -144,40 +162,46 @@ conv_first_fwd_kernel(const T* __restrict__ in, int N, int H, int W, const T* __
     __syncthreads();
     const int oc = threadIdx.x & 7, ln = threadIdx.x >> 3;
     const int g = blockIdx.y;
-    const long long HW = static_cast<long long>(H) * W;
-    const long long p_begin = static_cast<long long>(g) * group_images * HW;
-    const long long p_end = static_cast<long long>(g == static_cast<int>(gridDim.y) - 1 ? N : (g + 1) * group_images) * HW;
+    const int W4 = W >> 2;
+    const long long QW = static_cast<long long>(H) * W4;      // pixel quads per image
+    const long long q_begin = static_cast<long long>(g) * group_images * QW;
+    const long long q_end = static_cast<long long>(g == static_cast<int>(gridDim.y) - 1 ? N : (g + 1) * group_images) * QW;
     float a1[8] = {}, a2[8] = {};
-    for (long long p = p_begin + blockIdx.x * 32LL + ln; p < p_end; p += gridDim.x * 32LL) {
-        const int w = static_cast<int>(p % W), h = static_cast<int>((p / W) % H);
-        const long long nb = p - static_cast<long long>(h) * W - w;      // n*H*W
-        float x[K];
+    for (long long q = q_begin + blockIdx.x * 32LL + ln; q < q_end; q += gridDim.x * 32LL) {
+        const int w0 = static_cast<int>(q % W4) * 4, h = static_cast<int>((q / W4) % H);
+        const long long nb = (q / QW) * H * W;
+        float x[3][6][CIN];
+        load_patch<T, CIN>(in, nb, h, w0, H, W, x);
+        float acc[4][8] = {};
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            const int hh = h + t / 3 - 1, ww = w + t % 3 - 1;
-            const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
+        for (int t = 0; t < 9; ++t)
 #pragma unroll
-            for (int c = 0; c < CIN; ++c)
-                x[t * CIN + c] = ok ? to_f<T>(in[(nb + static_cast<long long>(hh) * W + ww) * CIN + c]) : 0.f;
-        }
-        float acc[8] = {};
+            for (int c = 0; c < CIN; ++c) {
+                float wv[8];
 #pragma unroll
-        for (int k = 0; k < K; ++k)
+                for (int i = 0; i < 8; ++i) wv[i] = ws[t * CIN + c][oc * 8 + i];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = fmaf(x[k], ws[k][oc * 8 + i], acc[i]);
-        T o[8];
+                for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            o[i] = from_f<T>(acc[i]);
-            const float f = to_f<T>(o[i]);
-            a1[i] += f;
-            a2[i] = fmaf(f, f, a2[i]);
-        }
-        if (sizeof(T) == 2) {
-            *reinterpret_cast<uint4*>(out + p * 64 + oc * 8) = *reinterpret_cast<const uint4*>(o);
-        } else {
-            *reinterpret_cast<float4*>(out + p * 64 + oc * 8) = *reinterpret_cast<const float4*>(o);
-            *reinterpret_cast<float4*>(out + p * 64 + oc * 8 + 4) = *reinterpret_cast<const float4*>(o + 4);
+                    for (int i = 0; i < 8; ++i) acc[j][i] = fmaf(x[t / 3][j + t % 3][c], wv[i], acc[j][i]);
+            }
+        const long long p0 = nb + static_cast<long long>(h) * W + w0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            T o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                o[i] = from_f<T>(acc[j][i]);
+                const float f = to_f<T>(o[i]);
+                a1[i] += f;
+                a2[i] = fmaf(f, f, a2[i]);
+            }
+            if (sizeof(T) == 2) {
+                *reinterpret_cast<uint4*>(out + (p0 + j) * 64 + oc * 8) = *reinterpret_cast<const uint4*>(o);
+            } else {
+                *reinterpret_cast<float4*>(out + (p0 + j) * 64 + oc * 8) = *reinterpret_cast<const float4*>(o);
+                *reinterpret_cast<float4*>(out + (p0 + j) * 64 + oc * 8 + 4) = *reinterpret_cast<const float4*>(o + 4);
+            }
         }
     }
     if (stat_sum != nullptr) {
@@ -198,48 +222,54 @@ conv_first_fwd_kernel(const T* __restrict__ in, int N, int H, int W, const T* __
     }
 }
 
-// dW[co][ci][tap] += sum_px G[px][co] * In[px + tap][ci] for the first convolution (CIN <= 4, Cout = 64).
-// One thread = CPT output channels x all 9*CIN taps, pixels strided over lanes/blocks; warp-shuffle + atomics.
+// dW[co][ci][tap] += sum_px G[px][co] * In[px + tap][ci] for the first convolution (CIN <= 4, Cout = 64, W % 4 == 0).
+// One thread = CPT output channels x all 9*CIN taps, 4 adjacent pixels per step; warp-shuffle + atomics at the end.
 template <typename T, int CIN, int CPT>
 __global__ void __launch_bounds__(256)
 conv_first_wgrad_kernel(const T* __restrict__ g, const T* __restrict__ in, int N, int H, int W, float* __restrict__ dw) {
     constexpr int K = 9 * CIN;
     constexpr int NG = 64 / CPT;            // channel groups
-    constexpr int LANES = 256 / NG;         // pixel lanes per block
+    constexpr int LANES = 256 / NG;         // pixel-quad lanes per block
     const int cg = threadIdx.x % NG, ln = threadIdx.x / NG;
-    const long long M = static_cast<long long>(N) * H * W;
+    const int W4 = W >> 2;
+    const long long QW = static_cast<long long>(H) * W4;
+    const long long Q = static_cast<long long>(N) * QW;
     float acc[CPT][K];
 #pragma unroll
     for (int i = 0; i < CPT; ++i)
 #pragma unroll
         for (int k = 0; k < K; ++k) acc[i][k] = 0.f;
-    for (long long p = blockIdx.x * static_cast<long long>(LANES) + ln; p < M; p += static_cast<long long>(gridDim.x) * LANES) {
-        const int w = static_cast<int>(p % W), h = static_cast<int>((p / W) % H);
-        const long long nb = p - static_cast<long long>(h) * W - w;
-        float gv[CPT];
-        if (CPT == 8 && sizeof(T) == 2) {
-            const uint4 u = *reinterpret_cast<const uint4*>(g + p * 64 + cg * 8);
-            const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+    for (long long q = blockIdx.x * static_cast<long long>(LANES) + ln; q < Q; q += static_cast<long long>(gridDim.x) * LANES) {
+        const int w0 = static_cast<int>(q % W4) * 4, h = static_cast<int>((q / W4) % H);
+        const long long nb = (q / QW) * H * W;
+        const long long p0 = nb + static_cast<long long>(h) * W + w0;
+        float gv[4][CPT];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                gv[(2 * i) % CPT] = __uint_as_float(wv[i] << 16);
-                gv[(2 * i + 1) % CPT] = __uint_as_float(wv[i] & 0xffff0000u);
-            }
-        } else {
+        for (int j = 0; j < 4; ++j) {
+            if (CPT == 8 && sizeof(T) == 2) {
+                const uint4 u = *reinterpret_cast<const uint4*>(g + (p0 + j) * 64 + cg * 8);
+                const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-            for (int i = 0; i < CPT; ++i) gv[i] = to_f<T>(g[p * 64 + cg * CPT + i]);
-        }
+                for (int i = 0; i < 4; ++i) {
+                    gv[j][(2 * i) % CPT] = __uint_as_float(wv[i] << 16);
+                    gv[j][(2 * i + 1) % CPT] = __uint_as_float(wv[i] & 0xffff0000u);
+                }
+            } else {
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            const int hh = h + t / 3 - 1, ww = w + t % 3 - 1;
-            const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
-#pragma unroll
-            for (int c = 0; c < CIN; ++c) {
-                const float xv = ok ? to_f<T>(in[(nb + static_cast<long long>(hh) * W + ww) * CIN + c]) : 0.f;
-#pragma unroll
-                for (int i = 0; i < CPT; ++i) acc[i][t * CIN + c] = fmaf(gv[i], xv, acc[i][t * CIN + c]);
+                for (int i = 0; i < CPT; ++i) gv[j][i] = to_f<T>(g[(p0 + j) * 64 + cg * CPT + i]);
             }
         }
+        float x[3][6][CIN];
+        load_patch<T, CIN>(in, nb, h, w0, H, W, x);
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+            for (int c = 0; c < CIN; ++c)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int i = 0; i < CPT; ++i)
+                        acc[i][t * CIN + c] = fmaf(gv[j][i], x[t / 3][j + t % 3][c], acc[i][t * CIN + c]);
     }
     // lanes of the same channel group inside a warp sit NG threads apart
 #pragma unroll

@@ -124,33 +124,33 @@ tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
-        int stage = 0;
-        uint32_t phase = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
-            mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * BN;
-            for (int k = 0; k < k_iters; ++k) {
-                mbar_wait(bar_full + 8 * stage, phase);
+        // ------------------------------------------------------------ MMA issuer (one elected thread)
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
-                if (elect_one()) {
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int k = 0; k < k_iters; ++k) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
                     const uint32_t sA = base + stage * Cfg::kStageBytes, sB = sA + Cfg::kABytes;
                     const uint64_t da = umma_smem_desc(sA, 16, 1024), db = umma_smem_desc(sB, 16, 1024);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)   // 4 x (K = 16 bf16 = 32 B) inside the 128-B swizzle row
                         umma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0);
                     umma_commit(bar_empty + 8 * stage);
-                    if (k == k_iters - 1) umma_commit(bar_tfull + 8 * acc);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                umma_commit(bar_tfull + 8 * acc);
             }
         }
+        __syncwarp();
     } else {
         // ------------------------------------------------------------ epilogue (4 warps)
         const int q = warp & 3;            // TMEM lane quarter this warp may access
@@ -236,27 +236,29 @@ tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                 }
             } else {
-                // EPI_CONVT: column = (tap, co); scatter to the 2x upsampled grid, add bias
-                const int tap = co0 / p.co_per_tap, cbase = co0 % p.co_per_tap;
-                const int dy = tap >> 1, dx = tap & 1;
-                __nv_bfloat16* orow = p.out +
-                                      ((static_cast<long long>(n) * (2 * p.H) + (2 * h + dy)) * (2 * p.W) + (2 * w + dx)) * p.ldo +
-                                      p.out_coff + cbase;
+                // EPI_CONVT: column = (tap, co); scatter to the 2x upsampled grid, add bias.  A tile may span several
+                // taps (BN up to 4 * co_per_tap); every 32-column chunk lies inside one tap (co_per_tap % 32 == 0).
 #pragma unroll 1
                 for (int ch = 0; ch < BN / 32; ++ch) {
+                    const int colg = co0 + ch * 32;
+                    const int tap = colg / p.co_per_tap, cbase = colg % p.co_per_tap;
+                    const int dy = tap >> 1, dx = tap & 1;
+                    __nv_bfloat16* dst16 = p.out +
+                                           ((static_cast<long long>(n) * (2 * p.H) + (2 * h + dy)) * (2 * p.W) + (2 * w + dx)) * p.ldo +
+                                           p.out_coff + cbase;
                     uint32_t r[32];
                     tmem_ld_32x32(t_addr + ch * 32, r);
                     tmem_ld_wait();
                     if (valid) {
-                        uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
+                        uint4* dst = reinterpret_cast<uint4*>(dst16);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             uint32_t pk[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                const int c = ch * 32 + j * 8 + i * 2;
-                                pk[i] = pack_bf16x2(__uint_as_float(r[j * 8 + i * 2]) + __ldg(p.bias + cbase + c),
-                                                    __uint_as_float(r[j * 8 + i * 2 + 1]) + __ldg(p.bias + cbase + c + 1));
+                                const int c = cbase + j * 8 + i * 2;
+                                pk[i] = pack_bf16x2(__uint_as_float(r[j * 8 + i * 2]) + __ldg(p.bias + c),
+                                                    __uint_as_float(r[j * 8 + i * 2 + 1]) + __ldg(p.bias + c + 1));
                             }
                             dst[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         }
@@ -389,22 +391,22 @@ tapgemm_wg_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = umma_idesc_bf16(128, BNW, 1, 1);   // both operands MN-major
-        int stage = 0;
-        uint32_t phase = 0;
-        int it = 0;
-        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
-            const int ks = unit % p.ksplit;
-            const int g = unit / (p.ksplit * p.num_n_tiles * p.num_m_tiles);
-            const int nacc = p.groups[g].nacc;
-            const int px_begin = ks * p.px_tiles_per_split;
-            const int px_end = min(px_begin + p.px_tiles_per_split, p.num_px_tiles);
-            mbar_wait(bar_tempty, (it & 1) ^ 1);
-            tc_fence_after();
-            for (int pt = px_begin; pt < px_end; ++pt) {
-                mbar_wait(bar_full + 8 * stage, phase);
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, BNW, 1, 1);   // both operands MN-major
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+                const int ks = unit % p.ksplit;
+                const int g = unit / (p.ksplit * p.num_n_tiles * p.num_m_tiles);
+                const int nacc = p.groups[g].nacc;
+                const int px_begin = ks * p.px_tiles_per_split;
+                const int px_end = min(px_begin + p.px_tiles_per_split, p.num_px_tiles);
+                mbar_wait(bar_tempty, (it & 1) ^ 1);
                 tc_fence_after();
-                if (elect_one()) {
+                for (int pt = px_begin; pt < px_end; ++pt) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
                     const uint32_t sN = base + stage * Cfg::kStageBytes, sM = sN + Cfg::kNBytes;
                     const uint64_t db = umma_smem_desc(sN, 8192, 1024);
                     for (int a = 0; a < nacc; ++a) {
@@ -414,12 +416,12 @@ tapgemm_wg_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                             umma_bf16(tmem_base + a * BNW, da + 128 * kk, db + 128 * kk, idesc, (pt > px_begin) || kk);
                     }
                     umma_commit(bar_empty + 8 * stage);
-                    if (pt == px_end - 1) umma_commit(bar_tfull);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                umma_commit(bar_tfull);
             }
         }
+        __syncwarp();
     } else {
         const int q = warp & 3;
         const int row = q * 32 + lane;

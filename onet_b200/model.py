@@ -320,12 +320,14 @@ class _Engine:
             aff = torch.empty(4, G, cout, dtype=torch.float32, device=self.dev)
             call("onet_bn_eval_prepare", G, cout, ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var),
                  ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var), ptr(aff[2]), ptr(aff[3]), st)
+        amax = None
+        if pool is not None and rec.save:
+            amax = torch.empty(n, h // 2, w // 2, cout, dtype=torch.uint8, device=self.dev)
         call("onet_bn_relu_apply", ptr(Y), n, h, w, cout, ptr(aff[2]), ptr(aff[3]), seg.group_images,
              ptr(dst, self._img_off(dst, n0) + off_dst), ld_dst, 0,
-             ptr(pool, self._img_off(pool, n0)) if pool is not None else None, self.dt, st)
+             ptr(pool, self._img_off(pool, n0)) if pool is not None else None, ptr(amax), self.dt, st)
         if rec.save:
-            rec.saved[(si, li)] = dict(Y=Y, aff=aff, src=(src, ld_src, off_src), h=h, w=w, cin=cin, cout=cout,
-                                       pooled=pool is not None)
+            rec.saved[(si, li)] = dict(Y=Y, aff=aff, src=(src, ld_src, off_src), h=h, w=w, cin=cin, cout=cout, amax=amax)
 
     def _upconv(self, seg, up, x, cx, n0, n, h, w, cat, ld_cat, off_cat):
         cin, co = up.weight.shape[0], up.weight.shape[1]
@@ -421,7 +423,7 @@ class _Engine:
         count = float(seg.group_images * h * w)
         call("onet_bn_relu_bwd", ptr(Y), n, h, w, cout, ptr(aff[2]), ptr(aff[3]), ptr(aff[0]), ptr(aff[1]),
              seg.group_images, ptr(g1, off1), ld1, 0, ptr(g2, off2) if g2 is not None else None, ld2, 0,
-             ptr(gp) if gp is not None else None, ptr(sums), count, ptr(dY),
+             ptr(gp) if gp is not None else None, ptr(sv["amax"]) if gp is not None else None, ptr(sums), count, ptr(dY),
              ptr(grad_of(bn.weight)), ptr(grad_of(bn.bias)), ptr(grad_of(bn.weight)), ptr(grad_of(bn.bias)), self.dt, st)
         eng = self._engine_for(cin, cout)
         src, ld_src, off_src = sv["src"]

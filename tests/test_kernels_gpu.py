@@ -177,7 +177,9 @@ def test_bn_relu_fwd_bwd(dt_name, n, h, w, c, pool):
          ptr(rm), ptr(rv), 0.1, ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]), U.stream())
     out = torch.zeros(n, h, w, 2 * c, dtype=tdt, device="cuda")         # skip half of a concat buffer
     pl = torch.empty(n, h // 2, w // 2, c, dtype=tdt, device="cuda") if pool else None
-    call("onet_bn_relu_apply", ptr(yn), n, h, w, c, ptr(aff[2]), ptr(aff[3]), g, ptr(out), 2 * c, 0, ptr(pl), dt, U.stream())
+    am = torch.empty(n, h // 2, w // 2, c, dtype=torch.uint8, device="cuda") if pool else None
+    call("onet_bn_relu_apply", ptr(yn), n, h, w, c, ptr(aff[2]), ptr(aff[3]), g, ptr(out), 2 * c, 0, ptr(pl), ptr(am), dt,
+         U.stream())
     # torch reference, branch by branch (shared BN module called twice)
     bn = torch.nn.BatchNorm2d(c).cuda()
     with torch.no_grad():
@@ -211,7 +213,8 @@ def test_bn_relu_fwd_bwd(dt_name, n, h, w, c, pool):
     g1n, g2n = U.to_nhwc(g1, tdt), U.to_nhwc(g2, tdt)
     gpn = U.to_nhwc(gp, tdt) if pool else None
     call("onet_bn_relu_bwd", ptr(yn), n, h, w, c, ptr(aff[2]), ptr(aff[3]), ptr(aff[0]), ptr(aff[1]), g, ptr(g1n), c, 0,
-         ptr(g2n), c, 0, ptr(gpn), ptr(sums), count, ptr(dy), ptr(dgam), ptr(dbet), ptr(dgam), ptr(dbet), dt, U.stream())
+         ptr(g2n), c, 0, ptr(gpn), ptr(am), ptr(sums), count, ptr(dy), ptr(dgam), ptr(dbet), ptr(dgam), ptr(dbet), dt,
+         U.stream())
     btol = 2e-5 if dt == U.F32 else 8e-3
     assert U.rel_l2(U.from_nhwc(dy), yr.grad) < btol
     assert U.rel_l2(dgam, bn.weight.grad) < btol
