@@ -154,14 +154,18 @@ def _family(name, a):
     return name.replace("onet_", ""), 0.0
 
 
-def profile_steps(trainer, x, nsteps):
+def profile_steps(trainer, x, nsteps, record=True):
+    """Per-call CUDA-event timing of `nsteps` more steps.  Every rank must run the steps (they contain the gradient
+    all-reduce); only ranks with record=True keep the events."""
     import torch
     from onet_b200 import _lib
-    _lib.PROFILE = []
+    _lib.PROFILE = [] if record else None
     for _ in range(nsteps):
         trainer.step(x)
     torch.cuda.synchronize()
     prof, _lib.PROFILE = _lib.PROFILE, None
+    if not record:
+        return {}
     detail = os.environ.get("ONET_BENCH_DETAIL")
     if detail:      # per-call dump of the LAST profiled step: name, integer args, ms, TFLOP/s
         per = len(prof) // nsteps
@@ -215,7 +219,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=4))
 
     B = args.batch
     torch.manual_seed(1981)
@@ -263,7 +268,7 @@ def main():
     ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
-    fam = profile_steps(trainer, resident[0], 2) if rank == 0 else {}
+    fam = profile_steps(trainer, resident[0], 2, record=(rank == 0))
     if world > 1:
         dist.barrier()
 

@@ -48,6 +48,12 @@ int onet_prep_input(const float* x, int B, int Cin, int H, int W, float bias, vo
 int onet_pack_conv_weights(const float* w, int Cout, int Cin, void* wf, void* wd, int dtype, void* stream);
 int onet_pack_convT_weights(const float* w, int Cin, int Cout, void* wf, void* wd, int dtype, void* stream);
 
+/* The same packing for up to 24 layers in one launch (the per-step refresh after the optimizer update).  Host arrays
+ * of length n: w[i] fp32 master weight, d0/d1 its outer/inner channel counts (conv: Cout, Cin; convT: Cin, Cout),
+ * taps[i] = 9 (conv) or 4 (convT), wf[i]/wd[i] the packed destinations (wd[i] may be NULL for a conv). */
+int onet_pack_all_weights(int n, const float* const* w, const int* d0, const int* d1, const int* taps, void* const* wf,
+                          void* const* wd, int dtype, void* stream);
+
 /* 3x3 / pad 1 / no-bias convolution on packed weights wp[Cout][9][Cin]; writes the RAW output and, when
  * stat_sum != NULL, accumulates per-group per-channel sum / sum-of-squares (doubles, [groups][Cout]) for the
  * training-mode BatchNorm that follows.  Used for forward (nn.Conv2d, Onet_vanilla_20240606.py:47,51) and,
@@ -75,18 +81,16 @@ int onet_bn_eval_prepare(int G, int C, const float* gamma0, const float* beta0, 
 
 /* y -> relu(y*scale+shift) written to out (+ooff, ld ldo; e.g. the skip half of a concat buffer) and, when
  * pool != NULL, the 2x2 max-pooled map [N,H/2,W/2,C] in the same pass (nn.ReLU :49,53 + nn.MaxPool2d(2) :67
- * + the skip half of torch.cat :100).  amax (optional, uint8 [N,H/2,W/2,C]) receives the position 0..3 of the first
- * maximum of every window, which is what the backward pass routes the pooled gradient to. */
+ * + the skip half of torch.cat :100).  Nothing else is saved: the backward pass recomputes the window arg-max. */
 int onet_bn_relu_apply(const void* y, int N, int H, int W, int C, const float* scale, const float* shift,
-                       int group_images, void* out, int64_t ldo, int ooff, void* pool, void* amax, int dtype,
-                       void* stream);
+                       int group_images, void* out, int64_t ldo, int ooff, void* pool, int dtype, void* stream);
 
 /* Backward of BN -> ReLU (-> skip / max-pool): gradient sources g1 (+ optional g2, optional pooled gp routed to
- * the window maximum recorded in amax), produces dy [N,H,W,C] and accumulates dgamma/dbeta.  `sums` is a
- * zero-initialised [G][2][C] double workspace. */
+ * the first maximum of each 2x2 window, recomputed from y), produces dy [N,H,W,C] and accumulates dgamma/dbeta.
+ * `sums` is a zero-initialised [G][2][C] double workspace. */
 int onet_bn_relu_bwd(const void* y, int N, int H, int W, int C, const float* scale, const float* shift,
                      const float* mean, const float* invstd, int group_images, const void* g1, int64_t ld1, int off1,
-                     const void* g2, int64_t ld2, int off2, const void* gp, const void* amax, double* sums, double count,
+                     const void* g2, int64_t ld2, int off2, const void* gp, double* sums, double count,
                      void* dy, float* dgamma0, float* dbeta0, float* dgamma1, float* dbeta1, int dtype, void* stream);
 
 /* ConvTranspose2d(Cin, Co, 2, 2) + bias written directly into channels [ooff, ooff+Co) of the concat buffer
@@ -98,6 +102,11 @@ int onet_convT2x2_dgrad(const void* go, int64_t ldg, int goff, int N, int H, int
                         void* dx, int64_t ldd, int doff, int dtype, int engine, void* stream);
 int onet_convT2x2_wgrad(const void* x, int64_t ldx, int xoff, const void* go, int64_t ldg, int goff, int N, int H,
                         int W, int Cin, int Co, float* dw, float* dbias, int dtype, int engine, void* stream);
+
+/* dst[c] += sums[c] for c < C.  The bias gradient of the transposed convolution is the column sum of d(concat)'s
+ * up half; onet_conv3x3_fwd accumulates it (stat_sum) while it writes d(concat), this folds it into the fp32 .grad,
+ * and onet_convT2x2_wgrad is then called with dbias = NULL (no separate pass over d(concat)). */
+int onet_add_colsums(const double* sums, int C, float* dst, void* stream);
 
 /* Head + loss (Onet.forward :176-189 and compute_loss/jensen_shannon_divergence/log1pexp :221-267) in one
  * bandwidth-bound pass: Vt, Vd, S=softmax([Vt,Vd]), a=sum_p Lt_p, b=sum_p Ld_p, and the sum over pixels of the

@@ -49,16 +49,18 @@ SIGNATURES = {
     "onet_prep_input": [_p, _i, _i, _i, _i, _f, _p, _i, _p],
     "onet_pack_conv_weights": [_p, _i, _i, _p, _p, _i, _p],
     "onet_pack_convT_weights": [_p, _i, _i, _p, _p, _i, _p],
+    "onet_pack_all_weights": [_i, _p, _p, _p, _p, _p, _p, _i, _p],
     "onet_conv3x3_fwd": [_p, _i64, _i, _i, _i, _i, _i, _p, _i, _p, _i64, _i, _p, _p, _i, _i, _i, _p],
     "onet_conv3x3_wgrad": [_p, _i64, _i, _p, _i64, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p],
     "onet_bn_finalize": [_p, _p, _i, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p],
     "onet_bn_eval_prepare": [_i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
-    "onet_bn_relu_apply": [_p, _i, _i, _i, _i, _p, _p, _i, _p, _i64, _i, _p, _p, _i, _p],
-    "onet_bn_relu_bwd": [_p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _i64, _i, _p, _i64, _i, _p, _p, _p, _d, _p,
+    "onet_bn_relu_apply": [_p, _i, _i, _i, _i, _p, _p, _i, _p, _i64, _i, _p, _i, _p],
+    "onet_bn_relu_bwd": [_p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _i64, _i, _p, _i64, _i, _p, _p, _d, _p,
                          _p, _p, _p, _p, _i, _p],
     "onet_convT2x2_fwd": [_p, _i64, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i64, _i, _i, _i, _p],
     "onet_convT2x2_dgrad": [_p, _i64, _i, _i, _i, _i, _i, _p, _i, _p, _i64, _i, _i, _i, _p],
     "onet_convT2x2_wgrad": [_p, _i64, _i, _p, _i64, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p],
+    "onet_add_colsums": [_p, _i, _p, _p],
     "onet_head_fwd": [_p, _i64, _i, _p, _i64, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p],
     "onet_head_bwd": [_p, _i64, _i, _p, _i64, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
     "onet_predict_label": [_p, _p, _i64, _p, _p],

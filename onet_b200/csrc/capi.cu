@@ -484,6 +484,26 @@ int onet_pack_convT_weights(const float* w, int Cin, int Cout, void* wf, void* w
     return check_launch("pack_convT_weights");
 }
 
+int onet_pack_all_weights(int n, const float* const* w, const int* d0, const int* d1, const int* taps, void* const* wf,
+                          void* const* wd, int dtype, void* stream) {
+    if (n < 1 || n > kPackMaxLayers) return fail("pack_all_weights: between 1 and %d layers per call", kPackMaxLayers);
+    PackJobs jobs;
+    memset(&jobs, 0, sizeof(jobs));
+    jobs.n = n;
+    int tiles = 0;
+    for (int i = 0; i < n; ++i) {
+        if (taps[i] != 9 && taps[i] != 4) return fail("pack_all_weights: taps must be 9 (conv) or 4 (convT)");
+        if (taps[i] == 4 && wd[i] == nullptr) return fail("pack_all_weights: convT needs both packed layouts");
+        PackJob& j = jobs.job[i];
+        j.w = w[i]; j.wf = wf[i]; j.wd = wd[i]; j.d0 = d0[i]; j.d1 = d1[i]; j.taps = taps[i];
+        j.tile_begin = tiles;
+        tiles += ((d0[i] + 31) / 32) * ((d1[i] + 31) / 32);
+    }
+    if (dtype == ONET_F32) pack_all_weights_kernel<float><<<tiles, 256, 0, ST(stream)>>>(jobs);
+    else pack_all_weights_kernel<bf16><<<tiles, 256, 0, ST(stream)>>>(jobs);
+    return check_launch("pack_all_weights");
+}
+
 int onet_conv3x3_fwd(const void* in, int64_t ldi, int ci_off, int N, int H, int W, int Cin, const void* wp, int Cout,
                      void* out, int64_t ldo, int co_off, double* stat_sum, double* stat_sq, int group_images,
                      int dtype, int engine, void* stream) {
@@ -584,18 +604,18 @@ int onet_bn_eval_prepare(int G, int C, const float* gamma0, const float* beta0, 
 }
 
 int onet_bn_relu_apply(const void* y, int N, int H, int W, int C, const float* scale, const float* shift,
-                       int group_images, void* out, int64_t ldo, int ooff, void* pool, void* amax, int dtype, void* stream) {
+                       int group_images, void* out, int64_t ldo, int ooff, void* pool, int dtype, void* stream) {
     if (C % 8 || ldo % 8 || ooff % 8) return fail("bn_relu_apply: channel counts/offsets must be multiples of 8");
     const long long total = static_cast<long long>(N) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
     const int gi = group_images > 0 ? group_images : N;
+    constexpr int UNR = 2;
+    const int grid = grid_for((total + UNR - 1) / UNR, 256, 148 * 24);
     if (dtype == ONET_F32)
-        bn_relu_apply_kernel<float><<<grid_for(total, 256, 148 * 32), 256, 0, ST(stream)>>>(
-            static_cast<const float*>(y), N, H, W, C, scale, shift, gi, static_cast<float*>(out), ldo, ooff, static_cast<float*>(pool),
-            static_cast<uint8_t*>(amax));
+        bn_relu_apply_kernel<float, UNR><<<grid, 256, 0, ST(stream)>>>(
+            static_cast<const float*>(y), N, H, W, C, scale, shift, gi, static_cast<float*>(out), ldo, ooff, static_cast<float*>(pool));
     else
-        bn_relu_apply_kernel<bf16><<<grid_for(total, 256, 148 * 32), 256, 0, ST(stream)>>>(
-            static_cast<const bf16*>(y), N, H, W, C, scale, shift, gi, static_cast<bf16*>(out), ldo, ooff, static_cast<bf16*>(pool),
-            static_cast<uint8_t*>(amax));
+        bn_relu_apply_kernel<bf16, UNR><<<grid, 256, 0, ST(stream)>>>(
+            static_cast<const bf16*>(y), N, H, W, C, scale, shift, gi, static_cast<bf16*>(out), ldo, ooff, static_cast<bf16*>(pool));
     return check_launch("bn_relu_apply");
 }
 
@@ -604,7 +624,7 @@ int onet_bn_relu_apply(const void* y, int N, int H, int W, int C, const float* s
 template <typename T>
 static int bn_bwd_impl(const void* y, int N, int H, int W, int C, const float* scale, const float* shift, const float* mean,
                        const float* invstd, int group_images, const void* g1, int64_t ld1, int off1, const void* g2,
-                       int64_t ld2, int off2, const void* gp, const void* amax, double* sums, double count, void* dy,
+                       int64_t ld2, int off2, const void* gp, double* sums, double count, void* dy,
                        float* dgamma0, float* dbeta0, float* dgamma1, float* dbeta1, cudaStream_t st) {
     BnBwdArgs<T> a;
     a.y = static_cast<const T*>(y); a.N = N; a.H = H; a.W = W; a.C = C;
@@ -613,26 +633,37 @@ static int bn_bwd_impl(const void* y, int N, int H, int W, int C, const float* s
     a.g1 = static_cast<const T*>(g1); a.ld1 = ld1; a.off1 = off1;
     a.g2 = static_cast<const T*>(g2); a.ld2 = ld2; a.off2 = off2;
     a.gp = static_cast<const T*>(gp);
-    a.amax = static_cast<const uint8_t*>(amax);
     a.sums = sums; a.count = count; a.dy = static_cast<T*>(dy);
     const int G = std::min(2, (N + a.group_images - 1) / a.group_images);
-    const int OC = C / 8, lanes = 256 / OC;
-    {
-        constexpr int UNR = 4, UNRP = 2;     // the pooled variant keeps fewer pixels in flight to stay at 2 blocks / SM
-        const long long px = static_cast<long long>(a.group_images) * H * W;
-        const int unr = gp != nullptr ? UNRP : UNR;
-        const int gx = static_cast<int>(std::max(1LL, std::min<long long>((px + lanes * unr - 1) / (lanes * unr), 148 * 8 / G)));
-        if (gp != nullptr) {
-            bn_bwd_reduce_px_kernel<T, UNRP, true><<<dim3(gx, G), 256, 0, st>>>(a);
+    const int OC = C / 8, lanes = std::max(1, 256 / OC);
+    const int max_blocks = 148 * 4 / G;        // 2 resident blocks per SM, two rounds
+    if (gp != nullptr) {
+        const long long wins = static_cast<long long>(a.group_images) * ((H + 1) / 2) * ((W + 1) / 2);
+        const int gx = static_cast<int>(std::max(1LL, std::min<long long>((wins + lanes - 1) / lanes, max_blocks)));
+        if (g2 != nullptr) {
+            bn_bwd_win_kernel<T, true, false><<<dim3(gx, G), 256, 0, st>>>(a);
             if (check_launch("bn_bwd_reduce")) return 1;
-            bn_bwd_apply_px_kernel<T, UNRP, true><<<dim3(gx, G), 256, 0, st>>>(a);
+            bn_bwd_win_kernel<T, true, true><<<dim3(gx, G), 256, 0, st>>>(a);
         } else {
-            bn_bwd_reduce_px_kernel<T, UNR, false><<<dim3(gx, G), 256, 0, st>>>(a);
+            bn_bwd_win_kernel<T, false, false><<<dim3(gx, G), 256, 0, st>>>(a);
             if (check_launch("bn_bwd_reduce")) return 1;
-            bn_bwd_apply_px_kernel<T, UNR, false><<<dim3(gx, G), 256, 0, st>>>(a);
+            bn_bwd_win_kernel<T, false, true><<<dim3(gx, G), 256, 0, st>>>(a);
         }
-        if (check_launch("bn_bwd_apply")) return 1;
+    } else {
+        constexpr int UNR = 4;
+        const long long px = static_cast<long long>(a.group_images) * H * W;
+        const int gx = static_cast<int>(std::max(1LL, std::min<long long>((px + lanes * UNR - 1) / (lanes * UNR), max_blocks)));
+        if (g2 != nullptr) {
+            bn_bwd_px_kernel<T, UNR, true, false><<<dim3(gx, G), 256, 0, st>>>(a);
+            if (check_launch("bn_bwd_reduce")) return 1;
+            bn_bwd_px_kernel<T, UNR, true, true><<<dim3(gx, G), 256, 0, st>>>(a);
+        } else {
+            bn_bwd_px_kernel<T, UNR, false, false><<<dim3(gx, G), 256, 0, st>>>(a);
+            if (check_launch("bn_bwd_reduce")) return 1;
+            bn_bwd_px_kernel<T, UNR, false, true><<<dim3(gx, G), 256, 0, st>>>(a);
+        }
     }
+    if (check_launch("bn_bwd_apply")) return 1;
     if (dgamma0 != nullptr) {
         bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, G, C, dgamma0, dbeta0, dgamma1 ? dgamma1 : dgamma0,
                                                               dbeta1 ? dbeta1 : dbeta0);
@@ -645,17 +676,16 @@ extern "C" {
 
 int onet_bn_relu_bwd(const void* y, int N, int H, int W, int C, const float* scale, const float* shift,
                      const float* mean, const float* invstd, int group_images, const void* g1, int64_t ld1, int off1,
-                     const void* g2, int64_t ld2, int off2, const void* gp, const void* amax, double* sums, double count,
+                     const void* g2, int64_t ld2, int off2, const void* gp, double* sums, double count,
                      void* dy, float* dgamma0, float* dbeta0, float* dgamma1, float* dbeta1, int dtype, void* stream) {
-    if ((gp == nullptr) != (amax == nullptr)) return fail("bn_relu_bwd: gp and amax must be given together");
     if (static_cast<long long>(N) * H * W >= (1LL << 31)) return fail("bn_relu_bwd: more than 2^31 pixels");
     if (C % 8 || C > 2048) return fail("bn_relu_bwd: C must be a multiple of 8 and <= 2048");
-    if (256 % (C / 8) != 0 && (C / 8) < 256) return fail("bn_relu_bwd: C/8 must divide 256");
+    if (256 % (C / 8) != 0) return fail("bn_relu_bwd: C/8 must divide 256");
     if (g1 == nullptr) return fail("bn_relu_bwd: g1 is required");
     if (dtype == ONET_F32)
         return bn_bwd_impl<float>(y, N, H, W, C, scale, shift, mean, invstd, group_images, g1, ld1, off1, g2, ld2, off2, gp,
-                                  amax, sums, count, dy, dgamma0, dbeta0, dgamma1, dbeta1, ST(stream));
-    return bn_bwd_impl<bf16>(y, N, H, W, C, scale, shift, mean, invstd, group_images, g1, ld1, off1, g2, ld2, off2, gp, amax,
+                                  sums, count, dy, dgamma0, dbeta0, dgamma1, dbeta1, ST(stream));
+    return bn_bwd_impl<bf16>(y, N, H, W, C, scale, shift, mean, invstd, group_images, g1, ld1, off1, g2, ld2, off2, gp,
                              sums, count, dy, dgamma0, dbeta0, dgamma1, dbeta1, ST(stream));
 }
 
@@ -691,6 +721,11 @@ int onet_convT2x2_dgrad(const void* go, int64_t ldg, int goff, int N, int H, int
         convT2x2_dgrad_simt_kernel<bf16><<<grid_for(total, 256, 148 * 64), 256, 0, ST(stream)>>>(
             static_cast<const bf16*>(go), ldg, goff, N, H, W, Cin, static_cast<const float*>(w), Co, static_cast<bf16*>(dx), ldd, doff);
     return check_launch("convT2x2_dgrad_simt");
+}
+
+int onet_add_colsums(const double* sums, int C, float* dst, void* stream) {
+    add_colsums_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(sums, C, dst);
+    return check_launch("add_colsums");
 }
 
 int onet_convT2x2_wgrad(const void* x, int64_t ldx, int xoff, const void* go, int64_t ldg, int goff, int N, int H,

@@ -89,82 +89,13 @@ __global__ void bn_eval_prepare_kernel(int G, int C, BnGroupPtrs ptrs, float* __
 }
 
 // ------------------------------------------------------------------------------------------------
-// BN + ReLU apply, optional fused 2x2 max-pool.  One thread = one 2x2 pixel quad x 8 channels.
+// BN + ReLU apply, optional fused 2x2 max-pool.  One thread = one 2x2 pixel window x 8 channels, UNR windows
+// in flight per thread (all loads issued before the first use).
 //   y   : raw conv output [N,H,W,C]
 //   out : [N,H,W,ldo] (+ooff)  (e.g. the skip half of a concat buffer)
 //   pool: [N,H/2,W/2,C] or nullptr (floor semantics of nn.MaxPool2d(2))
+// The backward pass recomputes the window arg-max from y with the same arithmetic, so nothing else is saved.
 // ------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256)
-bn_relu_apply_kernel(const T* __restrict__ y, int N, int H, int W, int C, const float* __restrict__ scale,
-                     const float* __restrict__ shift, int group_images, T* __restrict__ out, long long ldo, int ooff,
-                     T* __restrict__ pool, uint8_t* __restrict__ amax) {
-    const int OC = C >> 3, H2 = (H + 1) >> 1, W2 = (W + 1) >> 1, HP = H >> 1, WP = W >> 1;
-    const long long total = static_cast<long long>(N) * H2 * W2 * OC;
-    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int oc = static_cast<int>(idx % OC);
-        long long q = idx / OC;
-        const int w2 = static_cast<int>(q % W2); q /= W2;
-        const int h2 = static_cast<int>(q % H2);
-        const int n = static_cast<int>(q / H2);
-        const int g = min(n / group_images, 1);
-        float sc[8], sh[8], mx[8];
-        uint32_t best[8];
-        load8<float>(scale + g * C + oc * 8, sc);
-        load8<float>(shift + g * C + oc * 8, sh);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { mx[i] = -1.f; best[i] = 0; }   // post-ReLU values are >= 0 -> first pixel always wins first
-#pragma unroll
-        for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 2; ++dx) {
-                const int h = 2 * h2 + dy, w = 2 * w2 + dx;
-                if (h < H && w < W) {
-                    const long long px = (static_cast<long long>(n) * H + h) * W + w;
-                    float v[8];
-                    load8<T>(y + px * C + oc * 8, v);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        v[i] = round_to<T>(fmaxf(fmaf(v[i], sc[i], sh[i]), 0.f));
-                        if (v[i] > mx[i]) { mx[i] = v[i]; best[i] = dy * 2 + dx; }   // first maximum, like ATen
-                    }
-                    store8<T>(out + px * ldo + ooff + oc * 8, v);
-                }
-            }
-        if (pool != nullptr && h2 < HP && w2 < WP) {
-            const long long po = ((static_cast<long long>(n) * HP + h2) * WP + w2) * C + oc * 8;
-            store8<T>(pool + po, mx);
-            if (amax != nullptr)
-                *reinterpret_cast<uint2*>(amax + po) = make_uint2(best[0] | (best[1] << 8) | (best[2] << 16) | (best[3] << 24),
-                                                                  best[4] | (best[5] << 8) | (best[6] << 16) | (best[7] << 24));
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Backward of (BN -> ReLU [-> skip / 2x2 max-pool]).  The gradient w.r.t. the post-ReLU activation is the
-// sum of up to two dense sources (g1, g2: e.g. the skip half of d(concat) and the head's dL) and a pooled
-// source gp (gradient of the max-pool output, routed to the first maximum of each 2x2 window exactly as
-// ATen's max_pool2d backward does).  Pass 1 (reduce): s1 = sum dZ, s2 = sum dZ * xhat per group/channel.
-// Pass 2 (apply): dY = gamma * invstd * (dZ - s1/n - xhat * s2/n).
-// ------------------------------------------------------------------------------------------------
-template <typename T>
-struct BnBwdArgs {
-    const T* y; int N, H, W, C;
-    const float* scale; const float* shift; const float* mean; const float* invstd;   // [G][C]
-    int group_images;
-    const T* g1; long long ld1; int off1;
-    const T* g2; long long ld2; int off2;
-    const T* gp;                                 // [N,H/2,W/2,C] or nullptr
-    const uint8_t* amax;                         // [N,H/2,W/2,C] position (0..3) of the window maximum, with gp
-    double* sums;                                // [G][2][C]
-    double count;                                // elements per channel per group
-    T* dy;                                       // [N,H,W,C]
-};
-
-// raw 8-channel vector (16 B of bf16 / 32 B of fp32) kept packed so that all loads of a work item can be issued
-// before any of them is consumed
 template <typename T> struct Raw8;
 template <> struct Raw8<float> { float4 a, b; };
 template <> struct Raw8<__nv_bfloat16> { uint4 u; };
@@ -199,37 +130,90 @@ __device__ __forceinline__ void unpack(const Raw8<__nv_bfloat16>& r, float (&v)[
     }
 }
 
-// Gradient w.r.t. the BN output (dz) and xhat of one pixel x 8 channels.
+// post-activation value exactly as the forward pass stores it (the backward pass relies on this being one expression)
 template <typename T>
-__device__ __forceinline__ void bn_bwd_pixel(const Raw8<T>& ry, const Raw8<T>& rg1, const Raw8<T>& rg2, bool has_g2,
-                                             const float (&sc)[8], const float (&sh)[8], const float (&mu)[8],
-                                             const float (&is)[8], const float (&extra)[8], float (&dz)[8], float (&xh)[8]) {
-    float y[8], g[8];
-    unpack(ry, y);
-    unpack(rg1, g);
-    if (has_g2) {
-        float g2[8];
-        unpack(rg2, g2);
+__device__ __forceinline__ float bn_relu_value(float y, float sc, float sh) {
+    return round_to<T>(fmaxf(fmaf(y, sc, sh), 0.f));
+}
+
+template <typename T, int UNR>
+__global__ void __launch_bounds__(256, 3)
+bn_relu_apply_kernel(const T* __restrict__ y, int N, int H, int W, int C, const float* __restrict__ scale,
+                     const float* __restrict__ shift, int group_images, T* __restrict__ out, long long ldo, int ooff,
+                     T* __restrict__ pool) {
+    const int OC = C >> 3, H2 = (H + 1) >> 1, W2 = (W + 1) >> 1, HP = H >> 1, WP = W >> 1;
+    const long long total = static_cast<long long>(N) * H2 * W2 * OC;
+    const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long idx0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx0 < total; idx0 += nthreads * UNR) {
+        Raw8<T> r[UNR][4];
+        int oc_[UNR], n_[UNR], h2_[UNR], w2_[UNR];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] += g2[i];
-    }
+        for (int u = 0; u < UNR; ++u) {
+            const long long idx = idx0 + u * nthreads;
+            const bool live = idx < total;
+            long long q = live ? idx : 0;
+            oc_[u] = static_cast<int>(q % OC); q /= OC;
+            w2_[u] = static_cast<int>(q % W2); q /= W2;
+            h2_[u] = static_cast<int>(q % H2);
+            n_[u] = live ? static_cast<int>(q / H2) : -1;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float z = fmaf(y[i], sc[i], sh[i]);
-        xh[i] = (y[i] - mu[i]) * is[i];
-        dz[i] = (round_to<T>(fmaxf(z, 0.f)) > 0.f) ? g[i] + extra[i] : 0.f;
+            for (int d = 0; d < 4; ++d) {
+                const int h = 2 * h2_[u] + (d >> 1), w = 2 * w2_[u] + (d & 1);
+                const bool ok = live && h < H && w < W;
+                r[u][d] = ok ? ldraw<T>(y + ((static_cast<long long>(n_[u]) * H + h) * W + w) * C + oc_[u] * 8) : zero_raw<T>();
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            if (n_[u] < 0) break;
+            const int n = n_[u], oc = oc_[u];
+            const int g = min(n / group_images, 1);
+            float sc[8], sh[8], mx[8];
+            load8<float>(scale + g * C + oc * 8, sc);
+            load8<float>(shift + g * C + oc * 8, sh);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mx[i] = 0.f;            // post-ReLU values are >= 0
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const int h = 2 * h2_[u] + (d >> 1), w = 2 * w2_[u] + (d & 1);
+                if (h < H && w < W) {
+                    float v[8];
+                    unpack(r[u][d], v);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        v[i] = bn_relu_value<T>(v[i], sc[i], sh[i]);
+                        mx[i] = fmaxf(mx[i], v[i]);
+                    }
+                    store8<T>(out + ((static_cast<long long>(n) * H + h) * W + w) * ldo + ooff + oc * 8, v);
+                }
+            }
+            if (pool != nullptr && h2_[u] < HP && w2_[u] < WP)
+                store8<T>(pool + ((static_cast<long long>(n) * HP + h2_[u]) * WP + w2_[u]) * C + oc * 8, mx);
+        }
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward of (BN -> ReLU [-> skip / 2x2 max-pool]).  The gradient w.r.t. the post-ReLU activation is the
+// sum of up to two dense sources (g1, g2: e.g. the skip half of d(concat) and the head's dL) and a pooled
+// source gp (gradient of the max-pool output, routed to the first maximum of each 2x2 window exactly as
+// ATen's max_pool2d backward does; the arg-max is recomputed from y).
+// Pass 1 (reduce): s1 = sum dZ, s2 = sum dZ * xhat per group/channel  (accumulated as sum dZ*(y-mean), scaled by
+//                  invstd once per thread at the end).
+// Pass 2 (apply):  dY = gamma*invstd * (dZ - s1/n - xhat * s2/n)  =  sc*dZ - k1 - (y-mean)*k2.
+// Two thread mappings: one pixel x 8 channels (no pooled source) and one 2x2 window x 8 channels (pooled source).
+// ------------------------------------------------------------------------------------------------
 template <typename T>
-struct BnBwdCtx {      // per-thread channel constants
-    float sc[8], sh[8], mu[8], is[8];
-    __device__ __forceinline__ void load(const BnBwdArgs<T>& a, int g, int oc) {
-        load8<float>(a.scale + g * a.C + oc * 8, sc);
-        load8<float>(a.shift + g * a.C + oc * 8, sh);
-        load8<float>(a.mean + g * a.C + oc * 8, mu);
-        load8<float>(a.invstd + g * a.C + oc * 8, is);
-    }
+struct BnBwdArgs {
+    const T* y; int N, H, W, C;
+    const float* scale; const float* shift; const float* mean; const float* invstd;   // [G][C]
+    int group_images;
+    const T* g1; long long ld1; int off1;
+    const T* g2; long long ld2; int off2;
+    const T* gp;                                 // [N,H/2,W/2,C] or nullptr
+    double* sums;                                // [G][2][C]
+    double count;                                // elements per channel per group
+    T* dy;                                       // [N,H,W,C]
 };
 
 // block-wide reduction of the per-thread (acc1, acc2) over the pixel lanes and one double atomic per channel
@@ -252,135 +236,192 @@ __device__ __forceinline__ void bn_bwd_block_reduce(const BnBwdArgs<T>& a, int g
     }
 }
 
-// Pooled-gradient contribution for pixel q: gp[n,h/2,w/2,c] where this pixel is the window maximum.
-template <typename T>
-__device__ __forceinline__ void pooled_extra(const BnBwdArgs<T>& a, long long q, int oc, Raw8<T>& rp, uint2& am, int& pos) {
-    const unsigned W = a.W, H = a.H;
-    const unsigned qq = static_cast<unsigned>(q);
-    const unsigned w = qq % W, t = qq / W;
-    const unsigned h = t % H, n = t / H;
-    const unsigned HP = H >> 1, WP = W >> 1;
-    const unsigned h2 = h >> 1, w2 = w >> 1;
-    pos = (h & 1) * 2 + (w & 1);
-    if (h2 < HP && w2 < WP) {
-        const long long po = ((static_cast<long long>(n) * HP + h2) * WP + w2) * a.C + oc * 8;
-        rp = ldraw<T>(a.gp + po);
-        am = __ldg(reinterpret_cast<const uint2*>(a.amax + po));
-    } else {
-        rp = zero_raw<T>();
-        am = make_uint2(0xffffffffu, 0xffffffffu);
-    }
-}
-__device__ __forceinline__ void select_extra(const float (&gpv)[8], uint2 am, int pos, float (&extra)[8]) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const unsigned b = ((i < 4 ? am.x : am.y) >> (8 * (i & 3))) & 0xffu;
-        extra[i] = (b == static_cast<unsigned>(pos)) ? gpv[i] : 0.f;
-    }
-}
-
-// ---- one thread = one pixel x 8 channels, UNROLL pixels in flight
-template <typename T, int UNROLL, bool POOL>
-__global__ void __launch_bounds__(256)
-bn_bwd_reduce_px_kernel(const BnBwdArgs<T> a) {
-    __shared__ float s_red[16][256];
+// ---- pixel mapping: one thread = one pixel x 8 channels, UNROLL pixels in flight
+template <typename T, int UNROLL, bool HAS_G2, bool APPLY>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_px_kernel(const BnBwdArgs<T> a) {
+    __shared__ float s_red[APPLY ? 1 : 16][256];
     const int OC = a.C >> 3, LANES = 256 / OC;
     const int oc = threadIdx.x % OC, ln = threadIdx.x / OC;
     const int g = blockIdx.y;
     const long long HW = static_cast<long long>(a.H) * a.W;
     const long long p_begin = static_cast<long long>(g) * a.group_images * HW;
     const long long p_end = static_cast<long long>(g == static_cast<int>(gridDim.y) - 1 ? a.N : (g + 1) * a.group_images) * HW;
-    const bool has_g2 = a.g2 != nullptr;
-    constexpr bool has_gp = POOL;
+    constexpr bool has_g2 = HAS_G2;
     float acc1[8] = {}, acc2[8] = {};
     if (ln < LANES) {
-        BnBwdCtx<T> c;
-        c.load(a, g, oc);
+        float sc[8], sh[8], mu[8], k1[8], k2[8];
+        load8<float>(a.scale + g * a.C + oc * 8, sc);
+        load8<float>(a.shift + g * a.C + oc * 8, sh);
+        load8<float>(a.mean + g * a.C + oc * 8, mu);
+        if (APPLY) {
+            const float inv_n = static_cast<float>(1.0 / a.count);
+            float is[8];
+            load8<float>(a.invstd + g * a.C + oc * 8, is);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float m1 = static_cast<float>(a.sums[(static_cast<long long>(g) * 2 + 0) * a.C + oc * 8 + i]) * inv_n;
+                const float m2 = static_cast<float>(a.sums[(static_cast<long long>(g) * 2 + 1) * a.C + oc * 8 + i]) * inv_n;
+                k1[i] = sc[i] * m1;
+                k2[i] = sc[i] * is[i] * m2;
+            }
+        }
         const long long stride = static_cast<long long>(gridDim.x) * LANES;
         for (long long p = p_begin + blockIdx.x * static_cast<long long>(LANES) + ln; p < p_end; p += stride * UNROLL) {
-            Raw8<T> ry[UNROLL], rg1[UNROLL], rg2[UNROLL], rp[UNROLL];
-            uint2 am[UNROLL];
-            int pos[UNROLL];
+            Raw8<T> ry[UNROLL], rg1[UNROLL], rg2[has_g2 ? UNROLL : 1];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const long long q = p + u * stride;
                 const bool ok = q < p_end;
                 ry[u] = ok ? ldraw<T>(a.y + q * a.C + oc * 8) : zero_raw<T>();
                 rg1[u] = ok ? ldraw<T>(a.g1 + q * a.ld1 + a.off1 + oc * 8) : zero_raw<T>();
-                rg2[u] = (ok && has_g2) ? ldraw<T>(a.g2 + q * a.ld2 + a.off2 + oc * 8) : zero_raw<T>();
-                if (ok && has_gp) pooled_extra<T>(a, q, oc, rp[u], am[u], pos[u]);
-                else { rp[u] = zero_raw<T>(); am[u] = make_uint2(0xffffffffu, 0xffffffffu); pos[u] = 0; }
+                if (has_g2) rg2[has_g2 ? u : 0] = ok ? ldraw<T>(a.g2 + q * a.ld2 + a.off2 + oc * 8) : zero_raw<T>();
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
-                float dz[8], xh[8], gpv[8], extra[8] = {};
-                if (has_gp) {
-                    unpack(rp[u], gpv);
-                    select_extra(gpv, am[u], pos[u], extra);
+                const long long q = p + u * stride;
+                if (q >= p_end) break;
+                float y[8], gg[8], o[8];
+                unpack(ry[u], y);
+                unpack(rg1[u], gg);
+                if (has_g2) {
+                    float g2v[8];
+                    unpack(rg2[has_g2 ? u : 0], g2v);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) gg[i] += g2v[i];
                 }
-                bn_bwd_pixel<T>(ry[u], rg1[u], rg2[u], has_g2, c.sc, c.sh, c.mu, c.is, extra, dz, xh);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    acc1[i] += dz[i];
-                    acc2[i] = fmaf(dz[i], xh[i], acc2[i]);
+                    const float dz = bn_relu_value<T>(y[i], sc[i], sh[i]) > 0.f ? gg[i] : 0.f;
+                    const float yc = y[i] - mu[i];
+                    if (APPLY) {
+                        o[i] = fmaf(sc[i], dz, -fmaf(yc, k2[i], k1[i]));
+                    } else {
+                        acc1[i] += dz;
+                        acc2[i] = fmaf(dz, yc, acc2[i]);
+                    }
                 }
+                if (APPLY) store8<T>(a.dy + q * a.C + oc * 8, o);
             }
         }
+        if (!APPLY) {
+            float is[8];
+            load8<float>(a.invstd + g * a.C + oc * 8, is);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc2[i] *= is[i];
+        }
     }
-    bn_bwd_block_reduce<T>(a, g, acc1, acc2, s_red);
+    if (!APPLY) bn_bwd_block_reduce<T>(a, g, acc1, acc2, s_red);
 }
 
-template <typename T, int UNROLL, bool POOL>
-__global__ void __launch_bounds__(256)
-bn_bwd_apply_px_kernel(const BnBwdArgs<T> a) {
+// ---- window mapping: one thread = one 2x2 window x 8 channels (pooled gradient source present)
+template <typename T, bool HAS_G2, bool APPLY>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_win_kernel(const BnBwdArgs<T> a) {
+    __shared__ float s_red[APPLY ? 1 : 16][256];
     const int OC = a.C >> 3, LANES = 256 / OC;
     const int oc = threadIdx.x % OC, ln = threadIdx.x / OC;
     const int g = blockIdx.y;
-    if (ln >= LANES) return;
-    const long long HW = static_cast<long long>(a.H) * a.W;
-    const long long p_begin = static_cast<long long>(g) * a.group_images * HW;
-    const long long p_end = static_cast<long long>(g == static_cast<int>(gridDim.y) - 1 ? a.N : (g + 1) * a.group_images) * HW;
-    const bool has_g2 = a.g2 != nullptr;
-    constexpr bool has_gp = POOL;
-    const float inv_n = static_cast<float>(1.0 / a.count);
-    BnBwdCtx<T> c;
-    c.load(a, g, oc);
-    float m1[8], m2[8];
+    const int H = a.H, W = a.W, H2 = (H + 1) >> 1, W2 = (W + 1) >> 1, HP = H >> 1, WP = W >> 1;
+    const long long win_per_img = static_cast<long long>(H2) * W2;
+    const int n_begin = g * a.group_images;
+    const int n_end = (g == static_cast<int>(gridDim.y) - 1) ? a.N : (g + 1) * a.group_images;
+    const long long q_end = static_cast<long long>(n_end - n_begin) * win_per_img;
+    float acc1[8] = {}, acc2[8] = {};
+    if (ln < LANES) {
+        float sc[8], sh[8], mu[8], k1[8], k2[8];
+        load8<float>(a.scale + g * a.C + oc * 8, sc);
+        load8<float>(a.shift + g * a.C + oc * 8, sh);
+        load8<float>(a.mean + g * a.C + oc * 8, mu);
+        if (APPLY) {
+            const float inv_n = static_cast<float>(1.0 / a.count);
+            float is[8];
+            load8<float>(a.invstd + g * a.C + oc * 8, is);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        m1[i] = static_cast<float>(a.sums[(static_cast<long long>(g) * 2 + 0) * a.C + oc * 8 + i]) * inv_n;
-        m2[i] = static_cast<float>(a.sums[(static_cast<long long>(g) * 2 + 1) * a.C + oc * 8 + i]) * inv_n;
-    }
-    const long long stride = static_cast<long long>(gridDim.x) * LANES;
-    for (long long p = p_begin + blockIdx.x * static_cast<long long>(LANES) + ln; p < p_end; p += stride * UNROLL) {
-        Raw8<T> ry[UNROLL], rg1[UNROLL], rg2[UNROLL], rp[UNROLL];
-        uint2 am[UNROLL];
-        int pos[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const long long q = p + u * stride;
-            const bool ok = q < p_end;
-            ry[u] = ok ? ldraw<T>(a.y + q * a.C + oc * 8) : zero_raw<T>();
-            rg1[u] = ok ? ldraw<T>(a.g1 + q * a.ld1 + a.off1 + oc * 8) : zero_raw<T>();
-            rg2[u] = (ok && has_g2) ? ldraw<T>(a.g2 + q * a.ld2 + a.off2 + oc * 8) : zero_raw<T>();
-            if (ok && has_gp) pooled_extra<T>(a, q, oc, rp[u], am[u], pos[u]);
-            else { rp[u] = zero_raw<T>(); am[u] = make_uint2(0xffffffffu, 0xffffffffu); pos[u] = 0; }
-        }
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const long long q = p + u * stride;
-            if (q >= p_end) break;
-            float dz[8], xh[8], o[8], gpv[8], extra[8] = {};
-            if (has_gp) {
-                unpack(rp[u], gpv);
-                select_extra(gpv, am[u], pos[u], extra);
+            for (int i = 0; i < 8; ++i) {
+                const float m1 = static_cast<float>(a.sums[(static_cast<long long>(g) * 2 + 0) * a.C + oc * 8 + i]) * inv_n;
+                const float m2 = static_cast<float>(a.sums[(static_cast<long long>(g) * 2 + 1) * a.C + oc * 8 + i]) * inv_n;
+                k1[i] = sc[i] * m1;
+                k2[i] = sc[i] * is[i] * m2;
             }
-            bn_bwd_pixel<T>(ry[u], rg1[u], rg2[u], has_g2, c.sc, c.sh, c.mu, c.is, extra, dz, xh);
+        }
+        const long long stride = static_cast<long long>(gridDim.x) * LANES;
+        for (long long q = blockIdx.x * static_cast<long long>(LANES) + ln; q < q_end; q += stride) {
+            const int w2 = static_cast<int>(q % W2);
+            const long long t = q / W2;
+            const int h2 = static_cast<int>(t % H2);
+            const int n = n_begin + static_cast<int>(t / H2);
+            Raw8<T> ry[4], rg1[4], rg2[HAS_G2 ? 4 : 1], rp;
+            bool ok[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = c.sc[i] * (dz[i] - m1[i] - xh[i] * m2[i]);
-            store8<T>(a.dy + q * a.C + oc * 8, o);
+            for (int d = 0; d < 4; ++d) {
+                const int h = 2 * h2 + (d >> 1), w = 2 * w2 + (d & 1);
+                ok[d] = h < H && w < W;
+                const long long px = (static_cast<long long>(n) * H + h) * W + w;
+                ry[d] = ok[d] ? ldraw<T>(a.y + px * a.C + oc * 8) : zero_raw<T>();
+                rg1[d] = ok[d] ? ldraw<T>(a.g1 + px * a.ld1 + a.off1 + oc * 8) : zero_raw<T>();
+                if (HAS_G2) rg2[HAS_G2 ? d : 0] = ok[d] ? ldraw<T>(a.g2 + px * a.ld2 + a.off2 + oc * 8) : zero_raw<T>();
+            }
+            const bool pooled = h2 < HP && w2 < WP;
+            rp = pooled ? ldraw<T>(a.gp + ((static_cast<long long>(n) * HP + h2) * WP + w2) * a.C + oc * 8) : zero_raw<T>();
+            // first maximum of the window per channel (2 bits each), exactly as the forward pass pooled it
+            uint32_t best = 0;
+            {
+                float mx[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) mx[i] = -1.f;
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    float y[8];
+                    unpack(ry[d], y);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float act = bn_relu_value<T>(y[i], sc[i], sh[i]);
+                        if (act > mx[i]) { mx[i] = act; best = (best & ~(3u << (2 * i))) | (static_cast<uint32_t>(d) << (2 * i)); }
+                    }
+                }
+            }
+            float gpv[8];
+            unpack(rp, gpv);
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                if (!ok[d]) continue;
+                float y[8], gg[8], o[8];
+                unpack(ry[d], y);
+                unpack(rg1[d], gg);
+                if (HAS_G2) {
+                    float g2v[8];
+                    unpack(rg2[HAS_G2 ? d : 0], g2v);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) gg[i] += g2v[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const bool is_best = pooled && ((best >> (2 * i)) & 3u) == static_cast<uint32_t>(d);
+                    const float gsum = gg[i] + (is_best ? gpv[i] : 0.f);
+                    const float dz = bn_relu_value<T>(y[i], sc[i], sh[i]) > 0.f ? gsum : 0.f;
+                    const float yc = y[i] - mu[i];
+                    if (APPLY) {
+                        o[i] = fmaf(sc[i], dz, -fmaf(yc, k2[i], k1[i]));
+                    } else {
+                        acc1[i] += dz;
+                        acc2[i] = fmaf(dz, yc, acc2[i]);
+                    }
+                }
+                if (APPLY) {
+                    const int h = 2 * h2 + (d >> 1), w = 2 * w2 + (d & 1);
+                    store8<T>(a.dy + ((static_cast<long long>(n) * H + h) * W + w) * a.C + oc * 8, o);
+                }
+            }
+        }
+        if (!APPLY) {
+            float is[8];
+            load8<float>(a.invstd + g * a.C + oc * 8, is);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc2[i] *= is[i];
         }
     }
+    if (!APPLY) bn_bwd_block_reduce<T>(a, g, acc1, acc2, s_red);
 }
 
 // dgamma[c] (+)= sum_g s2[g][c], dbeta[c] (+)= sum_g s1[g][c]; per-group targets may alias (shared twin)
@@ -394,6 +435,13 @@ __global__ void bn_param_grad_kernel(const double* __restrict__ sums, int G, int
         db[c] += static_cast<float>(sums[(static_cast<long long>(g) * 2 + 0) * C + c]);
         dg[c] += static_cast<float>(sums[(static_cast<long long>(g) * 2 + 1) * C + c]);
     }
+}
+
+// dst[c] += sums[c]: folds double column sums (e.g. the transposed convolution's bias gradient, accumulated by the
+// epilogue of the convolution that produced d(concat)) into an fp32 gradient
+__global__ void add_colsums_kernel(const double* __restrict__ sums, int C, float* __restrict__ dst) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) dst[c] += static_cast<float>(sums[c]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -597,6 +645,61 @@ __global__ void pack_convT_w_kernel(const float* __restrict__ w, int Ci, int Co,
         const T v = from_f<T>(w[i]);
         wf[(static_cast<long long>(tap) * Co + co) * Ci + ci] = v;
         wd[static_cast<long long>(ci) * 4 * Co + tap * Co + co] = v;
+    }
+}
+
+// All layers in ONE launch with coalesced reads and 64-byte write segments: a block transposes a 32 x 32 (outer x
+// inner channel) tile through shared memory.
+constexpr int kPackMaxLayers = 24;
+struct PackJob {
+    const float* w;      // conv: [Co][Ci][3][3]; convT: [Ci][Co][2][2]
+    void* wf;
+    void* wd;            // may be nullptr (conv only)
+    int d0, d1;          // outer / inner channel counts of w (conv: Co, Ci; convT: Ci, Co)
+    int taps;            // 9 (conv) or 4 (convT)
+    int tile_begin;      // first block index of this layer
+};
+struct PackJobs {
+    int n;
+    PackJob job[kPackMaxLayers];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_all_weights_kernel(const PackJobs jobs) {
+    __shared__ T s[9][32][34];
+    int li = 0;
+    while (li + 1 < jobs.n && static_cast<int>(blockIdx.x) >= jobs.job[li + 1].tile_begin) ++li;
+    const PackJob& j = jobs.job[li];
+    const int tiles1 = (j.d1 + 31) / 32;
+    const int t = blockIdx.x - j.tile_begin;
+    const int o0 = (t / tiles1) * 32, i0 = (t % tiles1) * 32;
+    const int n1 = min(32, j.d1 - i0), taps = j.taps;
+    const int row = n1 * taps;                       // contiguous floats per outer index inside this tile
+    for (int idx = threadIdx.x; idx < 32 * row; idx += 256) {
+        const int ol = idx / row, r = idx - ol * row;
+        const int il = r / taps, tap = r - il * taps;
+        if (o0 + ol < j.d0)
+            s[tap][ol][il] = from_f<T>(j.w[(static_cast<long long>(o0 + ol) * j.d1 + i0) * taps + r]);
+    }
+    __syncthreads();
+    T* wf = static_cast<T*>(j.wf);
+    T* wd = static_cast<T*>(j.wd);
+    for (int idx = threadIdx.x; idx < taps * 32 * 32; idx += 256) {
+        const int fast = idx & 31, slow = (idx >> 5) & 31, tap = idx >> 10;
+        if (taps == 9) {
+            // conv: outer = co, inner = ci.  wf[co][tap][ci] (ci fastest), wd[ci][8-tap][co] (co fastest)
+            if (o0 + slow < j.d0 && fast < n1)
+                wf[(static_cast<long long>(o0 + slow) * 9 + tap) * j.d1 + i0 + fast] = s[tap][slow][fast];
+            if (wd != nullptr && o0 + fast < j.d0 && slow < n1)
+                wd[(static_cast<long long>(i0 + slow) * 9 + (8 - tap)) * j.d0 + o0 + fast] = s[tap][fast][slow];
+        } else {
+            // convT: outer = ci, inner = co.  wf[(tap,co)][ci] (ci fastest), wd[ci][(tap,co)] (co fastest)
+            if (o0 + fast < j.d0 && slow < n1)
+                wf[(static_cast<long long>(tap) * j.d1 + i0 + slow) * j.d0 + o0 + fast] = s[tap][fast][slow];
+            if (o0 + slow < j.d0 && fast < n1)
+                wd[static_cast<long long>(o0 + slow) * 4 * j.d1 + tap * j.d1 + i0 + fast] = s[tap][slow][fast];
+        }
     }
 }
 

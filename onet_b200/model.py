@@ -196,13 +196,47 @@ class _Engine:
     def _empty(self, *shape, dtype=None):
         return torch.empty(*shape, dtype=dtype or self.tdt, device=self.dev)
 
+    def _pack_key(self, mod, kind):
+        w = mod.weight
+        return (w.data_ptr(), w._version, _PACK_GEN[0], self.dt, kind)
+
+    def _pack_all(self):
+        """Refresh the packed operand copies of every stale conv / up-conv weight in ONE launch (per 24 layers)."""
+        import ctypes
+        jobs = []
+        for seg in self.segments:
+            mods = [(conv, "conv") for _, conv, _ in seg.unet.conv_layers()]
+            if self.use_tc:
+                mods += [(up, "convT") for up in seg.unet.up_layers()]
+            for mod, kind in mods:
+                key = self._pack_key(mod, kind)
+                cache = mod.__dict__.get("_onet_pack")
+                if cache is not None and cache[0] == key:
+                    continue
+                w = mod.weight
+                d0, d1 = w.shape[0], w.shape[1]
+                taps = 9 if kind == "conv" else 4
+                if cache is not None and cache[1].dtype == self.tdt and cache[1].numel() == w.numel() and cache[1].device == w.device:
+                    wf, wd = cache[1], cache[2]                      # reuse the buffers, only the contents are stale
+                elif kind == "conv":
+                    wf, wd = self._empty(d0, 9, d1), self._empty(d1, 9, d0)
+                else:
+                    wf, wd = self._empty(4 * d1, d0), self._empty(d0, 4 * d1)
+                mod.__dict__["_onet_pack"] = (key, wf, wd)
+                jobs.append((ptr(w), d0, d1, taps, ptr(wf), ptr(wd)))
+        for i in range(0, len(jobs), 24):
+            chunk = jobs[i:i + 24]
+            n = len(chunk)
+            vp, ip = ctypes.c_void_p * n, ctypes.c_int * n
+            call("onet_pack_all_weights", n, vp(*[c[0] for c in chunk]), ip(*[c[1] for c in chunk]), ip(*[c[2] for c in chunk]),
+                 ip(*[c[3] for c in chunk]), vp(*[c[4] for c in chunk]), vp(*[c[5] for c in chunk]), self.dt, self.stream)
+
     def _packed(self, mod, kind):
         """Packed operand copies of a conv / up-conv weight, refreshed when the parameter changed."""
-        w = mod.weight
-        key = (w.data_ptr(), w._version, _PACK_GEN[0], self.dt, kind)
         cache = mod.__dict__.get("_onet_pack")
-        if cache is not None and cache[0] == key:
+        if cache is not None and cache[0] == self._pack_key(mod, kind):
             return cache[1], cache[2]
+        w = mod.weight
         if kind == "conv":
             co, ci = w.shape[0], w.shape[1]
             wf = self._empty(co, 9, ci)
@@ -213,7 +247,7 @@ class _Engine:
             wf = self._empty(4 * co, ci)
             wd = self._empty(ci, 4 * co)
             call("onet_pack_convT_weights", ptr(w), ci, co, ptr(wf), ptr(wd), self.dt, self.stream)
-        mod.__dict__["_onet_pack"] = (key, wf, wd)
+        mod.__dict__["_onet_pack"] = (self._pack_key(mod, kind), wf, wd)
         return wf, wd
 
     # -------------------------------------------------------------------------------- forward
@@ -251,6 +285,7 @@ class _Engine:
         rec.stat_pool = torch.zeros(2 * 5888 * nseg_groups, dtype=torch.float64, device=self.dev) if training_stats else None
         rec.stat_off = 0
         rec.nbt = []
+        self._pack_all()
 
         for si, seg in enumerate(self.segments):
             layers = seg.unet.conv_layers()
@@ -320,14 +355,11 @@ class _Engine:
             aff = torch.empty(4, G, cout, dtype=torch.float32, device=self.dev)
             call("onet_bn_eval_prepare", G, cout, ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var),
                  ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var), ptr(aff[2]), ptr(aff[3]), st)
-        amax = None
-        if pool is not None and rec.save:
-            amax = torch.empty(n, h // 2, w // 2, cout, dtype=torch.uint8, device=self.dev)
         call("onet_bn_relu_apply", ptr(Y), n, h, w, cout, ptr(aff[2]), ptr(aff[3]), seg.group_images,
              ptr(dst, self._img_off(dst, n0) + off_dst), ld_dst, 0,
-             ptr(pool, self._img_off(pool, n0)) if pool is not None else None, ptr(amax), self.dt, st)
+             ptr(pool, self._img_off(pool, n0)) if pool is not None else None, self.dt, st)
         if rec.save:
-            rec.saved[(si, li)] = dict(Y=Y, aff=aff, src=(src, ld_src, off_src), h=h, w=w, cin=cin, cout=cout, amax=amax)
+            rec.saved[(si, li)] = dict(Y=Y, aff=aff, src=(src, ld_src, off_src), h=h, w=w, cin=cin, cout=cout)
 
     def _upconv(self, seg, up, x, cx, n0, n, h, w, cat, ld_cat, off_cat):
         cin, co = up.weight.shape[0], up.weight.shape[1]
@@ -375,9 +407,9 @@ class _Engine:
             ups = seg.unet.up_layers()
             n0, n = seg.n0, seg.n
 
-            def bwd(li, g1, ld1, off1, g2=None, ld2=0, off2=0, gp=None, need_dgrad=True):
+            def bwd(li, g1, ld1, off1, g2=None, ld2=0, off2=0, gp=None, need_dgrad=True, colsum=None):
                 return self._conv_bn_relu_bwd(rec, si, seg, li, layers[li][1], layers[li][2], n0, n, g1, ld1, off1, g2,
-                                              ld2, off2, gp, need_dgrad, grad_of)
+                                              ld2, off2, gp, need_dgrad, grad_of, colsum)
 
             # decoder, top (level 0) to bottom (level 3): layer indices 10+2j, 11+2j for j = 0..3 (k = 3-j)
             g_out = dH[n0:n0 + n]            # gradient w.r.t. the block output at level k
@@ -387,11 +419,15 @@ class _Engine:
                 li = 10 + 2 * j
                 c = cs[k]
                 d_mid = bwd(li + 1, g_out, c, 0)                       # -> grad wrt mid activation [n,h,w,c]
-                dcat[k] = bwd(li, d_mid, c, 0)                          # -> grad wrt concat buffer [n,h,w,2c]
+                # grad wrt concat buffer [n,h,w,2c]; its column sums (up half = the up-conv's bias gradient) come
+                # out of the same kernel's epilogue
+                colsum = torch.zeros(2, 2 * c, dtype=torch.float64, device=self.dev)
+                dcat[k] = bwd(li, d_mid, c, 0, colsum=colsum)
                 # transposed conv: go = up half of dcat
                 up = ups[j]
                 below = rec.x5 if k == 3 else rec.mid[("dec_out", k + 1)]
-                g_out = self._upconv_bwd(seg, up, below, 2 * c, n0, n, hs[k + 1], ws[k + 1], dcat[k], 2 * c, c, grad_of)
+                g_out = self._upconv_bwd(seg, up, below, 2 * c, n0, n, hs[k + 1], ws[k + 1], dcat[k], 2 * c, c, grad_of,
+                                         colsum[0, c:])
                 if after_block is not None:
                     after_block(seg.unet, _DEC[j][0])
             # encoder, bottom (level 4) to top
@@ -411,7 +447,8 @@ class _Engine:
                 if after_block is not None:
                     after_block(seg.unet, "inc" if k == 0 else _ENC[k - 1][0])
 
-    def _conv_bn_relu_bwd(self, rec, si, seg, li, conv, bn, n0, n, g1, ld1, off1, g2, ld2, off2, gp, need_dgrad, grad_of):
+    def _conv_bn_relu_bwd(self, rec, si, seg, li, conv, bn, n0, n, g1, ld1, off1, g2, ld2, off2, gp, need_dgrad, grad_of,
+                          colsum=None):
         """g1/g2/gp are SEGMENT-LOCAL tensors (first image = image n0 of the batch)."""
         sv = rec.saved[(si, li)]
         Y, aff, h, w, cin, cout = sv["Y"], sv["aff"], sv["h"], sv["w"], sv["cin"], sv["cout"]
@@ -423,7 +460,7 @@ class _Engine:
         count = float(seg.group_images * h * w)
         call("onet_bn_relu_bwd", ptr(Y), n, h, w, cout, ptr(aff[2]), ptr(aff[3]), ptr(aff[0]), ptr(aff[1]),
              seg.group_images, ptr(g1, off1), ld1, 0, ptr(g2, off2) if g2 is not None else None, ld2, 0,
-             ptr(gp) if gp is not None else None, ptr(sv["amax"]) if gp is not None else None, ptr(sums), count, ptr(dY),
+             ptr(gp) if gp is not None else None, ptr(sums), count, ptr(dY),
              ptr(grad_of(bn.weight)), ptr(grad_of(bn.bias)), ptr(grad_of(bn.weight)), ptr(grad_of(bn.bias)), self.dt, st)
         eng = self._engine_for(cin, cout)
         src, ld_src, off_src = sv["src"]
@@ -433,16 +470,18 @@ class _Engine:
             return None
         _, wd = self._packed(conv, "conv")
         dX = self._empty(n, h, w, cin)
-        call("onet_conv3x3_fwd", ptr(dY), cout, 0, n, h, w, cout, ptr(wd), cin, ptr(dX), cin, 0, None, None,
-             seg.group_images, self.dt, eng, st)
+        call("onet_conv3x3_fwd", ptr(dY), cout, 0, n, h, w, cout, ptr(wd), cin, ptr(dX), cin, 0,
+             ptr(colsum[0]) if colsum is not None else None, ptr(colsum[1]) if colsum is not None else None,
+             n if colsum is not None else seg.group_images, self.dt, eng, st)
         return dX
 
-    def _upconv_bwd(self, seg, up, x, ld_go_total, n0, n, h, w, dcat, ld_cat, off_cat, grad_of):
+    def _upconv_bwd(self, seg, up, x, ld_go_total, n0, n, h, w, dcat, ld_cat, off_cat, grad_of, bias_sums):
         cin, co = up.weight.shape[0], up.weight.shape[1]
         eng = self._engine_for(cin, co)
         st = self.stream
+        call("onet_add_colsums", ptr(bias_sums), co, ptr(grad_of(up.bias)), st)
         call("onet_convT2x2_wgrad", ptr(x, self._img_off(x, n0)), cin, 0, ptr(dcat, off_cat), ld_cat, 0, n, h, w, cin, co,
-             ptr(grad_of(up.weight)), ptr(grad_of(up.bias)), self.dt, eng, st)
+             ptr(grad_of(up.weight)), None, self.dt, eng, st)
         dX = self._empty(n, h, w, cin)
         if eng == ENGINE_TC:
             _, wd = self._packed(up, "convT")

@@ -177,8 +177,7 @@ def test_bn_relu_fwd_bwd(dt_name, n, h, w, c, pool):
          ptr(rm), ptr(rv), 0.1, ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]), U.stream())
     out = torch.zeros(n, h, w, 2 * c, dtype=tdt, device="cuda")         # skip half of a concat buffer
     pl = torch.empty(n, h // 2, w // 2, c, dtype=tdt, device="cuda") if pool else None
-    am = torch.empty(n, h // 2, w // 2, c, dtype=torch.uint8, device="cuda") if pool else None
-    call("onet_bn_relu_apply", ptr(yn), n, h, w, c, ptr(aff[2]), ptr(aff[3]), g, ptr(out), 2 * c, 0, ptr(pl), ptr(am), dt,
+    call("onet_bn_relu_apply", ptr(yn), n, h, w, c, ptr(aff[2]), ptr(aff[3]), g, ptr(out), 2 * c, 0, ptr(pl), dt,
          U.stream())
     # torch reference, branch by branch (shared BN module called twice)
     bn = torch.nn.BatchNorm2d(c).cuda()
@@ -213,7 +212,7 @@ def test_bn_relu_fwd_bwd(dt_name, n, h, w, c, pool):
     g1n, g2n = U.to_nhwc(g1, tdt), U.to_nhwc(g2, tdt)
     gpn = U.to_nhwc(gp, tdt) if pool else None
     call("onet_bn_relu_bwd", ptr(yn), n, h, w, c, ptr(aff[2]), ptr(aff[3]), ptr(aff[0]), ptr(aff[1]), g, ptr(g1n), c, 0,
-         ptr(g2n), c, 0, ptr(gpn), ptr(am), ptr(sums), count, ptr(dy), ptr(dgam), ptr(dbet), ptr(dgam), ptr(dbet), dt,
+         ptr(g2n), c, 0, ptr(gpn), ptr(sums), count, ptr(dy), ptr(dgam), ptr(dbet), ptr(dgam), ptr(dbet), dt,
          U.stream())
     btol = 2e-5 if dt == U.F32 else 8e-3
     assert U.rel_l2(U.from_nhwc(dy), yr.grad) < btol
@@ -276,3 +275,55 @@ def test_adam_kernel_matches_torch():
         opt.step()
         call("onet_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), n, 5e-6, 0.9, 0.999, 1e-8, step, 1.0, U.stream())
     assert torch.allclose(p, ref.detach(), rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize("dt_name", ["fp32", "bf16"])
+def test_pack_all_weights_matches_per_layer_packing(dt_name):
+    """One-launch packing of several conv / up-conv weights (ragged channel counts included) is bit-identical to the
+    per-layer packing kernels."""
+    import ctypes
+    U = _imports()
+    call, ptr = U.call, U.ptr
+    dt = U.F32 if dt_name == "fp32" else U.BF16
+    tdt = U.TDT[dt]
+    torch.manual_seed(3)
+    convs = [torch.randn(co, ci, 3, 3, device="cuda") for co, ci in ((64, 1), (64, 3), (64, 64), (128, 64), (96, 40), (256, 128))]
+    ups = [torch.randn(ci, ci // 2, 2, 2, device="cuda") for ci in (128, 256, 72)]
+    jobs, want = [], []
+    for w in convs:
+        co, ci = w.shape[:2]
+        wf, wd = torch.zeros(co, 9, ci, dtype=tdt, device="cuda"), torch.zeros(ci, 9, co, dtype=tdt, device="cuda")
+        jobs.append((ptr(w), co, ci, 9, ptr(wf), ptr(wd)))
+        want.append((wf, wd) + U.pack_conv(w, dt))
+    for w in ups:
+        ci, co = w.shape[:2]
+        wf, wd = torch.zeros(4 * co, ci, dtype=tdt, device="cuda"), torch.zeros(ci, 4 * co, dtype=tdt, device="cuda")
+        jobs.append((ptr(w), ci, co, 4, ptr(wf), ptr(wd)))
+        want.append((wf, wd) + U.pack_convT(w, dt))
+    n = len(jobs)
+    vp, ip = ctypes.c_void_p * n, ctypes.c_int * n
+    call("onet_pack_all_weights", n, vp(*[j[0] for j in jobs]), ip(*[j[1] for j in jobs]), ip(*[j[2] for j in jobs]),
+         ip(*[j[3] for j in jobs]), vp(*[j[4] for j in jobs]), vp(*[j[5] for j in jobs]), dt, U.stream())
+    torch.cuda.synchronize()
+    for wf, wd, rf, rd in want:
+        assert torch.equal(wf.view(-1), rf.view(-1)) and torch.equal(wd.view(-1), rd.view(-1))
+
+
+def test_dgrad_epilogue_column_sums_feed_upconv_bias_grad():
+    """onet_conv3x3_fwd's statistics output used as column sums of d(concat) + onet_add_colsums == the bias gradient
+    that a separate reduction over the up half of d(concat) gives."""
+    U = _imports()
+    call, ptr = U.call, U.ptr
+    torch.manual_seed(9)
+    n, h, w, cin, cout = 2, 16, 16, 64, 128
+    x = torch.randn(n, h, w, cin, device="cuda").to(torch.bfloat16)
+    wt = torch.randn(cout, cin, 3, 3, device="cuda") * 0.05
+    wf, _ = U.pack_conv(wt, U.BF16)
+    out = torch.empty(n, h, w, cout, dtype=torch.bfloat16, device="cuda")
+    cs = torch.zeros(2, cout, dtype=torch.float64, device="cuda")
+    call("onet_conv3x3_fwd", ptr(x), cin, 0, n, h, w, cin, ptr(wf), cout, ptr(out), cout, 0, ptr(cs[0]), ptr(cs[1]), n, U.BF16,
+         U.ENGINE_TC, U.stream())
+    dbias = torch.full((64,), 0.5, device="cuda")
+    call("onet_add_colsums", ptr(cs[0], 64), 64, ptr(dbias), U.stream())
+    want = 0.5 + out[..., 64:].float().sum(dim=(0, 1, 2))
+    assert torch.allclose(dbias, want, rtol=1e-5, atol=1e-3)
