@@ -18,6 +18,15 @@ def make_runner(kind, n, h, w, cin, cout):
     call, ptr, st = U.call, U.ptr, U.stream
     bf = torch.bfloat16
     dev = "cuda"
+    if kind in ("first_fwd", "first_wgrad"):          # first layer of the U-Net (Cin = 1 or 3): CUDA-core direct kernels
+        x = torch.rand(n, h, w, cin, device=dev).to(bf)
+        wt = torch.randn(cout, cin, 3, 3, device=dev) * 0.3
+        wf, _ = U.pack_conv(wt, U.BF16)
+        gy = torch.randn(n, h, w, cout, device=dev).to(bf)
+        byts = 2.0 * n * h * w * (cin + cout)
+        if kind == "first_fwd":
+            return (lambda: U.conv3x3(x, wf, cout, U.BF16, U.ENGINE_SIMT, group_images=max(n // 2, 1), stats=True)), 0.0, byts
+        return (lambda: U.conv3x3_wgrad(gy, x, U.BF16, U.ENGINE_SIMT)), 0.0, byts
     if kind in ("fwd", "dgrad", "wgrad"):
         x = torch.randn(n, h, w, cin, device=dev).to(bf)
         wt = torch.randn(cout, cin, 3, 3, device=dev) * 0.05
@@ -125,6 +134,23 @@ def main():
                 for kind in ("convT", "convT_dgrad", "convT_wgrad"):
                     time_kind(kind, B2, s // 2, s // 2, 2 * c, c, 3, flush)
         time_kind("bnbwd_pool_g2", B2, 256, 256, 64, 64, 3, flush)
+        time_kind("first_fwd", B2, 256, 256, 1, 64, 3, flush)
+        time_kind("first_wgrad", B2, 256, 256, 1, 64, 3, flush)
+        return
+    if sys.argv[1] == "sweep_bw":   # only the bandwidth-bound kinds
+        B2 = 2 * (int(sys.argv[2]) if len(sys.argv) > 2 else 64)
+        chans = [64, 128, 256, 512, 1024]
+        for k in range(5):
+            s = 256 >> k
+            c = chans[k]
+            for kind in ("bnapply", "bnbwd") + (("bnapply_pool", "bnbwd_pool") if k < 4 else ()):
+                time_kind(kind, B2, s, s, c, c, 3, flush)
+            if k < 4:
+                for kind in ("convT", "convT_dgrad", "convT_wgrad"):
+                    time_kind(kind, B2, s // 2, s // 2, 2 * c, c, 3, flush)
+        time_kind("bnbwd_pool_g2", B2, 256, 256, 64, 64, 3, flush)
+        time_kind("first_fwd", B2, 256, 256, 1, 64, 3, flush)
+        time_kind("first_wgrad", B2, 256, 256, 1, 64, 3, flush)
         return
     kind = sys.argv[1]
     n, h, w, cin, cout = (int(v) for v in sys.argv[2:7])
