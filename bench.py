@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying one CUDA graph per step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -225,7 +226,7 @@ def main():
     B = args.batch
     torch.manual_seed(1981)
     net = onet_b200.Onet(CIN, True, True, mode=args.mode).to(dev)
-    trainer = OnetTrainer(net, lr=LR)
+    trainer = OnetTrainer(net, lr=LR, graph=not args.no_graph)
     trainer.broadcast_parameters(0)
 
     POOL = 4
@@ -258,12 +259,13 @@ def main():
     l0 = _lib.launch_count()
     ms_dev = timed(lambda i: trainer.step(resident[i % POOL]), args.steps)
     launches = _lib.launch_count() - l0
+    if trainer.use_graph:       # replays do not pass through the library's counter: kernels captured per step x steps
+        launches = trainer.launches_per_step * args.steps
 
     losses = []
 
-    def e2e_step(i):
-        x = host[i % POOL].to(dev, non_blocking=True)
-        losses.append(trainer.step(x).item())
+    def e2e_step(i):      # pinned host batch -> device inside the step, loss read back on the host every step
+        losses.append(trainer.step(host[i % POOL]).item())
     e2e_step(0)
     ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None

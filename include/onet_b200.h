@@ -127,6 +127,12 @@ int onet_predict_label(const float* Vt, const float* Vd, int64_t n, int64_t* out
 int onet_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, int step, float grad_scale, void* stream);
 
+/* The same update with the step count and the hyper-parameters in DEVICE memory (hyper = {lr, beta1, beta2, eps};
+ * *step is incremented first and then used as the 1-based step), so that a launch captured in a CUDA graph stays
+ * valid across steps and learning-rate schedules. */
+int onet_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, int* step,
+                       float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -518,13 +518,13 @@ int onet_conv3x3_fwd(const void* in, int64_t ldi, int ci_off, int N, int H, int 
     const int gi = group_images > 0 ? group_images : N;
     if ((Cin == 1 || Cin == 3) && Cout == 64 && ldi == Cin && ci_off == 0 && ldo == 64 && co_off == 0 && W % 4 == 0) {
         // first layer of the U-Net: direct bandwidth-bound kernel
-        const int G = std::min(2, (N + gi - 1) / gi);
-        const long long quads = static_cast<long long>(gi) * H * (W / 4);
-        dim3 fg(static_cast<unsigned>(std::max(1LL, std::min<long long>((quads + 31) / 32, 148 * 8 / G))), G);
-#define ONET_FIRST(TT, CC)                                                                                          \
-    conv_first_fwd_kernel<TT, CC><<<fg, 256, 0, ST(stream)>>>(static_cast<const TT*>(in), N, H, W,                  \
-                                                              static_cast<const TT*>(wp), static_cast<TT*>(out),   \
-                                                              stat_sum, stat_sq, gi)
+        constexpr int ROWS = 32;
+        const int wgb = (W / 4 + 31) / 32, chunks = (H + ROWS - 1) / ROWS;
+        const unsigned fg = static_cast<unsigned>(N) * chunks * wgb;
+#define ONET_FIRST(TT, CC)                                                                                               \
+    conv_first_fwd_rows_kernel<TT, CC, ROWS><<<fg, 256, 0, ST(stream)>>>(static_cast<const TT*>(in), N, H, W,            \
+                                                                         static_cast<const TT*>(wp), static_cast<TT*>(out), \
+                                                                         stat_sum, stat_sq, gi)
         if (dtype == ONET_F32) { if (Cin == 1) ONET_FIRST(float, 1); else ONET_FIRST(float, 3); }
         else { if (Cin == 1) ONET_FIRST(bf16, 1); else ONET_FIRST(bf16, 3); }
 #undef ONET_FIRST
@@ -550,14 +550,16 @@ int onet_conv3x3_wgrad(const void* g, int64_t ldg, int g_off, const void* in, in
     }
     const long long M = static_cast<long long>(N) * H * W;
     if ((Cin == 1 || Cin == 3) && Cout == 64 && ldi == Cin && ci_off == 0 && ldg == 64 && g_off == 0 && W % 4 == 0) {
-        const int lanes = Cin == 1 ? 32 : 8;
-        const int gx = static_cast<int>(std::max(1LL, std::min<long long>((M / 4 + lanes - 1) / lanes, 148 * 4)));
+        constexpr int ROWS = 32;
+        const int lanes = Cin == 1 ? 32 : 8;       // column groups per block = 256 / (64 / CPT)
+        const int wgb = (W / 4 + lanes - 1) / lanes, chunks = (H + ROWS - 1) / ROWS;
+        const unsigned gx = static_cast<unsigned>(N) * chunks * wgb;
         if (dtype == ONET_F32) {
-            if (Cin == 1) conv_first_wgrad_kernel<float, 1, 8><<<gx, 256, 0, ST(stream)>>>(static_cast<const float*>(g), static_cast<const float*>(in), N, H, W, dw);
-            else conv_first_wgrad_kernel<float, 3, 2><<<gx, 256, 0, ST(stream)>>>(static_cast<const float*>(g), static_cast<const float*>(in), N, H, W, dw);
+            if (Cin == 1) conv_first_wgrad_rows_kernel<float, 1, 8, ROWS><<<gx, 256, 0, ST(stream)>>>(static_cast<const float*>(g), static_cast<const float*>(in), N, H, W, dw);
+            else conv_first_wgrad_rows_kernel<float, 3, 2, ROWS><<<gx, 256, 0, ST(stream)>>>(static_cast<const float*>(g), static_cast<const float*>(in), N, H, W, dw);
         } else {
-            if (Cin == 1) conv_first_wgrad_kernel<bf16, 1, 8><<<gx, 256, 0, ST(stream)>>>(static_cast<const bf16*>(g), static_cast<const bf16*>(in), N, H, W, dw);
-            else conv_first_wgrad_kernel<bf16, 3, 2><<<gx, 256, 0, ST(stream)>>>(static_cast<const bf16*>(g), static_cast<const bf16*>(in), N, H, W, dw);
+            if (Cin == 1) conv_first_wgrad_rows_kernel<bf16, 1, 8, ROWS><<<gx, 256, 0, ST(stream)>>>(static_cast<const bf16*>(g), static_cast<const bf16*>(in), N, H, W, dw);
+            else conv_first_wgrad_rows_kernel<bf16, 3, 2, ROWS><<<gx, 256, 0, ST(stream)>>>(static_cast<const bf16*>(g), static_cast<const bf16*>(in), N, H, W, dw);
         }
         return check_launch("conv_first_wgrad");
     }
@@ -828,6 +830,15 @@ int onet_adam_step(float* p, const float* g, float* m, float* v, int64_t n, floa
     const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
     adam_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale);
     return check_launch("adam");
+}
+
+int onet_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, int* step,
+                       float grad_scale, void* stream) {
+    if (hyper == nullptr || step == nullptr) return fail("adam_step_dev: hyper and step must be device pointers");
+    adam_tick_kernel<<<1, 1, 0, ST(stream)>>>(step);
+    if (check_launch("adam_tick")) return 1;
+    adam_dev_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, ST(stream)>>>(p, g, m, v, n, hyper, step, grad_scale);
+    return check_launch("adam_dev");
 }
 
 }  // extern "C"

@@ -721,6 +721,29 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// Graph-capturable variant: the step count and the hyper-parameters live in device memory so that a captured
+// launch stays valid while they change.  hyper = {lr, beta1, beta2, eps}; *step is the 1-based count of THIS step
+// (adam_tick_kernel increments it right before).
+__global__ void adam_tick_kernel(int* step) { *step += 1; }
+
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                long long n, const float* __restrict__ hyper, const int* __restrict__ step, float grad_scale) {
+    const float lr = hyper[0], beta1 = hyper[1], beta2 = hyper[2], eps = hyper[3];
+    const float t = static_cast<float>(*step);
+    const float bc1 = 1.f - powf(beta1, t);
+    const float bc2_sqrt = sqrtf(1.f - powf(beta2, t));
+    const float stepsz = lr / bc1;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float gi = g[i] * grad_scale;
+        const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+        const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        p[i] -= stepsz * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    }
+}
+
 // label = 1 iff Vd > Vt (argmax of the 2-way softmax, ties -> 0), Onet_vanilla_20240606.py:193-202
 __global__ void predict_label_kernel(const float* __restrict__ Vt, const float* __restrict__ Vd, long long n,
                                      long long* __restrict__ out) {

@@ -134,14 +134,14 @@ conv3x3_simt_kernel(const T* __restrict__ in, long long ldi, int ci_off, int N, 
 // kernel: one thread = 4 horizontally adjacent pixels x 8 output channels (the 3 x 6 input patch is shared by the
 // four pixels), weights in shared memory, BatchNorm partial sums fused.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int CIN>
+template <typename T, int CIN, int PX>
 __device__ __forceinline__ void load_patch(const T* __restrict__ in, long long nb, int h, int w0, int H, int W,
-                                           float (&x)[3][6][CIN]) {
+                                           float (&x)[3][PX + 2][CIN]) {
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         const int hh = h + r - 1;
 #pragma unroll
-        for (int cidx = 0; cidx < 6; ++cidx) {
+        for (int cidx = 0; cidx < PX + 2; ++cidx) {
             const int ww = w0 + cidx - 1;
             const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
 #pragma unroll
@@ -151,8 +151,10 @@ __device__ __forceinline__ void load_patch(const T* __restrict__ in, long long n
     }
 }
 
-template <typename T, int CIN>
-__global__ void __launch_bounds__(256)
+// One thread = PX horizontally adjacent pixels x 8 output channels; the 3 x (PX+2) input patch is shared by the PX
+// pixels.  W % PX == 0.
+template <typename T, int CIN, int PX>
+__global__ void __launch_bounds__(256, PX == 4 ? 2 : 3)
 conv_first_fwd_kernel(const T* __restrict__ in, int N, int H, int W, const T* __restrict__ wp, T* __restrict__ out,
                       double* __restrict__ stat_sum, double* __restrict__ stat_sq, int group_images) {
     constexpr int K = 9 * CIN;
@@ -162,17 +164,18 @@ conv_first_fwd_kernel(const T* __restrict__ in, int N, int H, int W, const T* __
     __syncthreads();
     const int oc = threadIdx.x & 7, ln = threadIdx.x >> 3;
     const int g = blockIdx.y;
-    const int W4 = W >> 2;
-    const long long QW = static_cast<long long>(H) * W4;      // pixel quads per image
+    const int WG = W / PX;
+    const long long QW = static_cast<long long>(H) * WG;      // pixel groups per image
     const long long q_begin = static_cast<long long>(g) * group_images * QW;
     const long long q_end = static_cast<long long>(g == static_cast<int>(gridDim.y) - 1 ? N : (g + 1) * group_images) * QW;
     float a1[8] = {}, a2[8] = {};
     for (long long q = q_begin + blockIdx.x * 32LL + ln; q < q_end; q += gridDim.x * 32LL) {
-        const int w0 = static_cast<int>(q % W4) * 4, h = static_cast<int>((q / W4) % H);
+        const int w0 = static_cast<int>(q % WG) * PX, h = static_cast<int>((q / WG) % H);
         const long long nb = (q / QW) * H * W;
-        float x[3][6][CIN];
-        load_patch<T, CIN>(in, nb, h, w0, H, W, x);
-        float acc[4][8] = {};
+        float x[3][PX + 2][CIN];
+        load_patch<T, CIN, PX>(in, nb, h, w0, H, W, x);
+        asm volatile("" ::: "memory");     // keep the weight reads inside the loop (hoisting 9*CIN*8 of them spills)
+        float acc[PX][8] = {};
 #pragma unroll
         for (int t = 0; t < 9; ++t)
 #pragma unroll
@@ -181,13 +184,13 @@ conv_first_fwd_kernel(const T* __restrict__ in, int N, int H, int W, const T* __
 #pragma unroll
                 for (int i = 0; i < 8; ++i) wv[i] = ws[t * CIN + c][oc * 8 + i];
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < PX; ++j)
 #pragma unroll
                     for (int i = 0; i < 8; ++i) acc[j][i] = fmaf(x[t / 3][j + t % 3][c], wv[i], acc[j][i]);
             }
         const long long p0 = nb + static_cast<long long>(h) * W + w0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < PX; ++j) {
             T o[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -225,7 +228,7 @@ conv_first_fwd_kernel(const T* __restrict__ in, int N, int H, int W, const T* __
 // dW[co][ci][tap] += sum_px G[px][co] * In[px + tap][ci] for the first convolution (CIN <= 4, Cout = 64, W % 4 == 0).
 // One thread = CPT output channels x all 9*CIN taps, 4 adjacent pixels per step; warp-shuffle + atomics at the end.
 template <typename T, int CIN, int CPT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 conv_first_wgrad_kernel(const T* __restrict__ g, const T* __restrict__ in, int N, int H, int W, float* __restrict__ dw) {
     constexpr int K = 9 * CIN;
     constexpr int NG = 64 / CPT;            // channel groups
@@ -260,7 +263,7 @@ conv_first_wgrad_kernel(const T* __restrict__ g, const T* __restrict__ in, int N
             }
         }
         float x[3][6][CIN];
-        load_patch<T, CIN>(in, nb, h, w0, H, W, x);
+        load_patch<T, CIN, 4>(in, nb, h, w0, H, W, x);
 #pragma unroll
         for (int t = 0; t < 9; ++t)
 #pragma unroll
@@ -283,6 +286,203 @@ conv_first_wgrad_kernel(const T* __restrict__ g, const T* __restrict__ in, int N
                 atomicAdd(dw + (static_cast<long long>(co) * CIN + ci) * 9 + tap, v);
             }
         }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row-sliding variants of the two first-layer kernels.  A thread owns 4 adjacent columns x CPT output channels and
+// walks down ROWS image rows keeping the 3 x 6 input patch in registers: every new row costs one row of input
+// (one 8-byte + two 2-byte loads for bf16, in_chns = 1) instead of the whole patch, and no index arithmetic.
+// Block = 256 threads = (64 / CPT) channel groups x (256 * CPT / 64) column groups of ONE image row range, so a
+// block never mixes BatchNorm statistics groups.  grid.x = N * ceil(H / ROWS) * ceil((W/4) / column groups).
+// ------------------------------------------------------------------------------------------------
+template <typename T, int CIN>
+__device__ __forceinline__ void load_row6(const T* __restrict__ in, long long nb, int hh, int w0, int H, int W,
+                                          float (&x)[6][CIN]) {
+    const bool row_ok = hh >= 0 && hh < H;
+    if (sizeof(T) == 2 && CIN == 1) {
+        const unsigned short* base = reinterpret_cast<const unsigned short*>(in) + nb + static_cast<long long>(row_ok ? hh : 0) * W + w0;
+        uint2 mid = make_uint2(0u, 0u);
+        unsigned short lft = 0, rgt = 0;
+        if (row_ok) {
+            mid = __ldg(reinterpret_cast<const uint2*>(base));
+            if (w0 > 0) lft = __ldg(base - 1);
+            if (w0 + 4 < W) rgt = __ldg(base + 4);
+        }
+        x[0][0] = __uint_as_float(static_cast<uint32_t>(lft) << 16);
+        x[1][0] = __uint_as_float(mid.x << 16);
+        x[2][0] = __uint_as_float(mid.x & 0xffff0000u);
+        x[3][0] = __uint_as_float(mid.y << 16);
+        x[4][0] = __uint_as_float(mid.y & 0xffff0000u);
+        x[5][0] = __uint_as_float(static_cast<uint32_t>(rgt) << 16);
+    } else {
+#pragma unroll
+        for (int cidx = 0; cidx < 6; ++cidx) {
+            const int ww = w0 + cidx - 1;
+            const bool ok = row_ok && ww >= 0 && ww < W;
+#pragma unroll
+            for (int c = 0; c < CIN; ++c)
+                x[cidx][c] = ok ? to_f<T>(in[(nb + static_cast<long long>(hh) * W + ww) * CIN + c]) : 0.f;
+        }
+    }
+}
+
+template <typename T, int CIN, int ROWS>
+__global__ void __launch_bounds__(256, CIN == 1 ? 3 : 2)
+conv_first_fwd_rows_kernel(const T* __restrict__ in, int N, int H, int W, const T* __restrict__ wp, T* __restrict__ out,
+                           double* __restrict__ stat_sum, double* __restrict__ stat_sq, int group_images) {
+    constexpr int K = 9 * CIN;
+    __shared__ float ws[K][64];
+    __shared__ float s_red[16][256];
+    for (int i = threadIdx.x; i < K * 64; i += 256) ws[i % K][i / K] = to_f<T>(wp[i]);   // wp is [64][K]
+    __syncthreads();
+    const int oc = threadIdx.x & 7, ln = threadIdx.x >> 3;
+    const int WG = W >> 2, wgb = (WG + 31) >> 5, chunks = (H + ROWS - 1) / ROWS;
+    int b = blockIdx.x;
+    const int wg = (b % wgb) * 32 + ln; b /= wgb;
+    const int h0 = (b % chunks) * ROWS;
+    const int n = b / chunks;
+    const int h1 = min(H, h0 + ROWS);
+    const int w0 = wg * 4;
+    const long long nb = static_cast<long long>(n) * H * W;
+    float a1[8] = {}, a2[8] = {};
+    if (wg < WG) {
+        float x[3][6][CIN];
+        load_row6<T, CIN>(in, nb, h0 - 1, w0, H, W, x[0]);
+        load_row6<T, CIN>(in, nb, h0, w0, H, W, x[1]);
+        for (int h = h0; h < h1; ++h) {
+            load_row6<T, CIN>(in, nb, h + 1, w0, H, W, x[2]);
+            asm volatile("" ::: "memory");     // keep the weight reads inside the loop (hoisting all of them spills)
+            float acc[4][8] = {};
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+#pragma unroll
+                for (int c = 0; c < CIN; ++c) {
+                    float wv[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) wv[i] = ws[t * CIN + c][oc * 8 + i];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[j][i] = fmaf(x[t / 3][j + t % 3][c], wv[i], acc[j][i]);
+                }
+            const long long p0 = nb + static_cast<long long>(h) * W + w0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                T o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    o[i] = from_f<T>(acc[j][i]);
+                    const float f = to_f<T>(o[i]);
+                    a1[i] += f;
+                    a2[i] = fmaf(f, f, a2[i]);
+                }
+                if (sizeof(T) == 2) {
+                    *reinterpret_cast<uint4*>(out + (p0 + j) * 64 + oc * 8) = *reinterpret_cast<const uint4*>(o);
+                } else {
+                    *reinterpret_cast<float4*>(out + (p0 + j) * 64 + oc * 8) = *reinterpret_cast<const float4*>(o);
+                    *reinterpret_cast<float4*>(out + (p0 + j) * 64 + oc * 8 + 4) = *reinterpret_cast<const float4*>(o + 4);
+                }
+            }
+#pragma unroll
+            for (int cidx = 0; cidx < 6; ++cidx)
+#pragma unroll
+                for (int c = 0; c < CIN; ++c) { x[0][cidx][c] = x[1][cidx][c]; x[1][cidx][c] = x[2][cidx][c]; }
+        }
+    }
+    if (stat_sum != nullptr) {
+        const int g = min(n / group_images, 1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            s_red[i][threadIdx.x] = a1[i];
+            s_red[8 + i][threadIdx.x] = a2[i];
+        }
+        __syncthreads();
+        if (threadIdx.x < 128) {
+            const int which = threadIdx.x >> 3, o8 = threadIdx.x & 7;   // which in 0..15, octet o8
+            float sacc = 0.f;
+            for (int l = 0; l < 32; ++l) sacc += s_red[which][l * 8 + o8];
+            const int c = o8 * 8 + (which & 7);
+            double* dst = (which < 8 ? stat_sum : stat_sq) + static_cast<long long>(g) * 64 + c;
+            atomicAdd(dst, static_cast<double>(sacc));
+        }
+    }
+}
+
+template <typename T, int CIN, int CPT, int ROWS>
+__global__ void __launch_bounds__(256, 2)
+conv_first_wgrad_rows_kernel(const T* __restrict__ g, const T* __restrict__ in, int N, int H, int W, float* __restrict__ dw) {
+    constexpr int K = 9 * CIN;
+    constexpr int NG = 64 / CPT;            // channel groups
+    constexpr int LANES = 256 / NG;         // column groups per block
+    __shared__ float s_acc[64 * K];
+    for (int i = threadIdx.x; i < 64 * K; i += 256) s_acc[i] = 0.f;
+    __syncthreads();
+    const int cg = threadIdx.x % NG, ln = threadIdx.x / NG;
+    const int WG = W >> 2, wgb = (WG + LANES - 1) / LANES, chunks = (H + ROWS - 1) / ROWS;
+    int b = blockIdx.x;
+    const int wg = (b % wgb) * LANES + ln; b /= wgb;
+    const int h0 = (b % chunks) * ROWS;
+    const int n = b / chunks;
+    const int h1 = min(H, h0 + ROWS);
+    const int w0 = wg * 4;
+    const long long nb = static_cast<long long>(n) * H * W;
+    float acc[CPT][K];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i)
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[i][k] = 0.f;
+    if (wg < WG) {
+        float x[3][6][CIN];
+        load_row6<T, CIN>(in, nb, h0 - 1, w0, H, W, x[0]);
+        load_row6<T, CIN>(in, nb, h0, w0, H, W, x[1]);
+        for (int h = h0; h < h1; ++h) {
+            load_row6<T, CIN>(in, nb, h + 1, w0, H, W, x[2]);
+            const long long p0 = nb + static_cast<long long>(h) * W + w0;
+            float gv[4][CPT];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (CPT == 8 && sizeof(T) == 2) {
+                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(g + (p0 + j) * 64 + cg * 8));
+                    const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        gv[j][(2 * i) % CPT] = __uint_as_float(wv[i] << 16);
+                        gv[j][(2 * i + 1) % CPT] = __uint_as_float(wv[i] & 0xffff0000u);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < CPT; ++i) gv[j][i] = to_f<T>(g[(p0 + j) * 64 + cg * CPT + i]);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+#pragma unroll
+                for (int c = 0; c < CIN; ++c)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int i = 0; i < CPT; ++i)
+                            acc[i][t * CIN + c] = fmaf(gv[j][i], x[t / 3][j + t % 3][c], acc[i][t * CIN + c]);
+#pragma unroll
+            for (int cidx = 0; cidx < 6; ++cidx)
+#pragma unroll
+                for (int c = 0; c < CIN; ++c) { x[0][cidx][c] = x[1][cidx][c]; x[1][cidx][c] = x[2][cidx][c]; }
+        }
+    }
+    // lanes of the same channel group inside a warp sit NG threads apart; then one shared-memory pass per block
+#pragma unroll
+    for (int i = 0; i < CPT; ++i)
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float v = acc[i][k];
+            for (int off = NG; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if ((threadIdx.x & 31) < NG) atomicAdd(&s_acc[(cg * CPT + i) * K + k], v);
+        }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * K; i += 256) {
+        const int co = i / K, k = i % K, tap = k / CIN, ci = k % CIN;
+        atomicAdd(dw + (static_cast<long long>(co) * CIN + ci) * 9 + tap, s_acc[i]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -239,28 +239,30 @@ tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 // EPI_CONVT: column = (tap, co); scatter to the 2x upsampled grid, add bias.  A tile may span several
                 // taps (BN up to 4 * co_per_tap); every 32-column chunk lies inside one tap (co_per_tap % 32 == 0).
 #pragma unroll 1
-                for (int ch = 0; ch < BN / 32; ++ch) {
-                    const int colg = co0 + ch * 32;
-                    const int tap = colg / p.co_per_tap, cbase = colg % p.co_per_tap;
-                    const int dy = tap >> 1, dx = tap & 1;
-                    __nv_bfloat16* dst16 = p.out +
-                                           ((static_cast<long long>(n) * (2 * p.H) + (2 * h + dy)) * (2 * p.W) + (2 * w + dx)) * p.ldo +
-                                           p.out_coff + cbase;
-                    uint32_t r[32];
-                    tmem_ld_32x32(t_addr + ch * 32, r);
+                for (int ch = 0; ch < BN / 32; ch += 2) {        // two 32-column chunks in flight per iteration
+                    uint32_t r[2][32];
+                    tmem_ld_32x32(t_addr + ch * 32, r[0]);
+                    tmem_ld_32x32(t_addr + ch * 32 + 32, r[1]);
                     tmem_ld_wait();
-                    if (valid) {
-                        uint4* dst = reinterpret_cast<uint4*>(dst16);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint32_t pk[4];
+                    for (int u = 0; u < 2; ++u) {
+                        const int colg = co0 + (ch + u) * 32;
+                        const int tap = colg / p.co_per_tap, cbase = colg % p.co_per_tap;
+                        const int dy = tap >> 1, dx = tap & 1;
+                        __nv_bfloat16* dst16 = p.out +
+                                               ((static_cast<long long>(n) * (2 * p.H) + (2 * h + dy)) * (2 * p.W) + (2 * w + dx)) * p.ldo +
+                                               p.out_coff + cbase;
+                        const float4* bias4 = reinterpret_cast<const float4*>(p.bias + cbase);
+                        if (valid) {
+                            uint4* dst = reinterpret_cast<uint4*>(dst16);
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int c = cbase + j * 8 + i * 2;
-                                pk[i] = pack_bf16x2(__uint_as_float(r[j * 8 + i * 2]) + __ldg(p.bias + c),
-                                                    __uint_as_float(r[j * 8 + i * 2 + 1]) + __ldg(p.bias + c + 1));
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 b0 = __ldg(bias4 + 2 * j), b1 = __ldg(bias4 + 2 * j + 1);
+                                dst[j] = make_uint4(pack_bf16x2(__uint_as_float(r[u][j * 8 + 0]) + b0.x, __uint_as_float(r[u][j * 8 + 1]) + b0.y),
+                                                    pack_bf16x2(__uint_as_float(r[u][j * 8 + 2]) + b0.z, __uint_as_float(r[u][j * 8 + 3]) + b0.w),
+                                                    pack_bf16x2(__uint_as_float(r[u][j * 8 + 4]) + b1.x, __uint_as_float(r[u][j * 8 + 5]) + b1.y),
+                                                    pack_bf16x2(__uint_as_float(r[u][j * 8 + 6]) + b1.z, __uint_as_float(r[u][j * 8 + 7]) + b1.w));
                             }
-                            dst[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         }
                     }
                 }

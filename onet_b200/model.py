@@ -500,7 +500,10 @@ class _OnetFn(torch.autograd.Function):
     0-dim tensor whose incoming gradient carries d(loss) of the fused JSD loss (see Onet.compute_loss)."""
 
     @staticmethod
-    def forward(ctx, onet, X, *params):
+    def forward(ctx, onet, X, leaf):
+        # `leaf` is a throw-away 0-dim tensor that requires grad: it makes the outputs differentiable without putting
+        # the parameters' AccumulateGrad nodes (which remember the stream they were created on, and would tie a CUDA-graph
+        # capture to uncaptured streams) into the autograd graph.  Parameter gradients are accumulated by the kernels.
         eng, rec = onet._run_forward(X, save=True)
         ctx.onet, ctx.eng, ctx.rec = onet, eng, rec
         ctx.set_materialize_grads(False)
@@ -522,7 +525,7 @@ class _OnetFn(torch.autograd.Function):
             eng.backward(rec, f32(g_anchor), f32(gVt), f32(gVd), f32(gS), gLt, gLd, grad_of,
                          after_block=getattr(onet, "_after_block", None))
         ctx.rec = None
-        return (None, None) + (None,) * (len(ctx.needs_input_grad) - 2)
+        return None, None, None
 
 
 class _FusedJsdFn(torch.autograd.Function):
@@ -614,8 +617,8 @@ class Onet(nn.Module):
     def forward(self, X):
         assert X.dim() == 4
         if torch.is_grad_enabled() and self.training:
-            params = list(self.parameters())
-            Lt, Vt, Ld, Vd, S, anchor = _OnetFn.apply(self, X, *params)
+            leaf = torch.zeros((), dtype=torch.float32, device=X.device, requires_grad=True)
+            Lt, Vt, Ld, Vd, S, anchor = _OnetFn.apply(self, X, leaf)
             self._last = dict(Lt=Lt, Ld=Ld, S=S, anchor=anchor, rec=self._fwd_rec)
             self._fwd_rec = None
             return Lt, Vt, Ld, Vd, S

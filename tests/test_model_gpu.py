@@ -164,3 +164,42 @@ def test_generic_autograd_path_matches_fused():
     loss.backward()
     for k, p in net2.named_parameters():
         assert _rel(p.grad, fused[k]) < 2e-2, k     # two fp32 runs differ by atomics order; ill-conditioned gradient
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_graph_replayed_step_matches_eager_step(mode):
+    """OnetTrainer(graph=True) — one captured CUDA graph replayed per step, Adam step count and lr in device memory —
+    against the eager trainer: same losses, same parameter trajectory, same BatchNorm buffers after 4 steps (the
+    warm-up step that precedes the capture must leave no trace), and an lr change takes effect inside the captured
+    graph.  lr is small so that the run-to-run noise of the fp32 atomics does not get amplified by Adam's
+    sign-like first steps."""
+    import onet_b200
+    from onet_b200.data import rayleigh_target_frames
+    from onet_b200.trainer import OnetTrainer
+    xs = [rayleigh_target_frames(2, 1, 32, 32, seed=40 + i).cuda() for i in range(4)]
+    out = {}
+    for graph in (False, True):
+        torch.manual_seed(21)
+        net = onet_b200.Onet(1, True, True, mode=mode).cuda()
+        tr = OnetTrainer(net, lr=1e-5, graph=graph)
+        losses, traj = [], [tr.flat.clone()]
+        for i, x in enumerate(xs):
+            if i == 2:
+                tr.set_lr(3e-6)
+            losses.append(float(tr.step(x if i % 2 else x.cpu().pin_memory())))   # host and device inputs both accepted
+            traj.append(tr.flat.clone())
+        torch.cuda.synchronize()
+        out[graph] = (losses, traj, [b.clone().float() for b in net.buffers()], tr.step_count)
+    (l0, t0, b0, s0), (l1, t1, b1, s1) = out[False], out[True]
+    assert s0 == s1 == 4
+    assert torch.equal(t0[0], t1[0])
+    ltol = 2e-5 if mode == "fp32" else 5e-3
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= ltol * abs(a), (l0, l1)
+    for traj in (t0, t1):      # Adam's update is ~lr per element: the third step must shrink with the new lr
+        d2, d3 = float((traj[2] - traj[1]).norm()), float((traj[3] - traj[2]).norm())
+        assert 0.2 < d3 / d2 < 0.45, (d2, d3)
+    # same trajectory: total displacement agrees (elements whose gradient is ~0 may flip sign under atomic-order noise)
+    assert _rel(t1[4] - t1[0], t0[4] - t0[0]) < (2e-2 if mode == "fp32" else 0.3)
+    for a, b in zip(b0, b1):
+        assert torch.allclose(a, b, rtol=1e-3 if mode == "fp32" else 5e-2, atol=1e-3)
