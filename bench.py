@@ -71,7 +71,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, pw = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [t.strip() for t in ln.split(",")]
@@ -80,13 +80,16 @@ class ClockSampler:
             try:
                 sm.append(float(f[0]))
                 mx = float(f[1])
+                pw.append(float(f[2]))
             except ValueError:
                 continue
             for nm, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         sm.sort()
-        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        pw.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm),
+                    power_w_median=pw[len(pw) // 2] if pw else None, power_w_max=pw[-1] if pw else None)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -178,6 +178,37 @@ static int launch_halo_px(const CUtensorMap& tA, const CUtensorMap& tB, const Px
     return check_launch("conv3x3_halo_px_kernel");
 }
 
+// CTA-pair (cta_group::2) variant: grid = 2 x min(pair tiles, co-resident clusters)
+template <int BN>
+static int launch_halo2_px(const CUtensorMap& tA, const CUtensorMap& tB, const PxParams& p, cudaStream_t st) {
+    using Cfg = Halo2Cfg<BN>;
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_halo2_px_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (e != cudaSuccess) return fail("cudaFuncSetAttribute(halo2_px<%d>): %s", BN, cudaGetErrorString(e));
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(sm_count() & ~1);
+        cfg.blockDim = dim3(192);
+        cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, conv3x3_halo2_px_kernel<BN>, &cfg) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = sm_count() / 2;
+        }
+        max_clusters = std::min(n, sm_count() / 2);
+    }
+    const int units = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+    const int grid = 2 * std::min(units, max_clusters);
+    conv3x3_halo2_px_kernel<BN><<<grid, 192, Cfg::kSmemBytes, st>>>(tA, tB, p);
+    return check_launch("conv3x3_halo2_px_kernel");
+}
+
 // Split-K factor for the weight-gradient kernels: minimise (waves x K-steps per unit + fixed per-unit epilogue cost).
 static void pick_ksplit(int base_units, int num_px_tiles, int* ksplit, int* per_split) {
     const int sms = sm_count();
@@ -220,6 +251,15 @@ static int conv3x3_tc(const bf16* in, long long ldi, int ci_off, int N, int H, i
         CUtensorMap tA, tB;
         const uint32_t hbox[5] = {64, 8, 1, 18, 1};
         if (make_act_map(&tA, in + ci_off, Cin, N, H, W, ldi, hbox)) return 1;
+        const char* min_kc_env = getenv("ONET_2CTA_MIN_KC");
+        const int min_kc = min_kc_env ? atoi(min_kc_env) : 2;
+        if (p.num_m_tiles >= 2 && p.k_chunks >= min_kc && !getenv("ONET_NO_2CTA")) {
+            // CTA pairs: two pixel tiles per MMA, each CTA stages half of the weight tile
+            if (make_map2(&tB, wp, 9ULL * Cin, Cout, 64, BN / 2)) return 1;
+            if (BN == 256) return launch_halo2_px<256>(tA, tB, p, st);
+            if (BN == 128) return launch_halo2_px<128>(tA, tB, p, st);
+            return launch_halo2_px<64>(tA, tB, p, st);
+        }
         if (make_map2(&tB, wp, 9ULL * Cin, Cout, 64, BN)) return 1;
         if (BN == 256) return launch_halo_px<256>(tA, tB, p, st);
         if (BN == 128) return launch_halo_px<128>(tA, tB, p, st);

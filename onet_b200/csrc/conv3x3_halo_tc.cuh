@@ -30,12 +30,12 @@ struct HaloCfg {
 };
 
 // Epilogue shared with tapgemm_px_kernel's EPI_STORE path: raw bf16 output + BatchNorm partial sums.
+// `arrive_bar`: the accumulator-drained barrier; `remote`: it is a shared::cluster address in the peer (leader) CTA.
 template <int BN>
-__device__ __forceinline__ void px_store_epilogue(const PxParams& p, int tile, int acc, uint32_t tmem_base, int q, int ew,
-                                                  int lane, float* s_part, uint32_t bar_tempty) {
+__device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile, int n_tile, int acc, uint32_t tmem_base, int q,
+                                                  int ew, int lane, float* s_part, uint32_t arrive_bar, bool remote) {
     const int row = q * 32 + lane;
     const int w_l = row & (p.TW - 1), h_l = (row >> p.log_tw) & (p.TH - 1), n_l = row >> (p.log_tw + p.log_th);
-    const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
     const int wt = m_tile % p.tiles_w, ht = (m_tile / p.tiles_w) % p.tiles_h, nt = m_tile / (p.tiles_w * p.tiles_h);
     const int w = wt * p.TW + w_l, h = ht * p.TH + h_l, n = nt * p.TN + n_l, co0 = n_tile * BN;
     const bool valid = (row < p.valid_rows) && (w < p.W) && (h < p.H) && (n < p.N);
@@ -83,10 +83,13 @@ __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int tile, i
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+    if (lane == 0) {
+        if (remote) mbar_arrive_cluster(arrive_bar);
+        else mbar_arrive(arrive_bar);
+    }
     if (do_stats) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int grp = (nt * p.TN) / p.group_images;
+        const int grp = min((nt * p.TN) / p.group_images, 1);     // at most two statistics groups (twin branches)
         for (int c = ew * 32 + lane; c < BN; c += 128) {
             float s = 0.f, sq = 0.f;
 #pragma unroll
@@ -212,7 +215,8 @@ conv3x3_halo_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
-            px_store_epilogue<BN>(p, tile, acc, tmem_base, q, ew, lane, s_part, bar_tempty);
+            px_store_epilogue<BN>(p, tile % p.num_m_tiles, tile / p.num_m_tiles, acc, tmem_base, q, ew, lane, s_part,
+                                  bar_tempty + 8 * acc, false);
         }
     }
     tc_fence_before();
@@ -220,6 +224,163 @@ conv3x3_halo_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+// =====================================================================================================
+// CTA-pair variant (cta_group::2): a cluster of two CTAs computes TWO adjacent pixel tiles (M = 256) x BN couts per
+// tcgen05.mma.  Each CTA stages its own activation boxes and only HALF of the weight tile (BN/2 rows), which cuts
+// the shared-memory-port traffic per CTA (TMA fills + operand reads) by 21-37 % - the resource that bounds the
+// single-CTA kernel.  The leader CTA (cluster rank 0) issues every MMA; TMA completions of both
+// CTAs are signalled on the leader's "full" barriers, MMA completions are multicast to both CTAs' "empty" /
+// "accumulator full" barriers, and both CTAs' epilogue warps arrive on the leader's "accumulator empty" barrier.
+// =====================================================================================================
+template <int BN>
+struct Halo2Cfg {
+    static constexpr int kABytes = 144 * 128;
+    static constexpr int kBHalfBytes = (BN / 2) * 128;
+    static constexpr int kTapsPerB = (BN == 256) ? 1 : 3;
+    static constexpr int kBStageBytes = kTapsPerB * kBHalfBytes;
+    static constexpr int kSA = (BN == 256) ? 4 : (BN == 128 ? 5 : 6);
+    static constexpr int kSB = (BN == 256) ? 6 : (BN == 128 ? 4 : 6);
+    static constexpr int kTmemCols = 2 * BN;
+    static constexpr int kAuxBytes = 1024 + 4 * 2 * BN * 4;
+    static constexpr int kSmemBytes = kSA * kABytes + kSB * kBStageBytes + kAuxBytes + 1024;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+conv3x3_halo2_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PxParams p) {
+    using Cfg = Halo2Cfg<BN>;
+    constexpr int SA = Cfg::kSA, SB = Cfg::kSB, TPB = Cfg::kTapsPerB;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (base - raw);
+    const uint32_t ringA = base, ringB = base + SA * Cfg::kABytes;
+    const uint32_t aux = ringB + SB * Cfg::kBStageBytes;
+    uint8_t* gen_aux = gen_base + SA * Cfg::kABytes + SB * Cfg::kBStageBytes;
+    const uint32_t bar_fullA = aux, bar_emptyA = aux + 8 * SA, bar_fullB = aux + 16 * SA, bar_emptyB = bar_fullB + 8 * SB,
+                   bar_tfull = bar_emptyB + 8 * SB, bar_tempty = bar_tfull + 16;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gen_aux + 16 * SA + 16 * SB + 32);
+    float* s_part = reinterpret_cast<float*>(gen_aux + 1024);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < SA; ++s) { mbar_init(bar_fullA + 8 * s, 1); mbar_init(bar_emptyA + 8 * s, 1); }
+        for (int s = 0; s < SB; ++s) { mbar_init(bar_fullB + 8 * s, 1); mbar_init(bar_emptyB + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc_2cta<Cfg::kTmemCols>(smem_u32(tmem_ptr_smem));
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // the peer's barriers are initialised and its TMEM is allocated
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int num_pair_m = (p.num_m_tiles + 1) >> 1;
+    const int num_units = num_pair_m * p.num_n_tiles;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            const uint32_t lead_fullA = mapa_shared(bar_fullA, 0), lead_fullB = mapa_shared(bar_fullB, 0);
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            for (int unit = pair; unit < num_units; unit += npairs) {
+                const int m_tile = 2 * (unit % num_pair_m) + static_cast<int>(rank), n_tile = unit / num_pair_m;
+                // an m_tile == num_m_tiles (odd tile count) decodes to image index N: every row is out of bounds -> zeros
+                const int wt = m_tile % p.tiles_w, ht = (m_tile / p.tiles_w) % p.tiles_h, nt = m_tile / (p.tiles_w * p.tiles_h);
+                const int w0 = wt * 8, h0 = ht * 16, co0 = n_tile * BN + static_cast<int>(rank) * (BN / 2);
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    for (int kw = 0; kw < 3; ++kw) {
+                        mbar_wait(bar_emptyA + 8 * sa, pa ^ 1);
+                        if (rank == 0) mbar_expect_tx(bar_fullA + 8 * sa, 2 * Cfg::kABytes);
+                        tma_load_5d_2cta(ringA + sa * Cfg::kABytes, &tmA, lead_fullA + 8 * sa, kc * 64, w0 + kw - 1, 0, h0 - 1, nt);
+                        if (++sa == SA) { sa = 0; pa ^= 1; }
+                        for (int kh = 0; kh < 3; kh += TPB) {
+                            mbar_wait(bar_emptyB + 8 * sb, pb ^ 1);
+                            if (rank == 0) mbar_expect_tx(bar_fullB + 8 * sb, 2 * Cfg::kBStageBytes);
+#pragma unroll
+                            for (int j = 0; j < TPB; ++j)
+                                tma_load_2d_2cta(ringB + sb * Cfg::kBStageBytes + j * Cfg::kBHalfBytes, &tmB, lead_fullB + 8 * sb,
+                                                 ((kh + j) * 3 + kw) * p.cin + kc * 64, co0);
+                            if (++sb == SB) { sb = 0; pb ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0 && elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            int it = 0;
+            for (int unit = pair; unit < num_units; unit += npairs, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                uint32_t accumulate = 0;
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    for (int kw = 0; kw < 3; ++kw) {
+                        mbar_wait(bar_fullA + 8 * sa, pa);
+                        const uint32_t sA = ringA + sa * Cfg::kABytes;
+                        for (int kh = 0; kh < 3; kh += TPB) {
+                            mbar_wait(bar_fullB + 8 * sb, pb);
+                            tc_fence_after();
+#pragma unroll
+                            for (int j = 0; j < TPB; ++j) {
+                                const uint64_t da = umma_smem_desc(sA + (kh + j) * 1024, 16, 1024);
+                                const uint64_t db = umma_smem_desc(ringB + sb * Cfg::kBStageBytes + j * Cfg::kBHalfBytes, 16, 1024);
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk) {
+                                    umma_bf16_2cta(d_tmem, da + 2 * kk, db + 2 * kk, idesc, accumulate);
+                                    accumulate = 1;
+                                }
+                            }
+                            umma_commit_2cta(bar_emptyB + 8 * sb);
+                            if (++sb == SB) { sb = 0; pb ^= 1; }
+                        }
+                        umma_commit_2cta(bar_emptyA + 8 * sa);
+                        if (++sa == SA) { sa = 0; pa ^= 1; }
+                    }
+                }
+                umma_commit_2cta(bar_tfull + 8 * acc);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3, ew = warp - 2;
+        const uint32_t lead_tempty = mapa_shared(bar_tempty, 0);
+        int it = 0;
+        for (int unit = pair; unit < num_units; unit += npairs, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int m_tile = 2 * (unit % num_pair_m) + static_cast<int>(rank), n_tile = unit / num_pair_m;
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+            if (m_tile < p.num_m_tiles) {
+                px_store_epilogue<BN>(p, m_tile, n_tile, acc, tmem_base, q, ew, lane, s_part, lead_tempty + 8 * acc, true);
+            } else {           // padding tile of an odd tile count: nothing to store
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(lead_tempty + 8 * acc);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // no CTA frees tensor memory or exits while its peer may still signal / multicast to it
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2cta<Cfg::kTmemCols>(tmem_base);
     }
 }
 

@@ -222,7 +222,7 @@ tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
                 if (do_stats) {
                     asm volatile("bar.sync 1, 128;" ::: "memory");
-                    const int grp = (nt * p.TN) / p.group_images;
+                    const int grp = min((nt * p.TN) / p.group_images, 1);     // at most two statistics groups
                     for (int c = ew * 32 + lane; c < BN; c += 128) {
                         float s = 0.f, sq = 0.f;
 #pragma unroll
