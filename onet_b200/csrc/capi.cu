@@ -363,9 +363,71 @@ static int launch_wh(const CUtensorMap& tG, const CUtensorMap& tI, const WhParam
     return check_launch("wgrad3x3_halo_kernel");
 }
 
+// CTA-pair weight gradient (Mc, Nc multiples of 128)
+static int wgrad3x3_halo2_tc(const bf16* g, long long ldg, int goff, int Mc, const bf16* in, long long ldi, int ioff, int Nc,
+                             int N, int H, int W, float* dw, cudaStream_t st) {
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad3x3_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Wh2Cfg::kSmemBytes);
+        if (e != cudaSuccess) return fail("cudaFuncSetAttribute(wh2): %s", cudaGetErrorString(e));
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(sm_count() & ~1);
+        cfg.blockDim = dim3(192);
+        cfg.dynamicSmemBytes = Wh2Cfg::kSmemBytes;
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, wgrad3x3_halo2_kernel, &cfg) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = sm_count() / 2;
+        }
+        max_clusters = std::min(n, sm_count() / 2);
+    }
+    Wh2Params p;
+    memset(&p, 0, sizeof(p));
+    p.N = N; p.H = H; p.W = W;
+    p.tiles_w = (W + 7) / 8; p.tiles_h = (H + 7) / 8;
+    p.num_px_tiles = p.tiles_w * p.tiles_h * N;
+    p.num_m_units = (Mc / 128) * 3;
+    p.num_m_pairs = (p.num_m_units + 1) / 2;
+    p.num_n_tiles = Nc / 128;
+    // split-K over the co-resident clusters
+    {
+        const int base_units = p.num_m_pairs * p.num_n_tiles;
+        long long best_cost = -1;
+        int best_per = p.num_px_tiles;
+        const int max_ks = std::min(p.num_px_tiles, 8 * max_clusters);
+        for (int ks = 1; ks <= max_ks; ++ks) {
+            const int per = (p.num_px_tiles + ks - 1) / ks;
+            const int ks_eff = (p.num_px_tiles + per - 1) / per;
+            const long long units = static_cast<long long>(base_units) * ks_eff;
+            const long long waves = (units + max_clusters - 1) / max_clusters;
+            const long long cost = waves * (per + 8);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_per = per; }
+        }
+        p.px_tiles_per_split = best_per;
+        p.ksplit = (p.num_px_tiles + best_per - 1) / best_per;
+    }
+    p.out = dw; p.m_total = Mc; p.n_total = Nc;
+    CUtensorMap tG, tI;
+    const uint32_t gbox[5] = {64, 8, 1, 10, 1}, ibox[5] = {64, 8, 1, 8, 1};
+    if (make_act_map(&tG, g + goff, Mc, N, H, W, ldg, gbox)) return 1;
+    if (make_act_map(&tI, in + ioff, Nc, N, H, W, ldi, ibox)) return 1;
+    const int units = p.num_m_pairs * p.num_n_tiles * p.ksplit;
+    wgrad3x3_halo2_kernel<<<2 * std::min(units, max_clusters), 192, Wh2Cfg::kSmemBytes, st>>>(tG, tI, p);
+    return check_launch("wgrad3x3_halo2_kernel");
+}
+
 // 3x3 weight gradient, H-halo variant: dW[co][ci][kh][kw] += sum_px G[px - (kh-1,kw-1)][co] * In[px][ci]
 static int wgrad3x3_halo_tc(const bf16* g, long long ldg, int goff, int Mc, const bf16* in, long long ldi, int ioff, int Nc,
                             int N, int H, int W, float* dw, cudaStream_t st) {
+    // CTA pairs need an even number of (128-channel block, filter column) units to be worth it: Mc >= 256
+    if (Mc % 256 == 0 && Nc % 128 == 0 && !getenv("ONET_NO_2CTA") && !getenv("ONET_NO_2CTA_WGRAD"))
+        return wgrad3x3_halo2_tc(g, ldg, goff, Mc, in, ldi, ioff, Nc, N, H, W, dw, st);
     WhParams p;
     memset(&p, 0, sizeof(p));
     p.N = N; p.H = H; p.W = W;

@@ -553,4 +553,167 @@ wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_const
     }
 }
 
+// =====================================================================================================
+// CTA-pair variant of the weight gradient (cta_group::2, M = 256): the two CTAs of a cluster own two different
+// "M units" - (64-channel-pair block mt, filter column kw) combinations - over the SAME pixel slabs and the same
+// 128 input channels.  Each CTA stages its own shifted G boxes and only HALF (64 channels) of the In tile.
+// Requires Mc % 128 == 0 and BNW == 128.  M unit index = mt * 3 + kw; an odd count is padded with a dummy unit whose
+// loads are out of bounds (zeros) and whose epilogue is skipped.
+// =====================================================================================================
+struct Wh2Params {
+    int N, H, W;
+    int tiles_w, tiles_h, num_px_tiles;
+    int ksplit, px_tiles_per_split;
+    int num_m_units, num_m_pairs, num_n_tiles;     // M units = (Mc / 128) * 3
+    float* out;
+    int m_total, n_total;
+};
+
+struct Wh2Cfg {
+    static constexpr int kNBytes = 8192;                        // 64 px x 64 channels (this CTA's half of the N operand)
+    static constexpr int kMBytes = 2 * kWhBoxBytes;             // two 64-channel G boxes with h-halo
+    static constexpr int kStageBytes = kNBytes + kMBytes;       // 28 KB
+    static constexpr int kStages = 6;
+    static constexpr int kTmemCols = 512;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 1024;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+wgrad3x3_halo2_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmI, const Wh2Params p) {
+    using Cfg = Wh2Cfg;
+    constexpr int STAGES = Cfg::kStages;
+    constexpr int BNW = 128;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (base - raw);
+    const uint32_t aux = base + STAGES * Cfg::kStageBytes;
+    uint8_t* gen_aux = gen_base + STAGES * Cfg::kStageBytes;
+    const uint32_t bar_full = aux, bar_empty = aux + 8 * STAGES, bar_tfull = aux + 16 * STAGES, bar_tempty = bar_tfull + 8;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gen_aux + 16 * STAGES + 32);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmG);
+        tma_prefetch_desc(&tmI);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tempty, 8);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc_2cta<Cfg::kTmemCols>(smem_u32(tmem_ptr_smem));
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    // unit = (m_pair * num_n_tiles + nt) * ksplit + ks
+    const int num_units = p.num_m_pairs * p.num_n_tiles * p.ksplit;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            const uint32_t lead_full = mapa_shared(bar_full, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int unit = pair; unit < num_units; unit += npairs) {
+                const int ks = unit % p.ksplit;
+                const int nt = (unit / p.ksplit) % p.num_n_tiles;
+                const int mu = 2 * (unit / (p.ksplit * p.num_n_tiles)) + static_cast<int>(rank);
+                const bool live = mu < p.num_m_units;
+                const int mt = mu / 3, kw = mu - 3 * mt;
+                const int m0 = mt * 128, n0 = nt * BNW + static_cast<int>(rank) * 64;
+                const int px_begin = ks * p.px_tiles_per_split;
+                const int px_end = min(px_begin + p.px_tiles_per_split, p.num_px_tiles);
+                for (int pt = px_begin; pt < px_end; ++pt) {
+                    const int wt = pt % p.tiles_w, ht = (pt / p.tiles_w) % p.tiles_h, n = pt / (p.tiles_w * p.tiles_h);
+                    const int w0 = wt * 8, h0 = ht * 8;
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t sN = base + stage * Cfg::kStageBytes, sM = sN + Cfg::kNBytes;
+                    if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * Cfg::kStageBytes);
+                    const uint32_t fb = lead_full + 8 * stage;
+                    tma_load_5d_2cta(sN, &tmI, fb, n0, w0, 0, h0, n);
+                    // G shifted by -(kw-1) in w, one-row halo in h; a padding unit reads image index N (all zeros)
+                    const int ng = live ? n : p.N;
+                    tma_load_5d_2cta(sM, &tmG, fb, m0, w0 - (kw - 1), 0, h0 - 1, ng);
+                    tma_load_5d_2cta(sM + kWhBoxBytes, &tmG, fb, m0 + 64, w0 - (kw - 1), 0, h0 - 1, ng);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0 && elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(256, BNW, 1, 1);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int unit = pair; unit < num_units; unit += npairs, ++it) {
+                const int ks = unit % p.ksplit;
+                const int px_begin = ks * p.px_tiles_per_split;
+                const int px_end = min(px_begin + p.px_tiles_per_split, p.num_px_tiles);
+                mbar_wait(bar_tempty, (it & 1) ^ 1);
+                tc_fence_after();
+                for (int pt = px_begin; pt < px_end; ++pt) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sN = base + stage * Cfg::kStageBytes, sM = sN + Cfg::kNBytes;
+                    const uint64_t db = umma_smem_desc(sN, 8192, 1024);
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh) {
+                        const uint64_t da = umma_smem_desc(sM + (2 - kh) * 1024, kWhBoxBytes, 1024);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_bf16_2cta(tmem_base + kh * BNW, da + 128 * kk, db + 128 * kk, idesc, (pt > px_begin) || kk);
+                    }
+                    umma_commit_2cta(bar_empty + 8 * stage);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_2cta(bar_tfull);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lead_tempty = mapa_shared(bar_tempty, 0);
+        int it = 0;
+        for (int unit = pair; unit < num_units; unit += npairs, ++it) {
+            const int nt = (unit / p.ksplit) % p.num_n_tiles;
+            const int mu = 2 * (unit / (p.ksplit * p.num_n_tiles)) + static_cast<int>(rank);
+            const int mt = mu / 3, kw = mu - 3 * mt;
+            const int m = mt * 128 + row, n0 = nt * BNW;
+            mbar_wait(bar_tfull, it & 1);
+            tc_fence_after();
+            if (mu < p.num_m_units) {
+#pragma unroll 1
+                for (int kh = 0; kh < 3; ++kh) {
+                    const int tap = kh * 3 + kw;
+                    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kh * BNW;
+#pragma unroll 1
+                    for (int ch = 0; ch < BNW / 32; ++ch) {
+                        uint32_t r[32];
+                        tmem_ld_32x32(t_addr + ch * 32, r);
+                        tmem_ld_wait();
+                        float* dst = p.out + (static_cast<long long>(m) * p.n_total + n0 + ch * 32) * 9 + tap;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) atomicAdd(dst + j * 9, __uint_as_float(r[j]));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(lead_tempty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2cta<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
 }  // namespace onet

@@ -1,7 +1,12 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-ONET_BENCH_DETAIL=gpurun_out/detail.tsv python bench.py --steps 10 --warmup 3 > gpurun_out/bench_j.json 2> gpurun_out/bench_j.err
-echo "bench graph rc=$?"; tail -3 gpurun_out/bench_j.err
-python -c "
-import json; d=json.load(open('gpurun_out/bench_j.json')); print(d['value'], d['ms_per_step'], d['e2e'], d['gpu_launches'], d['clocks']); print(sum(v['ms_per_step'] for v in d['kernels'].values())); [print(k, v) for k,v in d['kernels'].items()]"
+python -m pytest tests -m gpu -x -q --durations=8 2>&1 | tail -16
+python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ab_a.json 2>/dev/null
+ONET_NO_2CTA_WGRAD=1 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ab_b.json 2>/dev/null
+python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ab_c.json 2>/dev/null
+python - <<'PY'
+import json
+for n in ("ab_a","ab_b","ab_c"):
+    d=json.load(open(f"gpurun_out/{n}.json")); print(n, round(d["value"],1), round(d["ms_per_step"],2), d["e2e"]["value"], d["clocks"], round(sum(v["ms_per_step"] for v in d["kernels"].values()),2))
+d=json.load(open("gpurun_out/ab_c.json")); [print(k, v) for k,v in d['kernels'].items()]
+PY
