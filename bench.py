@@ -134,7 +134,7 @@ def run_reference(args):
                                      f"CPU sample batch {batch}", per_gpu_batch=batch, image=[CIN, H, W]),
                 cpu_baseline=dict(value=ips, unit=UNIT, cores=threads, kind="port", sample=sample),
                 e2e=dict(value=ips, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -192,7 +192,26 @@ def profile_steps(trainer, x, nsteps, record=True):
     return fam
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Keep fd 1 for the ONE JSON line: libraries that print to stdout (NCCL prints its version there) go to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -314,9 +333,13 @@ def main():
             line["cpu_baseline"] = dict(value=ips, unit=UNIT, cores=threads, kind="port",
                                         sample=f"batch 4 of the same 1x{H}x{W} frames, 1 warm-up + 2 timed steps "
                                                f"({sec:.1f} s/step), oracle port on ATen CPU kernels")
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        # a captured graph holds NCCL work; tear down in order and do not rely on interpreter-exit destructors
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

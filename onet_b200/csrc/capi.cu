@@ -140,7 +140,7 @@ static int launch_px(const CUtensorMap& tA, const CUtensorMap& tB, const PxParam
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     const int grid = std::min(tiles, sm_count());
-    tapgemm_px_kernel<BN><<<grid, 192, Cfg::kSmemBytes, st>>>(tA, tB, p);
+    tapgemm_px_kernel<BN><<<grid, kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, p);
     return check_launch("tapgemm_px_kernel");
 }
 
@@ -174,7 +174,7 @@ static int launch_halo_px(const CUtensorMap& tA, const CUtensorMap& tB, const Px
         attr_set = true;
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
-    conv3x3_halo_px_kernel<BN><<<std::min(tiles, sm_count()), 192, Cfg::kSmemBytes, st>>>(tA, tB, p);
+    conv3x3_halo_px_kernel<BN><<<std::min(tiles, sm_count()), kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, p);
     return check_launch("conv3x3_halo_px_kernel");
 }
 
@@ -189,7 +189,7 @@ static int launch_halo2_px(const CUtensorMap& tA, const CUtensorMap& tB, const P
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(sm_count() & ~1);
-        cfg.blockDim = dim3(192);
+        cfg.blockDim = dim3(kPxThreads);
         cfg.dynamicSmemBytes = Cfg::kSmemBytes;
         cudaLaunchAttribute at;
         at.id = cudaLaunchAttributeClusterDimension;
@@ -205,7 +205,7 @@ static int launch_halo2_px(const CUtensorMap& tA, const CUtensorMap& tB, const P
     }
     const int units = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
     const int grid = 2 * std::min(units, max_clusters);
-    conv3x3_halo2_px_kernel<BN><<<grid, 192, Cfg::kSmemBytes, st>>>(tA, tB, p);
+    conv3x3_halo2_px_kernel<BN><<<grid, kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, p);
     return check_launch("conv3x3_halo2_px_kernel");
 }
 

@@ -29,83 +29,8 @@ struct HaloCfg {
     static constexpr int kSmemBytes = kSA * kABytes + kSB * kBStageBytes + kAuxBytes + 1024;
 };
 
-// Epilogue shared with tapgemm_px_kernel's EPI_STORE path: raw bf16 output + BatchNorm partial sums.
-// `arrive_bar`: the accumulator-drained barrier; `remote`: it is a shared::cluster address in the peer (leader) CTA.
 template <int BN>
-__device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile, int n_tile, int acc, uint32_t tmem_base, int q,
-                                                  int ew, int lane, float* s_part, uint32_t arrive_bar, bool remote) {
-    const int row = q * 32 + lane;
-    const int w_l = row & (p.TW - 1), h_l = (row >> p.log_tw) & (p.TH - 1), n_l = row >> (p.log_tw + p.log_th);
-    const int wt = m_tile % p.tiles_w, ht = (m_tile / p.tiles_w) % p.tiles_h, nt = m_tile / (p.tiles_w * p.tiles_h);
-    const int w = wt * p.TW + w_l, h = ht * p.TH + h_l, n = nt * p.TN + n_l, co0 = n_tile * BN;
-    const bool valid = (row < p.valid_rows) && (w < p.W) && (h < p.H) && (n < p.N);
-    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-    __nv_bfloat16* orow = p.out + ((static_cast<long long>(n) * p.H + h) * p.W + w) * p.ldo + p.out_coff + co0;
-    const bool do_stats = p.stat_sum != nullptr;
-#pragma unroll 1
-    for (int ch = 0; ch < BN / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_addr + ch * 32, r);
-        tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-        if (valid) {
-            uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-        }
-        if (do_stats) {
-            float v[32], s2[32];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
-                const float lo = valid ? __low2float(b) : 0.f, hi = valid ? __high2float(b) : 0.f;
-                v[2 * j] = lo; v[2 * j + 1] = hi;
-                s2[2 * j] = lo * lo; s2[2 * j + 1] = hi * hi;
-            }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-                const bool up = (lane & off) != 0;
-#pragma unroll
-                for (int i = 0; i < off; ++i) {
-                    const float send = up ? v[i] : v[i + off];
-                    const float keep = up ? v[i + off] : v[i];
-                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                    const float send2 = up ? s2[i] : s2[i + off];
-                    const float keep2 = up ? s2[i + off] : s2[i];
-                    s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
-                }
-            }
-            s_part[(ew * 2 + 0) * BN + ch * 32 + lane] = v[0];
-            s_part[(ew * 2 + 1) * BN + ch * 32 + lane] = s2[0];
-        }
-    }
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) {
-        if (remote) mbar_arrive_cluster(arrive_bar);
-        else mbar_arrive(arrive_bar);
-    }
-    if (do_stats) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int grp = min((nt * p.TN) / p.group_images, 1);     // at most two statistics groups (twin branches)
-        for (int c = ew * 32 + lane; c < BN; c += 128) {
-            float s = 0.f, sq = 0.f;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                s += s_part[(e * 2 + 0) * BN + c];
-                sq += s_part[(e * 2 + 1) * BN + c];
-            }
-            atomicAdd(p.stat_sum + static_cast<long long>(grp) * p.cout_total + co0 + c, static_cast<double>(s));
-            atomicAdd(p.stat_sq + static_cast<long long>(grp) * p.cout_total + co0 + c, static_cast<double>(sq));
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-    }
-}
-
-template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kPxThreads, 1)
 conv3x3_halo_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PxParams p) {
     using Cfg = HaloCfg<BN>;
     constexpr int SA = Cfg::kSA, SB = Cfg::kSB;
@@ -128,7 +53,7 @@ conv3x3_halo_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < SA; ++s) { mbar_init(bar_fullA + 8 * s, 1); mbar_init(bar_emptyA + 8 * s, 1); }
         for (int s = 0; s < SB; ++s) { mbar_init(bar_fullB + 8 * s, 1); mbar_init(bar_emptyB + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, kPxEpiWarps); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<Cfg::kTmemCols>(smem_u32(tmem_ptr_smem));
@@ -209,6 +134,8 @@ conv3x3_halo_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         __syncwarp();
     } else {
         const int q = warp & 3, ew = warp - 2;
+        PxStatAcc sacc;
+        sacc.reset(-1);
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -216,8 +143,9 @@ conv3x3_halo_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             px_store_epilogue<BN>(p, tile % p.num_m_tiles, tile / p.num_m_tiles, acc, tmem_base, q, ew, lane, s_part,
-                                  bar_tempty + 8 * acc, false);
+                                  bar_tempty + 8 * acc, false, sacc);
         }
+        px_stat_flush<BN>(p, sacc, ew, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -249,7 +177,7 @@ struct Halo2Cfg {
 };
 
 template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPxThreads, 1)
 conv3x3_halo2_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PxParams p) {
     using Cfg = Halo2Cfg<BN>;
     constexpr int SA = Cfg::kSA, SB = Cfg::kSB, TPB = Cfg::kTapsPerB;
@@ -272,7 +200,7 @@ conv3x3_halo2_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < SA; ++s) { mbar_init(bar_fullA + 8 * s, 1); mbar_init(bar_emptyA + 8 * s, 1); }
         for (int s = 0; s < SB; ++s) { mbar_init(bar_fullB + 8 * s, 1); mbar_init(bar_emptyB + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 2 * kPxEpiWarps); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc_2cta<Cfg::kTmemCols>(smem_u32(tmem_ptr_smem));
@@ -359,6 +287,8 @@ conv3x3_halo2_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     } else {
         const int q = warp & 3, ew = warp - 2;
         const uint32_t lead_tempty = mapa_shared(bar_tempty, 0);
+        PxStatAcc sacc;
+        sacc.reset(-1);
         int it = 0;
         for (int unit = pair; unit < num_units; unit += npairs, ++it) {
             const int acc = it & 1;
@@ -367,13 +297,14 @@ conv3x3_halo2_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             if (m_tile < p.num_m_tiles) {
-                px_store_epilogue<BN>(p, m_tile, n_tile, acc, tmem_base, q, ew, lane, s_part, lead_tempty + 8 * acc, true);
+                px_store_epilogue<BN>(p, m_tile, n_tile, acc, tmem_base, q, ew, lane, s_part, lead_tempty + 8 * acc, true, sacc);
             } else {           // padding tile of an odd tile count: nothing to store
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(lead_tempty + 8 * acc);
             }
         }
+        px_stat_flush<BN>(p, sacc, ew, lane);
     }
     tc_fence_before();
     __syncthreads();

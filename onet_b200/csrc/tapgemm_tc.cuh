@@ -12,8 +12,8 @@
 //   weight-gradient kernel (tapgemm_wg_kernel): dW[m][n][tap] = sum_pixels G[pixel (-) tap][m] * In[pixel][n]
 //       both operands MN-major (pixels are the K dimension), split-K over pixel slabs, fp32 atomics.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
-// warps 2..5 = epilogue (one TMEM lane quarter each).  Persistent CTAs, static round-robin tile schedule,
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer, then the epilogue warps (pixel-major
+// kernels: 8, two per TMEM lane quarter splitting the column chunks; weight-gradient kernels: 4).  Persistent CTAs, static round-robin tile schedule,
 // smem ring of STAGES operand stages, double-buffered TMEM accumulators (pixel-major kernel).
 #pragma once
 #include "tc_common.cuh"
@@ -57,8 +57,117 @@ struct PxCfg {
     static constexpr int kSmemBytes = kStages * kStageBytes + kAuxBytes + 1024;  // + alignment slack
 };
 
+// Per-thread running BatchNorm statistics of the persistent CTA: epilogue thread (ew, lane) owns output column
+// c = ew * 32 + lane of the current n-tile (BN <= 32 * kPxEpiWarps) for both statistics groups.  The sums are flushed
+// with fp64 atomics only when the n-tile changes and at the end of the kernel - not once per tile: with 65536 tiles
+// hitting the same 2 x 64 addresses the per-tile atomics were serialised in L2.
+struct PxStatAcc {
+    double s0, q0, s1, q1;
+    int n_tile;
+    __device__ __forceinline__ void reset(int nt) { s0 = q0 = s1 = q1 = 0.0; n_tile = nt; }
+};
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__device__ __forceinline__ void px_stat_flush(const PxParams& p, PxStatAcc& a, int ew, int lane) {
+    const int c = ew * 32 + lane;
+    if (a.n_tile >= 0 && c < BN && p.stat_sum != nullptr) {
+        const long long col = static_cast<long long>(a.n_tile) * BN + c;
+        if (a.s0 != 0.0 || a.q0 != 0.0) {
+            atomicAdd(p.stat_sum + col, a.s0);
+            atomicAdd(p.stat_sq + col, a.q0);
+        }
+        if (a.s1 != 0.0 || a.q1 != 0.0) {
+            atomicAdd(p.stat_sum + p.cout_total + col, a.s1);
+            atomicAdd(p.stat_sq + p.cout_total + col, a.q1);
+        }
+    }
+    a.reset(-1);
+}
+
+// Store epilogue of the pixel-major kernels: raw bf16 output + BatchNorm partial sums.
+// `arrive_bar`: the accumulator-drained barrier; `remote`: it is a shared::cluster address in the peer (leader) CTA.
+template <int BN>
+__device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile, int n_tile, int acc, uint32_t tmem_base, int q,
+                                                  int ew, int lane, float* s_part, uint32_t arrive_bar, bool remote,
+                                                  PxStatAcc& sacc) {
+    // ew = 0 .. kPxEpiWarps-1; warps ew and ew+4 share TMEM lane quarter q and split the 32-column chunks
+    const int half = ew >> 2;
+    const int row = q * 32 + lane;
+    const int w_l = row & (p.TW - 1), h_l = (row >> p.log_tw) & (p.TH - 1), n_l = row >> (p.log_tw + p.log_th);
+    const int wt = m_tile % p.tiles_w, ht = (m_tile / p.tiles_w) % p.tiles_h, nt = m_tile / (p.tiles_w * p.tiles_h);
+    const int w = wt * p.TW + w_l, h = ht * p.TH + h_l, n = nt * p.TN + n_l, co0 = n_tile * BN;
+    const bool valid = (row < p.valid_rows) && (w < p.W) && (h < p.H) && (n < p.N);
+    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+    __nv_bfloat16* orow = p.out + ((static_cast<long long>(n) * p.H + h) * p.W + w) * p.ldo + p.out_coff + co0;
+    const bool do_stats = p.stat_sum != nullptr;
+#pragma unroll 1
+    for (int ch = half; ch < BN / 32; ch += kPxEpiWarps / 4) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_addr + ch * 32, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+        if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        }
+        if (do_stats) {
+            float v[32], s2[32];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
+                const float lo = valid ? __low2float(b) : 0.f, hi = valid ? __high2float(b) : 0.f;
+                v[2 * j] = lo; v[2 * j + 1] = hi;
+                s2[2 * j] = lo * lo; s2[2 * j + 1] = hi * hi;
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int i = 0; i < off; ++i) {
+                    const float send = up ? v[i] : v[i + off];
+                    const float keep = up ? v[i + off] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    const float send2 = up ? s2[i] : s2[i + off];
+                    const float keep2 = up ? s2[i + off] : s2[i];
+                    s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+                }
+            }
+            s_part[(q * 2 + 0) * BN + ch * 32 + lane] = v[0];
+            s_part[(q * 2 + 1) * BN + ch * 32 + lane] = s2[0];
+        }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+        if (remote) mbar_arrive_cluster(arrive_bar);
+        else mbar_arrive(arrive_bar);
+    }
+    if (do_stats) {
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kPxEpiWarps) : "memory");
+        const int grp = min((nt * p.TN) / p.group_images, 1);     // at most two statistics groups (twin branches)
+        if (sacc.n_tile != n_tile) {
+            px_stat_flush<BN>(p, sacc, ew, lane);
+            sacc.reset(n_tile);
+        }
+        const int c = ew * 32 + lane;
+        if (c < BN) {
+            float s = 0.f, sq = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                s += s_part[(e * 2 + 0) * BN + c];
+                sq += s_part[(e * 2 + 1) * BN + c];
+            }
+            if (grp == 0) { sacc.s0 += static_cast<double>(s); sacc.q0 += static_cast<double>(sq); }
+            else { sacc.s1 += static_cast<double>(s); sacc.q1 += static_cast<double>(sq); }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kPxEpiWarps) : "memory");
+    }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kPxThreads, 1)
 tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PxParams p) {
     using Cfg = PxCfg<BN>;
     constexpr int STAGES = Cfg::kStages;
@@ -85,7 +194,7 @@ tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);
-            mbar_init(bar_tempty + 8 * a, 4);
+            mbar_init(bar_tempty + 8 * a, kPxEpiWarps);
         }
         fence_mbar_init();
     }
@@ -154,9 +263,12 @@ tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else {
         // ------------------------------------------------------------ epilogue (4 warps)
         const int q = warp & 3;            // TMEM lane quarter this warp may access
-        const int ew = warp - 2;           // 0..3
+        const int ew = warp - 2;           // 0..kPxEpiWarps-1; warps ew and ew+4 share quarter q and split the column chunks
+        const int half = ew >> 2;
         const int row = q * 32 + lane;
         const int w_l = row & (p.TW - 1), h_l = (row >> p.log_tw) & (p.TH - 1), n_l = row >> (p.log_tw + p.log_th);
+        PxStatAcc sacc;
+        sacc.reset(-1);
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -171,75 +283,12 @@ tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 
             if (p.epi_mode == EPI_STORE) {
-                __nv_bfloat16* orow =
-                    p.out + ((static_cast<long long>(n) * p.H + h) * p.W + w) * p.ldo + p.out_coff + co0;
-                const bool do_stats = p.stat_sum != nullptr;
-#pragma unroll 1
-                for (int ch = 0; ch < BN / 32; ++ch) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(t_addr + ch * 32, r);
-                    tmem_ld_wait();
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-                    if (valid) {
-                        uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-                    }
-                    if (do_stats) {
-                        // statistics of the STORED (bf16-rounded) values; transposing butterfly so that
-                        // lane j ends with the sum over this warp's 32 rows of column j
-                        float v[32], s2[32];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
-                            const float lo = valid ? __low2float(b) : 0.f, hi = valid ? __high2float(b) : 0.f;
-                            v[2 * j] = lo; v[2 * j + 1] = hi;
-                            s2[2 * j] = lo * lo; s2[2 * j + 1] = hi * hi;
-                        }
-#pragma unroll
-                        for (int off = 16; off >= 1; off >>= 1) {
-                            const bool up = (lane & off) != 0;
-#pragma unroll
-                            for (int i = 0; i < off; ++i) {
-                                const float send = up ? v[i] : v[i + off];
-                                const float keep = up ? v[i + off] : v[i];
-                                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                                const float send2 = up ? s2[i] : s2[i + off];
-                                const float keep2 = up ? s2[i + off] : s2[i];
-                                s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
-                            }
-                        }
-                        s_part[(ew * 2 + 0) * BN + ch * 32 + lane] = v[0];
-                        s_part[(ew * 2 + 1) * BN + ch * 32 + lane] = s2[0];
-                    }
-                }
-                // accumulator drained -> hand the TMEM buffer back to the MMA warp
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-                if (do_stats) {
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    const int grp = min((nt * p.TN) / p.group_images, 1);     // at most two statistics groups
-                    for (int c = ew * 32 + lane; c < BN; c += 128) {
-                        float s = 0.f, sq = 0.f;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            s += s_part[(e * 2 + 0) * BN + c];
-                            sq += s_part[(e * 2 + 1) * BN + c];
-                        }
-                        atomicAdd(p.stat_sum + static_cast<long long>(grp) * p.cout_total + co0 + c, static_cast<double>(s));
-                        atomicAdd(p.stat_sq + static_cast<long long>(grp) * p.cout_total + co0 + c, static_cast<double>(sq));
-                    }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                }
+                px_store_epilogue<BN>(p, m_tile, n_tile, acc, tmem_base, q, ew, lane, s_part, bar_tempty + 8 * acc, false, sacc);
             } else {
                 // EPI_CONVT: column = (tap, co); scatter to the 2x upsampled grid, add bias.  A tile may span several
                 // taps (BN up to 4 * co_per_tap); every 32-column chunk lies inside one tap (co_per_tap % 32 == 0).
 #pragma unroll 1
-                for (int ch = 0; ch < BN / 32; ch += 2) {        // two 32-column chunks in flight per iteration
+                for (int ch = 2 * half; ch < BN / 32; ch += kPxEpiWarps / 2) {   // two 32-column chunks in flight per iteration
                     uint32_t r[2][32];
                     tmem_ld_32x32(t_addr + ch * 32, r[0]);
                     tmem_ld_32x32(t_addr + ch * 32 + 32, r[1]);
@@ -271,6 +320,7 @@ tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
             }
         }
+        px_stat_flush<BN>(p, sacc, ew, lane);
     }
 
     tc_fence_before();

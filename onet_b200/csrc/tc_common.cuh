@@ -9,6 +9,11 @@
 
 namespace onet {
 
+// pixel-major kernels: warp 0 = TMA producer, warp 1 = MMA issuer, then kPxEpiWarps epilogue warps (two per TMEM lane
+// quarter, each taking every other 32-column chunk of the accumulator)
+constexpr int kPxEpiWarps = 8;
+constexpr int kPxThreads = 64 + 32 * kPxEpiWarps;
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
