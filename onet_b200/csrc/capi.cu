@@ -268,7 +268,13 @@ static int conv3x3_tc(const bf16* in, long long ldi, int ci_off, int N, int H, i
     px_tiling(p, N, H, W, ssum ? group_images : 0);
     p.num_n_tiles = Cout / BN;
     p.ntaps = 9; p.k_chunks = Cin / 64; p.cin = Cin;
-    for (int t = 0; t < 9; ++t) p.taps[t] = make_int4(0, t % 3 - 1, 0, t / 3 - 1);
+    // same accumulation order as the halo kernels (filter column outer, filter row inner): a pixel gets bit-identical
+    // results whichever kernel variant its image size selects (tiled inference relies on it)
+    for (int t = 0; t < 9; ++t) {
+        const int kw = t / 3, kh = t % 3;
+        p.taps[t] = make_int4(0, kw - 1, 0, kh - 1);
+        p.tap_w[t] = kh * 3 + kw;
+    }
     p.epi_mode = EPI_STORE;
     p.out = out; p.ldo = ldo; p.out_coff = co_off;
     p.stat_sum = ssum; p.stat_sq = ssq; p.cout_total = Cout; p.group_images = group_images > 0 ? group_images : N;
@@ -293,6 +299,7 @@ static int convT_fwd_tc(const bf16* x, long long ldx, int xoff, int N, int H, in
     p.num_n_tiles = 4 * Co / BN;
     p.ntaps = 1; p.k_chunks = Cin / 64; p.cin = Cin;
     p.taps[0] = make_int4(0, 0, 0, 0);
+    p.tap_w[0] = 0;
     p.epi_mode = EPI_CONVT;
     p.out = out; p.ldo = ldo; p.out_coff = ooff;
     p.bias = bias; p.co_per_tap = Co; p.cout_total = 4 * Co; p.group_images = N;
@@ -316,7 +323,10 @@ static int convT_dgrad_tc(const bf16* go, long long ldg, int goff, int N, int H,
     const int BN = pick_bn(Cin);
     p.num_n_tiles = Cin / BN;
     p.ntaps = 4; p.k_chunks = Co / 64; p.cin = Co;
-    for (int t = 0; t < 4; ++t) p.taps[t] = make_int4((t & 1) * static_cast<int>(ldg), 0, t >> 1, 0);
+    for (int t = 0; t < 4; ++t) {
+        p.taps[t] = make_int4((t & 1) * static_cast<int>(ldg), 0, t >> 1, 0);
+        p.tap_w[t] = t;
+    }
     p.epi_mode = EPI_STORE;
     p.out = dx; p.ldo = ldd; p.out_coff = doff;
     p.cout_total = Cin; p.group_images = N;

@@ -33,6 +33,7 @@ struct PxParams {
     int valid_rows;            // TW*TH*TN
     int ntaps, k_chunks, cin;  // K = ntaps * cin, cin = 64 * k_chunks
     int4 taps[kMaxTaps];       // coordinate offsets (dc, dw, dq, dh) of each tap in the 5-D input view
+    int tap_w[kMaxTaps];       // index of each tap in the packed weight tensor (K coordinate = tap_w * cin + channel)
     // epilogue
     int epi_mode;
     __nv_bfloat16* out;        // EPI_STORE: [N,H,W,ldo]; EPI_CONVT: [N,2H,2W,ldo]
@@ -226,7 +227,7 @@ tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         mbar_expect_tx(fb, a_tx + Cfg::kBBytes);
                         const int4 tp = p.taps[t];
                         tma_load_5d(sA, &tmA, fb, tp.x + kc * 64, w0 + tp.y, tp.z, h0 + tp.w, n0);
-                        tma_load_2d(sB, &tmB, fb, t * p.cin + kc * 64, co0);
+                        tma_load_2d(sB, &tmB, fb, p.tap_w[t] * p.cin + kc * 64, co0);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
