@@ -178,6 +178,19 @@ static int launch_halo_px(const CUtensorMap& tA, const CUtensorMap& tB, const Px
     return check_launch("conv3x3_halo_px_kernel");
 }
 
+template <int BN>
+static int launch_halo_res_px(const CUtensorMap& tA, const CUtensorMap& tB, const PxParams& p, cudaStream_t st) {
+    using Cfg = HaloResCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_res_px_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (e != cudaSuccess) return fail("cudaFuncSetAttribute(halo_res_px<%d>): %s", BN, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    conv3x3_halo_res_px_kernel<BN><<<std::min(p.num_m_tiles, sm_count()), kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, p);
+    return check_launch("conv3x3_halo_res_px_kernel");
+}
+
 // CTA-pair (cta_group::2) variant: grid = 2 x min(pair tiles, co-resident clusters)
 template <int BN>
 static int launch_halo2_px(const CUtensorMap& tA, const CUtensorMap& tB, const PxParams& p, cudaStream_t st) {
@@ -261,6 +274,11 @@ static int conv3x3_tc(const bf16* in, long long ldi, int ci_off, int N, int H, i
             return launch_halo2_px<64>(tA, tB, p, st);
         }
         if (make_map2(&tB, wp, 9ULL * Cin, Cout, 64, BN)) return 1;
+        if (p.k_chunks == 1 && p.num_n_tiles == 1 && BN <= 128 && p.num_m_tiles >= 4 * sm_count() && !getenv("ONET_NO_BRES")) {
+            // Cin = 64, Cout <= 128, many tiles per CTA: weights stay resident in shared memory
+            if (BN == 128) return launch_halo_res_px<128>(tA, tB, p, st);
+            return launch_halo_res_px<64>(tA, tB, p, st);
+        }
         if (BN == 256) return launch_halo_px<256>(tA, tB, p, st);
         if (BN == 128) return launch_halo_px<128>(tA, tB, p, st);
         return launch_halo_px<64>(tA, tB, p, st);

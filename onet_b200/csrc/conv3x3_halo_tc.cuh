@@ -156,6 +156,130 @@ conv3x3_halo_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 }
 
 // =====================================================================================================
+// Weight-resident variant for Cin = 64 (one K chunk) and Cout = BN <= 128: the whole packed weight tensor (9 taps x BN
+// rows x 128 B = 72 / 144 KB) is loaded into shared memory ONCE per persistent CTA and only the activation boxes
+// stream.  For these layers (the full-resolution ones) the weight re-fetch was 21-30 % of the shared-memory-port
+// traffic that bounds the kernel.
+// =====================================================================================================
+template <int BN>
+struct HaloResCfg {
+    static constexpr int kABytes = 144 * 128;
+    static constexpr int kBBytes = BN * 128;
+    static constexpr int kSA = (BN == 64) ? 7 : 4;
+    static constexpr int kTmemCols = 2 * BN;
+    static constexpr int kAuxBytes = 1024 + 4 * 2 * BN * 4;
+    static constexpr int kSmemBytes = kSA * kABytes + 9 * kBBytes + kAuxBytes + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kPxThreads, 1)
+conv3x3_halo_res_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PxParams p) {
+    using Cfg = HaloResCfg<BN>;
+    constexpr int SA = Cfg::kSA;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (base - raw);
+    const uint32_t ringA = base, resB = base + SA * Cfg::kABytes;
+    const uint32_t aux = resB + 9 * Cfg::kBBytes;
+    uint8_t* gen_aux = gen_base + SA * Cfg::kABytes + 9 * Cfg::kBBytes;
+    const uint32_t bar_fullA = aux, bar_emptyA = aux + 8 * SA, bar_bres = aux + 16 * SA, bar_tfull = bar_bres + 8,
+                   bar_tempty = bar_tfull + 16;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gen_aux + 16 * SA + 8 + 32 + 8);
+    float* s_part = reinterpret_cast<float*>(gen_aux + 1024);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < SA; ++s) { mbar_init(bar_fullA + 8 * s, 1); mbar_init(bar_emptyA + 8 * s, 1); }
+        mbar_init(bar_bres, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, kPxEpiWarps); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::kTmemCols>(smem_u32(tmem_ptr_smem));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const int num_tiles = p.num_m_tiles;       // one n-tile, one K chunk
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_expect_tx(bar_bres, 9 * Cfg::kBBytes);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) tma_load_2d(resB + t * Cfg::kBBytes, &tmB, bar_bres, t * p.cin, 0);
+            int sa = 0;
+            uint32_t pa = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int wt = tile % p.tiles_w, ht = (tile / p.tiles_w) % p.tiles_h, nt = tile / (p.tiles_w * p.tiles_h);
+                const int w0 = wt * 8, h0 = ht * 16;
+                for (int kw = 0; kw < 3; ++kw) {
+                    mbar_wait(bar_emptyA + 8 * sa, pa ^ 1);
+                    mbar_expect_tx(bar_fullA + 8 * sa, Cfg::kABytes);
+                    tma_load_5d(ringA + sa * Cfg::kABytes, &tmA, bar_fullA + 8 * sa, 0, w0 + kw - 1, 0, h0 - 1, nt);
+                    if (++sa == SA) { sa = 0; pa ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+            mbar_wait(bar_bres, 0);
+            int sa = 0;
+            uint32_t pa = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                uint32_t accumulate = 0;
+                for (int kw = 0; kw < 3; ++kw) {
+                    mbar_wait(bar_fullA + 8 * sa, pa);
+                    tc_fence_after();
+                    const uint32_t sA = ringA + sa * Cfg::kABytes;
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh) {
+                        const uint64_t da = umma_smem_desc(sA + kh * 1024, 16, 1024);
+                        const uint64_t db = umma_smem_desc(resB + (kh * 3 + kw) * Cfg::kBBytes, 16, 1024);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            umma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, accumulate);
+                            accumulate = 1;
+                        }
+                    }
+                    umma_commit(bar_emptyA + 8 * sa);
+                    if (++sa == SA) { sa = 0; pa ^= 1; }
+                }
+                umma_commit(bar_tfull + 8 * acc);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3, ew = warp - 2;
+        PxStatAcc sacc;
+        sacc.reset(-1);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+            px_store_epilogue<BN>(p, tile, 0, acc, tmem_base, q, ew, lane, s_part, bar_tempty + 8 * acc, false, sacc);
+        }
+        px_stat_flush<BN>(p, sacc, ew, lane);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+// =====================================================================================================
 // CTA-pair variant (cta_group::2): a cluster of two CTAs computes TWO adjacent pixel tiles (M = 256) x BN couts per
 // tcgen05.mma.  Each CTA stages its own activation boxes and only HALF of the weight tile (BN/2 rows), which cuts
 // the shared-memory-port traffic per CTA (TMA fills + operand reads) by 21-37 % - the resource that bounds the

@@ -51,7 +51,8 @@ def test_conv3x3_simt_fp32(n, h, w, cin, cout):
 TC_SHAPES = [(2, 16, 16, 64, 64), (4, 16, 16, 128, 256), (2, 32, 32, 64, 128), (8, 4, 4, 256, 256), (4, 2, 2, 128, 64),
              (2, 24, 40, 128, 64), (6, 8, 8, 192, 384), (1, 19, 21, 64, 128),
              (1, 16, 24, 64, 64), (3, 48, 40, 64, 256), (5, 32, 16, 128, 128),   # odd pixel-tile counts for the CTA-pair kernels
-             (2, 16, 16, 256, 256), (3, 8, 24, 128, 384)]
+             (2, 16, 16, 256, 256), (3, 8, 24, 128, 384),
+             (8, 128, 96, 64, 64), (7, 112, 104, 64, 128)]   # >= 4 tiles per SM with Cin = 64: weight-resident kernel
 
 
 @pytest.mark.parametrize("n,h,w,cin,cout", TC_SHAPES)
