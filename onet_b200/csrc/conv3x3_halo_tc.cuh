@@ -136,6 +136,8 @@ conv3x3_halo_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int q = warp & 3, ew = warp - 2;
         PxStatAcc sacc;
         sacc.reset(-1);
+        sacc.reset_rows();
+        sacc.grp = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -145,7 +147,7 @@ conv3x3_halo_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             px_store_epilogue<BN>(p, tile % p.num_m_tiles, tile / p.num_m_tiles, acc, tmem_base, q, ew, lane, s_part,
                                   bar_tempty + 8 * acc, false, sacc);
         }
-        px_stat_flush<BN>(p, sacc, ew, lane);
+        px_stat_flush<BN>(p, sacc, ew, lane, s_part);
     }
     tc_fence_before();
     __syncthreads();
@@ -261,6 +263,8 @@ conv3x3_halo_res_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         const int q = warp & 3, ew = warp - 2;
         PxStatAcc sacc;
         sacc.reset(-1);
+        sacc.reset_rows();
+        sacc.grp = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -269,7 +273,7 @@ conv3x3_halo_res_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             tc_fence_after();
             px_store_epilogue<BN>(p, tile, 0, acc, tmem_base, q, ew, lane, s_part, bar_tempty + 8 * acc, false, sacc);
         }
-        px_stat_flush<BN>(p, sacc, ew, lane);
+        px_stat_flush<BN>(p, sacc, ew, lane, s_part);
     }
     tc_fence_before();
     __syncthreads();
@@ -413,6 +417,8 @@ conv3x3_halo2_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const uint32_t lead_tempty = mapa_shared(bar_tempty, 0);
         PxStatAcc sacc;
         sacc.reset(-1);
+        sacc.reset_rows();
+        sacc.grp = 0;
         int it = 0;
         for (int unit = pair; unit < num_units; unit += npairs, ++it) {
             const int acc = it & 1;
@@ -428,7 +434,7 @@ conv3x3_halo2_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 if (lane == 0) mbar_arrive_cluster(lead_tempty + 8 * acc);
             }
         }
-        px_stat_flush<BN>(p, sacc, ew, lane);
+        px_stat_flush<BN>(p, sacc, ew, lane, s_part);
     }
     tc_fence_before();
     __syncthreads();

@@ -65,10 +65,62 @@ struct PxCfg {
 struct PxStatAcc {
     double s0, q0, s1, q1;
     int n_tile;
+    // BN == 64 only: per-ROW (per-thread) running sums of this warp's 32 columns, folded across lanes only when the
+    // statistics group changes and at the end - the per-tile shuffle butterfly (124 warp shuffles per tile through the
+    // shared-memory crossbar the MMAs and TMA also use) made the forward 64-channel layers 0.25 ms slower than dgrad
+    float rs[32], rq[32];
+    int grp, pending;
     __device__ __forceinline__ void reset(int nt) { s0 = q0 = s1 = q1 = 0.0; n_tile = nt; }
+    __device__ __forceinline__ void reset_rows() {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { rs[j] = 0.f; rq[j] = 0.f; }
+        pending = 0;
+    }
 };
+
+// transposing butterfly: on return lane j holds in v[0] / s2[0] the sum over the warp's 32 lanes of element j
+__device__ __forceinline__ void px_butterfly(float (&v)[32], float (&s2)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = up ? v[i] : v[i + off];
+            const float keep = up ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            const float send2 = up ? s2[i] : s2[i + off];
+            const float keep2 = up ? s2[i + off] : s2[i];
+            s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+        }
+    }
+}
+
+// BN == 64: fold the per-row running sums into the per-column fp64 accumulators of the owner threads.  Collective over
+// the kPxEpiWarps epilogue warps (named barrier 1).
+__device__ __forceinline__ void px_stat_fold64(PxStatAcc& a, int q, int ew, int lane, float* s_part) {
+    constexpr int BN = 64;
+    const int half = ew >> 2;
+    px_butterfly(a.rs, a.rq, lane);
+    s_part[(q * 2 + 0) * BN + half * 32 + lane] = a.rs[0];
+    s_part[(q * 2 + 1) * BN + half * 32 + lane] = a.rq[0];
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kPxEpiWarps) : "memory");
+    const int c = ew * 32 + lane;
+    if (c < BN) {
+        float s = 0.f, sq = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            s += s_part[(e * 2 + 0) * BN + c];
+            sq += s_part[(e * 2 + 1) * BN + c];
+        }
+        if (a.grp == 0) { a.s0 += static_cast<double>(s); a.q0 += static_cast<double>(sq); }
+        else { a.s1 += static_cast<double>(s); a.q1 += static_cast<double>(sq); }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kPxEpiWarps) : "memory");
+    a.reset_rows();
+}
 template <int BN>
-__device__ __forceinline__ void px_stat_flush(const PxParams& p, PxStatAcc& a, int ew, int lane) {
+__device__ __forceinline__ void px_stat_flush(const PxParams& p, PxStatAcc& a, int ew, int lane, float* s_part) {
+    if (BN == 64 && p.stat_sum != nullptr && a.pending) px_stat_fold64(a, (ew & 3), ew, lane, s_part);
     const int c = ew * 32 + lane;
     if (a.n_tile >= 0 && c < BN && p.stat_sum != nullptr) {
         const long long col = static_cast<long long>(a.n_tile) * BN + c;
@@ -100,6 +152,18 @@ __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile,
     const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
     __nv_bfloat16* orow = p.out + ((static_cast<long long>(n) * p.H + h) * p.W + w) * p.ldo + p.out_coff + co0;
     const bool do_stats = p.stat_sum != nullptr;
+    if (BN == 64 && do_stats) {      // (collective) fold the running row sums when the statistics group or n-tile changes
+        const int grp = min((nt * p.TN) / p.group_images, 1);
+        if (sacc.n_tile != n_tile) {
+            px_stat_flush<BN>(p, sacc, ew, lane, s_part);
+            sacc.reset(n_tile);
+            sacc.grp = grp;
+        } else if (sacc.grp != grp) {
+            if (sacc.pending) px_stat_fold64(sacc, q, ew, lane, s_part);
+            sacc.grp = grp;
+        }
+        sacc.pending = 1;
+    }
 #pragma unroll 1
     for (int ch = half; ch < BN / 32; ch += kPxEpiWarps / 4) {
         uint32_t r[32];
@@ -122,21 +186,14 @@ __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile,
                 v[2 * j] = lo; v[2 * j + 1] = hi;
                 s2[2 * j] = lo * lo; s2[2 * j + 1] = hi * hi;
             }
+            if (BN == 64) {          // one chunk per warp: keep per-row running sums, no cross-lane traffic per tile
 #pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-                const bool up = (lane & off) != 0;
-#pragma unroll
-                for (int i = 0; i < off; ++i) {
-                    const float send = up ? v[i] : v[i + off];
-                    const float keep = up ? v[i + off] : v[i];
-                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                    const float send2 = up ? s2[i] : s2[i + off];
-                    const float keep2 = up ? s2[i + off] : s2[i];
-                    s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
-                }
+                for (int j = 0; j < 32; ++j) { sacc.rs[j] += v[j]; sacc.rq[j] += s2[j]; }
+            } else {
+                px_butterfly(v, s2, lane);
+                s_part[(q * 2 + 0) * BN + ch * 32 + lane] = v[0];
+                s_part[(q * 2 + 1) * BN + ch * 32 + lane] = s2[0];
             }
-            s_part[(q * 2 + 0) * BN + ch * 32 + lane] = v[0];
-            s_part[(q * 2 + 1) * BN + ch * 32 + lane] = s2[0];
         }
     }
     tc_fence_before();
@@ -145,11 +202,11 @@ __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile,
         if (remote) mbar_arrive_cluster(arrive_bar);
         else mbar_arrive(arrive_bar);
     }
-    if (do_stats) {
+    if (do_stats && BN != 64) {
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kPxEpiWarps) : "memory");
         const int grp = min((nt * p.TN) / p.group_images, 1);     // at most two statistics groups (twin branches)
         if (sacc.n_tile != n_tile) {
-            px_stat_flush<BN>(p, sacc, ew, lane);
+            px_stat_flush<BN>(p, sacc, ew, lane, s_part);
             sacc.reset(n_tile);
         }
         const int c = ew * 32 + lane;
@@ -270,6 +327,8 @@ tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int w_l = row & (p.TW - 1), h_l = (row >> p.log_tw) & (p.TH - 1), n_l = row >> (p.log_tw + p.log_th);
         PxStatAcc sacc;
         sacc.reset(-1);
+        sacc.reset_rows();
+        sacc.grp = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -321,7 +380,7 @@ tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
             }
         }
-        px_stat_flush<BN>(p, sacc, ew, lane);
+        px_stat_flush<BN>(p, sacc, ew, lane, s_part);
     }
 
     tc_fence_before();
