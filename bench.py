@@ -149,11 +149,11 @@ def _family(name, a):
         fl = 2.0 * 9 * a[6] * a[7] * a[8] * a[9] * a[10]
         return ("tapgemm_wg (conv3x3 wgrad, tcgen05)" if a[13] == 1 else "conv3x3_wgrad_simt"), fl
     if name == "onet_convT2x2_fwd":
-        return ("tapgemm_px (convT, tcgen05)" if a[14] == 1 else "convT_simt"), 2.0 * 4 * a[3] * a[4] * a[5] * a[6] * a[9]
+        return ("tapgemm_px (convT, tcgen05)" if a[16] == 1 else "convT_simt"), 2.0 * 4 * a[3] * a[4] * a[5] * a[6] * a[9]
     if name == "onet_convT2x2_dgrad":
-        return ("tapgemm_px (convT, tcgen05)" if a[13] == 1 else "convT_simt"), 2.0 * 4 * a[3] * a[4] * a[5] * a[6] * a[8]
+        return ("tapgemm_px (convT, tcgen05)" if a[15] == 1 else "convT_simt"), 2.0 * 4 * a[3] * a[4] * a[5] * a[6] * a[8]
     if name == "onet_convT2x2_wgrad":
-        return ("tapgemm_wg (convT wgrad, tcgen05)" if a[14] == 1 else "convT_simt"), 2.0 * 4 * a[6] * a[7] * a[8] * a[9] * a[10]
+        return ("tapgemm_wg (convT wgrad, tcgen05)" if a[16] == 1 else "convT_simt"), 2.0 * 4 * a[6] * a[7] * a[8] * a[9] * a[10]
     return name.replace("onet_", ""), 0.0
 
 

@@ -56,7 +56,7 @@ int onet_pack_all_weights(int n, const float* const* w, const int* d0, const int
 
 /* 3x3 / pad 1 / no-bias convolution on packed weights wp[Cout][9][Cin]; writes the RAW output and, when
  * stat_sum != NULL, accumulates per-group per-channel sum / sum-of-squares (doubles, [groups][Cout]) for the
- * training-mode BatchNorm that follows.  Used for forward (nn.Conv2d, Onet_vanilla_20240606.py:47,51) and,
+ * training-mode BatchNorm that follows (with the tensor-core engine stat_sq may be NULL: column sums only).  Used for forward (nn.Conv2d, Onet_vanilla_20240606.py:47,51) and,
  * with wd, for the data gradient (autograd of the same lines). */
 int onet_conv3x3_fwd(const void* in, int64_t ldi, int ci_off, int N, int H, int W, int Cin, const void* wp, int Cout,
                      void* out, int64_t ldo, int co_off, double* stat_sum, double* stat_sq, int group_images,
@@ -94,14 +94,21 @@ int onet_bn_relu_bwd(const void* y, int N, int H, int W, int C, const float* sca
                      void* dy, float* dgamma0, float* dbeta0, float* dgamma1, float* dbeta1, int dtype, void* stream);
 
 /* ConvTranspose2d(Cin, Co, 2, 2) + bias written directly into channels [ooff, ooff+Co) of the concat buffer
- * (nn.ConvTranspose2d :86 + F.pad :92-96 (no-op when sizes divide) + the up half of torch.cat :100).
+ * (nn.ConvTranspose2d :86 + F.pad :92-96 + the up half of torch.cat :100).  The buffer holds a fine grid of Ho x Wo
+ * pixels per image (0 = exactly 2H x 2W); when the skip tensor is one pixel larger (odd sizes after floor pooling) the
+ * reference's F.pad puts the up-sampled map at offset (0,0) and zero-fills the last row / column: the caller zeroes that
+ * border with onet_zero_border and passes Ho, Wo.
  * SIMT engine takes the fp32 master weight w[Cin][Co][2][2]; TC engine takes the packed wf / wd. */
 int onet_convT2x2_fwd(const void* x, int64_t ldx, int xoff, int N, int H, int W, int Cin, const void* w,
-                      const float* bias, int Co, void* out, int64_t ldo, int ooff, int dtype, int engine, void* stream);
+                      const float* bias, int Co, void* out, int64_t ldo, int ooff, int Ho, int Wo, int dtype, int engine,
+                      void* stream);
 int onet_convT2x2_dgrad(const void* go, int64_t ldg, int goff, int N, int H, int W, int Cin, const void* w, int Co,
-                        void* dx, int64_t ldd, int doff, int dtype, int engine, void* stream);
+                        void* dx, int64_t ldd, int doff, int Ho, int Wo, int dtype, int engine, void* stream);
+/* dbias (optional) = column sums of go over the valid 2H x 2W window only */
 int onet_convT2x2_wgrad(const void* x, int64_t ldx, int xoff, const void* go, int64_t ldg, int goff, int N, int H,
-                        int W, int Cin, int Co, float* dw, float* dbias, int dtype, int engine, void* stream);
+                        int W, int Cin, int Co, float* dw, float* dbias, int Ho, int Wo, int dtype, int engine, void* stream);
+/* zero channels [coff, coff+C) of every pixel with h >= Hv or w >= Wv of a [N,Ho,Wo,ld] buffer (the F.pad border) */
+int onet_zero_border(void* buf, int N, int Ho, int Wo, int64_t ld, int coff, int C, int Hv, int Wv, int dtype, void* stream);
 
 /* dst[c] += sums[c] for c < C.  The bias gradient of the transposed convolution is the column sum of d(concat)'s
  * up half; onet_conv3x3_fwd accumulates it (stat_sum) while it writes d(concat), this folds it into the fp32 .grad,

@@ -106,12 +106,13 @@ static int make_act_map(CUtensorMap* m, const bf16* base, int C, int N, int H, i
                             static_cast<uint64_t>(ld) * W * H};
     return make_map5(m, base, dims, st, box);
 }
-// 2x-upsampled grid [N,2H,2W,ld] seen from the coarse grid: (c' = dx*ld + c, w, q = dy, h, n)
-static int make_up_map(CUtensorMap* m, const bf16* base, int C, int N, int H, int W, long long ld, const uint32_t box[5]) {
+// fine grid [N,Ho,Wo,ld] (Ho >= 2H, Wo >= 2W) seen from the coarse grid: (c' = dx*ld + c, w, q = dy, h, n)
+static int make_up_map(CUtensorMap* m, const bf16* base, int C, int N, int H, int W, long long ld, const uint32_t box[5],
+                       int Ho, int Wo) {
     const uint64_t dims[5] = {static_cast<uint64_t>(ld + C), static_cast<uint64_t>(W), 2, static_cast<uint64_t>(H),
                               static_cast<uint64_t>(N)};
-    const uint64_t st[4] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(ld) * 2 * W,
-                            static_cast<uint64_t>(ld) * 4 * W, static_cast<uint64_t>(ld) * 4 * W * H};
+    const uint64_t st[4] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(ld) * Wo,
+                            static_cast<uint64_t>(ld) * 2 * Wo, static_cast<uint64_t>(ld) * Wo * Ho};
     return make_map5(m, base, dims, st, box);
 }
 
@@ -307,7 +308,7 @@ static int conv3x3_tc(const bf16* in, long long ldi, int ci_off, int N, int H, i
 
 // convT fwd on tensor cores: D[px][(tap,co)] = X[px][:] . wf[(tap,co)][:], scatter epilogue
 static int convT_fwd_tc(const bf16* x, long long ldx, int xoff, int N, int H, int W, int Cin, const bf16* wf,
-                        const float* bias, int Co, bf16* out, long long ldo, int ooff, cudaStream_t st) {
+                        const float* bias, int Co, bf16* out, long long ldo, int ooff, int Ho, int Wo, cudaStream_t st) {
     if (Cin % 64 || Co % 64) return fail("tc convT needs Cin, Co multiples of 64 (got %d, %d)", Cin, Co);
     if (ldo % 8 || ooff % 8) return fail("tc convT output channel stride/offset must be multiples of 8");
     PxParams p;
@@ -321,6 +322,7 @@ static int convT_fwd_tc(const bf16* x, long long ldx, int xoff, int N, int H, in
     p.epi_mode = EPI_CONVT;
     p.out = out; p.ldo = ldo; p.out_coff = ooff;
     p.bias = bias; p.co_per_tap = Co; p.cout_total = 4 * Co; p.group_images = N;
+    p.Ho = Ho; p.Wo = Wo;
     CUtensorMap tA, tB;
     const uint32_t box[5] = {64, static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
     if (make_act_map(&tA, x + xoff, Cin, N, H, W, ldx, box)) return 1;
@@ -332,7 +334,7 @@ static int convT_fwd_tc(const bf16* x, long long ldx, int xoff, int N, int H, in
 
 // convT dgrad on tensor cores: dX[px][ci] = sum_{tap,co} dO[2px+tap][co] * wd[ci][(tap,co)]
 static int convT_dgrad_tc(const bf16* go, long long ldg, int goff, int N, int H, int W, int Cin, const bf16* wd, int Co,
-                          bf16* dx, long long ldd, int doff, cudaStream_t st) {
+                          bf16* dx, long long ldd, int doff, int Ho, int Wo, cudaStream_t st) {
     if (Cin % 64 || Co % 64) return fail("tc convT dgrad needs Cin, Co multiples of 64 (got %d, %d)", Cin, Co);
     if (ldd % 8 || doff % 8) return fail("tc convT dgrad output channel stride/offset must be multiples of 8");
     PxParams p;
@@ -350,7 +352,7 @@ static int convT_dgrad_tc(const bf16* go, long long ldg, int goff, int N, int H,
     p.cout_total = Cin; p.group_images = N;
     CUtensorMap tA, tB;
     const uint32_t box[5] = {64, static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
-    if (make_up_map(&tA, go + goff, Co, N, H, W, ldg, box)) return 1;
+    if (make_up_map(&tA, go + goff, Co, N, H, W, ldg, box, Ho, Wo)) return 1;
     if (make_map2(&tB, wd, 4ULL * Co, Cin, 64, BN)) return 1;
     if (BN == 256) return launch_px<256>(tA, tB, p, st);
     if (BN == 128) return launch_px<128>(tA, tB, p, st);
@@ -506,7 +508,7 @@ static int wgrad3x3_halo_tc(const bf16* g, long long ldg, int goff, int Mc, cons
 }
 
 static int wgrad_tc(const bf16* g, long long ldg, int goff, int Mc, bool g_is_up, const bf16* in, long long ldi, int ioff,
-                    int Nc, int N, int H, int W, int ntaps, float* dw, bool transposed, cudaStream_t st) {
+                    int Nc, int N, int H, int W, int ntaps, float* dw, bool transposed, cudaStream_t st, int Ho = 0, int Wo = 0) {
     if (Mc % 64 || Nc % 64) return fail("tc wgrad needs channel counts multiples of 64 (got %d, %d)", Mc, Nc);
     if (!g_is_up && ntaps == 9 && !transposed && H >= 8 && W >= 8 && !getenv("ONET_NO_HALO"))
         return wgrad3x3_halo_tc(g, ldg, goff, Mc, in, ldi, ioff, Nc, N, H, W, dw, st);
@@ -558,7 +560,7 @@ static int wgrad_tc(const bf16* g, long long ldg, int goff, int Mc, bool g_is_up
     p.m_total = Mc; p.n_total = Nc; p.out_transposed = transposed ? 1 : 0;
     CUtensorMap tG, tI;
     const uint32_t box[5] = {64, static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
-    if (g_is_up) { if (make_up_map(&tG, g + goff, Mc, N, H, W, ldg, box)) return 1; }
+    if (g_is_up) { if (make_up_map(&tG, g + goff, Mc, N, H, W, ldg, box, Ho, Wo)) return 1; }
     else { if (make_act_map(&tG, g + goff, Mc, N, H, W, ldg, box)) return 1; }
     if (make_act_map(&tI, in + ioff, Nc, N, H, W, ldi, box)) return 1;
     if (BNW == 128) return launch_wg<128>(tG, tI, p, st);
@@ -822,37 +824,55 @@ int onet_bn_relu_bwd(const void* y, int N, int H, int W, int C, const float* sca
 }
 
 int onet_convT2x2_fwd(const void* x, int64_t ldx, int xoff, int N, int H, int W, int Cin, const void* w,
-                      const float* bias, int Co, void* out, int64_t ldo, int ooff, int dtype, int engine, void* stream) {
+                      const float* bias, int Co, void* out, int64_t ldo, int ooff, int Ho, int Wo, int dtype, int engine,
+                      void* stream) {
+    if (Ho == 0) Ho = 2 * H;
+    if (Wo == 0) Wo = 2 * W;
+    if (Ho < 2 * H || Wo < 2 * W) return fail("convT2x2_fwd: output grid %dx%d smaller than 2H x 2W", Ho, Wo);
     if (engine == ONET_ENGINE_TC) {
         if (dtype != ONET_BF16) return fail("tc engine is bf16 only");
         return convT_fwd_tc(static_cast<const bf16*>(x), ldx, xoff, N, H, W, Cin, static_cast<const bf16*>(w), bias, Co,
-                            static_cast<bf16*>(out), ldo, ooff, ST(stream));
+                            static_cast<bf16*>(out), ldo, ooff, Ho, Wo, ST(stream));
     }
     const long long total = 4LL * N * H * W * Co;
     if (dtype == ONET_F32)
         convT2x2_fwd_simt_kernel<float><<<grid_for(total, 256, 148 * 64), 256, 0, ST(stream)>>>(
-            static_cast<const float*>(x), ldx, xoff, N, H, W, Cin, static_cast<const float*>(w), bias, Co, static_cast<float*>(out), ldo, ooff, 0);
+            static_cast<const float*>(x), ldx, xoff, N, H, W, Cin, static_cast<const float*>(w), bias, Co, static_cast<float*>(out), ldo, ooff, 0, Ho, Wo);
     else
         convT2x2_fwd_simt_kernel<bf16><<<grid_for(total, 256, 148 * 64), 256, 0, ST(stream)>>>(
-            static_cast<const bf16*>(x), ldx, xoff, N, H, W, Cin, static_cast<const float*>(w), bias, Co, static_cast<bf16*>(out), ldo, ooff, 1);
+            static_cast<const bf16*>(x), ldx, xoff, N, H, W, Cin, static_cast<const float*>(w), bias, Co, static_cast<bf16*>(out), ldo, ooff, 1, Ho, Wo);
     return check_launch("convT2x2_fwd_simt");
 }
 
 int onet_convT2x2_dgrad(const void* go, int64_t ldg, int goff, int N, int H, int W, int Cin, const void* w, int Co,
-                        void* dx, int64_t ldd, int doff, int dtype, int engine, void* stream) {
+                        void* dx, int64_t ldd, int doff, int Ho, int Wo, int dtype, int engine, void* stream) {
+    if (Ho == 0) Ho = 2 * H;
+    if (Wo == 0) Wo = 2 * W;
+    if (Ho < 2 * H || Wo < 2 * W) return fail("convT2x2_dgrad: gradient grid %dx%d smaller than 2H x 2W", Ho, Wo);
     if (engine == ONET_ENGINE_TC) {
         if (dtype != ONET_BF16) return fail("tc engine is bf16 only");
         return convT_dgrad_tc(static_cast<const bf16*>(go), ldg, goff, N, H, W, Cin, static_cast<const bf16*>(w), Co,
-                              static_cast<bf16*>(dx), ldd, doff, ST(stream));
+                              static_cast<bf16*>(dx), ldd, doff, Ho, Wo, ST(stream));
     }
     const long long total = static_cast<long long>(N) * H * W * Cin;
     if (dtype == ONET_F32)
         convT2x2_dgrad_simt_kernel<float><<<grid_for(total, 256, 148 * 64), 256, 0, ST(stream)>>>(
-            static_cast<const float*>(go), ldg, goff, N, H, W, Cin, static_cast<const float*>(w), Co, static_cast<float*>(dx), ldd, doff);
+            static_cast<const float*>(go), ldg, goff, N, H, W, Cin, static_cast<const float*>(w), Co, static_cast<float*>(dx), ldd, doff, Ho, Wo);
     else
         convT2x2_dgrad_simt_kernel<bf16><<<grid_for(total, 256, 148 * 64), 256, 0, ST(stream)>>>(
-            static_cast<const bf16*>(go), ldg, goff, N, H, W, Cin, static_cast<const float*>(w), Co, static_cast<bf16*>(dx), ldd, doff);
+            static_cast<const bf16*>(go), ldg, goff, N, H, W, Cin, static_cast<const float*>(w), Co, static_cast<bf16*>(dx), ldd, doff, Ho, Wo);
     return check_launch("convT2x2_dgrad_simt");
+}
+
+int onet_zero_border(void* buf, int N, int Ho, int Wo, int64_t ld, int coff, int C, int Hv, int Wv, int dtype, void* stream) {
+    if (Hv > Ho || Wv > Wo) return fail("zero_border: valid window larger than the buffer");
+    const long long total = static_cast<long long>(N) * ((Ho - Hv) * Wo + Hv * (Wo - Wv)) * C;
+    if (total == 0) return 0;
+    if (dtype == ONET_F32)
+        zero_border_kernel<float><<<grid_for(total, 256), 256, 0, ST(stream)>>>(static_cast<float*>(buf), N, Ho, Wo, ld, coff, C, Hv, Wv);
+    else
+        zero_border_kernel<bf16><<<grid_for(total, 256), 256, 0, ST(stream)>>>(static_cast<bf16*>(buf), N, Ho, Wo, ld, coff, C, Hv, Wv);
+    return check_launch("zero_border");
 }
 
 int onet_add_colsums(const double* sums, int C, float* dst, void* stream) {
@@ -861,23 +881,26 @@ int onet_add_colsums(const double* sums, int C, float* dst, void* stream) {
 }
 
 int onet_convT2x2_wgrad(const void* x, int64_t ldx, int xoff, const void* go, int64_t ldg, int goff, int N, int H,
-                        int W, int Cin, int Co, float* dw, float* dbias, int dtype, int engine, void* stream) {
+                        int W, int Cin, int Co, float* dw, float* dbias, int Ho, int Wo, int dtype, int engine, void* stream) {
+    if (Ho == 0) Ho = 2 * H;
+    if (Wo == 0) Wo = 2 * W;
+    if (Ho < 2 * H || Wo < 2 * W) return fail("convT2x2_wgrad: gradient grid %dx%d smaller than 2H x 2W", Ho, Wo);
     const long long M = static_cast<long long>(N) * H * W;
     if (dbias != nullptr) {
         // bias gradient = column sums of dO over the whole upsampled grid
         const int cpb = std::min(Co, 64);
         dim3 grid(static_cast<unsigned>(std::min<long long>(148 * 4, (4 * M + (256 / cpb) - 1) / (256 / cpb))), (Co + cpb - 1) / cpb);
         if (dtype == ONET_F32)
-            colsum_kernel<float><<<grid, 256, 0, ST(stream)>>>(static_cast<const float*>(go), ldg, goff, 4 * M, Co, dbias);
+            colsum_kernel<float><<<grid, 256, 0, ST(stream)>>>(static_cast<const float*>(go), ldg, goff, 4 * M, Co, dbias, 2 * H, 2 * W, Ho, Wo);
         else
-            colsum_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(static_cast<const bf16*>(go), ldg, goff, 4 * M, Co, dbias);
+            colsum_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(static_cast<const bf16*>(go), ldg, goff, 4 * M, Co, dbias, 2 * H, 2 * W, Ho, Wo);
         if (check_launch("colsum")) return 1;
     }
     if (engine == ONET_ENGINE_TC) {
         if (dtype != ONET_BF16) return fail("tc engine is bf16 only");
         // M-side = dO on the upsampled grid (m = co), N-side = X (n = ci); dW[ci][co][tap] -> transposed output
         return wgrad_tc(static_cast<const bf16*>(go), ldg, goff, Co, true, static_cast<const bf16*>(x), ldx, xoff, Cin, N, H, W,
-                        4, dw, true, ST(stream));
+                        4, dw, true, ST(stream), Ho, Wo);
     }
     const long long nthreads = 4LL * Cin * Co;
     int splits = static_cast<int>(std::max<long long>(1, std::min<long long>(M, (148LL * 2048) / std::max<long long>(1, nthreads))));
@@ -886,10 +909,10 @@ int onet_convT2x2_wgrad(const void* x, int64_t ldx, int xoff, const void* go, in
     dim3 grid(static_cast<unsigned>((nthreads + 255) / 256), splits);
     if (dtype == ONET_F32)
         convT2x2_wgrad_simt_kernel<float><<<grid, 256, 0, ST(stream)>>>(static_cast<const float*>(x), ldx, xoff,
-                                                                        static_cast<const float*>(go), ldg, goff, N, H, W, Cin, Co, dw, per);
+                                                                        static_cast<const float*>(go), ldg, goff, N, H, W, Cin, Co, dw, per, Ho, Wo);
     else
         convT2x2_wgrad_simt_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), ldx, xoff,
-                                                                       static_cast<const bf16*>(go), ldg, goff, N, H, W, Cin, Co, dw, per);
+                                                                       static_cast<const bf16*>(go), ldg, goff, N, H, W, Cin, Co, dw, per, Ho, Wo);
     return check_launch("convT2x2_wgrad_simt");
 }
 

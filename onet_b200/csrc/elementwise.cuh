@@ -437,6 +437,25 @@ __global__ void bn_param_grad_kernel(const double* __restrict__ sums, int G, int
     }
 }
 
+// zero channels [coff, coff+C) of the pixels with h >= Hv or w >= Wv of a [N,Ho,Wo,ld] buffer: the border F.pad adds when the
+// skip tensor is one pixel larger than the up-sampled map (Onet_vanilla_20240606.py:92-96)
+template <typename T>
+__global__ void zero_border_kernel(T* __restrict__ buf, int N, int Ho, int Wo, long long ld, int coff, int C, int Hv, int Wv) {
+    const int nb = (Ho - Hv) * Wo + Hv * (Wo - Wv);          // border pixels per image: bottom rows, then right columns
+    const long long total = static_cast<long long>(N) * nb * C;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C);
+        long long r = i / C;
+        const int b = static_cast<int>(r % nb);
+        const long long n = r / nb;
+        int h, w;
+        if (b < (Ho - Hv) * Wo) { h = Hv + b / Wo; w = b % Wo; }
+        else { const int bb = b - (Ho - Hv) * Wo; h = bb / (Wo - Wv); w = Wv + bb % (Wo - Wv); }
+        buf[((n * Ho + h) * Wo + w) * ld + coff + c] = from_f<T>(0.f);
+    }
+}
+
 // dst[c] += sums[c]: folds double column sums (e.g. the transposed convolution's bias gradient, accumulated by the
 // epilogue of the convolution that produced d(concat)) into an fp32 gradient
 __global__ void add_colsums_kernel(const double* __restrict__ sums, int C, float* __restrict__ dst) {

@@ -568,7 +568,7 @@ conv3x3_wgrad_simt_kernel(const T* __restrict__ g, long long ldg, int co_off, co
 template <typename T>
 __global__ void convT2x2_fwd_simt_kernel(const T* __restrict__ x, long long ldx, int xoff, int N, int H, int W, int Cin,
                                          const float* __restrict__ w, const float* __restrict__ bias, int Co,
-                                         T* __restrict__ out, long long ldo, int ooff, int round_w_bf16) {
+                                         T* __restrict__ out, long long ldo, int ooff, int round_w_bf16, int Ho, int Wo) {
     const long long total = static_cast<long long>(N) * 2 * H * 2 * W * Co;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -585,14 +585,15 @@ __global__ void convT2x2_fwd_simt_kernel(const T* __restrict__ x, long long ldx,
             if (round_w_bf16) wv = __bfloat162float(__float2bfloat16_rn(wv));
             acc = fmaf(to_f<T>(xp[ci]), wv, acc);
         }
-        out[((static_cast<long long>(n) * 2 * H + oh) * 2 * W + ow) * ldo + ooff + co] = from_f<T>(acc + bias[co]);
+        out[((static_cast<long long>(n) * Ho + oh) * Wo + ow) * ldo + ooff + co] = from_f<T>(acc + bias[co]);
     }
 }
 
 // dX[n,h,w,ci] = sum_{tap,co} dO[n,2h+dy,2w+dx,co] * W[ci][co][tap]
 template <typename T>
 __global__ void convT2x2_dgrad_simt_kernel(const T* __restrict__ go, long long ldg, int goff, int N, int H, int W, int Cin,
-                                           const float* __restrict__ w, int Co, T* __restrict__ dx, long long ldd, int doff) {
+                                           const float* __restrict__ w, int Co, T* __restrict__ dx, long long ldd, int doff,
+                                           int Ho, int Wo) {
     const long long total = static_cast<long long>(N) * H * W * Cin;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -603,7 +604,7 @@ __global__ void convT2x2_dgrad_simt_kernel(const T* __restrict__ go, long long l
         const int n = static_cast<int>(r / H);
         float acc = 0.f;
         for (int tap = 0; tap < 4; ++tap) {
-            const T* gp = go + ((static_cast<long long>(n) * 2 * H + 2 * hh + (tap >> 1)) * 2 * W + 2 * ww + (tap & 1)) * ldg + goff;
+            const T* gp = go + ((static_cast<long long>(n) * Ho + 2 * hh + (tap >> 1)) * Wo + 2 * ww + (tap & 1)) * ldg + goff;
             const float* wr = w + static_cast<long long>(ci) * Co * 4 + tap;
             for (int co = 0; co < Co; ++co) acc = fmaf(to_f<T>(gp[co]), wr[co * 4], acc);
         }
@@ -615,7 +616,7 @@ __global__ void convT2x2_dgrad_simt_kernel(const T* __restrict__ go, long long l
 template <typename T>
 __global__ void convT2x2_wgrad_simt_kernel(const T* __restrict__ x, long long ldx, int xoff, const T* __restrict__ go,
                                            long long ldg, int goff, int N, int H, int W, int Cin, int Co,
-                                           float* __restrict__ dw, long long px_per_split) {
+                                           float* __restrict__ dw, long long px_per_split, int Ho, int Wo) {
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<long long>(Cin) * Co * 4) return;
     const int tap = static_cast<int>(idx & 3);
@@ -629,15 +630,17 @@ __global__ void convT2x2_wgrad_simt_kernel(const T* __restrict__ x, long long ld
                   n = static_cast<int>(pm / (static_cast<long long>(W) * H));
         const float xv = to_f<T>(x[pm * ldx + xoff + ci]);
         const float gv = to_f<T>(
-            go[((static_cast<long long>(n) * 2 * H + 2 * hh + (tap >> 1)) * 2 * W + 2 * ww + (tap & 1)) * ldg + goff + co]);
+            go[((static_cast<long long>(n) * Ho + 2 * hh + (tap >> 1)) * Wo + 2 * ww + (tap & 1)) * ldg + goff + co]);
         acc = fmaf(xv, gv, acc);
     }
     atomicAdd(dw + idx, acc);
 }
 
-// column sums: out[c] += sum over rows of v[row*ld + off + c]  (bias gradient of the transposed conv)
+// column sums over the valid [N, Hv, Wv] window of a [N, Ho, Wo, ld] buffer: out[c] += sum v[n,h,w, off + c]
+// (bias gradient of the transposed conv; the F.pad border of the concat buffer is excluded)
 template <typename T>
-__global__ void colsum_kernel(const T* __restrict__ v, long long ld, int off, long long rows, int C, float* __restrict__ out) {
+__global__ void colsum_kernel(const T* __restrict__ v, long long ld, int off, long long rows, int C, float* __restrict__ out,
+                              int Hv, int Wv, int Ho, int Wo) {
     // blockDim.x = 256: thread -> channel c = tid % cpb, row lane = tid / cpb
     const int cpb = min(C, 64);
     const int lanes = 256 / cpb;
@@ -645,8 +648,11 @@ __global__ void colsum_kernel(const T* __restrict__ v, long long ld, int off, lo
     const int rl = threadIdx.x / cpb;
     float acc = 0.f;
     if (c < C && rl < lanes)
-        for (long long r = blockIdx.x * static_cast<long long>(lanes) + rl; r < rows; r += static_cast<long long>(gridDim.x) * lanes)
-            acc += to_f<T>(v[r * ld + off + c]);
+        for (long long r = blockIdx.x * static_cast<long long>(lanes) + rl; r < rows; r += static_cast<long long>(gridDim.x) * lanes) {
+            const long long w_ = r % Wv, t_ = r / Wv;
+            const long long px = ((t_ / Hv) * Ho + (t_ % Hv)) * Wo + w_;
+            acc += to_f<T>(v[px * ld + off + c]);
+        }
     __shared__ float s[256];
     s[threadIdx.x] = acc;
     __syncthreads();

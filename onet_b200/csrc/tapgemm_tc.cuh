@@ -45,6 +45,7 @@ struct PxParams {
     int group_images;          // images per BatchNorm statistics group (twin branch)
     const float* bias;         // EPI_CONVT: [co_per_tap]
     int co_per_tap;            // EPI_CONVT: output channels per 2x2 position
+    int Ho, Wo;                // EPI_CONVT: height / width of the fine grid the buffer holds (>= 2H, 2W; F.pad border beyond)
 };
 
 template <int BN>
@@ -95,6 +96,19 @@ __device__ __forceinline__ void px_butterfly(float (&v)[32], float (&s2)[32], in
     }
 }
 
+__device__ __forceinline__ void px_butterfly1(float (&v)[32], int lane) {     // sums only (column sums without squares)
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = up ? v[i] : v[i + off];
+            const float keep = up ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+}
+
 // BN == 64: fold the per-row running sums into the per-column fp64 accumulators of the owner threads.  Collective over
 // the kPxEpiWarps epilogue warps (named barrier 1).
 __device__ __forceinline__ void px_stat_fold64(PxStatAcc& a, int q, int ew, int lane, float* s_part) {
@@ -126,11 +140,11 @@ __device__ __forceinline__ void px_stat_flush(const PxParams& p, PxStatAcc& a, i
         const long long col = static_cast<long long>(a.n_tile) * BN + c;
         if (a.s0 != 0.0 || a.q0 != 0.0) {
             atomicAdd(p.stat_sum + col, a.s0);
-            atomicAdd(p.stat_sq + col, a.q0);
+            if (p.stat_sq != nullptr) atomicAdd(p.stat_sq + col, a.q0);
         }
         if (a.s1 != 0.0 || a.q1 != 0.0) {
             atomicAdd(p.stat_sum + p.cout_total + col, a.s1);
-            atomicAdd(p.stat_sq + p.cout_total + col, a.q1);
+            if (p.stat_sq != nullptr) atomicAdd(p.stat_sq + p.cout_total + col, a.q1);
         }
     }
     a.reset(-1);
@@ -189,10 +203,14 @@ __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile,
             if (BN == 64) {          // one chunk per warp: keep per-row running sums, no cross-lane traffic per tile
 #pragma unroll
                 for (int j = 0; j < 32; ++j) { sacc.rs[j] += v[j]; sacc.rq[j] += s2[j]; }
-            } else {
+            } else if (p.stat_sq != nullptr) {
                 px_butterfly(v, s2, lane);
                 s_part[(q * 2 + 0) * BN + ch * 32 + lane] = v[0];
                 s_part[(q * 2 + 1) * BN + ch * 32 + lane] = s2[0];
+            } else {                 // column sums only (bias gradient of the up-convolution)
+                px_butterfly1(v, lane);
+                s_part[(q * 2 + 0) * BN + ch * 32 + lane] = v[0];
+                s_part[(q * 2 + 1) * BN + ch * 32 + lane] = 0.f;
             }
         }
     }
@@ -359,7 +377,7 @@ tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         const int tap = colg / p.co_per_tap, cbase = colg % p.co_per_tap;
                         const int dy = tap >> 1, dx = tap & 1;
                         __nv_bfloat16* dst16 = p.out +
-                                               ((static_cast<long long>(n) * (2 * p.H) + (2 * h + dy)) * (2 * p.W) + (2 * w + dx)) * p.ldo +
+                                               ((static_cast<long long>(n) * p.Ho + (2 * h + dy)) * p.Wo + (2 * w + dx)) * p.ldo +
                                                p.out_coff + cbase;
                         const float4* bias4 = reinterpret_cast<const float4*>(p.bias + cbase);
                         if (valid) {

@@ -256,9 +256,8 @@ class _Engine:
         buffers); save: keep what backward needs."""
         x = self.x
         B, Cin, H, W = x.shape
-        if H % 16 or W % 16:
-            raise NotImplementedError("H and W must be multiples of 16 (the F.pad branch of the reference's Up "
-                                      "block, :92-96, is not implemented yet)")
+        if H < 16 or W < 16:
+            raise ValueError("Onet needs at least 16 x 16 pixels (four 2x2 poolings)")
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.contiguous().float()
         N2 = 2 * B if x_is_twin else B
@@ -269,7 +268,7 @@ class _Engine:
             call("onet_prep_input", ptr(x), B, Cin, H, W, float(bias), ptr(rec.xin), self.dt, self.stream)
         else:
             rec.xin.copy_(x.permute(0, 2, 3, 1))
-        hs = [H >> k for k in range(5)]
+        hs = [H >> k for k in range(5)]        # nn.MaxPool2d(2) floors odd sizes; the Up blocks pad back (F.pad, :92-96)
         ws = [W >> k for k in range(5)]
         cs = [64, 128, 256, 512, 1024]
         rec.hs, rec.ws = hs, ws
@@ -315,7 +314,7 @@ class _Engine:
                 k = 3 - j                      # level of the skip connection
                 c = cs[k]
                 up = ups[j]
-                self._upconv(seg, up, below, c_below, n0, n, hs[k + 1], ws[k + 1], rec.cat[k], 2 * c, c)
+                self._upconv(seg, up, below, c_below, n0, n, hs[k + 1], ws[k + 1], rec.cat[k], 2 * c, c, hs[k], ws[k])
                 mid = rec.mid.setdefault(("dec", k), self._empty(N2, hs[k], ws[k], c))
                 run(li, rec.cat[k], 2 * c, 0, hs[k], ws[k], mid, c, 0, None)
                 out = rec.mid.setdefault(("dec_out", k), self._empty(N2, hs[k], ws[k], c))
@@ -361,7 +360,9 @@ class _Engine:
         if rec.save:
             rec.saved[(si, li)] = dict(Y=Y, aff=aff, src=(src, ld_src, off_src), h=h, w=w, cin=cin, cout=cout)
 
-    def _upconv(self, seg, up, x, cx, n0, n, h, w, cat, ld_cat, off_cat):
+    def _upconv(self, seg, up, x, cx, n0, n, h, w, cat, ld_cat, off_cat, ho, wo):
+        """x [n,h,w,cin] -> channels [off_cat, off_cat+co) of the concat buffer [n,ho,wo,ld_cat]; ho - 2h, wo - 2w in {0,1}:
+        the reference's F.pad (:92-96) puts the up-sampled map at offset (0,0) and zero-fills the last row / column."""
         cin, co = up.weight.shape[0], up.weight.shape[1]
         eng = self._engine_for(cin, co)
         if eng == ENGINE_TC:
@@ -369,8 +370,11 @@ class _Engine:
             wptr = ptr(wf)
         else:
             wptr = ptr(up.weight)
+        dst = ptr(cat, self._img_off(cat, n0) + off_cat)
+        if ho != 2 * h or wo != 2 * w:
+            call("onet_zero_border", dst, n, ho, wo, ld_cat, 0, co, 2 * h, 2 * w, self.dt, self.stream)
         call("onet_convT2x2_fwd", ptr(x, self._img_off(x, n0)), cx, 0, n, h, w, cin, wptr, ptr(up.bias), co,
-             ptr(cat, self._img_off(cat, n0) + off_cat), ld_cat, 0, self.dt, eng, self.stream)
+             dst, ld_cat, 0, ho, wo, self.dt, eng, self.stream)
 
     # -------------------------------------------------------------------------------- head
     def head_forward(self, rec):
@@ -427,7 +431,7 @@ class _Engine:
                 up = ups[j]
                 below = rec.x5 if k == 3 else rec.mid[("dec_out", k + 1)]
                 g_out = self._upconv_bwd(seg, up, below, 2 * c, n0, n, hs[k + 1], ws[k + 1], dcat[k], 2 * c, c, grad_of,
-                                         colsum[0, c:])
+                                         colsum[0, c:], hs[k], ws[k])
                 if after_block is not None:
                     after_block(seg.unet, _DEC[j][0])
             # encoder, bottom (level 4) to top
@@ -471,24 +475,28 @@ class _Engine:
         _, wd = self._packed(conv, "conv")
         dX = self._empty(n, h, w, cin)
         call("onet_conv3x3_fwd", ptr(dY), cout, 0, n, h, w, cout, ptr(wd), cin, ptr(dX), cin, 0,
-             ptr(colsum[0]) if colsum is not None else None, ptr(colsum[1]) if colsum is not None else None,
+             ptr(colsum[0]) if colsum is not None else None,
+             ptr(colsum[1]) if (colsum is not None and eng != ENGINE_TC) else None,     # tcgen05 epilogue: sums only
              n if colsum is not None else seg.group_images, self.dt, eng, st)
         return dX
 
-    def _upconv_bwd(self, seg, up, x, ld_go_total, n0, n, h, w, dcat, ld_cat, off_cat, grad_of, bias_sums):
+    def _upconv_bwd(self, seg, up, x, ld_go_total, n0, n, h, w, dcat, ld_cat, off_cat, grad_of, bias_sums, ho, wo):
         cin, co = up.weight.shape[0], up.weight.shape[1]
         eng = self._engine_for(cin, co)
         st = self.stream
-        call("onet_add_colsums", ptr(bias_sums), co, ptr(grad_of(up.bias)), st)
+        padded = ho != 2 * h or wo != 2 * w
+        if not padded:       # bias gradient = column sums of d(concat)'s up half, already reduced by the dgrad epilogue
+            call("onet_add_colsums", ptr(bias_sums), co, ptr(grad_of(up.bias)), st)
+        # with an F.pad border the gradient of the border pixels is dropped: reduce over the valid window only
         call("onet_convT2x2_wgrad", ptr(x, self._img_off(x, n0)), cin, 0, ptr(dcat, off_cat), ld_cat, 0, n, h, w, cin, co,
-             ptr(grad_of(up.weight)), None, self.dt, eng, st)
+             ptr(grad_of(up.weight)), ptr(grad_of(up.bias)) if padded else None, ho, wo, self.dt, eng, st)
         dX = self._empty(n, h, w, cin)
         if eng == ENGINE_TC:
             _, wd = self._packed(up, "convT")
             wptr = ptr(wd)
         else:
             wptr = ptr(up.weight)
-        call("onet_convT2x2_dgrad", ptr(dcat, off_cat), ld_cat, 0, n, h, w, cin, wptr, co, ptr(dX), cin, 0, self.dt, eng, st)
+        call("onet_convT2x2_dgrad", ptr(dcat, off_cat), ld_cat, 0, n, h, w, cin, wptr, co, ptr(dX), cin, 0, ho, wo, self.dt, eng, st)
         return dX
 
 

@@ -108,42 +108,54 @@ def test_conv3x3_tc_wgrad(n, h, w, cin, cout):
     assert err < 1e-4, err                       # bf16-exact inputs, fp32 accumulate
 
 
+@pytest.mark.parametrize("pad", [(0, 0), (1, 1), (1, 0)])
 @pytest.mark.parametrize("engine_name", ["simt_fp32", "simt_bf16", "tc"])
 @pytest.mark.parametrize("n,h,w,cin", [(2, 4, 4, 128), (3, 8, 8, 256), (2, 16, 16, 128), (4, 2, 2, 1024)])
-def test_convT2x2(engine_name, n, h, w, cin):
+def test_convT2x2(engine_name, n, h, w, cin, pad):
+    """ConvTranspose2d(C, C/2, 2, 2) + bias written into the up half of a concat buffer whose fine grid is
+    (2h + ph) x (2w + pw): the reference's F.pad (Onet_vanilla_20240606.py:92-96) for odd skip sizes puts the map at (0,0)
+    and zero-fills the last row / column; backward ignores the border."""
     U = _imports()
     call, ptr = U.call, U.ptr
-    dt = U.F32 if engine_name == "simt_fp32" else U.BF16
-    eng = U.ENGINE_TC if engine_name == "tc" else U.ENGINE_SIMT
+    dt, eng = {"simt_fp32": (U.F32, U.ENGINE_SIMT), "simt_bf16": (U.BF16, U.ENGINE_SIMT), "tc": (U.BF16, U.ENGINE_TC)}[engine_name]
     tdt = U.TDT[dt]
     rnd = (lambda t: t) if dt == U.F32 else _bf16r
+    ph, pw = pad
+    ho, wo = 2 * h + ph, 2 * w + pw
     co = cin // 2
     torch.manual_seed(4)
     x = rnd(torch.randn(n, cin, h, w, device="cuda"))
     wt = rnd(torch.randn(cin, co, 2, 2, device="cuda") * (1.0 / cin) ** 0.5)
     b = torch.randn(co, device="cuda") * 0.1
-    # forward into the upper half of a concat buffer
-    cat = torch.zeros(n, 2 * h, 2 * w, 2 * co, dtype=tdt, device="cuda")
+    # forward into the upper half of a concat buffer (border pre-filled with garbage, skip half must stay untouched)
+    cat = torch.zeros(n, ho, wo, 2 * co, dtype=tdt, device="cuda")
+    cat[..., co:] = 7.0
     xn = U.to_nhwc(x, tdt)
     wf, wd = U.pack_convT(wt, dt)
+    call("onet_zero_border", ptr(cat, co), n, ho, wo, 2 * co, 0, co, 2 * h, 2 * w, dt, U.stream())
     call("onet_convT2x2_fwd", ptr(xn), cin, 0, n, h, w, cin, ptr(wf) if eng == U.ENGINE_TC else ptr(wt), ptr(b), co,
-         ptr(cat, co), 2 * co, 0, dt, eng, U.stream())
-    ref = F.conv_transpose2d(x, wt, b, stride=2)
+         ptr(cat, co), 2 * co, 0, ho, wo, dt, eng, U.stream())
+    ref = F.pad(F.conv_transpose2d(x, wt, b, stride=2), [0, pw, 0, ph])
     tol = 2e-6 if dt == U.F32 else 4e-3
     assert U.rel_l2(cat[..., co:].float().permute(0, 3, 1, 2), ref) < tol
     assert float(cat[..., :co].float().abs().max()) == 0.0
-    # backward: go lives in the upper half of a [n,2h,2w,2co] gradient buffer
-    go = rnd(torch.randn(n, co, 2 * h, 2 * w, device="cuda"))
-    gbuf = torch.zeros(n, 2 * h, 2 * w, 2 * co, dtype=tdt, device="cuda")
-    gbuf[..., co:] = go.permute(0, 2, 3, 1).to(tdt)
+    if ph:
+        assert float(cat[:, 2 * h:, :, co:].float().abs().max()) == 0.0
+    if pw:
+        assert float(cat[:, :, 2 * w:, co:].float().abs().max()) == 0.0
+    # backward: go lives in the upper half of a [n,ho,wo,2co] gradient buffer; the border gradient is dropped by F.pad
+    go_full = rnd(torch.randn(n, co, ho, wo, device="cuda"))
+    go = go_full[:, :, :2 * h, :2 * w].contiguous()
+    gbuf = torch.zeros(n, ho, wo, 2 * co, dtype=tdt, device="cuda")
+    gbuf[..., co:] = go_full.permute(0, 2, 3, 1).to(tdt)
     dx = torch.empty(n, h, w, cin, dtype=tdt, device="cuda")
     call("onet_convT2x2_dgrad", ptr(gbuf, co), 2 * co, 0, n, h, w, cin, ptr(wd) if eng == U.ENGINE_TC else ptr(wt), co,
-         ptr(dx), cin, 0, dt, eng, U.stream())
+         ptr(dx), cin, 0, ho, wo, dt, eng, U.stream())
     dref = F.conv2d(go, wt, stride=2)            # adjoint of conv_transpose2d
     assert U.rel_l2(U.from_nhwc(dx), dref) < tol
     dw = torch.zeros(cin, co, 2, 2, device="cuda")
     db = torch.zeros(co, device="cuda")
-    call("onet_convT2x2_wgrad", ptr(xn), cin, 0, ptr(gbuf, co), 2 * co, 0, n, h, w, cin, co, ptr(dw), ptr(db), dt, eng,
+    call("onet_convT2x2_wgrad", ptr(xn), cin, 0, ptr(gbuf, co), 2 * co, 0, n, h, w, cin, co, ptr(dw), ptr(db), ho, wo, dt, eng,
          U.stream())
     xr = x.clone().requires_grad_(True)
     wr = wt.clone().requires_grad_(True)
@@ -324,7 +336,8 @@ def test_dgrad_epilogue_column_sums_feed_upconv_bias_grad():
     wf, _ = U.pack_conv(wt, U.BF16)
     out = torch.empty(n, h, w, cout, dtype=torch.bfloat16, device="cuda")
     cs = torch.zeros(2, cout, dtype=torch.float64, device="cuda")
-    call("onet_conv3x3_fwd", ptr(x), cin, 0, n, h, w, cin, ptr(wf), cout, ptr(out), cout, 0, ptr(cs[0]), ptr(cs[1]), n, U.BF16,
+    # sums only: the tcgen05 epilogue accepts stat_sq = NULL
+    call("onet_conv3x3_fwd", ptr(x), cin, 0, n, h, w, cin, ptr(wf), cout, ptr(out), cout, 0, ptr(cs[0]), None, n, U.BF16,
          U.ENGINE_TC, U.stream())
     dbias = torch.full((64,), 0.5, device="cuda")
     call("onet_add_colsums", ptr(cs[0], 64), 64, ptr(dbias), U.stream())

@@ -20,7 +20,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-GOLDEN = ["c1_b2_32x32", "c3_b1_48x32", "c1_b2_32x32_noshare"]
+GOLDEN = ["c1_b2_32x32", "c3_b1_48x32", "c1_b2_32x32_noshare", "c1_b2_40x56_pad"]   # the last one: F.pad branch (:92-96)
 SAMPLE_STRIDE = 9973
 
 

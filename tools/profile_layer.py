@@ -53,12 +53,12 @@ def make_runner(kind, n, h, w, cin, cout):
         byts = 2.0 * n * h * w * (cin + 4 * co)
         if kind == "convT":
             return (lambda: call("onet_convT2x2_fwd", ptr(x), cin, 0, n, h, w, cin, ptr(wf), ptr(bias), co, ptr(cat, co), 2 * co,
-                                 0, U.BF16, U.ENGINE_TC, st())), flops, byts
+                                 0, 0, 0, U.BF16, U.ENGINE_TC, st())), flops, byts
         if kind == "convT_dgrad":
             return (lambda: call("onet_convT2x2_dgrad", ptr(cat, co), 2 * co, 0, n, h, w, cin, ptr(wd), co, ptr(dx), cin, 0,
-                                 U.BF16, U.ENGINE_TC, st())), flops, byts
+                                 0, 0, U.BF16, U.ENGINE_TC, st())), flops, byts
         return (lambda: call("onet_convT2x2_wgrad", ptr(x), cin, 0, ptr(cat, co), 2 * co, 0, n, h, w, cin, co, ptr(dw), ptr(db),
-                             U.BF16, U.ENGINE_TC, st())), flops, byts
+                             0, 0, U.BF16, U.ENGINE_TC, st())), flops, byts
     # ---- BatchNorm kinds
     c = cout
     g = max(n // 2, 1)
