@@ -109,14 +109,22 @@ __device__ __forceinline__ void px_butterfly1(float (&v)[32], int lane) {     //
     }
 }
 
-// BN == 64: fold the per-row running sums into the per-column fp64 accumulators of the owner threads.  Collective over
-// the kPxEpiWarps epilogue warps (named barrier 1).
-__device__ __forceinline__ void px_stat_fold64(PxStatAcc& a, int q, int ew, int lane, float* s_part) {
-    constexpr int BN = 64;
+// Fold the per-row running sums into the per-column fp64 accumulators of the owner threads.  Collective over the
+// kPxEpiWarps epilogue warps (named barrier 1).  BN == 64: rs / rq = sums / sums of squares of this warp's chunk;
+// BN == 128 (sums only): rs / rq = sums of this warp's chunks `half` and `half + 2`.
+template <int BN>
+__device__ __forceinline__ void px_stat_fold_rows(PxStatAcc& a, int q, int ew, int lane, float* s_part) {
     const int half = ew >> 2;
     px_butterfly(a.rs, a.rq, lane);
-    s_part[(q * 2 + 0) * BN + half * 32 + lane] = a.rs[0];
-    s_part[(q * 2 + 1) * BN + half * 32 + lane] = a.rq[0];
+    if (BN == 64) {
+        s_part[(q * 2 + 0) * BN + half * 32 + lane] = a.rs[0];
+        s_part[(q * 2 + 1) * BN + half * 32 + lane] = a.rq[0];
+    } else {
+        s_part[(q * 2 + 0) * BN + half * 32 + lane] = a.rs[0];
+        s_part[(q * 2 + 0) * BN + (half + 2) * 32 + lane] = a.rq[0];
+        s_part[(q * 2 + 1) * BN + half * 32 + lane] = 0.f;
+        s_part[(q * 2 + 1) * BN + (half + 2) * 32 + lane] = 0.f;
+    }
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kPxEpiWarps) : "memory");
     const int c = ew * 32 + lane;
     if (c < BN) {
@@ -134,7 +142,7 @@ __device__ __forceinline__ void px_stat_fold64(PxStatAcc& a, int q, int ew, int 
 }
 template <int BN>
 __device__ __forceinline__ void px_stat_flush(const PxParams& p, PxStatAcc& a, int ew, int lane, float* s_part) {
-    if (BN == 64 && p.stat_sum != nullptr && a.pending) px_stat_fold64(a, (ew & 3), ew, lane, s_part);
+    if ((BN == 64 || BN == 128) && p.stat_sum != nullptr && a.pending) px_stat_fold_rows<(BN == 64 ? 64 : 128)>(a, (ew & 3), ew, lane, s_part);
     const int c = ew * 32 + lane;
     if (a.n_tile >= 0 && c < BN && p.stat_sum != nullptr) {
         const long long col = static_cast<long long>(a.n_tile) * BN + c;
@@ -166,14 +174,17 @@ __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile,
     const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
     __nv_bfloat16* orow = p.out + ((static_cast<long long>(n) * p.H + h) * p.W + w) * p.ldo + p.out_coff + co0;
     const bool do_stats = p.stat_sum != nullptr;
-    if (BN == 64 && do_stats) {      // (collective) fold the running row sums when the statistics group or n-tile changes
+    // per-row running sums (no per-tile cross-lane traffic): 64-column tiles always; 128-column tiles when only column
+    // sums are wanted (rs / rq then hold this warp's two chunks)
+    const bool rowacc = do_stats && (BN == 64 || (BN == 128 && p.stat_sq == nullptr));
+    if (rowacc) {      // (collective) fold the running row sums when the statistics group or n-tile changes
         const int grp = min((nt * p.TN) / p.group_images, 1);
         if (sacc.n_tile != n_tile) {
             px_stat_flush<BN>(p, sacc, ew, lane, s_part);
             sacc.reset(n_tile);
             sacc.grp = grp;
         } else if (sacc.grp != grp) {
-            if (sacc.pending) px_stat_fold64(sacc, q, ew, lane, s_part);
+            if (sacc.pending) px_stat_fold_rows<BN>(sacc, q, ew, lane, s_part);
             sacc.grp = grp;
         }
         sacc.pending = 1;
@@ -203,6 +214,14 @@ __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile,
             if (BN == 64) {          // one chunk per warp: keep per-row running sums, no cross-lane traffic per tile
 #pragma unroll
                 for (int j = 0; j < 32; ++j) { sacc.rs[j] += v[j]; sacc.rq[j] += s2[j]; }
+            } else if (rowacc) {     // BN == 128, sums only: rs = this warp's first chunk, rq = its second chunk
+                if (ch < 2) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sacc.rs[j] += v[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sacc.rq[j] += v[j];
+                }
             } else if (p.stat_sq != nullptr) {
                 px_butterfly(v, s2, lane);
                 s_part[(q * 2 + 0) * BN + ch * 32 + lane] = v[0];
@@ -220,7 +239,7 @@ __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile,
         if (remote) mbar_arrive_cluster(arrive_bar);
         else mbar_arrive(arrive_bar);
     }
-    if (do_stats && BN != 64) {
+    if (do_stats && !rowacc) {
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kPxEpiWarps) : "memory");
         const int grp = min((nt * p.TN) / p.group_images, 1);     // at most two statistics groups (twin branches)
         if (sacc.n_tile != n_tile) {
