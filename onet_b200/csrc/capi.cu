@@ -443,6 +443,7 @@ static int wgrad3x3_halo2_tc(const bf16* g, long long ldg, int goff, int Mc, con
         p.ksplit = (p.num_px_tiles + best_per - 1) / best_per;
     }
     p.out = dw; p.m_total = Mc; p.n_total = Nc;
+    p.ks_slowest = getenv("ONET_WG_KS_FASTEST") ? 0 : 1;
     CUtensorMap tG, tI;
     const uint32_t gbox[5] = {64, 8, 1, 10, 1}, ibox[5] = {64, 8, 1, 8, 1};
     if (make_act_map(&tG, g + goff, Mc, N, H, W, ldg, gbox)) return 1;
@@ -499,6 +500,7 @@ static int wgrad3x3_halo_tc(const bf16* g, long long ldg, int goff, int Mc, cons
     p.num_n_tiles = Nc / BNW;
     pick_ksplit(p.ntypes * p.num_m_tiles * p.num_n_tiles, p.num_px_tiles, &p.ksplit, &p.px_tiles_per_split);
     p.out = dw; p.m_total = Mc; p.n_total = Nc;
+    p.ks_slowest = getenv("ONET_WG_KS_FASTEST") ? 0 : 1;
     CUtensorMap tG, tI;
     const uint32_t gbox[5] = {64, 8, 1, 10, 1}, ibox[5] = {64, 8, 1, 8, 1};
     if (make_act_map(&tG, g + goff, Mc, N, H, W, ldg, gbox)) return 1;
@@ -558,6 +560,7 @@ static int wgrad_tc(const bf16* g, long long ldg, int goff, int Mc, bool g_is_up
     pick_ksplit(p.ngroups * p.num_m_tiles * p.num_n_tiles, p.num_px_tiles, &p.ksplit, &p.px_tiles_per_split);
     p.out = dw;
     p.m_total = Mc; p.n_total = Nc; p.out_transposed = transposed ? 1 : 0;
+    p.ks_slowest = getenv("ONET_WG_KS_FASTEST") ? 0 : 1;
     CUtensorMap tG, tI;
     const uint32_t box[5] = {64, static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
     if (g_is_up) { if (make_up_map(&tG, g + goff, Mc, N, H, W, ldg, box, Ho, Wo)) return 1; }

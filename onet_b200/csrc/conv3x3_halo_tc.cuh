@@ -469,6 +469,7 @@ struct WhParams {
     int ksplit, px_tiles_per_split;
     int ntypes, num_m_tiles, num_n_tiles, m_tile_channels;
     WhUnit types[3];
+    int ks_slowest;                           // unit order: all (type, m, n) tiles of one pixel range run together (L2 reuse)
     float* out;                               // dW [m_total][n_total][9], accumulated with atomics
     int m_total, n_total;
 };
@@ -519,7 +520,8 @@ wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_const
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+            for (int unit_ = blockIdx.x; unit_ < num_units; unit_ += gridDim.x) {
+                const int unit = wg_unit_index(unit_, num_units, p.ksplit, p.ks_slowest);
                 const int ks = unit % p.ksplit;
                 const int nt = (unit / p.ksplit) % p.num_n_tiles;
                 const int mt = (unit / (p.ksplit * p.num_n_tiles)) % p.num_m_tiles;
@@ -549,7 +551,8 @@ wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+            for (int unit_ = blockIdx.x; unit_ < num_units; unit_ += gridDim.x, ++it) {
+                const int unit = wg_unit_index(unit_, num_units, p.ksplit, p.ks_slowest);
                 const int ks = unit % p.ksplit;
                 const WhUnit& u = p.types[unit / (p.ksplit * p.num_n_tiles * p.num_m_tiles)];
                 const int px_begin = ks * p.px_tiles_per_split;
@@ -578,7 +581,8 @@ wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_const
         const int q = warp & 3;
         const int row = q * 32 + lane;
         int it = 0;
-        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+        for (int unit_ = blockIdx.x; unit_ < num_units; unit_ += gridDim.x, ++it) {
+            const int unit = wg_unit_index(unit_, num_units, p.ksplit, p.ks_slowest);
             const int nt = (unit / p.ksplit) % p.num_n_tiles;
             const int mt = (unit / (p.ksplit * p.num_n_tiles)) % p.num_m_tiles;
             const WhUnit& u = p.types[unit / (p.ksplit * p.num_n_tiles * p.num_m_tiles)];
@@ -626,6 +630,7 @@ struct Wh2Params {
     int tiles_w, tiles_h, num_px_tiles;
     int ksplit, px_tiles_per_split;
     int num_m_units, num_m_pairs, num_n_tiles;     // M units = (Mc / 128) * 3
+    int ks_slowest;
     float* out;
     int m_total, n_total;
 };
@@ -679,7 +684,8 @@ wgrad3x3_halo2_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
             const uint32_t lead_full = mapa_shared(bar_full, 0);
             int stage = 0;
             uint32_t phase = 0;
-            for (int unit = pair; unit < num_units; unit += npairs) {
+            for (int unit_ = pair; unit_ < num_units; unit_ += npairs) {
+                const int unit = wg_unit_index(unit_, num_units, p.ksplit, p.ks_slowest);
                 const int ks = unit % p.ksplit;
                 const int nt = (unit / p.ksplit) % p.num_n_tiles;
                 const int mu = 2 * (unit / (p.ksplit * p.num_n_tiles)) + static_cast<int>(rank);
@@ -710,7 +716,8 @@ wgrad3x3_halo2_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int unit = pair; unit < num_units; unit += npairs, ++it) {
+            for (int unit_ = pair; unit_ < num_units; unit_ += npairs, ++it) {
+                const int unit = wg_unit_index(unit_, num_units, p.ksplit, p.ks_slowest);
                 const int ks = unit % p.ksplit;
                 const int px_begin = ks * p.px_tiles_per_split;
                 const int px_end = min(px_begin + p.px_tiles_per_split, p.num_px_tiles);
@@ -740,7 +747,8 @@ wgrad3x3_halo2_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_cons
         const int row = q * 32 + lane;
         const uint32_t lead_tempty = mapa_shared(bar_tempty, 0);
         int it = 0;
-        for (int unit = pair; unit < num_units; unit += npairs, ++it) {
+        for (int unit_ = pair; unit_ < num_units; unit_ += npairs, ++it) {
+            const int unit = wg_unit_index(unit_, num_units, p.ksplit, p.ks_slowest);
             const int nt = (unit / p.ksplit) % p.num_n_tiles;
             const int mu = 2 * (unit / (p.ksplit * p.num_n_tiles)) + static_cast<int>(rank);
             const int mt = mu / 3, kw = mu - 3 * mt;

@@ -431,6 +431,15 @@ tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // =====================================================================================================
 // weight-gradient kernel
 // =====================================================================================================
+// Work-unit order of the split-K weight-gradient kernels.  The decode below expects index = tile * ksplit + ks; with
+// ks_slowest the CTAs walk the units pixel range by pixel range instead, so that all (m, n) tiles of one pixel range run
+// at the same time and share its G / In slabs through L2 (ncu: 2.6x fewer DRAM bytes for 256 -> 256 at 64 x 64).
+__device__ __forceinline__ int wg_unit_index(int u, int num_units, int ksplit, int ks_slowest) {
+    if (!ks_slowest) return u;
+    const int tiles = num_units / ksplit;
+    return (u % tiles) * ksplit + u / tiles;
+}
+
 constexpr int kWgMaxAcc = 3;
 constexpr int kWgMaxGroups = 4;
 
@@ -453,6 +462,7 @@ struct WgParams {
     float* out;                          // dW, PyTorch layout, accumulated with atomics
     int m_total, n_total;                // out index = (m*n_total + n)*ntaps + t, or (n*m_total + m)*ntaps + t
     int out_transposed;
+    int ks_slowest;
 };
 
 template <int BNW>
@@ -505,7 +515,8 @@ tapgemm_wg_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+            for (int unit_ = blockIdx.x; unit_ < num_units; unit_ += gridDim.x) {
+                const int unit = wg_unit_index(unit_, num_units, p.ksplit, p.ks_slowest);
                 const int ks = unit % p.ksplit;
                 const int nt = (unit / p.ksplit) % p.num_n_tiles;
                 const int mt = (unit / (p.ksplit * p.num_n_tiles)) % p.num_m_tiles;
@@ -545,7 +556,8 @@ tapgemm_wg_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+            for (int unit_ = blockIdx.x; unit_ < num_units; unit_ += gridDim.x, ++it) {
+                const int unit = wg_unit_index(unit_, num_units, p.ksplit, p.ks_slowest);
                 const int ks = unit % p.ksplit;
                 const int g = unit / (p.ksplit * p.num_n_tiles * p.num_m_tiles);
                 const int nacc = p.groups[g].nacc;
@@ -575,7 +587,8 @@ tapgemm_wg_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         const int q = warp & 3;
         const int row = q * 32 + lane;
         int it = 0;
-        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+        for (int unit_ = blockIdx.x; unit_ < num_units; unit_ += gridDim.x, ++it) {
+            const int unit = wg_unit_index(unit_, num_units, p.ksplit, p.ks_slowest);
             const int nt = (unit / p.ksplit) % p.num_n_tiles;
             const int mt = (unit / (p.ksplit * p.num_n_tiles)) % p.num_m_tiles;
             const int g = unit / (p.ksplit * p.num_n_tiles * p.num_m_tiles);
