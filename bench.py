@@ -144,16 +144,16 @@ def _family(name, a):
     """(family, algorithmic FLOPs) of one C-ABI call from its integer arguments."""
     if name == "onet_conv3x3_fwd":
         fl = 2.0 * 9 * a[3] * a[4] * a[5] * a[6] * a[8]
-        return ("tapgemm_px (conv3x3 fwd/dgrad, tcgen05)" if a[16] == 1 else "conv3x3_simt"), fl
+        return ("conv3x3 fwd/dgrad (tcgen05 implicit GEMM)" if a[16] == 1 else "conv_first fwd (CUDA cores)"), fl
     if name == "onet_conv3x3_wgrad":
         fl = 2.0 * 9 * a[6] * a[7] * a[8] * a[9] * a[10]
-        return ("tapgemm_wg (conv3x3 wgrad, tcgen05)" if a[13] == 1 else "conv3x3_wgrad_simt"), fl
+        return ("conv3x3 wgrad (tcgen05 split-K)" if a[13] == 1 else "conv_first wgrad (CUDA cores)"), fl
     if name == "onet_convT2x2_fwd":
-        return ("tapgemm_px (convT, tcgen05)" if a[16] == 1 else "convT_simt"), 2.0 * 4 * a[3] * a[4] * a[5] * a[6] * a[9]
+        return ("up-conv fwd/dgrad (tcgen05)" if a[16] == 1 else "convT_simt"), 2.0 * 4 * a[3] * a[4] * a[5] * a[6] * a[9]
     if name == "onet_convT2x2_dgrad":
-        return ("tapgemm_px (convT, tcgen05)" if a[15] == 1 else "convT_simt"), 2.0 * 4 * a[3] * a[4] * a[5] * a[6] * a[8]
+        return ("up-conv fwd/dgrad (tcgen05)" if a[15] == 1 else "convT_simt"), 2.0 * 4 * a[3] * a[4] * a[5] * a[6] * a[8]
     if name == "onet_convT2x2_wgrad":
-        return ("tapgemm_wg (convT wgrad, tcgen05)" if a[16] == 1 else "convT_simt"), 2.0 * 4 * a[6] * a[7] * a[8] * a[9] * a[10]
+        return ("up-conv wgrad (tcgen05)" if a[16] == 1 else "convT_simt"), 2.0 * 4 * a[6] * a[7] * a[8] * a[9] * a[10]
     return name.replace("onet_", ""), 0.0
 
 
@@ -309,7 +309,12 @@ def main():
             ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
             roof = dict(bound="tensor", kernel=top, achieved=ach, peak=pk["bf16_sustained"], unit="TFLOP/s",
                         frac=ach / pk["bf16_sustained"], traffic=None, peak_source=pk["src"] + ", sustained figure",
-                        share_of_step=d["ms"] / total_ms)
+                        share_of_step=d["ms"] / total_ms, launches_per_step=d["calls"],
+                        note="family of kernels (halo / CTA-pair / weight-resident variants) over 34 launches of different "
+                             "shapes; achieved = sum of algorithmic FLOPs / sum of CUDA-event times of those launches")
+            cap = os.path.join(ROOT, "profiles", "r1_ncu_traffic_v3.json")
+            if os.path.isfile(cap):      # DRAM bytes of representative launches from committed ncu --set full captures
+                roof["ncu_captures"] = [c for c in json.load(open(cap)) if "conv3x3" in c["kernel"] or "wgrad" in c["kernel"]]
         kernels = {k: dict(ms_per_step=round(d["ms"], 3), share=round(d["ms"] / total_ms, 4), calls=d["calls"],
                            tflops=(round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 1) if d["flops"] else None))
                    for k, d in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
