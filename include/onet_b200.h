@@ -62,6 +62,15 @@ int onet_conv3x3_fwd(const void* in, int64_t ldi, int ci_off, int N, int H, int 
                      void* out, int64_t ldo, int co_off, double* stat_sum, double* stat_sq, int group_images,
                      int dtype, int engine, void* stream);
 
+/* Inference: the same convolution with BatchNorm(eval) + ReLU folded into the epilogue, out = relu(conv * scale + shift)
+ * (scale / shift [G][Cout] from onet_bn_eval_prepare), written straight to its destination (e.g. a concat-buffer slice):
+ * nn.Conv2d + nn.BatchNorm2d(eval) + nn.ReLU, Onet_vanilla_20240606.py:47-53.  Tensor-core engine, bf16 only. */
+int onet_conv3x3_bn_relu_infer(const void* in, int64_t ldi, int ci_off, int N, int H, int W, int Cin, const void* wp, int Cout,
+                               const float* scale, const float* shift, int group_images, void* out, int64_t ldo, int co_off,
+                               int dtype, int engine, void* stream);
+/* nn.MaxPool2d(2) (floor) of channels [ioff, ioff+C) of an NHWC buffer -> dense [N,H/2,W/2,C] (inference path, :67) */
+int onet_maxpool2x2(const void* in, int64_t ldi, int ioff, int N, int H, int W, int C, void* out, int dtype, void* stream);
+
 /* Weight gradient of the same convolution, accumulated (atomics) into dw fp32 [Cout][Cin][3][3]. */
 int onet_conv3x3_wgrad(const void* g, int64_t ldg, int g_off, const void* in, int64_t ldi, int ci_off, int N, int H,
                        int W, int Cin, int Cout, float* dw, int dtype, int engine, void* stream);

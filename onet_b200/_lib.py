@@ -51,6 +51,8 @@ SIGNATURES = {
     "onet_pack_convT_weights": [_p, _i, _i, _p, _p, _i, _p],
     "onet_pack_all_weights": [_i, _p, _p, _p, _p, _p, _p, _i, _p],
     "onet_conv3x3_fwd": [_p, _i64, _i, _i, _i, _i, _i, _p, _i, _p, _i64, _i, _p, _p, _i, _i, _i, _p],
+    "onet_conv3x3_bn_relu_infer": [_p, _i64, _i, _i, _i, _i, _i, _p, _i, _p, _p, _i, _p, _i64, _i, _i, _i, _p],
+    "onet_maxpool2x2": [_p, _i64, _i, _i, _i, _i, _i, _p, _i, _p],
     "onet_conv3x3_wgrad": [_p, _i64, _i, _p, _i64, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p],
     "onet_bn_finalize": [_p, _p, _i, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p],
     "onet_bn_eval_prepare": [_i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],

@@ -244,7 +244,8 @@ static void pick_ksplit(int base_units, int num_px_tiles, int* ksplit, int* per_
 static int pick_bn(int cout) { return (cout % 256 == 0) ? 256 : (cout % 128 == 0 ? 128 : 64); }
 
 static int conv3x3_tc(const bf16* in, long long ldi, int ci_off, int N, int H, int W, int Cin, const bf16* wp, int Cout,
-                      bf16* out, long long ldo, int co_off, double* ssum, double* ssq, int group_images, cudaStream_t st) {
+                      bf16* out, long long ldo, int co_off, double* ssum, double* ssq, int group_images, cudaStream_t st,
+                      const float* bn_scale = nullptr, const float* bn_shift = nullptr) {
     if (Cin % 64 || Cout % 64) return fail("tc conv needs Cin, Cout multiples of 64 (got %d, %d)", Cin, Cout);
     if (ldo % 8 || co_off % 8) return fail("tc conv output channel stride/offset must be multiples of 8");
     PxParams p;
@@ -262,6 +263,7 @@ static int conv3x3_tc(const bf16* in, long long ldi, int ci_off, int N, int H, i
         p.epi_mode = EPI_STORE;
         p.out = out; p.ldo = ldo; p.out_coff = co_off;
         p.stat_sum = ssum; p.stat_sq = ssq; p.cout_total = Cout; p.group_images = group_images > 0 ? group_images : N;
+        p.scale = bn_scale; p.shift = bn_shift;
         CUtensorMap tA, tB;
         const uint32_t hbox[5] = {64, 8, 1, 18, 1};
         if (make_act_map(&tA, in + ci_off, Cin, N, H, W, ldi, hbox)) return 1;
@@ -284,7 +286,7 @@ static int conv3x3_tc(const bf16* in, long long ldi, int ci_off, int N, int H, i
         if (BN == 128) return launch_halo_px<128>(tA, tB, p, st);
         return launch_halo_px<64>(tA, tB, p, st);
     }
-    px_tiling(p, N, H, W, ssum ? group_images : 0);
+    px_tiling(p, N, H, W, (ssum || bn_scale) ? group_images : 0);
     p.num_n_tiles = Cout / BN;
     p.ntaps = 9; p.k_chunks = Cin / 64; p.cin = Cin;
     // same accumulation order as the halo kernels (filter column outer, filter row inner): a pixel gets bit-identical
@@ -297,6 +299,7 @@ static int conv3x3_tc(const bf16* in, long long ldi, int ci_off, int N, int H, i
     p.epi_mode = EPI_STORE;
     p.out = out; p.ldo = ldo; p.out_coff = co_off;
     p.stat_sum = ssum; p.stat_sq = ssq; p.cout_total = Cout; p.group_images = group_images > 0 ? group_images : N;
+    p.scale = bn_scale; p.shift = bn_shift;
     CUtensorMap tA, tB;
     const uint32_t box[5] = {64, static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
     if (make_act_map(&tA, in + ci_off, Cin, N, H, W, ldi, box)) return 1;
@@ -674,6 +677,27 @@ int onet_conv3x3_fwd(const void* in, int64_t ldi, int ci_off, int N, int H, int 
                                                                 static_cast<const bf16*>(wp), Cout, static_cast<bf16*>(out), ldo,
                                                                 co_off, stat_sum, stat_sq, gi);
     return check_launch("conv3x3_simt");
+}
+
+int onet_conv3x3_bn_relu_infer(const void* in, int64_t ldi, int ci_off, int N, int H, int W, int Cin, const void* wp, int Cout,
+                               const float* scale, const float* shift, int group_images, void* out, int64_t ldo, int co_off,
+                               int dtype, int engine, void* stream) {
+    if (N <= 0 || H <= 0 || W <= 0) return fail("conv3x3_bn_relu_infer: empty tensor");
+    if (engine != ONET_ENGINE_TC || dtype != ONET_BF16) return fail("conv3x3_bn_relu_infer: tensor-core engine, bf16 only");
+    if (scale == nullptr || shift == nullptr) return fail("conv3x3_bn_relu_infer: scale and shift are required");
+    return conv3x3_tc(static_cast<const bf16*>(in), ldi, ci_off, N, H, W, Cin, static_cast<const bf16*>(wp), Cout,
+                      static_cast<bf16*>(out), ldo, co_off, nullptr, nullptr, group_images, ST(stream), scale, shift);
+}
+
+int onet_maxpool2x2(const void* in, int64_t ldi, int ioff, int N, int H, int W, int C, void* out, int dtype, void* stream) {
+    if (C % 8 || ldi % 8 || ioff % 8) return fail("maxpool2x2: channel counts/offsets must be multiples of 8");
+    const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
+    if (total == 0) return 0;
+    if (dtype == ONET_F32)
+        maxpool2x2_kernel<float><<<grid_for(total, 256, 148 * 16), 256, 0, ST(stream)>>>(static_cast<const float*>(in), ldi, ioff, N, H, W, C, static_cast<float*>(out));
+    else
+        maxpool2x2_kernel<bf16><<<grid_for(total, 256, 148 * 16), 256, 0, ST(stream)>>>(static_cast<const bf16*>(in), ldi, ioff, N, H, W, C, static_cast<bf16*>(out));
+    return check_launch("maxpool2x2");
 }
 
 int onet_conv3x3_wgrad(const void* g, int64_t ldg, int g_off, const void* in, int64_t ldi, int ci_off, int N, int H,

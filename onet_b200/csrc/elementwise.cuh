@@ -437,6 +437,36 @@ __global__ void bn_param_grad_kernel(const double* __restrict__ sums, int G, int
     }
 }
 
+// 2x2 max-pool (floor semantics) of a channel window of an NHWC buffer: the inference path, where BatchNorm + ReLU are folded
+// into the convolution epilogue and only the pooled map is still missing (nn.MaxPool2d(2), Onet_vanilla_20240606.py:67)
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool2x2_kernel(const T* __restrict__ in, long long ldi, int ioff, int N, int H, int W, int C, T* __restrict__ out) {
+    const int OC = C >> 3, HP = H >> 1, WP = W >> 1;
+    const long long total = static_cast<long long>(N) * HP * WP * OC;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int oc = static_cast<int>(idx % OC);
+        long long q = idx / OC;
+        const int w2 = static_cast<int>(q % WP); q /= WP;
+        const int h2 = static_cast<int>(q % HP);
+        const long long n = q / HP;
+        Raw8<T> r[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+            r[d] = ldraw<T>(in + ((n * H + 2 * h2 + (d >> 1)) * W + 2 * w2 + (d & 1)) * ldi + ioff + oc * 8);
+        float mx[8], v[8];
+        unpack(r[0], mx);
+#pragma unroll
+        for (int d = 1; d < 4; ++d) {
+            unpack(r[d], v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mx[i] = fmaxf(mx[i], v[i]);
+        }
+        store8<T>(out + ((n * HP + h2) * WP + w2) * C + oc * 8, mx);
+    }
+}
+
 // zero channels [coff, coff+C) of the pixels with h >= Hv or w >= Wv of a [N,Ho,Wo,ld] buffer: the border F.pad adds when the
 // skip tensor is one pixel larger than the up-sampled map (Onet_vanilla_20240606.py:92-96)
 template <typename T>

@@ -23,6 +23,7 @@ namespace onet {
 constexpr int kMaxTaps = 9;
 
 enum EpiMode : int { EPI_STORE = 0, EPI_CONVT = 1 };
+// (EPI_STORE with PxParams::scale != nullptr = inference: BatchNorm(eval) + ReLU folded into the store)
 
 struct PxParams {
     // output pixel grid and its tiling (all tile dims are powers of two, TW*TH*TN <= 128)
@@ -43,6 +44,8 @@ struct PxParams {
     double* stat_sq;
     int cout_total;
     int group_images;          // images per BatchNorm statistics group (twin branch)
+    const float* scale;        // EPI_STORE, inference: per-group per-channel BatchNorm(eval) scale / shift [G][cout_total];
+    const float* shift;        //   the epilogue then stores relu(acc * scale + shift) instead of the raw conv output
     const float* bias;         // EPI_CONVT: [co_per_tap]
     int co_per_tap;            // EPI_CONVT: output channels per 2x2 position
     int Ho, Wo;                // EPI_CONVT: height / width of the fine grid the buffer holds (>= 2H, 2W; F.pad border beyond)
@@ -195,8 +198,22 @@ __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile,
         tmem_ld_32x32(t_addr + ch * 32, r);
         tmem_ld_wait();
         uint32_t pk[16];
+        if (p.scale != nullptr) {      // inference: y = relu(acc * scale[c] + shift[c])
+            const int grp = min((nt * p.TN) / p.group_images, 1);
+            const float4* sc4 = reinterpret_cast<const float4*>(p.scale + static_cast<long long>(grp) * p.cout_total + co0 + ch * 32);
+            const float4* sh4 = reinterpret_cast<const float4*>(p.shift + static_cast<long long>(grp) * p.cout_total + co0 + ch * 32);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+            for (int j = 0; j < 8; ++j) {
+                const float4 sc = __ldg(sc4 + j), sh = __ldg(sh4 + j);
+                pk[2 * j] = pack_bf16x2(fmaxf(fmaf(__uint_as_float(r[4 * j]), sc.x, sh.x), 0.f),
+                                        fmaxf(fmaf(__uint_as_float(r[4 * j + 1]), sc.y, sh.y), 0.f));
+                pk[2 * j + 1] = pack_bf16x2(fmaxf(fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z), 0.f),
+                                            fmaxf(fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w), 0.f));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+        }
         if (valid) {
             uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
 #pragma unroll

@@ -334,8 +334,9 @@ class _Engine:
         wf, _ = self._packed(conv, "conv")
         eng = self._engine_for(cin, cout)
         G = seg.groups
-        Y = self._empty(n, h, w, cout)
         st = self.stream
+        fused_eval = (not rec.training_stats) and eng == ENGINE_TC and not rec.save
+        Y = None if fused_eval else self._empty(n, h, w, cout)
         if rec.training_stats:
             stats = rec.stat_pool[rec.stat_off:rec.stat_off + 2 * G * cout].view(2, G, cout)
             rec.stat_off += 2 * G * cout
@@ -349,11 +350,20 @@ class _Engine:
                  float(bn.momentum), ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]), st)
             rec.nbt.append((bn.num_batches_tracked, G))
         else:
-            call("onet_conv3x3_fwd", ptr(src, self._img_off(src, n0) + off_src), ld_src, 0, n, h, w, cin, ptr(wf), cout,
-                 ptr(Y), cout, 0, None, None, seg.group_images, self.dt, eng, st)
             aff = torch.empty(4, G, cout, dtype=torch.float32, device=self.dev)
             call("onet_bn_eval_prepare", G, cout, ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var),
                  ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var), ptr(aff[2]), ptr(aff[3]), st)
+            if fused_eval:
+                # inference: BatchNorm(eval) + ReLU folded into the conv epilogue, written straight to its destination
+                call("onet_conv3x3_bn_relu_infer", ptr(src, self._img_off(src, n0) + off_src), ld_src, 0, n, h, w, cin, ptr(wf),
+                     cout, ptr(aff[2]), ptr(aff[3]), seg.group_images, ptr(dst, self._img_off(dst, n0) + off_dst), ld_dst, 0,
+                     self.dt, eng, st)
+                if pool is not None:
+                    call("onet_maxpool2x2", ptr(dst, self._img_off(dst, n0) + off_dst), ld_dst, 0, n, h, w, cout,
+                         ptr(pool, self._img_off(pool, n0)), self.dt, st)
+                return
+            call("onet_conv3x3_fwd", ptr(src, self._img_off(src, n0) + off_src), ld_src, 0, n, h, w, cin, ptr(wf), cout,
+                 ptr(Y), cout, 0, None, None, seg.group_images, self.dt, eng, st)
         call("onet_bn_relu_apply", ptr(Y), n, h, w, cout, ptr(aff[2]), ptr(aff[3]), seg.group_images,
              ptr(dst, self._img_off(dst, n0) + off_dst), ld_dst, 0,
              ptr(pool, self._img_off(pool, n0)) if pool is not None else None, self.dt, st)
