@@ -138,6 +138,12 @@ int onet_head_bwd(const void* L, int64_t ldl, int offl, const void* Hf, int64_t 
 /* argmax of the 2-way softmax: 1 iff Vd > Vt (Onet.predict_label :193-202) */
 int onet_predict_label(const float* Vt, const float* Vd, int64_t n, int64_t* out, void* stream);
 
+/* Evaluation next to the path: counts[pred * 2 + gt] += 1 over n pixels, pred = (Vd > Vt) (predict_label :193-202), gt != 0
+ * -> 1.  counts is a zero-initialised int64[4]; accuracy / mIoU / detection rate / false-alarm rate / target IoU of
+ * utils_20231218.py:100-234 (evaluate_nau_segmentation_v2, re_assign_label) are functions of these four numbers
+ * (onet_b200/evaluate.py), so test_simclutter's per-batch host syncs collapse into one 32-byte read-back. */
+int onet_eval_confusion(const float* Vt, const float* Vd, const int64_t* gt, int64_t n, int64_t* counts, void* stream);
+
 /* torch.optim.Adam step (no weight decay, amsgrad=False; Train_Onet_on_simclutter_20250407.py:181-182) over a
  * flat fp32 arena; `step` is the 1-based step count, gradients are multiplied by grad_scale first. */
 int onet_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,

@@ -1003,6 +1003,13 @@ int onet_predict_label(const float* Vt, const float* Vd, int64_t n, int64_t* out
     return check_launch("predict_label");
 }
 
+int onet_eval_confusion(const float* Vt, const float* Vd, const int64_t* gt, int64_t n, int64_t* counts, void* stream) {
+    if (n <= 0) return 0;
+    eval_confusion_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, ST(stream)>>>(Vt, Vd, reinterpret_cast<const long long*>(gt), n,
+                                                                           reinterpret_cast<unsigned long long*>(counts));
+    return check_launch("eval_confusion");
+}
+
 int onet_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, int step, float grad_scale, void* stream) {
     if (step < 1) return fail("adam: step must be >= 1");

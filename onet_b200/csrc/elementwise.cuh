@@ -801,4 +801,31 @@ __global__ void predict_label_kernel(const float* __restrict__ Vt, const float* 
         out[i] = Vd[i] > Vt[i] ? 1 : 0;
 }
 
+// Evaluation step next to the path (test_simclutter, Train_Onet_on_simclutter_20250407.py:109-147): predicted label
+// (1 iff Vd > Vt, predict_label :193-202) against the ground-truth label, reduced on the device to the 2 x 2 confusion
+// counts counts[pred * 2 + gt] from which utils_20231218.py's _acc / _miou / _detection_rate / _false_alarm_rate /
+// _target_iou and re_assign_label all follow - one 32-byte read-back per batch instead of five reductions with .item().
+__global__ void __launch_bounds__(256)
+eval_confusion_kernel(const float* __restrict__ Vt, const float* __restrict__ Vd, const long long* __restrict__ gt, long long n,
+                      unsigned long long* __restrict__ counts) {
+    unsigned int c[4] = {0u, 0u, 0u, 0u};
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int pred = Vd[i] > Vt[i] ? 1 : 0;
+        const int g = gt[i] != 0 ? 1 : 0;
+        c[pred * 2 + g] += 1u;
+    }
+    __shared__ unsigned int s[4];
+    if (threadIdx.x < 4) s[threadIdx.x] = 0u;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        unsigned int v = c[k];
+        for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s[k], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 && s[threadIdx.x]) atomicAdd(counts + threadIdx.x, static_cast<unsigned long long>(s[threadIdx.x]));
+}
+
 }  // namespace onet

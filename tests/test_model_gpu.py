@@ -204,3 +204,28 @@ def test_graph_replayed_step_matches_eager_step(mode):
     assert _rel(t1[4] - t1[0], t0[4] - t0[0]) < (0.12 if mode == "fp32" else 0.6)
     for a, b in zip(b0, b1):
         assert torch.allclose(a, b, rtol=1e-3 if mode == "fp32" else 5e-2, atol=1e-3)
+
+
+def test_on_device_evaluation_matches_oracle(golden_dir):
+    """onet_eval_confusion + onet_b200.evaluate.segmentation_metrics against the CPU oracle of re_assign_label +
+    evaluate_nau_segmentation_v2 on random maps, and against the reference's golden metrics."""
+    from onet_b200.evaluate import confusion_counts, segmentation_metrics
+    from oracle import eval_oracle as ev
+    torch.manual_seed(8)
+    for shape, p_fg in (((3, 1, 40, 56), 0.15), ((2, 1, 256, 256), 0.7), ((1, 1, 16, 16), 0.0)):
+        Vt, Vd = torch.randn(shape, device="cuda"), torch.randn(shape, device="cuda")
+        gt = (torch.rand(shape[0], shape[2], shape[3], device="cuda") < p_fg).long()
+        counts = confusion_counts(Vt, Vd, gt)
+        pred = (Vd > Vt).squeeze(1).long().cpu()
+        want = [int(((pred == p) & (gt.cpu() == g)).sum()) for p in (0, 1) for g in (0, 1)]
+        assert counts.tolist() == want
+        m = segmentation_metrics(counts, reassign=True)
+        re = ev.re_assign_label(pred, gt.cpu())
+        ref = ev.evaluate(re, gt.cpu())
+        assert np.allclose([m["acc"], m["miou"], m["dr"], m["far"], m["t_iou"]], ref, rtol=1e-6, atol=1e-7)
+    z = np.load(os.path.join(golden_dir, "eval_kat.npz"))
+    for i in z["cases"]:
+        pred, gt = torch.from_numpy(z[f"pred{i}"]).cuda(), torch.from_numpy(z[f"gt{i}"]).cuda()
+        counts = confusion_counts(torch.zeros_like(pred, dtype=torch.float32), pred.float(), gt)   # Vd > Vt  <=>  pred == 1
+        m = segmentation_metrics(counts, reassign=True)
+        assert np.allclose([m["acc"], m["miou"], m["dr"], m["far"], m["t_iou"]], z[f"metrics{i}"], rtol=1e-6, atol=1e-7)

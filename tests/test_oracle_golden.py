@@ -141,3 +141,31 @@ def test_adam_matches_torch():
         opt.step()
         p, m, v = orc.adam_step(p, g, m, v, step, 5e-6)
     assert torch.allclose(p, ref.detach(), rtol=1e-6, atol=1e-9)
+
+
+def _eval_cases(golden_dir):
+    import os
+    z = np.load(os.path.join(golden_dir, "eval_kat.npz"))
+    return [(torch.from_numpy(z[f"pred{i}"]), torch.from_numpy(z[f"gt{i}"]), torch.from_numpy(z[f"re{i}"]), z[f"metrics{i}"])
+            for i in z["cases"]]
+
+
+def test_eval_oracle_matches_reference_golden(golden_dir):
+    """oracle/eval_oracle.py against re_assign_label + evaluate_nau_segmentation_v2 of the unmodified reference
+    (tests/golden/make_eval_golden.py)."""
+    from oracle import eval_oracle as ev
+    for pred, gt, re, metrics in _eval_cases(golden_dir):
+        got_re = ev.re_assign_label(pred, gt)
+        assert torch.equal(got_re, re)
+        assert np.allclose(np.array(ev.evaluate(got_re, gt)), metrics, rtol=1e-6, atol=1e-7)
+
+
+def test_metrics_from_confusion_counts_match_reference_golden(golden_dir):
+    """Host arithmetic of onet_b200.evaluate on the four confusion counts (the counts themselves come from the CUDA kernel,
+    tested with -m gpu; here they are formed with torch on CPU) against the reference's metrics."""
+    from onet_b200.evaluate import segmentation_metrics
+    for pred, gt, re, metrics in _eval_cases(golden_dir):
+        counts = [int(((pred == p) & (gt == g)).sum()) for p in (0, 1) for g in (0, 1)]
+        m = segmentation_metrics(counts, reassign=True)
+        assert m["flipped"] == (not torch.equal(re, pred))
+        assert np.allclose([m["acc"], m["miou"], m["dr"], m["far"], m["t_iou"]], metrics, rtol=1e-6, atol=1e-7)
