@@ -141,25 +141,30 @@ def run_reference(args):
 # per-kernel accounting for the roofline entry
 # --------------------------------------------------------------------------------------------------
 def _family(name, a):
-    """(family, algorithmic FLOPs) of one C-ABI call from its integer arguments."""
+    """(family, algorithmic FLOPs, shape string) of one C-ABI call from its integer arguments."""
     if name == "onet_conv3x3_fwd":
         fl = 2.0 * 9 * a[3] * a[4] * a[5] * a[6] * a[8]
-        return ("conv3x3 fwd/dgrad (tcgen05 implicit GEMM)" if a[16] == 1 else "conv_first fwd (CUDA cores)"), fl
+        return ("conv3x3 fwd/dgrad (tcgen05 implicit GEMM)" if a[16] == 1 else "conv_first fwd (CUDA cores)"), fl, \
+            f"{a[6]}->{a[8]} @{a[4]}x{a[5]} N={a[3]}"
     if name == "onet_conv3x3_wgrad":
         fl = 2.0 * 9 * a[6] * a[7] * a[8] * a[9] * a[10]
-        return ("conv3x3 wgrad (tcgen05 split-K)" if a[13] == 1 else "conv_first wgrad (CUDA cores)"), fl
+        return ("conv3x3 wgrad (tcgen05 split-K)" if a[13] == 1 else "conv_first wgrad (CUDA cores)"), fl, \
+            f"{a[9]}->{a[10]} @{a[7]}x{a[8]} N={a[6]}"
     if name == "onet_convT2x2_fwd":
-        return ("up-conv fwd/dgrad (tcgen05)" if a[16] == 1 else "convT_simt"), 2.0 * 4 * a[3] * a[4] * a[5] * a[6] * a[9]
+        return ("up-conv fwd/dgrad (tcgen05)" if a[16] == 1 else "convT_simt"), 2.0 * 4 * a[3] * a[4] * a[5] * a[6] * a[9], \
+            f"{a[6]}->{a[9]} @{a[4]}x{a[5]} N={a[3]}"
     if name == "onet_convT2x2_dgrad":
-        return ("up-conv fwd/dgrad (tcgen05)" if a[15] == 1 else "convT_simt"), 2.0 * 4 * a[3] * a[4] * a[5] * a[6] * a[8]
+        return ("up-conv fwd/dgrad (tcgen05)" if a[15] == 1 else "convT_simt"), 2.0 * 4 * a[3] * a[4] * a[5] * a[6] * a[8], \
+            f"{a[6]}->{a[8]} @{a[4]}x{a[5]} N={a[3]}"
     if name == "onet_convT2x2_wgrad":
-        return ("up-conv wgrad (tcgen05)" if a[16] == 1 else "convT_simt"), 2.0 * 4 * a[6] * a[7] * a[8] * a[9] * a[10]
-    return name.replace("onet_", ""), 0.0
+        return ("up-conv wgrad (tcgen05)" if a[16] == 1 else "convT_simt"), 2.0 * 4 * a[6] * a[7] * a[8] * a[9] * a[10], \
+            f"{a[9]}->{a[10]} @{a[7]}x{a[8]} N={a[6]}"
+    return name.replace("onet_", ""), 0.0, ""
 
 
 def profile_steps(trainer, x, nsteps, record=True):
     """Per-call CUDA-event timing of `nsteps` more steps.  Every rank must run the steps (they contain the gradient
-    all-reduce); only ranks with record=True keep the events."""
+    all-reduce); only ranks with record=True keep the events.  Returns (by family, by kernel variant, by variant+shape)."""
     import torch
     from onet_b200 import _lib
     _lib.PROFILE = [] if record else None
@@ -168,28 +173,31 @@ def profile_steps(trainer, x, nsteps, record=True):
     torch.cuda.synchronize()
     prof, _lib.PROFILE = _lib.PROFILE, None
     if not record:
-        return {}
+        return {}, {}, {}
     detail = os.environ.get("ONET_BENCH_DETAIL")
-    if detail:      # per-call dump of the LAST profiled step: name, integer args, ms, TFLOP/s
+    if detail:      # per-call dump of the LAST profiled step: name, kernel variant, integer args, ms, TFLOP/s
         per = len(prof) // nsteps
         with open(detail, "w") as f:
-            for name, a, e0, e1 in prof[-per:]:
-                fam_name, fl = _family(name, a)
+            for name, a, e0, e1, kern in prof[-per:]:
+                fam_name, fl, shape = _family(name, a)
                 ms = e0.elapsed_time(e1)
                 ints = [v for v in a if isinstance(v, int) and not isinstance(v, bool) and abs(v) < (1 << 40)]
-                f.write(f"{name}\t{fam_name}\t{ms:.4f}\t{(fl / (ms * 1e-3) / 1e12) if fl else 0:.1f}\t{ints}\n")
-    fam = {}
-    for name, a, e0, e1 in prof:
-        f, fl = _family(name, a)
-        d = fam.setdefault(f, dict(ms=0.0, flops=0.0, calls=0))
-        d["ms"] += e0.elapsed_time(e1)
-        d["flops"] += fl
-        d["calls"] += 1
-    for d in fam.values():
-        d["ms"] /= nsteps
-        d["flops"] /= nsteps
-        d["calls"] //= nsteps
-    return fam
+                f.write(f"{name}\t{kern}\t{fam_name}\t{ms:.4f}\t{(fl / (ms * 1e-3) / 1e12) if fl else 0:.1f}\t{ints}\n")
+    fam, kern_t, shape_t = {}, {}, {}
+    for name, a, e0, e1, kern in prof:
+        f, fl, shape = _family(name, a)
+        ms = e0.elapsed_time(e1)
+        for table, key in ((fam, f), (kern_t, kern), (shape_t, (kern, shape))):
+            d = table.setdefault(key, dict(ms=0.0, flops=0.0, calls=0))
+            d["ms"] += ms
+            d["flops"] += fl
+            d["calls"] += 1
+    for table in (fam, kern_t, shape_t):
+        for d in table.values():
+            d["ms"] /= nsteps
+            d["flops"] /= nsteps
+            d["calls"] //= nsteps
+    return fam, kern_t, shape_t
 
 
 _REAL_STDOUT = None
@@ -301,7 +309,7 @@ def main():
     ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
-    fam = profile_steps(trainer, resident[0], 2, record=(rank == 0))
+    fam, kern_t, shape_t = profile_steps(trainer, resident[0], 2, record=(rank == 0))
     if world > 1:
         dist.barrier()
 
@@ -310,20 +318,48 @@ def main():
         value = world * B * args.steps / (ms_dev / 1e3)
         e2e_v = world * B * args.steps / (ms_e2e / 1e3)
         total_ms = sum(d["ms"] for d in fam.values())
-        gemm = {k: d for k, d in fam.items() if d["flops"] > 0}
+        # dominant kernel = the kernel variant (one __global__ function) with the most time in the step; its launches
+        # have different layer shapes, so achieved = sum of algorithmic FLOPs / sum of CUDA-event times = the
+        # per-launch average of both.
+        gemm = {k: d for k, d in kern_t.items() if d["flops"] > 0}
         top = max(gemm, key=lambda k: gemm[k]["ms"]) if gemm else None
         roof = None
         if top:
             d = gemm[top]
             ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
+            shapes = {k[1]: v for k, v in shape_t.items() if k[0] == top}
             roof = dict(bound="tensor", kernel=top, achieved=ach, peak=pk["bf16_sustained"], unit="TFLOP/s",
-                        frac=ach / pk["bf16_sustained"], traffic=None, peak_source=pk["src"] + ", sustained figure",
+                        frac=ach / pk["bf16_sustained"], traffic=None,
+                        peak_source=pk["src"] + ", sustained bf16 figure (kernel timed inside a long step; burst figure "
+                                                f"{pk['bf16_burst']})",
                         share_of_step=d["ms"] / total_ms, launches_per_step=d["calls"],
-                        note="family of kernels (halo / CTA-pair / weight-resident variants) over 34 launches of different "
-                             "shapes; achieved = sum of algorithmic FLOPs / sum of CUDA-event times of those launches")
-            cap = os.path.join(ROOT, "profiles", "r1_ncu_traffic_v3.json")
-            if os.path.isfile(cap):      # DRAM bytes of representative launches from committed ncu --set full captures
-                roof["ncu_captures"] = [c for c in json.load(open(cap)) if "conv3x3" in c["kernel"] or "wgrad" in c["kernel"]]
+                        flops_per_launch=d["flops"] / max(d["calls"], 1), ms_per_launch=d["ms"] / max(d["calls"], 1),
+                        shapes={sh: dict(calls=v["calls"], ms_per_launch=round(v["ms"] / max(v["calls"], 1), 4),
+                                         tflops=round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)) for sh, v in
+                                sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])})
+            # DRAM bytes per launch from the committed `ncu --set full` captures (profiles/): the capture of this kernel
+            caps = []
+            for fn in sorted(os.listdir(os.path.join(ROOT, "profiles"))):
+                if "ncu_traffic" in fn and fn.endswith(".json"):
+                    caps = json.load(open(os.path.join(ROOT, "profiles", fn)))      # the newest round's file wins
+                    cap_file = fn
+            for c in caps:
+                if c["kernel"].replace(" ", "") == top.replace(" ", ""):
+                    roof["traffic"] = c["dram_bytes"]
+                    roof["traffic_capture"] = dict(file="profiles/" + cap_file, capture=c["capture"],
+                                                   algorithmic_bytes=c["algorithmic_bytes"], duration_us=c["duration_us"],
+                                                   tcgen05_pct_of_peak=c.get("tcgen05_pct_of_peak"),
+                                                   note="bytes of ONE launch of the captured layer shape "
+                                                        "(N_H_W_Cin_Cout in `capture`), cold cache")
+                    break
+            roof["ncu_captures"] = caps
+            famd = fam.get("conv3x3 fwd/dgrad (tcgen05 implicit GEMM)")
+            if famd:
+                roof["conv_fwd_dgrad_family"] = dict(tflops=famd["flops"] / (famd["ms"] * 1e-3) / 1e12, ms_per_step=famd["ms"],
+                                                     launches_per_step=famd["calls"], share_of_step=famd["ms"] / total_ms)
+        per_kernel = {k: dict(ms_per_step=round(d["ms"], 3), share=round(d["ms"] / total_ms, 4), calls=d["calls"],
+                              tflops=(round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 1) if d["flops"] else None))
+                      for k, d in sorted(kern_t.items(), key=lambda kv: -kv[1]["ms"])}
         kernels = {k: dict(ms_per_step=round(d["ms"], 3), share=round(d["ms"] / total_ms, 4), calls=d["calls"],
                            tflops=(round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 1) if d["flops"] else None))
                    for k, d in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
@@ -340,7 +376,7 @@ def main():
                                    "inputs rotate over 4 batches"),
                     e2e=dict(value=e2e_v, unit=UNIT, ms_per_step=ms_e2e / args.steps, h2d_bytes_per_step=B * CIN * H * W * 4,
                              d2h_bytes_per_step=4),
-                    gpu_launches=int(launches), clocks=clocks, roofline=roof, kernels=kernels,
+                    gpu_launches=int(launches), clocks=clocks, roofline=roof, kernels=kernels, per_kernel=per_kernel,
                     step_tflops=train_flops / (ms_dev / args.steps * 1e-3) / 1e12 if fam else None,
                     loss_last=losses[-1] if losses else None)
         if world == 1 and not args.no_cpu_baseline:

@@ -35,6 +35,9 @@ extern "C" {
 int onet_version(void);
 /* number of kernels this process has launched through the library so far */
 int64_t onet_launch_count(void);
+/* name of the kernel variant the most recent call on this thread launched, e.g. "conv3x3_halo2_px_kernel<256>"
+ * (measurement only: bench.py groups its per-launch CUDA-event times by it) */
+const char* onet_last_kernel(void);
 const char* onet_last_error(void);
 int onet_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

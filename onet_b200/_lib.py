@@ -89,6 +89,8 @@ def lib():
             fn.restype = ctypes.c_int
         _lib.onet_last_error.restype = ctypes.c_char_p
         _lib.onet_last_error.argtypes = []
+        _lib.onet_last_kernel.restype = ctypes.c_char_p
+        _lib.onet_last_kernel.argtypes = []
         _lib.onet_launch_count.restype = ctypes.c_int64
         _lib.onet_launch_count.argtypes = []
     return _lib
@@ -110,7 +112,7 @@ def call(name, *args):
     LAUNCHES += 1
     if PROFILE is not None:
         e1.record()
-        PROFILE.append((name, args, e0, e1))
+        PROFILE.append((name, args, e0, e1, lib().onet_last_kernel().decode()))
 
 
 def launch_count():

@@ -27,8 +27,11 @@ static int fail(const char* fmt, ...) {
     return 1;
 }
 static long long g_launches = 0;
-static int check_launch(const char* what) {
+static thread_local char g_last_kernel[96] = "";     // kernel variant of the most recent launch (onet_last_kernel)
+static int check_launch(const char* what, int variant = -1) {
     ++g_launches;
+    if (variant >= 0) snprintf(g_last_kernel, sizeof(g_last_kernel), "%s<%d>", what, variant);
+    else snprintf(g_last_kernel, sizeof(g_last_kernel), "%s", what);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("%s: %s", what, cudaGetErrorString(e));
     return 0;
@@ -142,7 +145,7 @@ static int launch_px(const CUtensorMap& tA, const CUtensorMap& tB, const PxParam
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     const int grid = std::min(tiles, sm_count());
     tapgemm_px_kernel<BN><<<grid, kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, p);
-    return check_launch("tapgemm_px_kernel");
+    return check_launch("tapgemm_px_kernel", BN);
 }
 
 // Fill the pixel tiling of PxParams; TN is restricted to divide `group_images` so that a tile never straddles
@@ -176,7 +179,7 @@ static int launch_halo_px(const CUtensorMap& tA, const CUtensorMap& tB, const Px
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     conv3x3_halo_px_kernel<BN><<<std::min(tiles, sm_count()), kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, p);
-    return check_launch("conv3x3_halo_px_kernel");
+    return check_launch("conv3x3_halo_px_kernel", BN);
 }
 
 template <int BN>
@@ -189,7 +192,7 @@ static int launch_halo_res_px(const CUtensorMap& tA, const CUtensorMap& tB, cons
         attr_set = true;
     }
     conv3x3_halo_res_px_kernel<BN><<<std::min(p.num_m_tiles, sm_count()), kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, p);
-    return check_launch("conv3x3_halo_res_px_kernel");
+    return check_launch("conv3x3_halo_res_px_kernel", BN);
 }
 
 // CTA-pair (cta_group::2) variant: grid = 2 x min(pair tiles, co-resident clusters)
@@ -220,7 +223,7 @@ static int launch_halo2_px(const CUtensorMap& tA, const CUtensorMap& tB, const P
     const int units = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
     const int grid = 2 * std::min(units, max_clusters);
     conv3x3_halo2_px_kernel<BN><<<grid, kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, p);
-    return check_launch("conv3x3_halo2_px_kernel");
+    return check_launch("conv3x3_halo2_px_kernel", BN);
 }
 
 // Split-K factor for the weight-gradient kernels: minimise (waves x K-steps per unit + fixed per-unit epilogue cost).
@@ -379,7 +382,7 @@ static int launch_wg(const CUtensorMap& tG, const CUtensorMap& tI, const WgParam
     const int units = p.ngroups * p.num_m_tiles * p.num_n_tiles * p.ksplit;
     const int grid = std::min(units, sm_count());
     tapgemm_wg_kernel<BNW><<<grid, 192, Cfg::kSmemBytes, st>>>(tG, tI, p);
-    return check_launch("tapgemm_wg_kernel");
+    return check_launch("tapgemm_wg_kernel", BNW);
 }
 
 template <int BNW>
@@ -393,7 +396,7 @@ static int launch_wh(const CUtensorMap& tG, const CUtensorMap& tI, const WhParam
     }
     const int units = p.ntypes * p.num_m_tiles * p.num_n_tiles * p.ksplit;
     wgrad3x3_halo_kernel<BNW><<<std::min(units, sm_count()), 192, Cfg::kSmemBytes, st>>>(tG, tI, p);
-    return check_launch("wgrad3x3_halo_kernel");
+    return check_launch("wgrad3x3_halo_kernel", BNW);
 }
 
 // CTA-pair weight gradient (Mc, Nc multiples of 128)
@@ -582,6 +585,7 @@ extern "C" {
 
 int onet_version(void) { return 100; }
 int64_t onet_launch_count(void) { return g_launches; }
+const char* onet_last_kernel(void) { return g_last_kernel; }
 const char* onet_last_error(void) { return g_err; }
 
 int onet_device_info(int* smc, int* major, int* minor) {
@@ -797,18 +801,43 @@ static int bn_bwd_impl(const void* y, int N, int H, int W, int C, const float* s
     a.sums = sums; a.count = count; a.dy = static_cast<T*>(dy);
     const int G = std::min(2, (N + a.group_images - 1) / a.group_images);
     const int OC = C / 8, lanes = std::max(1, 256 / OC);
-    const int max_blocks = 148 * 4 / G;        // 2 resident blocks per SM, two rounds
+    // The weight-gradient kernels of the previous layer run next to these kernels on a second stream (model.py): ask for the
+    // largest shared-memory carve-out so that an SM already holding BatchNorm CTAs can still take a 171 KB wgrad CTA
+    // (these kernels stream through L1 and do not need it).  ONET_BN_BWD_BLOCKS overrides the grid (A/B measurements).
+    static bool carveout_set = false;
+    if (!carveout_set) {
+        cudaFuncSetAttribute(bn_bwd_win_kernel<T, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(bn_bwd_win_kernel<T, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(bn_bwd_win_kernel<T, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(bn_bwd_win_kernel<T, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(bn_bwd_px_kernel<T, 4, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(bn_bwd_px_kernel<T, 4, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(bn_bwd_px_kernel<T, 4, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(bn_bwd_px_kernel<T, 4, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaGetLastError();
+        carveout_set = true;
+    }
+    static int blocks_override = -1;
+    if (blocks_override < 0) {
+        const char* e = getenv("ONET_BN_BWD_BLOCKS");
+        blocks_override = e ? atoi(e) : 0;
+    }
+    const int max_blocks = (blocks_override > 0 ? blocks_override : 148 * 4) / G;        // 2 resident blocks per SM, two rounds
     if (gp != nullptr) {
+        if (OC > kBnWinThreads) return fail("bn_relu_bwd: the pooled variant supports C <= %d", 8 * kBnWinThreads);
+        const int wlanes = kBnWinThreads / OC;
         const long long wins = static_cast<long long>(a.group_images) * ((H + 1) / 2) * ((W + 1) / 2);
-        const int gx = static_cast<int>(std::max(1LL, std::min<long long>((wins + lanes - 1) / lanes, max_blocks)));
+        // 3 resident blocks of 128 threads per SM, two rounds
+        const int wmax = (blocks_override > 0 ? blocks_override : 148 * 6) / G;
+        const int gx = static_cast<int>(std::max(1LL, std::min<long long>((wins + wlanes - 1) / wlanes, wmax)));
         if (g2 != nullptr) {
-            bn_bwd_win_kernel<T, true, false><<<dim3(gx, G), 256, 0, st>>>(a);
+            bn_bwd_win_kernel<T, true, false><<<dim3(gx, G), kBnWinThreads, 0, st>>>(a);
             if (check_launch("bn_bwd_reduce")) return 1;
-            bn_bwd_win_kernel<T, true, true><<<dim3(gx, G), 256, 0, st>>>(a);
+            bn_bwd_win_kernel<T, true, true><<<dim3(gx, G), kBnWinThreads, 0, st>>>(a);
         } else {
-            bn_bwd_win_kernel<T, false, false><<<dim3(gx, G), 256, 0, st>>>(a);
+            bn_bwd_win_kernel<T, false, false><<<dim3(gx, G), kBnWinThreads, 0, st>>>(a);
             if (check_launch("bn_bwd_reduce")) return 1;
-            bn_bwd_win_kernel<T, false, true><<<dim3(gx, G), 256, 0, st>>>(a);
+            bn_bwd_win_kernel<T, false, true><<<dim3(gx, G), kBnWinThreads, 0, st>>>(a);
         }
     } else {
         constexpr int UNR = 4;
@@ -842,6 +871,7 @@ int onet_bn_relu_bwd(const void* y, int N, int H, int W, int C, const float* sca
     if (static_cast<long long>(N) * H * W >= (1LL << 31)) return fail("bn_relu_bwd: more than 2^31 pixels");
     if (C % 8 || C > 2048) return fail("bn_relu_bwd: C must be a multiple of 8 and <= 2048");
     if (256 % (C / 8) != 0) return fail("bn_relu_bwd: C/8 must divide 256");
+    if (gp != nullptr && C > 1024) return fail("bn_relu_bwd: the pooled variant supports C <= 1024");
     if (g1 == nullptr) return fail("bn_relu_bwd: g1 is required");
     if (dtype == ONET_F32)
         return bn_bwd_impl<float>(y, N, H, W, C, scale, shift, mean, invstd, group_images, g1, ld1, off1, g2, ld2, off2, gp,

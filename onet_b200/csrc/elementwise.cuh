@@ -217,17 +217,17 @@ struct BnBwdArgs {
 };
 
 // block-wide reduction of the per-thread (acc1, acc2) over the pixel lanes and one double atomic per channel
-template <typename T>
+template <typename T, int NT = 256>
 __device__ __forceinline__ void bn_bwd_block_reduce(const BnBwdArgs<T>& a, int g, const float (&acc1)[8],
-                                                    const float (&acc2)[8], float (*s_red)[256]) {
-    const int OC = a.C >> 3, LANES = 256 / OC;
+                                                    const float (&acc2)[8], float (*s_red)[NT]) {
+    const int OC = a.C >> 3, LANES = NT / OC;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         s_red[i][threadIdx.x] = acc1[i];
         s_red[8 + i][threadIdx.x] = acc2[i];
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < 16 * OC; t += 256) {
+    for (int t = threadIdx.x; t < 16 * OC; t += NT) {
         const int which = t / OC, o = t % OC;
         float s = 0.f;
         for (int l = 0; l < LANES; ++l) s += s_red[which][l * OC + o];
@@ -315,11 +315,14 @@ bn_bwd_px_kernel(const BnBwdArgs<T> a) {
 }
 
 // ---- window mapping: one thread = one 2x2 window x 8 channels (pooled gradient source present)
+// 128 threads x 3 CTAs per SM: a window holds 13 16-byte loads plus 40 per-channel constants, which does not fit the
+// 128 registers of a 256 x 2 configuration (it spilled 136-160 B per thread); 170 registers are available here.
+constexpr int kBnWinThreads = 128;
 template <typename T, bool HAS_G2, bool APPLY>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(kBnWinThreads, 3)
 bn_bwd_win_kernel(const BnBwdArgs<T> a) {
-    __shared__ float s_red[APPLY ? 1 : 16][256];
-    const int OC = a.C >> 3, LANES = 256 / OC;
+    __shared__ float s_red[APPLY ? 1 : 16][kBnWinThreads];
+    const int OC = a.C >> 3, LANES = kBnWinThreads / OC;
     const int oc = threadIdx.x % OC, ln = threadIdx.x / OC;
     const int g = blockIdx.y;
     const int H = a.H, W = a.W, H2 = (H + 1) >> 1, W2 = (W + 1) >> 1, HP = H >> 1, WP = W >> 1;
@@ -421,7 +424,7 @@ bn_bwd_win_kernel(const BnBwdArgs<T> a) {
             for (int i = 0; i < 8; ++i) acc2[i] *= is[i];
         }
     }
-    if (!APPLY) bn_bwd_block_reduce<T>(a, g, acc1, acc2, s_red);
+    if (!APPLY) bn_bwd_block_reduce<T, kBnWinThreads>(a, g, acc1, acc2, s_red);
 }
 
 // dgamma[c] (+)= sum_g s2[g][c], dbeta[c] (+)= sum_g s1[g][c]; per-group targets may alias (shared twin)

@@ -18,6 +18,7 @@ copy exists.  There is no CPU / eager-PyTorch fallback: without a CUDA device or
 raises.
 """
 import math
+import os
 from collections import OrderedDict
 
 import torch
@@ -33,6 +34,18 @@ _DEC = [("up1", 1024, 512), ("up2", 512, 256), ("up3", 256, 128), ("up4", 128, 6
 _DTYPES = {"fp32": (F32, torch.float32), "bf16": (BF16, torch.bfloat16)}
 
 _PACK_GEN = [0]
+
+# Backward schedule: the weight-gradient kernels (tensor-core bound, one persistent CTA of <= 171 KB shared memory and
+# <= 96 registers x 192 threads per SM) run on a second stream NEXT TO the BatchNorm-backward kernels of the following
+# layer (HBM bound, small CTAs), which they do not depend on.  ONET_NO_WGRAD_OVERLAP=1 restores the serial order.
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev, priority=-1)
+    return _SIDE_STREAMS[key]
 
 
 def invalidate_packed_weights():
@@ -176,7 +189,9 @@ class _Engine:
         self.segments = segments
         self.x = x
         self.dev = x.device
-        self.stream = torch.cuda.current_stream(self.dev).cuda_stream
+        self._main = torch.cuda.current_stream(self.dev)
+        self.stream = self._main.cuda_stream
+        self._side = None
 
     @staticmethod
     def for_unets(unets, x, mode, use_tc, twin=False):
@@ -405,6 +420,11 @@ class _Engine:
         gradient must be ACCUMULATED into."""
         B, H, W, N2 = rec.B, rec.H, rec.W, rec.N2
         st = self.stream
+        # per-call event timing (bench.py's profile pass) records on the main stream only: keep that pass serial
+        overlap = os.environ.get("ONET_NO_WGRAD_OVERLAP") is None and _lib.PROFILE is None
+        self._side = _side_stream(self.dev) if overlap else None
+        self._deferred, self._inflight, self._hooks_deferred, self._hooks_ready = [], [], [], []
+        self._after_block = after_block
         dL = self._empty(N2, H, W, 64)
         dH = self._empty(N2, H, W, 64)
         call("onet_head_bwd", ptr(rec.cat0), 128, 0, ptr(rec.Hf), 64, 0, B, H, W, ptr(rec.Vt), ptr(rec.Vd), ptr(rec.a),
@@ -442,13 +462,11 @@ class _Engine:
                 below = rec.x5 if k == 3 else rec.mid[("dec_out", k + 1)]
                 g_out = self._upconv_bwd(seg, up, below, 2 * c, n0, n, hs[k + 1], ws[k + 1], dcat[k], 2 * c, c, grad_of,
                                          colsum[0, c:], hs[k], ws[k])
-                if after_block is not None:
-                    after_block(seg.unet, _DEC[j][0])
+                self._block_done(seg.unet, _DEC[j][0])
             # encoder, bottom (level 4) to top
             d_mid = bwd(9, g_out, 1024, 0)
             d_pool = bwd(8, d_mid, 1024, 0)                             # grad wrt pool[3]
-            if after_block is not None:
-                after_block(seg.unet, "down4")
+            self._block_done(seg.unet, "down4")
             for k in (3, 2, 1, 0):
                 c = cs[k]
                 li = 2 * k
@@ -458,8 +476,51 @@ class _Engine:
                 else:
                     d_mid = bwd(li + 1, dcat[k], 2 * c, 0, gp=d_pool)
                     d_pool = bwd(li, d_mid, c, 0)
-                if after_block is not None:
-                    after_block(seg.unet, "inc" if k == 0 else _ENC[k - 1][0])
+                self._block_done(seg.unet, "inc" if k == 0 else _ENC[k - 1][0])
+        self._flush_side()
+        self._join_side()
+
+    # ---- two-stream schedule of backward: weight gradients next to the following BatchNorm backward
+    def _wgrad(self, keep, name, *args):
+        """Issue a weight-gradient call (its last argument, the stream, is appended here).  With the side stream it is
+        deferred until the next `_flush_side`, i.e. until just before the next HBM-bound kernel goes to the main stream."""
+        if self._side is None:
+            call(name, *args, self.stream)
+        else:
+            self._deferred.append((keep, name, args))
+
+    def _flush_side(self):
+        """Everything issued on the main stream so far is a dependency of the deferred weight gradients: fork."""
+        if self._side is None or not (self._deferred or self._hooks_deferred):
+            return
+        if self._deferred:
+            self._side.wait_stream(self._main)
+            for keep, name, args in self._deferred:
+                call(name, *args, self._side.cuda_stream)
+                self._inflight.append(keep)          # operands stay alive until the main stream has joined
+            self._deferred = []
+        self._hooks_ready += self._hooks_deferred
+        self._hooks_deferred = []
+
+    def _join_side(self):
+        """Main stream waits for the side stream: the next tensor-core kernel runs alone, operand buffers may be reused,
+        and the finished blocks' gradient buckets can go to the all-reduce."""
+        if self._side is None:
+            return
+        if self._inflight:
+            self._main.wait_stream(self._side)
+            self._inflight = []
+        for unet, block in self._hooks_ready:
+            self._after_block(unet, block)
+        self._hooks_ready = []
+
+    def _block_done(self, unet, block):
+        if self._after_block is None:
+            return
+        if self._side is None:
+            self._after_block(unet, block)
+        else:
+            self._hooks_deferred.append((unet, block))
 
     def _conv_bn_relu_bwd(self, rec, si, seg, li, conv, bn, n0, n, g1, ld1, off1, g2, ld2, off2, gp, need_dgrad, grad_of,
                           colsum=None):
@@ -472,14 +533,16 @@ class _Engine:
         rec.sum_off += 2 * G * cout
         dY = self._empty(n, h, w, cout)
         count = float(seg.group_images * h * w)
+        self._flush_side()          # the previous layers' weight gradients run next to this BatchNorm backward
         call("onet_bn_relu_bwd", ptr(Y), n, h, w, cout, ptr(aff[2]), ptr(aff[3]), ptr(aff[0]), ptr(aff[1]),
              seg.group_images, ptr(g1, off1), ld1, 0, ptr(g2, off2) if g2 is not None else None, ld2, 0,
              ptr(gp) if gp is not None else None, ptr(sums), count, ptr(dY),
              ptr(grad_of(bn.weight)), ptr(grad_of(bn.bias)), ptr(grad_of(bn.weight)), ptr(grad_of(bn.bias)), self.dt, st)
+        self._join_side()
         eng = self._engine_for(cin, cout)
         src, ld_src, off_src = sv["src"]
-        call("onet_conv3x3_wgrad", ptr(dY), cout, 0, ptr(src, self._img_off(src, n0) + off_src), ld_src, 0, n, h, w, cin,
-             cout, ptr(grad_of(conv.weight)), self.dt, eng, st)
+        self._wgrad((dY, src), "onet_conv3x3_wgrad", ptr(dY), cout, 0, ptr(src, self._img_off(src, n0) + off_src), ld_src, 0,
+                    n, h, w, cin, cout, ptr(grad_of(conv.weight)), self.dt, eng)
         if not need_dgrad:
             return None
         _, wd = self._packed(conv, "conv")
@@ -498,8 +561,8 @@ class _Engine:
         if not padded:       # bias gradient = column sums of d(concat)'s up half, already reduced by the dgrad epilogue
             call("onet_add_colsums", ptr(bias_sums), co, ptr(grad_of(up.bias)), st)
         # with an F.pad border the gradient of the border pixels is dropped: reduce over the valid window only
-        call("onet_convT2x2_wgrad", ptr(x, self._img_off(x, n0)), cin, 0, ptr(dcat, off_cat), ld_cat, 0, n, h, w, cin, co,
-             ptr(grad_of(up.weight)), ptr(grad_of(up.bias)) if padded else None, ho, wo, self.dt, eng, st)
+        self._wgrad((x, dcat), "onet_convT2x2_wgrad", ptr(x, self._img_off(x, n0)), cin, 0, ptr(dcat, off_cat), ld_cat, 0, n, h, w,
+                    cin, co, ptr(grad_of(up.weight)), ptr(grad_of(up.bias)) if padded else None, ho, wo, self.dt, eng)
         dX = self._empty(n, h, w, cin)
         if eng == ENGINE_TC:
             _, wd = self._packed(up, "convT")

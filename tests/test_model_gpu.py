@@ -229,3 +229,28 @@ def test_on_device_evaluation_matches_oracle(golden_dir):
         counts = confusion_counts(torch.zeros_like(pred, dtype=torch.float32), pred.float(), gt)   # Vd > Vt  <=>  pred == 1
         m = segmentation_metrics(counts, reassign=True)
         assert np.allclose([m["acc"], m["miou"], m["dr"], m["far"], m["t_iou"]], z[f"metrics{i}"], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("mode,bshare", [("bf16", 1), ("fp32", 1), ("bf16", 0)])
+def test_two_stream_backward_matches_serial_backward(mode, bshare, monkeypatch):
+    """The weight-gradient kernels run on a second stream next to the following layer's BatchNorm backward
+    (model.py `_flush_side` / `_join_side`).  Same step with ONET_NO_WGRAD_OVERLAP=1 (everything on one stream): the
+    forward is untouched, so the loss is the same; the gradients may differ only by the order of the fp32 atomics of the
+    split-K weight-gradient kernels.  A missing dependency between the streams would show as a gross difference — the
+    step is repeated to give a race a chance."""
+    from oracle import onet_oracle as orc
+    meta = (1, 8, 128, 128, bshare, 57)
+    x = orc.rayleigh_frames(8, 1, 128, 128, seed=57).cuda()
+    net, _, _ = _build(meta, mode)
+    monkeypatch.setenv("ONET_NO_WGRAD_OVERLAP", "1")
+    loss0 = _step(net, x)[-1].item()
+    serial = {k: p.grad.clone() for k, p in net.named_parameters()}
+    monkeypatch.delenv("ONET_NO_WGRAD_OVERLAP")
+    for rep in range(3):
+        loss1 = _step(net, x)[-1].item()
+        assert abs(loss1 - loss0) <= 1e-6 * abs(loss0)     # BatchNorm statistics are summed with double atomics
+        # bf16: the tcgen05 kernels accumulate split-K partial sums with fp32 atomics (order noise ~1e-6); the fp32 CUDA-core
+        # path sums more terms per atomic and the gradient is ill-conditioned (two serial runs differ by up to 2e-2 as well)
+        tol = 1e-3 if mode == "bf16" else 2e-2
+        worst = max((_rel(p.grad, serial[k]), k) for k, p in net.named_parameters())
+        assert worst[0] < tol, (rep, worst)
