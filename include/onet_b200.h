@@ -147,6 +147,11 @@ int onet_predict_label(const float* Vt, const float* Vd, int64_t n, int64_t* out
  * (onet_b200/evaluate.py), so test_simclutter's per-batch host syncs collapse into one 32-byte read-back. */
 int onet_eval_confusion(const float* Vt, const float* Vd, const int64_t* gt, int64_t n, int64_t* counts, void* stream);
 
+/* tensor_normal_per_frame (utils_20231218.py:673-689): x [frames][hw] fp32 -> out[f][i] = (x - min_f) / (max_f - min_f +
+ * np.spacing(1)); out may alias x.  work: 2 * frames ints of device scratch (order-preserving min / max keys).  Used by the
+ * two-stage cascade (test_2nd_stage_simclutter, Train_Onet_on_simclutter_20250407.py:296-390) between the two Onets. */
+int onet_normalize_per_frame(const float* x, int frames, int64_t hw, int* work, float* out, void* stream);
+
 /* torch.optim.Adam step (no weight decay, amsgrad=False; Train_Onet_on_simclutter_20250407.py:181-182) over a
  * flat fp32 arena; `step` is the 1-based step count, gradients are multiplied by grad_scale first. */
 int onet_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,

@@ -1040,6 +1040,22 @@ int onet_eval_confusion(const float* Vt, const float* Vd, const int64_t* gt, int
     return check_launch("eval_confusion");
 }
 
+int onet_normalize_per_frame(const float* x, int frames, int64_t hw, int* work, float* out, void* stream) {
+    if (frames <= 0 || hw <= 0) return 0;
+    if (work == nullptr) return fail("normalize_per_frame: work (2 * frames ints) is required");
+    if (frames > 65535) return fail("normalize_per_frame: at most 65535 frames per call");
+    frame_minmax_init_kernel<<<(frames + 255) / 256, 256, 0, ST(stream)>>>(work, frames);
+    if (check_launch("frame_minmax_init")) return 1;
+    // enough blocks per frame to fill the GPU, not more than the frame has 1024-element chunks
+    const long long chunks = std::max<long long>(1, (hw + 1023) / 1024);
+    const int per_frame = static_cast<int>(std::min<long long>(chunks, std::max(1, 148 * 8 / frames)));
+    frame_minmax_kernel<<<dim3(per_frame, frames), 256, 0, ST(stream)>>>(x, hw, work);
+    if (check_launch("frame_minmax")) return 1;
+    const float eps = static_cast<float>(2.220446049250313e-16);        // np.spacing(1)
+    frame_normalize_kernel<<<dim3(per_frame, frames), 256, 0, ST(stream)>>>(x, hw, work, eps, out);
+    return check_launch("frame_normalize");
+}
+
 int onet_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, int step, float grad_scale, void* stream) {
     if (step < 1) return fail("adam: step must be >= 1");

@@ -831,4 +831,84 @@ eval_confusion_kernel(const float* __restrict__ Vt, const float* __restrict__ Vd
     if (threadIdx.x < 4 && s[threadIdx.x]) atomicAdd(counts + threadIdx.x, static_cast<unsigned long long>(s[threadIdx.x]));
 }
 
+// ------------------------------------------------------------------------------------------------
+// tensor_normal_per_frame (utils_20231218.py:673-689): every (image, channel) frame scaled to [0,1] by its own
+// minimum and maximum, out = (v - min) / (max - min + eps) with eps = np.spacing(1) rounded to fp32 as torch does when
+// it adds the Python float to an fp32 tensor.  Used on the stage-1 response maps that feed the second Onet of the
+// two-stage cascade (Train_Onet_on_simclutter_20250407.py:296-390) and on datasets at load time.
+// Pass 1: per-frame min / max as order-preserving integer keys (atomicMin / atomicMax); pass 2: scale.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int float_key(float f) {
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
+__global__ void frame_minmax_init_kernel(int* __restrict__ keys, int frames) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < frames) {
+        keys[2 * f] = 0x7fffffff;
+        keys[2 * f + 1] = static_cast<int>(0x80000000u);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+frame_minmax_kernel(const float* __restrict__ x, long long hw, int* __restrict__ keys) {
+    const int f = blockIdx.y;
+    const float* xf = x + static_cast<long long>(f) * hw;
+    float mn = INFINITY, mx = -INFINITY;
+    const long long start = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    if ((hw & 3) == 0 && (reinterpret_cast<uintptr_t>(xf) & 15) == 0) {
+        const float4* x4 = reinterpret_cast<const float4*>(xf);
+        for (long long i = start; i < (hw >> 2); i += stride) {
+            const float4 v = x4[i];
+            mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
+            mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
+        }
+    } else {
+        for (long long i = start; i < hw; i += stride) {
+            mn = fminf(mn, xf[i]);
+            mx = fmaxf(mx, xf[i]);
+        }
+    }
+    for (int off = 16; off >= 1; off >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    }
+    __shared__ float s_mn[8], s_mx[8];
+    if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); }
+        if (mn <= mx) {          // a block that saw no element keeps (+inf, -inf)
+            atomicMin(keys + 2 * f, float_key(mn));
+            atomicMax(keys + 2 * f + 1, float_key(mx));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+frame_normalize_kernel(const float* __restrict__ x, long long hw, const int* __restrict__ keys, float eps,
+                       float* __restrict__ out) {
+    const int f = blockIdx.y;
+    const float mn = key_float(keys[2 * f]);
+    const float den = (key_float(keys[2 * f + 1]) - mn) + eps;
+    const float* xf = x + static_cast<long long>(f) * hw;
+    float* of = out + static_cast<long long>(f) * hw;
+    const long long start = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    if ((hw & 3) == 0 && ((reinterpret_cast<uintptr_t>(xf) | reinterpret_cast<uintptr_t>(of)) & 15) == 0) {
+        const float4* x4 = reinterpret_cast<const float4*>(xf);
+        float4* o4 = reinterpret_cast<float4*>(of);
+        for (long long i = start; i < (hw >> 2); i += stride) {
+            float4 v = x4[i];
+            v.x = (v.x - mn) / den; v.y = (v.y - mn) / den; v.z = (v.z - mn) / den; v.w = (v.w - mn) / den;
+            o4[i] = v;
+        }
+    } else {
+        for (long long i = start; i < hw; i += stride) of[i] = (xf[i] - mn) / den;
+    }
+}
+
 }  // namespace onet

@@ -56,3 +56,70 @@ def segmentation_metrics(counts, reassign=True):
             flipped = True
     acc, miou, dr, far, t_iou = _metrics(c00, c01, c10, c11)
     return dict(acc=acc, miou=miou, dr=dr, far=far, t_iou=t_iou, flipped=flipped)
+
+
+def normalize_per_frame(x):
+    """`tensor_normal_per_frame` (utils_20231218.py:673-689) on the device: every (image, channel) frame of the 4-D fp32
+    tensor scaled to [0,1] by its own min / max.  One C-ABI call (min/max reduction + scaling kernels)."""
+    assert x.dim() == 4
+    if not x.is_cuda:
+        raise RuntimeError("onet_b200.evaluate has no CPU path")
+    x = x.contiguous().float()
+    nb, nc, h, w = x.shape
+    out = torch.empty_like(x)
+    work = torch.empty(2 * nb * nc, dtype=torch.int32, device=x.device)
+    call("onet_normalize_per_frame", ptr(x), nb * nc, h * w, ptr(work), ptr(out), torch.cuda.current_stream(x.device).cuda_stream)
+    return out
+
+
+def _batch_metrics(Vt, Vd, label):
+    m = segmentation_metrics(confusion_counts(Vt, Vd, label), reassign=True)
+    return m, (m["acc"], m["miou"], m["dr"], m["far"], m["t_iou"])
+
+
+def _device_of(config, onet):
+    dev = getattr(config, "device", None)
+    return torch.device(dev) if dev is not None else next(onet.parameters()).device
+
+
+def test_simclutter(str_txt, config, onet, test_loader, verbose=0, measure_snr=False):
+    """Same arguments and return value as the reference's `test_simclutter`
+    (Train_Onet_on_simclutter_20250407.py:97-172): eval-mode forward of every (X, label, psnr) batch, label =
+    predict_label re-assigned against the ground truth, five metrics per batch, means over the batches ->
+    (acc, miou, dr, far, tiou).  Plotting / saving of a random batch (`verbose`) is not part of the path."""
+    import numpy as np
+    onet.eval()
+    rows = []
+    dev = _device_of(config, onet)
+    with torch.no_grad():
+        for X, label, _ in test_loader:
+            _, Vt, _, Vd, _ = onet(X.to(dev))
+            rows.append(_batch_metrics(Vt, Vd, label.to(dev))[1])
+    return tuple(float(v) for v in np.array(rows, dtype=np.float64).mean(axis=0))
+
+
+def test_2nd_stage_simclutter(str_txt, config, onet, onet2nd, test_loader, verbose=0, return_all=False):
+    """Two-stage cascade, same arguments and return value as the reference's `test_2nd_stage_simclutter`
+    (Train_Onet_on_simclutter_20250407.py:296-390).  Per batch: stage-1 forward; the response map that represents the
+    foreground (Vd1 when `re_assign_label` kept the labels, Vt1 when it flipped them, :328-331) is normalised per frame
+    on the device and fed to the second Onet; both stages are scored against the ground truth.  Returns
+    (acc2, miou2, dr2, far2, tiou1) like the reference (:390); return_all=True returns both stages' five means."""
+    import numpy as np
+    onet.eval()
+    onet2nd.eval()
+    rows1, rows2 = [], []
+    dev = _device_of(config, onet)
+    with torch.no_grad():
+        for X1, label, _ in test_loader:
+            label = label.to(dev)
+            _, Vt1, _, Vd1, _ = onet(X1.to(dev))
+            m1, row1 = _batch_metrics(Vt1, Vd1, label)
+            rows1.append(row1)
+            X2 = normalize_per_frame(Vt1 if m1["flipped"] else Vd1)
+            _, Vt2, _, Vd2, _ = onet2nd(X2)
+            rows2.append(_batch_metrics(Vt2, Vd2, label)[1])
+    s1 = tuple(float(v) for v in np.array(rows1, dtype=np.float64).mean(axis=0))
+    s2 = tuple(float(v) for v in np.array(rows2, dtype=np.float64).mean(axis=0))
+    if return_all:
+        return s1, s2
+    return s2[0], s2[1], s2[2], s2[3], s1[4]

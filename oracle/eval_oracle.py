@@ -49,3 +49,35 @@ def re_assign_label(predict_label, gt_label):              # re_assign_label :41
 def evaluate(predict_label, gt_label):                     # evaluate_nau_segmentation_v2 :213-234
     p, g = predict_label.reshape(-1), gt_label.reshape(-1)
     return acc(p, g), miou(p, g), detection_rate(p, g), false_alarm_rate(p, g), target_iou(p, g)
+
+
+# ---- evaluation loops of Train_Onet_on_simclutter_20250407.py, restated over the oracle forward -----------------------
+def _means(rows):
+    return tuple(float(v) for v in np.array(rows, dtype=np.float64).mean(axis=0))
+
+
+def test_simclutter(st, loader):                           # test_simclutter :97-172 (verbose=0)
+    from oracle import onet_oracle as orc
+    rows = []
+    with torch.no_grad():
+        for X, label, _ in loader:
+            _, _, _, _, S = orc.onet_forward(st, X, training=False)
+            rows.append(evaluate(re_assign_label(orc.predict_label(S), label), label))
+    return _means(rows)
+
+
+def test_2nd_stage_simclutter(st1, st2, loader):           # test_2nd_stage_simclutter :296-390 (verbose=0)
+    """Returns (stage-1 means, stage-2 means); the reference returns (acc2, miou2, dr2, far2, tiou1)."""
+    from oracle import onet_oracle as orc
+    rows1, rows2 = [], []
+    with torch.no_grad():
+        for X1, label, _ in loader:
+            _, Vt1, _, Vd1, S1 = orc.onet_forward(st1, X1, training=False)
+            raw1 = orc.predict_label(S1)
+            pred1 = re_assign_label(raw1, label)
+            rows1.append(evaluate(pred1, label))
+            X2 = Vd1 if torch.equal(raw1, pred1) else Vt1                    # :328-331
+            X2 = orc.tensor_normal_per_frame(X2)
+            _, _, _, _, S2 = orc.onet_forward(st2, X2, training=False)
+            rows2.append(evaluate(re_assign_label(orc.predict_label(S2), label), label))
+    return _means(rows1), _means(rows2)

@@ -254,3 +254,47 @@ def test_two_stream_backward_matches_serial_backward(mode, bshare, monkeypatch):
         tol = 1e-3 if mode == "bf16" else 2e-2
         worst = max((_rel(p.grad, serial[k]), k) for k, p in net.named_parameters())
         assert worst[0] < tol, (rep, worst)
+
+
+def test_normalize_per_frame_kernel_bit_exact(golden_dir):
+    """onet_normalize_per_frame against the reference's tensor_normal_per_frame known answers (bit for bit, including a
+    constant frame whose denominator is np.spacing(1)) and against the oracle on larger / ragged frame sizes."""
+    import onet_b200.evaluate as oev
+    from oracle import onet_oracle as orc
+    z = np.load(os.path.join(golden_dir, "cascade.npz"))
+    got = oev.normalize_per_frame(torch.from_numpy(z["norm_in"]).cuda()).cpu().numpy()
+    assert np.array_equal(got, z["norm_out"])
+    torch.manual_seed(3)
+    for shape in ((2, 1, 256, 256), (1, 3, 37, 41), (5, 1, 16, 16), (1, 1, 1, 1)):
+        t = torch.randn(shape) * 7 - 2
+        assert torch.equal(oev.normalize_per_frame(t.cuda()).cpu(), orc.tensor_normal_per_frame(t)), shape
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_evaluation_loops_match_reference_golden(mode, golden_dir):
+    """onet_b200.evaluate.test_simclutter / test_2nd_stage_simclutter (the two-stage cascade) against the tuples
+    the UNMODIFIED reference functions returned on the same networks and batches (tests/golden/make_cascade_golden.py).
+    fp32: label maps agree on >= 99.9 % of the pixels, i.e. every metric within 2e-3; bf16 (tensor-core path): the
+    stage-2 input is a normalised bf16 response map of a random-init network, metrics within 5e-2."""
+    import types
+    import onet_b200
+    import onet_b200.evaluate as oev
+    from test_oracle_golden import _cascade_states
+    z = np.load(os.path.join(golden_dir, "cascade.npz"))
+    st1, st2, loader = _cascade_states(z)
+    nets = []
+    for st in (st1, st2):
+        net = onet_b200.Onet(1, True, True, mode=mode)
+        sd = OrderedDict()
+        for k, v in st.items():
+            sd["topu." + k] = v.clone()
+            sd["dwnu." + k] = v.clone()
+        net.load_state_dict(sd)
+        nets.append(net.cuda())
+    cfg = types.SimpleNamespace(device="cuda")
+    one = oev.test_simclutter("t", cfg, nets[0], loader, verbose=0)
+    two = oev.test_2nd_stage_simclutter("t", cfg, nets[0], nets[1], loader, verbose=0)
+    tol = 2e-3 if mode == "fp32" else 5e-2
+    print(mode, "one-stage", np.array(one) - z["one_stage"], "two-stage", np.array(two) - z["two_stage"])
+    assert np.allclose(one, z["one_stage"], rtol=0, atol=tol), (one, z["one_stage"])
+    assert np.allclose(two, z["two_stage"], rtol=0, atol=tol), (two, z["two_stage"])

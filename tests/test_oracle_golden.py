@@ -169,3 +169,34 @@ def test_metrics_from_confusion_counts_match_reference_golden(golden_dir):
         m = segmentation_metrics(counts, reassign=True)
         assert m["flipped"] == (not torch.equal(re, pred))
         assert np.allclose([m["acc"], m["miou"], m["dr"], m["far"], m["t_iou"]], metrics, rtol=1e-6, atol=1e-7)
+
+
+def _cascade_states(z):
+    """(st1, st2, loader) of tests/golden/cascade.npz: seeded weights + the reference's running buffers + its batches."""
+    from oracle import onet_oracle as orc
+    b, h, w, s1, s2 = (int(v) for v in z["meta"])
+    states = []
+    for tag, seed in (("net1", s1), ("net2", s2)):
+        st = orc.perturb_bn_affine(orc.init_state(1, seed=seed), seed=seed + 100)
+        for k in list(st):
+            if "running" in k or "num_batches" in k:
+                st[k] = torch.from_numpy(z[f"{tag}.{k}"]).clone()
+        states.append(st)
+    loader = [(torch.from_numpy(z[f"x{i}"]), torch.from_numpy(z[f"label{i}"]).long(), torch.zeros(b)) for i in range(2)]
+    return states[0], states[1], loader
+
+
+def test_cascade_oracle_matches_reference_golden(golden_dir):
+    """oracle/eval_oracle.py's restatement of test_simclutter / test_2nd_stage_simclutter against the tuples the unmodified
+    reference functions returned (tests/golden/make_cascade_golden.py), and tensor_normal_per_frame bit for bit."""
+    import os
+    from oracle import eval_oracle as ev
+    from oracle import onet_oracle as orc
+    z = np.load(os.path.join(golden_dir, "cascade.npz"))
+    assert np.array_equal(orc.tensor_normal_per_frame(torch.from_numpy(z["norm_in"])).numpy(), z["norm_out"])
+    st1, st2, loader = _cascade_states(z)
+    one = ev.test_simclutter(st1, loader)
+    assert np.allclose(one, z["one_stage"], rtol=0, atol=1e-7), (one, z["one_stage"])
+    s1, s2 = ev.test_2nd_stage_simclutter(st1, st2, loader)
+    got = (s2[0], s2[1], s2[2], s2[3], s1[4])
+    assert np.allclose(got, z["two_stage"], rtol=0, atol=1e-7), (got, z["two_stage"])
