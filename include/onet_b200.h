@@ -152,6 +152,22 @@ int onet_eval_confusion(const float* Vt, const float* Vd, const int64_t* gt, int
  * two-stage cascade (test_2nd_stage_simclutter, Train_Onet_on_simclutter_20250407.py:296-390) between the two Onets. */
 int onet_normalize_per_frame(const float* x, int frames, int64_t hw, int* work, float* out, void* stream);
 
+/* ---- on-device synthesis of training frames (Rayleigh_bg_Gaussian_EOT_generator_20230208.py) ------------
+ * Counter-based Philox4x32-10: element i of stream `stream_id` under `seed` is the same whatever the launch geometry. */
+/* Rayleigh(sigma) amplitudes: the background of get_rayleigh_frame (:219-221, scipy.stats.rayleigh.rvs(scale=sigma)). */
+int onet_synth_rayleigh(float* out, int64_t n, float sigma, int64_t seed, int stream_id, void* stream);
+/* K-distributed amplitudes as a compound Gaussian: Rayleigh(1) speckle x sqrt(Gamma(nu, 1/nu)) texture, integer nu.  The
+ * marginal of the reference's K generator (K_distributed_SeaClutter_Simulation_20210919.py:469-526), uncorrelated. */
+int onet_synth_kclutter(float* out, int64_t n, int nu, int64_t seed, int stream_id, void* stream);
+/* add_gaussian_template_on_clutter_v3 (:62-176, swerling type 0) for every frame: frames [n_frames][H][W] fp32 updated in
+ * place, masks [n_frames][H][W] bytes OR-ed with the target masks (caller zeroes them).  targets: device table of
+ * n_frames x targets_per_frame records of 8 x 4 bytes {int lx, ly, wr, hr; float a, b, c, thr} prepared on the host
+ * (onet_b200/synth.py) from (cx, cy, w, h, theta); applied in order, as the reference's loop does.  thr = the mask
+ * threshold kgauss.max() - 2 * kgauss.std() (:142), or negative to have the kernel reduce it over the window.  erc_out (optional):
+ * the average clutter energy mean(bg^2) per frame that scales the target amplitude, kcoef = sqrt(10^(snr/10) * erc). */
+int onet_synth_add_targets(float* frames, unsigned char* masks, int n_frames, int H, int W, const void* targets,
+                           int targets_per_frame, float snr_db, float* erc_out, void* stream);
+
 /* torch.optim.Adam step (no weight decay, amsgrad=False; Train_Onet_on_simclutter_20250407.py:181-182) over a
  * flat fp32 arena; `step` is the 1-based step count, gradients are multiplied by grad_scale first. */
 int onet_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,

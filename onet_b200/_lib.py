@@ -69,6 +69,9 @@ SIGNATURES = {
     "onet_predict_label": [_p, _p, _i64, _p, _p],
     "onet_eval_confusion": [_p, _p, _p, _i64, _p, _p],
     "onet_normalize_per_frame": [_p, _i, _i64, _p, _p, _p],
+    "onet_synth_rayleigh": [_p, _i64, _f, _i64, _i, _p],
+    "onet_synth_kclutter": [_p, _i64, _i, _i64, _i, _p],
+    "onet_synth_add_targets": [_p, _p, _i, _i, _i, _p, _i, _f, _p, _p],
     "onet_adam_step": [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i, _f, _p],
     "onet_adam_step_dev": [_p, _p, _p, _p, _i64, _p, _p, _f, _p],
 }

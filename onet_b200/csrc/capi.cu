@@ -11,6 +11,7 @@
 #include "../../include/onet_b200.h"
 #include "elementwise.cuh"
 #include "simt_conv.cuh"
+#include "synth.cuh"
 #include "tapgemm_tc.cuh"
 #include "conv3x3_halo_tc.cuh"
 
@@ -1054,6 +1055,32 @@ int onet_normalize_per_frame(const float* x, int frames, int64_t hw, int* work, 
     const float eps = static_cast<float>(2.220446049250313e-16);        // np.spacing(1)
     frame_normalize_kernel<<<dim3(per_frame, frames), 256, 0, ST(stream)>>>(x, hw, work, eps, out);
     return check_launch("frame_normalize");
+}
+
+int onet_synth_rayleigh(float* out, int64_t n, float sigma, int64_t seed, int stream_id, void* stream) {
+    if (n <= 0) return 0;
+    rayleigh_fill_kernel<<<grid_for((n + 3) / 4, 256, 148 * 8), 256, 0, ST(stream)>>>(
+        out, n, sigma, static_cast<uint32_t>(seed), static_cast<uint32_t>(static_cast<uint64_t>(seed) >> 32), static_cast<uint32_t>(stream_id));
+    return check_launch("synth_rayleigh");
+}
+
+int onet_synth_kclutter(float* out, int64_t n, int nu, int64_t seed, int stream_id, void* stream) {
+    if (n <= 0) return 0;
+    if (nu < 1 || nu > 64) return fail("synth_kclutter: integer texture shape nu in [1, 64]");
+    kclutter_fill_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, ST(stream)>>>(
+        out, n, nu, static_cast<uint32_t>(seed), static_cast<uint32_t>(static_cast<uint64_t>(seed) >> 32), static_cast<uint32_t>(stream_id));
+    return check_launch("synth_kclutter");
+}
+
+int onet_synth_add_targets(float* frames, unsigned char* masks, int n_frames, int H, int W, const void* targets,
+                           int targets_per_frame, float snr_db, float* erc_out, void* stream) {
+    if (n_frames <= 0) return 0;
+    if (frames == nullptr || masks == nullptr) return fail("synth_add_targets: frames and masks are required");
+    if (targets_per_frame > 0 && targets == nullptr) return fail("synth_add_targets: targets table is null");
+    static_assert(sizeof(SynthTarget) == 32, "SynthTarget is 8 x 4 bytes (onet_b200.h)");
+    add_targets_kernel<<<n_frames, 256, 0, ST(stream)>>>(frames, masks, H, W, static_cast<const SynthTarget*>(targets),
+                                                         targets_per_frame, powf(10.0f, snr_db / 20.0f), erc_out);
+    return check_launch("synth_add_targets");
 }
 
 int onet_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,

@@ -200,3 +200,30 @@ def test_cascade_oracle_matches_reference_golden(golden_dir):
     s1, s2 = ev.test_2nd_stage_simclutter(st1, st2, loader)
     got = (s2[0], s2[1], s2[2], s2[3], s1[4])
     assert np.allclose(got, z["two_stage"], rtol=0, atol=1e-7), (got, z["two_stage"])
+
+
+def test_synth_oracle_matches_reference_golden(golden_dir):
+    """oracle/synth_oracle.py (gaussian_kernel2d, add_gaussian_template_on_clutter_v3 swerling 0, the target loop of
+    get_rayleigh_frame) against outputs of the unmodified reference generator (tests/golden/make_synth_golden.py), and the
+    host-side target table of onet_b200.synth against the same formulas."""
+    import os
+    from oracle import synth_oracle as so
+    from onet_b200 import synth
+    z = np.load(os.path.join(golden_dir, "synth.npz"))
+    assert np.allclose(so.gaussian_kernel2d(2.25, 4.25, 37.0), z["kg"], rtol=1e-14, atol=0)
+    for f in range(3):
+        cx, cy, w, h, theta = z[f"par{f}"]
+        out, mask, erc = so.composite_frame(z[f"bg{f}"], cx, cy, w, h, theta, int(z[f"snr{f}"]))
+        assert np.allclose(out, z[f"out{f}"], rtol=1e-13, atol=0)
+        assert np.array_equal(mask.astype(np.uint8), z[f"mask{f}"])
+        tab = synth.target_table(cx[None], cy[None], w[None], h[None], theta[None], 128, 128, host_threshold=True)[0]
+        for i in range(len(cx)):
+            kg = so.gaussian_kernel2d((w[i] / 2 - 0.5) / 2, (h[i] / 2 - 0.5) / 2, theta[i])
+            assert kg.shape == (2 * tab["hr"][i] + 1, 2 * tab["wr"][i] + 1)
+            assert abs(tab["thr"][i] - (kg.max() - 2 * kg.std())) < 1e-6
+    with pytest.raises(ValueError):
+        so.composite_frame(z["bg0"], [3.0], [64.0], [10.0], [18.0], [0.0], 4)          # window leaves the frame
+    with pytest.raises(ValueError):
+        synth.target_table([[3.0]], [[64.0]], [[10.0]], [[18.0]], [[0.0]], 128, 128)
+    with pytest.raises(ValueError):
+        so.composite_frame(z["bg0"], [64.0], [64.0], [10.0], [18.0], [0.0], 13)         # snr outside the reference's table
