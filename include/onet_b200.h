@@ -105,6 +105,23 @@ int onet_bn_relu_bwd(const void* y, int N, int H, int W, int C, const float* sca
                      const void* g2, int64_t ld2, int off2, const void* gp, double* sums, double count,
                      void* dy, float* dgamma0, float* dbeta0, float* dgamma1, float* dbeta1, int dtype, void* stream);
 
+/* Backward fusion (tcgen05 bf16 path): the 3x3 data gradient whose OUTPUT is the gradient g w.r.t. the post-ReLU activation
+ * of the previous conv layer (the two convs of a DoubleConv, Onet_vanilla_20240606.py:46-53).  Same product as
+ * onet_conv3x3_fwd with the flipped weights `wp`; in addition the epilogue reduces that previous layer's BatchNorm-backward
+ * sums from g (as stored, bf16) and its raw conv output y_prev [N,H,W,Cout]:
+ *   sums[grp][0][c] += sum dz, sums[grp][1][c] += sum dz * (y - mean[grp][c]) * invstd[grp][c], dz = (relu(bn(y)) > 0) ? g : 0
+ * (sums: zero-initialised double [G][2][Cout]), so the previous layer's BatchNorm backward only needs its apply pass:
+ * onet_bn_relu_bwd_apply, same arguments as onet_bn_relu_bwd without the second / pooled gradient sources.  Layer shapes
+ * whose kernel variant has no fused epilogue (images smaller than 16 x 8, few tiles) run the plain launch followed by the
+ * standalone reduce pass: same results. */
+int onet_conv3x3_dgrad_bnred(const void* in, int64_t ldi, int ci_off, int N, int H, int W, int Cin, const void* wp, int Cout,
+                             void* out, const void* y_prev, const float* scale, const float* shift, const float* mean,
+                             const float* invstd, double* sums, int group_images, int dtype, int engine, void* stream);
+int onet_bn_relu_bwd_apply(const void* y, int N, int H, int W, int C, const float* scale, const float* shift,
+                           const float* mean, const float* invstd, int group_images, const void* g1, int64_t ld1, int off1,
+                           double* sums, double count, void* dy, float* dgamma0, float* dbeta0, float* dgamma1,
+                           float* dbeta1, int dtype, void* stream);
+
 /* ConvTranspose2d(Cin, Co, 2, 2) + bias written directly into channels [ooff, ooff+Co) of the concat buffer
  * (nn.ConvTranspose2d :86 + F.pad :92-96 + the up half of torch.cat :100).  The buffer holds a fine grid of Ho x Wo
  * pixels per image (0 = exactly 2H x 2W); when the skip tensor is one pixel larger (odd sizes after floor pooling) the

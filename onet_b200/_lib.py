@@ -59,6 +59,8 @@ SIGNATURES = {
     "onet_bn_relu_apply": [_p, _i, _i, _i, _i, _p, _p, _i, _p, _i64, _i, _p, _i, _p],
     "onet_bn_relu_bwd": [_p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _i64, _i, _p, _i64, _i, _p, _p, _d, _p,
                          _p, _p, _p, _p, _i, _p],
+    "onet_conv3x3_dgrad_bnred": [_p, _i64, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "onet_bn_relu_bwd_apply": [_p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _i64, _i, _p, _d, _p, _p, _p, _p, _p, _i, _p],
     "onet_convT2x2_fwd": [_p, _i64, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i64, _i, _i, _i, _i, _i, _p],
     "onet_convT2x2_dgrad": [_p, _i64, _i, _i, _i, _i, _i, _p, _i, _p, _i64, _i, _i, _i, _i, _i, _p],
     "onet_convT2x2_wgrad": [_p, _i64, _i, _p, _i64, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p],

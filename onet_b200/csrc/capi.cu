@@ -183,26 +183,26 @@ static int launch_halo_px(const CUtensorMap& tA, const CUtensorMap& tB, const Px
     return check_launch("conv3x3_halo_px_kernel", BN);
 }
 
-template <int BN>
+template <int BN, bool RED = false>
 static int launch_halo_res_px(const CUtensorMap& tA, const CUtensorMap& tB, const PxParams& p, cudaStream_t st) {
     using Cfg = HaloResCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_res_px_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_res_px_kernel<BN, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return fail("cudaFuncSetAttribute(halo_res_px<%d>): %s", BN, cudaGetErrorString(e));
         attr_set = true;
     }
-    conv3x3_halo_res_px_kernel<BN><<<std::min(p.num_m_tiles, sm_count()), kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, p);
-    return check_launch("conv3x3_halo_res_px_kernel", BN);
+    conv3x3_halo_res_px_kernel<BN, RED><<<std::min(p.num_m_tiles, sm_count()), kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, p);
+    return check_launch(RED ? "conv3x3_halo_res_px_kernel+bnred" : "conv3x3_halo_res_px_kernel", BN);
 }
 
 // CTA-pair (cta_group::2) variant: grid = 2 x min(pair tiles, co-resident clusters)
-template <int BN>
+template <int BN, bool RED = false>
 static int launch_halo2_px(const CUtensorMap& tA, const CUtensorMap& tB, const PxParams& p, cudaStream_t st) {
     using Cfg = Halo2Cfg<BN>;
     static int max_clusters = 0;
     if (max_clusters == 0) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_halo2_px_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_halo2_px_kernel<BN, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return fail("cudaFuncSetAttribute(halo2_px<%d>): %s", BN, cudaGetErrorString(e));
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
@@ -215,7 +215,7 @@ static int launch_halo2_px(const CUtensorMap& tA, const CUtensorMap& tB, const P
         cfg.attrs = &at;
         cfg.numAttrs = 1;
         int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, conv3x3_halo2_px_kernel<BN>, &cfg) != cudaSuccess || n <= 0) {
+        if (cudaOccupancyMaxActiveClusters(&n, conv3x3_halo2_px_kernel<BN, RED>, &cfg) != cudaSuccess || n <= 0) {
             cudaGetLastError();
             n = sm_count() / 2;
         }
@@ -223,8 +223,8 @@ static int launch_halo2_px(const CUtensorMap& tA, const CUtensorMap& tB, const P
     }
     const int units = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
     const int grid = 2 * std::min(units, max_clusters);
-    conv3x3_halo2_px_kernel<BN><<<grid, kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, p);
-    return check_launch("conv3x3_halo2_px_kernel", BN);
+    conv3x3_halo2_px_kernel<BN, RED><<<grid, kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, p);
+    return check_launch(RED ? "conv3x3_halo2_px_kernel+bnred" : "conv3x3_halo2_px_kernel", BN);
 }
 
 // Split-K factor for the weight-gradient kernels: minimise (waves x K-steps per unit + fixed per-unit epilogue cost).
@@ -245,11 +245,43 @@ static void pick_ksplit(int base_units, int num_px_tiles, int* ksplit, int* per_
     *ksplit = (num_px_tiles + best_per - 1) / best_per;
 }
 
+// BatchNorm-backward reduce of the previous layer folded into a dgrad launch (PxParams::red_y)
+struct BnRedArgs {
+    const bf16* y; const float* scale; const float* shift; const float* mean; const float* invstd;
+    double* sums;                                                                              // [G][2][Cout]
+};
+static void apply_bnred(PxParams& p, const BnRedArgs* red, int Cout) {
+    if (red == nullptr || red->y == nullptr) return;
+    p.red_y = red->y; p.red_scale = red->scale; p.red_shift = red->shift; p.red_mean = red->mean; p.red_invstd = red->invstd;
+    p.stat_sum = red->sums; p.stat_sq = red->sums + Cout; p.stat_gstride = 2 * Cout;
+}
+// The same sums from the standalone reduce pass (kernel variants without a fused-reduce instantiation: small images)
+static int bnred_standalone(const BnRedArgs& red, const bf16* g, int N, int H, int W, int C, int group_images, cudaStream_t st) {
+    BnBwdArgs<bf16> a;
+    memset(&a, 0, sizeof(a));
+    a.y = red.y; a.N = N; a.H = H; a.W = W; a.C = C;
+    a.scale = red.scale; a.shift = red.shift; a.mean = red.mean; a.invstd = red.invstd;
+    a.group_images = group_images > 0 ? group_images : N;
+    a.g1 = g; a.ld1 = C; a.off1 = 0;
+    a.sums = red.sums;
+    const int G = std::min(2, (N + a.group_images - 1) / a.group_images);
+    const int OC = C / 8, lanes = std::max(1, 256 / OC);
+    if (C % 8 || 256 % OC != 0) return fail("conv3x3_dgrad_bnred: C/8 must divide 256");
+    const long long px = static_cast<long long>(a.group_images) * H * W;
+    const int gx = static_cast<int>(std::max(1LL, std::min<long long>((px + lanes * 4 - 1) / (lanes * 4), 148 * 4 / G)));
+    bn_bwd_px_kernel<bf16, 4, false, false><<<dim3(gx, G), 256, 0, st>>>(a);
+    return check_launch("bn_bwd_reduce");
+}
+
 static int pick_bn(int cout) { return (cout % 256 == 0) ? 256 : (cout % 128 == 0 ? 128 : 64); }
+
+static int conv3x3_tc_then_reduce(const bf16* in, long long ldi, int ci_off, int N, int H, int W, int Cin, const bf16* wp,
+                                  int Cout, bf16* out, long long ldo, int co_off, int group_images, cudaStream_t st,
+                                  const BnRedArgs& red);
 
 static int conv3x3_tc(const bf16* in, long long ldi, int ci_off, int N, int H, int W, int Cin, const bf16* wp, int Cout,
                       bf16* out, long long ldo, int co_off, double* ssum, double* ssq, int group_images, cudaStream_t st,
-                      const float* bn_scale = nullptr, const float* bn_shift = nullptr) {
+                      const float* bn_scale = nullptr, const float* bn_shift = nullptr, const BnRedArgs* red = nullptr) {
     if (Cin % 64 || Cout % 64) return fail("tc conv needs Cin, Cout multiples of 64 (got %d, %d)", Cin, Cout);
     if (ldo % 8 || co_off % 8) return fail("tc conv output channel stride/offset must be multiples of 8");
     PxParams p;
@@ -266,8 +298,9 @@ static int conv3x3_tc(const bf16* in, long long ldi, int ci_off, int N, int H, i
         p.ntaps = 9; p.k_chunks = Cin / 64; p.cin = Cin;
         p.epi_mode = EPI_STORE;
         p.out = out; p.ldo = ldo; p.out_coff = co_off;
-        p.stat_sum = ssum; p.stat_sq = ssq; p.cout_total = Cout; p.group_images = group_images > 0 ? group_images : N;
+        p.stat_sum = ssum; p.stat_sq = ssq; p.cout_total = Cout; p.stat_gstride = Cout; p.group_images = group_images > 0 ? group_images : N;
         p.scale = bn_scale; p.shift = bn_shift;
+        apply_bnred(p, red, Cout);
         CUtensorMap tA, tB;
         const uint32_t hbox[5] = {64, 8, 1, 18, 1};
         if (make_act_map(&tA, in + ci_off, Cin, N, H, W, ldi, hbox)) return 1;
@@ -276,6 +309,9 @@ static int conv3x3_tc(const bf16* in, long long ldi, int ci_off, int N, int H, i
         if (p.num_m_tiles >= 2 && p.k_chunks >= min_kc && !getenv("ONET_NO_2CTA")) {
             // CTA pairs: two pixel tiles per MMA, each CTA stages half of the weight tile
             if (make_map2(&tB, wp, 9ULL * Cin, Cout, 64, BN / 2)) return 1;
+            if (red && BN == 256) return launch_halo2_px<256, true>(tA, tB, p, st);
+            if (red && BN == 128) return launch_halo2_px<128, true>(tA, tB, p, st);
+            if (red) return conv3x3_tc_then_reduce(in, ldi, ci_off, N, H, W, Cin, wp, Cout, out, ldo, co_off, group_images, st, *red);
             if (BN == 256) return launch_halo2_px<256>(tA, tB, p, st);
             if (BN == 128) return launch_halo2_px<128>(tA, tB, p, st);
             return launch_halo2_px<64>(tA, tB, p, st);
@@ -283,13 +319,17 @@ static int conv3x3_tc(const bf16* in, long long ldi, int ci_off, int N, int H, i
         if (make_map2(&tB, wp, 9ULL * Cin, Cout, 64, BN)) return 1;
         if (p.k_chunks == 1 && p.num_n_tiles == 1 && BN <= 128 && p.num_m_tiles >= 4 * sm_count() && !getenv("ONET_NO_BRES")) {
             // Cin = 64, Cout <= 128, many tiles per CTA: weights stay resident in shared memory
+            if (red && BN == 64) return launch_halo_res_px<64, true>(tA, tB, p, st);
+            if (red) return conv3x3_tc_then_reduce(in, ldi, ci_off, N, H, W, Cin, wp, Cout, out, ldo, co_off, group_images, st, *red);
             if (BN == 128) return launch_halo_res_px<128>(tA, tB, p, st);
             return launch_halo_res_px<64>(tA, tB, p, st);
         }
+        if (red) return conv3x3_tc_then_reduce(in, ldi, ci_off, N, H, W, Cin, wp, Cout, out, ldo, co_off, group_images, st, *red);
         if (BN == 256) return launch_halo_px<256>(tA, tB, p, st);
         if (BN == 128) return launch_halo_px<128>(tA, tB, p, st);
         return launch_halo_px<64>(tA, tB, p, st);
     }
+    if (red) return conv3x3_tc_then_reduce(in, ldi, ci_off, N, H, W, Cin, wp, Cout, out, ldo, co_off, group_images, st, *red);
     px_tiling(p, N, H, W, (ssum || bn_scale) ? group_images : 0);
     p.num_n_tiles = Cout / BN;
     p.ntaps = 9; p.k_chunks = Cin / 64; p.cin = Cin;
@@ -302,7 +342,7 @@ static int conv3x3_tc(const bf16* in, long long ldi, int ci_off, int N, int H, i
     }
     p.epi_mode = EPI_STORE;
     p.out = out; p.ldo = ldo; p.out_coff = co_off;
-    p.stat_sum = ssum; p.stat_sq = ssq; p.cout_total = Cout; p.group_images = group_images > 0 ? group_images : N;
+    p.stat_sum = ssum; p.stat_sq = ssq; p.cout_total = Cout; p.stat_gstride = Cout; p.group_images = group_images > 0 ? group_images : N;
     p.scale = bn_scale; p.shift = bn_shift;
     CUtensorMap tA, tB;
     const uint32_t box[5] = {64, static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
@@ -311,6 +351,15 @@ static int conv3x3_tc(const bf16* in, long long ldi, int ci_off, int N, int H, i
     if (BN == 256) return launch_px<256>(tA, tB, p, st);
     if (BN == 128) return launch_px<128>(tA, tB, p, st);
     return launch_px<64>(tA, tB, p, st);
+}
+
+// dgrad without a fused-reduce instantiation: the plain launch, then the standalone reduce pass over its output
+static int conv3x3_tc_then_reduce(const bf16* in, long long ldi, int ci_off, int N, int H, int W, int Cin, const bf16* wp,
+                                  int Cout, bf16* out, long long ldo, int co_off, int group_images, cudaStream_t st,
+                                  const BnRedArgs& red) {
+    if (ldo != Cout || co_off != 0) return fail("conv3x3_dgrad_bnred: dense output required");
+    if (conv3x3_tc(in, ldi, ci_off, N, H, W, Cin, wp, Cout, out, ldo, co_off, nullptr, nullptr, group_images, st)) return 1;
+    return bnred_standalone(red, out, N, H, W, Cout, group_images, st);
 }
 
 // convT fwd on tensor cores: D[px][(tap,co)] = X[px][:] . wf[(tap,co)][:], scatter epilogue
@@ -328,7 +377,7 @@ static int convT_fwd_tc(const bf16* x, long long ldx, int xoff, int N, int H, in
     p.tap_w[0] = 0;
     p.epi_mode = EPI_CONVT;
     p.out = out; p.ldo = ldo; p.out_coff = ooff;
-    p.bias = bias; p.co_per_tap = Co; p.cout_total = 4 * Co; p.group_images = N;
+    p.bias = bias; p.co_per_tap = Co; p.cout_total = 4 * Co; p.stat_gstride = 4 * Co; p.group_images = N;
     p.Ho = Ho; p.Wo = Wo;
     CUtensorMap tA, tB;
     const uint32_t box[5] = {64, static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
@@ -356,7 +405,7 @@ static int convT_dgrad_tc(const bf16* go, long long ldg, int goff, int N, int H,
     }
     p.epi_mode = EPI_STORE;
     p.out = dx; p.ldo = ldd; p.out_coff = doff;
-    p.cout_total = Cin; p.group_images = N;
+    p.cout_total = Cin; p.stat_gstride = Cin; p.group_images = N;
     CUtensorMap tA, tB;
     const uint32_t box[5] = {64, static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
     if (make_up_map(&tA, go + goff, Co, N, H, W, ldg, box, Ho, Wo)) return 1;
@@ -791,7 +840,7 @@ template <typename T>
 static int bn_bwd_impl(const void* y, int N, int H, int W, int C, const float* scale, const float* shift, const float* mean,
                        const float* invstd, int group_images, const void* g1, int64_t ld1, int off1, const void* g2,
                        int64_t ld2, int off2, const void* gp, double* sums, double count, void* dy,
-                       float* dgamma0, float* dbeta0, float* dgamma1, float* dbeta1, cudaStream_t st) {
+                       float* dgamma0, float* dbeta0, float* dgamma1, float* dbeta1, cudaStream_t st, bool prereduced = false) {
     BnBwdArgs<T> a;
     a.y = static_cast<const T*>(y); a.N = N; a.H = H; a.W = W; a.C = C;
     a.scale = scale; a.shift = shift; a.mean = mean; a.invstd = invstd;
@@ -824,6 +873,7 @@ static int bn_bwd_impl(const void* y, int N, int H, int W, int C, const float* s
         blocks_override = e ? atoi(e) : 0;
     }
     const int max_blocks = (blocks_override > 0 ? blocks_override : 148 * 4) / G;        // 2 resident blocks per SM, two rounds
+    if (prereduced && gp != nullptr) return fail("bn_relu_bwd_apply: a pooled gradient source cannot be pre-reduced");
     if (gp != nullptr) {
         if (OC > kBnWinThreads) return fail("bn_relu_bwd: the pooled variant supports C <= %d", 8 * kBnWinThreads);
         const int wlanes = kBnWinThreads / OC;
@@ -844,7 +894,11 @@ static int bn_bwd_impl(const void* y, int N, int H, int W, int C, const float* s
         constexpr int UNR = 4;
         const long long px = static_cast<long long>(a.group_images) * H * W;
         const int gx = static_cast<int>(std::max(1LL, std::min<long long>((px + lanes * UNR - 1) / (lanes * UNR), max_blocks)));
-        if (g2 != nullptr) {
+        if (prereduced) {
+            // sums already reduced by the producing dgrad launch (PxParams::red_y): only the apply pass is left
+            if (g2 != nullptr) return fail("bn_relu_bwd_apply: a second gradient source cannot be pre-reduced");
+            bn_bwd_px_kernel<T, UNR, false, true><<<dim3(gx, G), 256, 0, st>>>(a);
+        } else if (g2 != nullptr) {
             bn_bwd_px_kernel<T, UNR, true, false><<<dim3(gx, G), 256, 0, st>>>(a);
             if (check_launch("bn_bwd_reduce")) return 1;
             bn_bwd_px_kernel<T, UNR, true, true><<<dim3(gx, G), 256, 0, st>>>(a);
@@ -879,6 +933,31 @@ int onet_bn_relu_bwd(const void* y, int N, int H, int W, int C, const float* sca
                                   sums, count, dy, dgamma0, dbeta0, dgamma1, dbeta1, ST(stream));
     return bn_bwd_impl<bf16>(y, N, H, W, C, scale, shift, mean, invstd, group_images, g1, ld1, off1, g2, ld2, off2, gp,
                              sums, count, dy, dgamma0, dbeta0, dgamma1, dbeta1, ST(stream));
+}
+
+int onet_bn_relu_bwd_apply(const void* y, int N, int H, int W, int C, const float* scale, const float* shift,
+                           const float* mean, const float* invstd, int group_images, const void* g1, int64_t ld1, int off1,
+                           double* sums, double count, void* dy, float* dgamma0, float* dbeta0, float* dgamma1,
+                           float* dbeta1, int dtype, void* stream) {
+    if (static_cast<long long>(N) * H * W >= (1LL << 31)) return fail("bn_relu_bwd_apply: more than 2^31 pixels");
+    if (C % 8 || C > 2048 || 256 % (C / 8) != 0) return fail("bn_relu_bwd_apply: C must be a multiple of 8 with C/8 dividing 256");
+    if (g1 == nullptr || sums == nullptr) return fail("bn_relu_bwd_apply: g1 and sums are required");
+    if (dtype == ONET_F32)
+        return bn_bwd_impl<float>(y, N, H, W, C, scale, shift, mean, invstd, group_images, g1, ld1, off1, nullptr, 0, 0, nullptr,
+                                  sums, count, dy, dgamma0, dbeta0, dgamma1, dbeta1, ST(stream), true);
+    return bn_bwd_impl<bf16>(y, N, H, W, C, scale, shift, mean, invstd, group_images, g1, ld1, off1, nullptr, 0, 0, nullptr,
+                             sums, count, dy, dgamma0, dbeta0, dgamma1, dbeta1, ST(stream), true);
+}
+
+int onet_conv3x3_dgrad_bnred(const void* in, int64_t ldi, int ci_off, int N, int H, int W, int Cin, const void* wp, int Cout,
+                             void* out, const void* y_prev, const float* scale, const float* shift, const float* mean,
+                             const float* invstd, double* sums, int group_images, int dtype, int engine, void* stream) {
+    if (dtype != ONET_BF16 || engine != ONET_ENGINE_TC) return fail("conv3x3_dgrad_bnred: tcgen05 bf16 path only");
+    if (y_prev == nullptr || scale == nullptr || shift == nullptr || mean == nullptr || invstd == nullptr || sums == nullptr)
+        return fail("conv3x3_dgrad_bnred: y_prev, scale, shift, mean, invstd and sums are required");
+    BnRedArgs red{static_cast<const bf16*>(y_prev), scale, shift, mean, invstd, sums};
+    return conv3x3_tc(static_cast<const bf16*>(in), ldi, ci_off, N, H, W, Cin, static_cast<const bf16*>(wp), Cout,
+                      static_cast<bf16*>(out), Cout, 0, nullptr, nullptr, group_images, ST(stream), nullptr, nullptr, &red);
 }
 
 int onet_convT2x2_fwd(const void* x, int64_t ldx, int xoff, int N, int H, int W, int Cin, const void* w,

@@ -173,7 +173,7 @@ struct HaloResCfg {
     static constexpr int kSmemBytes = kSA * kABytes + 9 * kBBytes + kAuxBytes + 1024;
 };
 
-template <int BN>
+template <int BN, bool RED = false>
 __global__ void __launch_bounds__(kPxThreads, 1)
 conv3x3_halo_res_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PxParams p) {
     using Cfg = HaloResCfg<BN>;
@@ -266,12 +266,14 @@ conv3x3_halo_res_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         sacc.reset_rows();
         sacc.grp = 0;
         int it = 0;
+        if (RED) px_red_prefetch<BN>(p, blockIdx.x, 0, q, ew, lane);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
+            if (RED && tile + static_cast<int>(gridDim.x) < num_tiles) px_red_prefetch<BN>(p, tile + gridDim.x, 0, q, ew, lane);
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
-            px_store_epilogue<BN>(p, tile, 0, acc, tmem_base, q, ew, lane, s_part, bar_tempty + 8 * acc, false, sacc);
+            px_store_epilogue<BN, RED>(p, tile, 0, acc, tmem_base, q, ew, lane, s_part, bar_tempty + 8 * acc, false, sacc);
         }
         px_stat_flush<BN>(p, sacc, ew, lane, s_part);
     }
@@ -304,7 +306,7 @@ struct Halo2Cfg {
     static constexpr int kSmemBytes = kSA * kABytes + kSB * kBStageBytes + kAuxBytes + 1024;
 };
 
-template <int BN>
+template <int BN, bool RED = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPxThreads, 1)
 conv3x3_halo2_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PxParams p) {
     using Cfg = Halo2Cfg<BN>;
@@ -420,14 +422,18 @@ conv3x3_halo2_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         sacc.reset_rows();
         sacc.grp = 0;
         int it = 0;
+        if (RED && pair < num_units)
+            px_red_prefetch<BN>(p, 2 * (pair % num_pair_m) + static_cast<int>(rank), pair / num_pair_m, q, ew, lane);
         for (int unit = pair; unit < num_units; unit += npairs, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int m_tile = 2 * (unit % num_pair_m) + static_cast<int>(rank), n_tile = unit / num_pair_m;
+            if (RED && unit + npairs < num_units)
+                px_red_prefetch<BN>(p, 2 * ((unit + npairs) % num_pair_m) + static_cast<int>(rank), (unit + npairs) / num_pair_m, q, ew, lane);
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             if (m_tile < p.num_m_tiles) {
-                px_store_epilogue<BN>(p, m_tile, n_tile, acc, tmem_base, q, ew, lane, s_part, lead_tempty + 8 * acc, true, sacc);
+                px_store_epilogue<BN, RED>(p, m_tile, n_tile, acc, tmem_base, q, ew, lane, s_part, lead_tempty + 8 * acc, true, sacc);
             } else {           // padding tile of an odd tile count: nothing to store
                 tc_fence_before();
                 __syncwarp();

@@ -46,6 +46,16 @@ struct PxParams {
     int group_images;          // images per BatchNorm statistics group (twin branch)
     const float* scale;        // EPI_STORE, inference: per-group per-channel BatchNorm(eval) scale / shift [G][cout_total];
     const float* shift;        //   the epilogue then stores relu(acc * scale + shift) instead of the raw conv output
+    // EPI_STORE, backward: the conv output is the gradient g w.r.t. the post-ReLU activation of the PREVIOUS layer; with
+    // red_y set the epilogue reduces that layer's BatchNorm-backward sums instead of the output statistics:
+    //   stat_sum[grp][c] += sum dz,  stat_sq[grp][c] += sum dz * (y - mean) * invstd,  dz = (bn_relu(y) > 0) ? g : 0
+    // (the reduce pass of bn_bwd_px_kernel, elementwise.cuh, without re-reading g from HBM; kernels instantiated with RED)
+    const __nv_bfloat16* red_y;   // [N,H,W,cout_total] raw conv output of the previous layer, or nullptr
+    const float* red_scale;       // [G][cout_total]
+    const float* red_shift;
+    const float* red_mean;
+    const float* red_invstd;
+    int stat_gstride;             // doubles between the statistics groups of stat_sum / stat_sq (cout_total, or 2 * cout_total)
     const float* bias;         // EPI_CONVT: [co_per_tap]
     int co_per_tap;            // EPI_CONVT: output channels per 2x2 position
     int Ho, Wo;                // EPI_CONVT: height / width of the fine grid the buffer holds (>= 2H, 2W; F.pad border beyond)
@@ -154,16 +164,36 @@ __device__ __forceinline__ void px_stat_flush(const PxParams& p, PxStatAcc& a, i
             if (p.stat_sq != nullptr) atomicAdd(p.stat_sq + col, a.q0);
         }
         if (a.s1 != 0.0 || a.q1 != 0.0) {
-            atomicAdd(p.stat_sum + p.cout_total + col, a.s1);
-            if (p.stat_sq != nullptr) atomicAdd(p.stat_sq + p.cout_total + col, a.q1);
+            atomicAdd(p.stat_sum + p.stat_gstride + col, a.s1);
+            if (p.stat_sq != nullptr) atomicAdd(p.stat_sq + p.stat_gstride + col, a.q1);
         }
     }
     a.reset(-1);
 }
 
+// RED kernels: the epilogue of a tile reads the previous layer's raw output y for the tile's pixels.  Hint the rows of the
+// NEXT tile into the cache one tile ahead (L1 for 64-wide tiles: 16 KB per tile; L2 otherwise), so that the loads in the
+// epilogue do not stall it for a DRAM round trip per 32-channel chunk.
+template <int BN>
+__device__ __forceinline__ void px_red_prefetch(const PxParams& p, int m_tile, int n_tile, int q, int ew, int lane) {
+    if (m_tile >= p.num_m_tiles) return;
+    const int half = ew >> 2;
+    const int row = q * 32 + lane;
+    const int w_l = row & (p.TW - 1), h_l = (row >> p.log_tw) & (p.TH - 1), n_l = row >> (p.log_tw + p.log_th);
+    const int wt = m_tile % p.tiles_w, ht = (m_tile / p.tiles_w) % p.tiles_h, nt = m_tile / (p.tiles_w * p.tiles_h);
+    const int w = wt * p.TW + w_l, h = ht * p.TH + h_l, n = nt * p.TN + n_l;
+    if (!((row < p.valid_rows) && (w < p.W) && (h < p.H) && (n < p.N))) return;
+    const __nv_bfloat16* yrow = p.red_y + ((static_cast<long long>(n) * p.H + h) * p.W + w) * p.cout_total + n_tile * BN;
+#pragma unroll
+    for (int ch = half; ch < BN / 32; ch += kPxEpiWarps / 4) {
+        if (BN == 64) asm volatile("prefetch.global.L1 [%0];" ::"l"(yrow + ch * 32));
+        else asm volatile("prefetch.global.L2 [%0];" ::"l"(yrow + ch * 32));
+    }
+}
+
 // Store epilogue of the pixel-major kernels: raw bf16 output + BatchNorm partial sums.
 // `arrive_bar`: the accumulator-drained barrier; `remote`: it is a shared::cluster address in the peer (leader) CTA.
-template <int BN>
+template <int BN, bool RED = false>
 __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile, int n_tile, int acc, uint32_t tmem_base, int q,
                                                   int ew, int lane, float* s_part, uint32_t arrive_bar, bool remote,
                                                   PxStatAcc& sacc) {
@@ -227,6 +257,38 @@ __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile,
                 const float lo = valid ? __low2float(b) : 0.f, hi = valid ? __high2float(b) : 0.f;
                 v[2 * j] = lo; v[2 * j + 1] = hi;
                 s2[2 * j] = lo * lo; s2[2 * j + 1] = hi * hi;
+            }
+            if (RED) {      // BatchNorm-backward reduce of the previous layer: v = dz, s2 = dz * (y - mean) * invstd
+                const int grp = min((nt * p.TN) / p.group_images, 1);
+                const long long cbase = static_cast<long long>(grp) * p.cout_total + co0 + ch * 32;
+                const uint4* y4 = reinterpret_cast<const uint4*>(
+                    p.red_y + ((static_cast<long long>(n) * p.H + h) * p.W + w) * p.cout_total + co0 + ch * 32);
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const uint4 yr = valid ? __ldg(y4 + j4) : make_uint4(0u, 0u, 0u, 0u);
+                    const uint32_t yw[4] = {yr.x, yr.y, yr.z, yr.w};
+                    const float4 sca = __ldg(reinterpret_cast<const float4*>(p.red_scale + cbase) + 2 * j4);
+                    const float4 scb = __ldg(reinterpret_cast<const float4*>(p.red_scale + cbase) + 2 * j4 + 1);
+                    const float4 sha = __ldg(reinterpret_cast<const float4*>(p.red_shift + cbase) + 2 * j4);
+                    const float4 shb = __ldg(reinterpret_cast<const float4*>(p.red_shift + cbase) + 2 * j4 + 1);
+                    const float4 mua = __ldg(reinterpret_cast<const float4*>(p.red_mean + cbase) + 2 * j4);
+                    const float4 mub = __ldg(reinterpret_cast<const float4*>(p.red_mean + cbase) + 2 * j4 + 1);
+                    const float4 isa = __ldg(reinterpret_cast<const float4*>(p.red_invstd + cbase) + 2 * j4);
+                    const float4 isb = __ldg(reinterpret_cast<const float4*>(p.red_invstd + cbase) + 2 * j4 + 1);
+                    const float is[8] = {isa.x, isa.y, isa.z, isa.w, isb.x, isb.y, isb.z, isb.w};
+                    const float sc[8] = {sca.x, sca.y, sca.z, sca.w, scb.x, scb.y, scb.z, scb.w};
+                    const float sh[8] = {sha.x, sha.y, sha.z, sha.w, shb.x, shb.y, shb.z, shb.w};
+                    const float mu[8] = {mua.x, mua.y, mua.z, mua.w, mub.x, mub.y, mub.z, mub.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float y = __uint_as_float((e & 1) ? (yw[e >> 1] & 0xffff0000u) : (yw[e >> 1] << 16));
+                        // the stored post-ReLU activation is bf16(max(y * sc + sh, 0)) (bn_relu_value, elementwise.cuh)
+                        const float act = __bfloat162float(__float2bfloat16(fmaxf(fmaf(y, sc[e], sh[e]), 0.f)));
+                        const float dz = act > 0.f ? v[8 * j4 + e] : 0.f;
+                        v[8 * j4 + e] = dz;
+                        s2[8 * j4 + e] = dz * ((y - mu[e]) * is[e]);
+                    }
+                }
             }
             if (BN == 64) {          // one chunk per warp: keep per-row running sums, no cross-lane traffic per tile
 #pragma unroll

@@ -40,6 +40,12 @@ _PACK_GEN = [0]
 # layer (HBM bound, small CTAs), which they do not depend on.  ONET_NO_WGRAD_OVERLAP=1 restores the serial order.
 _SIDE_STREAMS = {}
 
+# BatchNorm-backward reduce folded into the producing dgrad epilogue for layers of at least this many channels
+# (`_conv_bn_relu_bwd`); ONET_NO_BNRED_FUSION=1 disables it.  Measured (profiles/r1_ab_bnred_fusion.txt): the 8 epilogue warps
+# of the 64- and 128-wide tile kernels have no slack for the extra work (the fused dgrad gets 2-2.6x slower), the 256-wide
+# CTA-pair kernel absorbs it (+14 % on its 5 launches against -0.43 ms of BatchNorm passes), hence 256.
+_BNRED_MIN_C = int(os.environ.get("ONET_BNRED_MIN_C", "256"))
+
 
 def _side_stream(dev):
     key = dev.index if dev.index is not None else torch.cuda.current_device()
@@ -529,15 +535,23 @@ class _Engine:
         Y, aff, h, w, cin, cout = sv["Y"], sv["aff"], sv["h"], sv["w"], sv["cin"], sv["cout"]
         G = seg.groups
         st = self.stream
-        sums = rec.sum_pool[rec.sum_off:rec.sum_off + 2 * G * cout]
-        rec.sum_off += 2 * G * cout
+        if sv.get("prered") is None:
+            sums = rec.sum_pool[rec.sum_off:rec.sum_off + 2 * G * cout]
+            rec.sum_off += 2 * G * cout
         dY = self._empty(n, h, w, cout)
         count = float(seg.group_images * h * w)
         self._flush_side()          # the previous layers' weight gradients run next to this BatchNorm backward
-        call("onet_bn_relu_bwd", ptr(Y), n, h, w, cout, ptr(aff[2]), ptr(aff[3]), ptr(aff[0]), ptr(aff[1]),
-             seg.group_images, ptr(g1, off1), ld1, 0, ptr(g2, off2) if g2 is not None else None, ld2, 0,
-             ptr(gp) if gp is not None else None, ptr(sums), count, ptr(dY),
-             ptr(grad_of(bn.weight)), ptr(grad_of(bn.bias)), ptr(grad_of(bn.weight)), ptr(grad_of(bn.bias)), self.dt, st)
+        if sv.get("prered") is not None:
+            # the dgrad launch that produced g1 already reduced this layer's sums in its epilogue: apply pass only
+            assert g2 is None and gp is None and ld1 == cout and off1 == 0
+            call("onet_bn_relu_bwd_apply", ptr(Y), n, h, w, cout, ptr(aff[2]), ptr(aff[3]), ptr(aff[0]), ptr(aff[1]),
+                 seg.group_images, ptr(g1), ld1, 0, ptr(sv["prered"]), count, ptr(dY),
+                 ptr(grad_of(bn.weight)), ptr(grad_of(bn.bias)), ptr(grad_of(bn.weight)), ptr(grad_of(bn.bias)), self.dt, st)
+        else:
+            call("onet_bn_relu_bwd", ptr(Y), n, h, w, cout, ptr(aff[2]), ptr(aff[3]), ptr(aff[0]), ptr(aff[1]),
+                 seg.group_images, ptr(g1, off1), ld1, 0, ptr(g2, off2) if g2 is not None else None, ld2, 0,
+                 ptr(gp) if gp is not None else None, ptr(sums), count, ptr(dY),
+                 ptr(grad_of(bn.weight)), ptr(grad_of(bn.bias)), ptr(grad_of(bn.weight)), ptr(grad_of(bn.bias)), self.dt, st)
         self._join_side()
         eng = self._engine_for(cin, cout)
         src, ld_src, off_src = sv["src"]
@@ -547,6 +561,19 @@ class _Engine:
             return None
         _, wd = self._packed(conv, "conv")
         dX = self._empty(n, h, w, cin)
+        prev = rec.saved.get((si, li - 1)) if (li & 1) else None
+        if (prev is not None and eng == ENGINE_TC and colsum is None and prev["cout"] == cin and prev["h"] == h
+                and cin >= _BNRED_MIN_C and os.environ.get("ONET_NO_BNRED_FUSION") is None):
+            # second conv of a DoubleConv: its data gradient is the gradient w.r.t. the first conv's activation - reduce the
+            # first conv's BatchNorm-backward sums in this launch's epilogue (saves one pass over (Y, g) in HBM)
+            paff = prev["aff"]
+            G = seg.groups
+            psums = rec.sum_pool[rec.sum_off:rec.sum_off + 2 * G * cin]
+            rec.sum_off += 2 * G * cin
+            call("onet_conv3x3_dgrad_bnred", ptr(dY), cout, 0, n, h, w, cout, ptr(wd), cin, ptr(dX), ptr(prev["Y"]),
+                 ptr(paff[2]), ptr(paff[3]), ptr(paff[0]), ptr(paff[1]), ptr(psums), seg.group_images, self.dt, eng, st)
+            prev["prered"] = psums
+            return dX
         call("onet_conv3x3_fwd", ptr(dY), cout, 0, n, h, w, cout, ptr(wd), cin, ptr(dX), cin, 0,
              ptr(colsum[0]) if colsum is not None else None,
              ptr(colsum[1]) if (colsum is not None and eng != ENGINE_TC) else None,     # tcgen05 epilogue: sums only

@@ -343,3 +343,53 @@ def test_dgrad_epilogue_column_sums_feed_upconv_bias_grad():
     call("onet_add_colsums", ptr(cs[0], 64), 64, ptr(dbias), U.stream())
     want = 0.5 + out[..., 64:].float().sum(dim=(0, 1, 2))
     assert torch.allclose(dbias, want, rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("n,h,w,c", [(4, 32, 32, 256),      # CTA-pair kernel, 256-wide tiles, fused epilogue reduce
+                                      (6, 32, 40, 128),      # CTA-pair kernel, 128-wide tiles (odd tile count per image row)
+                                      (150, 32, 32, 64),     # weight-resident kernel (>= 4 tiles per SM), per-row running sums
+                                      (2, 8, 8, 64),         # no fused instantiation for this variant: plain launch + standalone reduce
+                                      (2, 4, 4, 1024)])      # images smaller than a 16 x 8 tile: generic tap-GEMM + standalone reduce
+def test_dgrad_with_fused_bn_backward_reduce(n, h, w, c):
+    """onet_conv3x3_dgrad_bnred + onet_bn_relu_bwd_apply against the unfused pair onet_conv3x3_fwd (flipped weights) +
+    onet_bn_relu_bwd on the same inputs: identical data gradient (bit for bit), the same BatchNorm-backward sums (the fused
+    epilogue reduces the bf16 gradient it stores, exactly what the standalone pass reads back), the same dY / dgamma / dbeta."""
+    U = _imports()
+    call, ptr = U.call, U.ptr
+    torch.manual_seed(11)
+    bf = torch.bfloat16
+    g = n // 2
+    dy_next = (torch.randn(n, h, w, c, device="cuda") * 0.5).to(bf)               # dY of the block's second conv
+    wt = torch.randn(c, c, 3, 3, device="cuda") * (0.5 / (3 * c ** 0.5))
+    _, wd = U.pack_conv(wt, U.BF16)
+    y_prev = (torch.randn(n, h, w, c, device="cuda") * 1.5 + 0.3).to(bf)          # raw output of the block's first conv
+    aff = torch.empty(4, 2, c, device="cuda")                                      # mean, invstd, scale, shift per group
+    aff[0] = 0.3 + 0.1 * torch.randn(2, c, device="cuda")
+    aff[1] = 0.66 + 0.05 * torch.rand(2, c, device="cuda")
+    gamma = 1 + 0.2 * torch.randn(2, c, device="cuda")
+    aff[2] = gamma * aff[1]
+    aff[3] = 0.1 * torch.randn(2, c, device="cuda") - aff[0] * aff[2]
+    count = float(g * h * w)
+    # unfused
+    g_ref, _ = U.conv3x3(dy_next, wd, c, U.BF16, U.ENGINE_TC, group_images=g, stats=False)
+    sums_ref = torch.zeros(2, 2, c, dtype=torch.float64, device="cuda")
+    dy_ref = torch.empty(n, h, w, c, dtype=bf, device="cuda")
+    dgam_ref, dbet_ref = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+    call("onet_bn_relu_bwd", ptr(y_prev), n, h, w, c, ptr(aff[2]), ptr(aff[3]), ptr(aff[0]), ptr(aff[1]), g, ptr(g_ref), c, 0,
+         None, 0, 0, None, ptr(sums_ref), count, ptr(dy_ref), ptr(dgam_ref), ptr(dbet_ref), ptr(dgam_ref), ptr(dbet_ref),
+         U.BF16, U.stream())
+    # fused
+    g_fused = torch.empty(n, h, w, c, dtype=bf, device="cuda")
+    sums = torch.zeros(2, 2, c, dtype=torch.float64, device="cuda")
+    call("onet_conv3x3_dgrad_bnred", ptr(dy_next), c, 0, n, h, w, c, ptr(wd), c, ptr(g_fused), ptr(y_prev), ptr(aff[2]), ptr(aff[3]),
+         ptr(aff[0]), ptr(aff[1]), ptr(sums), g, U.BF16, U.ENGINE_TC, U.stream())
+    dy = torch.empty(n, h, w, c, dtype=bf, device="cuda")
+    dgam, dbet = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+    call("onet_bn_relu_bwd_apply", ptr(y_prev), n, h, w, c, ptr(aff[2]), ptr(aff[3]), ptr(aff[0]), ptr(aff[1]), g, ptr(g_fused), c, 0,
+         ptr(sums), count, ptr(dy), ptr(dgam), ptr(dbet), ptr(dgam), ptr(dbet), U.BF16, U.stream())
+    torch.cuda.synchronize()
+    assert torch.equal(g_fused, g_ref)
+    scale = sums_ref.abs().max(dim=2, keepdim=True)[0].clamp_min(1e-30)
+    assert float(((sums - sums_ref).abs() / scale).max()) < 2e-5, ((sums - sums_ref).abs() / scale).max()
+    assert U.rel_l2(dy.float(), dy_ref.float()) < 5e-4          # sums differ by ~1e-6: a few bf16 roundings flip
+    assert U.rel_l2(dgam, dgam_ref) < 1e-5 and U.rel_l2(dbet, dbet_ref) < 1e-5
