@@ -91,3 +91,14 @@ def test_no_cpu_fallback_in_product_package():
     net = onet_b200.Onet(1, True, True)
     with pytest.raises(_lib.OnetLibError):
         net(torch.rand(1, 1, 16, 16))
+
+
+def test_driver_entry_points_and_tools_compile():
+    """__graft_entry__.py (build / smoke), bench.py and every tool script must at least byte-compile and import."""
+    import glob
+    import importlib
+    import py_compile
+    for fn in ["__graft_entry__.py", "bench.py"] + sorted(glob.glob(os.path.join(ROOT, "tools", "*.py"))):
+        py_compile.compile(os.path.join(ROOT, fn), doraise=True)
+    ge = importlib.import_module("__graft_entry__")
+    assert callable(ge.build) and callable(ge.smoke)
