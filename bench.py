@@ -119,6 +119,23 @@ def cpu_steps(batch, steps, warmup, threads):
     return batch * len(times) / sum(times), sum(times) / len(times)
 
 
+def cpu_infer_baseline(threads):
+    """Inference leg of the CPU baseline (tools/bench_infer.py): eval-mode oracle forward of one 1x512x512 frame.
+    Returns (Mpix/s, seconds)."""
+    import torch
+    from oracle import onet_oracle as orc
+    from onet_b200.data import rayleigh_target_frames
+    torch.set_num_threads(threads)
+    st = orc.init_state(1, seed=1981)
+    xs = rayleigh_target_frames(1, 1, 512, 512, seed=9)
+    with torch.no_grad():
+        orc.onet_forward(st, xs[:, :, :64, :64], training=False)
+        t0 = time.perf_counter()
+        orc.onet_forward(st, xs, training=False)
+        dt = time.perf_counter() - t0
+    return 0.262144 / dt, dt
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:

@@ -1,10 +1,11 @@
-"""Comparator (NOT the product, not a bench.py arm): the reference algorithm as PyTorch eager on the SAME B200 — the
+"""Comparator script (test infrastructure, lives under tests/ because it executes the oracle; NOT the product, not a bench.py
+arm): the reference algorithm as PyTorch eager on the SAME B200 — the
 oracle port (oracle/onet_oracle.py: the ATen ops the reference module dispatches to; on a CUDA device these are
 cuDNN / cuBLAS kernels) running the training step of Train_Onet_on_simclutter_20250407.py:209-218 on the benchmark
 batch, in FP32 (TF32 tensor cores allowed) and under bf16 autocast with channels_last activations.  SURVEY.md §8d asks
 for it as "the honest GPU comparator" next to the CPU baseline.
 
-    python tools/bench_torch_gpu.py [--batch 64] [--steps 5]   ->  one JSON line per precision
+    python tests/compare_torch_gpu.py [--batch 64] [--steps 5]   ->  one JSON line per precision
 """
 import argparse
 import json

@@ -90,18 +90,11 @@ def main():
                                 frames=args.frames, tile=args.tile, halo=96),
                     e2e=dict(value=mpix / (ms_e2e * 1e-3), unit="Mpix/s", ms_per_step=ms_e2e, h2d_bytes_per_step=args.frames * S * S * 4,
                              d2h_bytes_per_step=args.frames * S * S * 8))
-        if not args.no_cpu_baseline:
-            from oracle import onet_oracle as orc
+        if not args.no_cpu_baseline:      # the CPU leg lives in bench.py (the one place outside tests/ that executes the oracle)
+            import bench
             threads = os.cpu_count() or 1
-            torch.set_num_threads(threads)
-            st = orc.init_state(1, seed=1981)
-            xs = rayleigh_target_frames(1, 1, 512, 512, seed=9)
-            with torch.no_grad():
-                orc.onet_forward(st, xs[:, :, :64, :64], training=False)
-                t0 = time.perf_counter()
-                orc.onet_forward(st, xs, training=False)
-                dt = time.perf_counter() - t0
-            line["cpu_baseline"] = dict(value=0.262144 / dt, unit="Mpix/s", cores=threads, kind="port",
+            mpix_cpu, dt = bench.cpu_infer_baseline(threads)
+            line["cpu_baseline"] = dict(value=mpix_cpu, unit="Mpix/s", cores=threads, kind="port",
                                         sample=f"one 1x512x512 frame, eval-mode oracle forward ({dt:.2f} s)")
         print(json.dumps(line), flush=True)
     if world > 1:

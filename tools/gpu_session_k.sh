@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 ONET_BENCH_DETAIL=gpurun_out/detail_v4.tsv python bench.py --steps 20 --warmup 3 > gpurun_out/bench_v4.json 2> gpurun_out/bench_v4.err
 echo "bench rc=$?"; tail -2 gpurun_out/bench_v4.err
-python tools/bench_torch_gpu.py --batch 64 --steps 5 > gpurun_out/torch_gpu.jsonl 2> gpurun_out/torch_gpu.err; echo "torch comparator rc=$?"; cat gpurun_out/torch_gpu.jsonl
+python tests/compare_torch_gpu.py --batch 64 --steps 5 > gpurun_out/torch_gpu.jsonl 2> gpurun_out/torch_gpu.err; echo "torch comparator rc=$?"; cat gpurun_out/torch_gpu.jsonl
 python tools/bench_infer.py --frames 4 --tile 2048 --steps 5 --no-cpu-baseline > gpurun_out/infer_n1_tile2048.json 2> gpurun_out/infer_n1_tile2048.err; echo "infer2048 rc=$?"; cat gpurun_out/infer_n1_tile2048.json
 python tools/bench_infer.py --frames 4 --tile 1024 --steps 5 > gpurun_out/infer_n1_tile1024.json 2> gpurun_out/infer_n1_tile1024.err; echo "infer1024 rc=$?"; cat gpurun_out/infer_n1_tile1024.json
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/plain.log 2>&1 && \
