@@ -185,6 +185,19 @@ int onet_synth_kclutter(float* out, int64_t n, int nu, int64_t seed, int stream_
 int onet_synth_add_targets(float* frames, unsigned char* masks, int n_frames, int H, int W, const void* targets,
                            int targets_per_frame, float snr_db, float* erc_out, void* stream);
 
+/* ---- correlated K-distributed clutter field (K_distributed_SeaClutter_Simulation_20210919.py:469-526), element-wise stages in
+ * double precision; the FFTs between them are the caller's (onet_b200/synth.py uses torch.fft). */
+/* standard normal white noise (the fields the reference draws with np.random.normal, :483 and :287) */
+int onet_synth_normal(double* out, int64_t n, int64_t seed, int stream_id, void* stream);
+/* mnlt(x, v) (:83-91): Gamma(shape v, scale 1) quantile of Phi(x), integer v */
+int onet_kfield_mnlt(const double* x, int64_t n, int v, double* y, void* stream);
+/* coeff_acf_polyn (:121-139): sums[f][n] += sum_i exp(-x^2) H_n(x) g, n = 0, 1, 2, per frame; sums zero-initialised */
+int onet_kfield_coeff_sums(const double* x, const double* g, int frames, int64_t per_frame, double* sums, void* stream);
+/* solve_acf_polyn (:141-164): out[f][i] = np.roots([a_f, b_f, 1 - acf[i]])[0] as interleaved (re, im); coeffs [frames][2] */
+int onet_kfield_acf_root(const double* coeffs, const double* acf, int frames, int64_t per_frame, double* out, void* stream);
+/* amplitude (:517-518): out[i] = | speckle[i] | * sqrt(texture[i]); speckle interleaved complex128 */
+int onet_kfield_amplitude(const double* speckle, const double* texture, int64_t n, float* out, void* stream);
+
 /* torch.optim.Adam step (no weight decay, amsgrad=False; Train_Onet_on_simclutter_20250407.py:181-182) over a
  * flat fp32 arena; `step` is the 1-based step count, gradients are multiplied by grad_scale first. */
 int onet_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,

@@ -74,6 +74,11 @@ SIGNATURES = {
     "onet_synth_rayleigh": [_p, _i64, _f, _i64, _i, _p],
     "onet_synth_kclutter": [_p, _i64, _i, _i64, _i, _p],
     "onet_synth_add_targets": [_p, _p, _i, _i, _i, _p, _i, _f, _p, _p],
+    "onet_synth_normal": [_p, _i64, _i64, _i, _p],
+    "onet_kfield_mnlt": [_p, _i64, _i, _p, _p],
+    "onet_kfield_coeff_sums": [_p, _p, _i, _i64, _p, _p],
+    "onet_kfield_acf_root": [_p, _p, _i, _i64, _p, _p],
+    "onet_kfield_amplitude": [_p, _p, _i64, _p, _p],
     "onet_adam_step": [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i, _f, _p],
     "onet_adam_step_dev": [_p, _p, _p, _p, _i64, _p, _p, _f, _p],
 }

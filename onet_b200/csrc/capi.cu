@@ -1162,6 +1162,42 @@ int onet_synth_add_targets(float* frames, unsigned char* masks, int n_frames, in
     return check_launch("synth_add_targets");
 }
 
+int onet_synth_normal(double* out, int64_t n, int64_t seed, int stream_id, void* stream) {
+    if (n <= 0) return 0;
+    normal_fill_kernel<<<grid_for((n + 1) / 2, 256, 148 * 8), 256, 0, ST(stream)>>>(
+        out, n, static_cast<uint32_t>(seed), static_cast<uint32_t>(static_cast<uint64_t>(seed) >> 32), static_cast<uint32_t>(stream_id));
+    return check_launch("synth_normal");
+}
+
+int onet_kfield_mnlt(const double* x, int64_t n, int v, double* y, void* stream) {
+    if (n <= 0) return 0;
+    if (v < 1 || v > 64) return fail("kfield_mnlt: integer gamma shape v in [1, 64]");
+    kfield_mnlt_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, ST(stream)>>>(x, n, v, y);
+    return check_launch("kfield_mnlt");
+}
+
+int onet_kfield_coeff_sums(const double* x, const double* g, int frames, int64_t per_frame, double* sums, void* stream) {
+    if (frames <= 0 || per_frame <= 0) return 0;
+    if (frames > 65535) return fail("kfield_coeff_sums: at most 65535 frames per call");
+    const int per = static_cast<int>(std::min<long long>((per_frame + 1023) / 1024, std::max(1, 148 * 4 / frames)));
+    kfield_coeff_sums_kernel<<<dim3(per, frames), 256, 0, ST(stream)>>>(x, g, per_frame, sums);
+    return check_launch("kfield_coeff_sums");
+}
+
+int onet_kfield_acf_root(const double* coeffs, const double* acf, int frames, int64_t per_frame, double* out, void* stream) {
+    if (frames <= 0 || per_frame <= 0) return 0;
+    if (frames > 65535) return fail("kfield_acf_root: at most 65535 frames per call");
+    const int per = static_cast<int>(std::min<long long>((per_frame + 255) / 256, std::max(1, 148 * 8 / frames)));
+    kfield_acf_root_kernel<<<dim3(per, frames), 256, 0, ST(stream)>>>(coeffs, acf, per_frame, reinterpret_cast<double2*>(out));
+    return check_launch("kfield_acf_root");
+}
+
+int onet_kfield_amplitude(const double* speckle, const double* texture, int64_t n, float* out, void* stream) {
+    if (n <= 0) return 0;
+    kfield_amplitude_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, ST(stream)>>>(reinterpret_cast<const double2*>(speckle), texture, n, out);
+    return check_launch("kfield_amplitude");
+}
+
 int onet_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, int step, float grad_scale, void* stream) {
     if (step < 1) return fail("adam: step must be >= 1");

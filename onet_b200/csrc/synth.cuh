@@ -155,4 +155,137 @@ add_targets_kernel(float* __restrict__ frames, unsigned char* __restrict__ masks
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Correlated K-distributed clutter field (K_distributed_SeaClutter_Simulation_20210919.py:469-526).  The two FFT pairs of
+// the pipeline run through torch.fft (cuFFT) on the host side (onet_b200/synth.py); the element-wise stages are here, in
+// double precision like the reference (the generator is offline work: fidelity first, and still ~10^3 x the CPU's 9 s/frame).
+// ------------------------------------------------------------------------------------------------
+
+// standard normal white noise (Box-Muller on Philox), one pair per counter value
+__global__ void __launch_bounds__(256)
+normal_fill_kernel(double* __restrict__ out, long long n, uint32_t seed_lo, uint32_t seed_hi, uint32_t stream_id) {
+    const long long pairs = (n + 1) >> 1;
+    for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < pairs;
+         q += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const Philox4 r = philox4x32_10(static_cast<uint32_t>(q), static_cast<uint32_t>(q >> 32), stream_id, 0u, seed_lo, seed_hi);
+        // 53-bit uniforms in (0, 1] and [0, 1)
+        const double u1 = (static_cast<double>((static_cast<unsigned long long>(r.x) << 21) | (r.y >> 11)) + 1.0) * (1.0 / 9007199254740992.0);
+        const double u2 = static_cast<double>((static_cast<unsigned long long>(r.z) << 21) | (r.w >> 11)) * (1.0 / 9007199254740992.0);
+        const double rad = sqrt(-2.0 * log(u1));
+        double sn, cs;
+        sincospi(2.0 * u2, &sn, &cs);
+        out[2 * q] = rad * cs;
+        if (2 * q + 1 < n) out[2 * q + 1] = rad * sn;
+    }
+}
+
+// Memoryless non-linear transform mnlt(x, v) (:83-91): the Gamma(shape v, scale 1) quantile of Phi(x), integer v.
+//   x <= 0: solve P(v, y) = p,      p = erfc(-x / sqrt 2) / 2,  P by its series  y^v e^-y / v! * (1 + y/(v+1) + ...)
+//   x >  0: solve Q(v, y) = q,      q = erfc( x / sqrt 2) / 2,  Q = e^-y sum_{k<v} y^k / k!          (no cancellation in either tail)
+// Halley iterations from the Wilson-Hilferty cube (or the leading term of the series in the far lower tail).
+__device__ __forceinline__ double mnlt_int(double x, int v) {
+    double fact = 1.0;                                   // (v-1)!
+    for (int k = 2; k < v; ++k) fact *= k;
+    const double c9 = 1.0 / (9.0 * v);
+    const double t = 1.0 - c9 + x * sqrt(c9);
+    const bool lower = x <= 0.0;
+    const double target = 0.5 * erfc((lower ? -x : x) * 0.70710678118654752440);
+    double y = v * t * t * t;
+    if (lower) {
+        const double y_tail = pow(target * fact * v, 1.0 / v);      // P ~ y^v / v!
+        if (!(t > 0.0) || y < y_tail) y = y_tail;
+    }
+    if (!(y > 1e-300)) y = 1e-300;
+#pragma unroll 1
+    for (int it = 0; it < 16; ++it) {
+        const double pdf = exp((v - 1) * log(y) - y) / fact;
+        double F;                                         // monotone increasing in y in both branches
+        if (lower) {
+            double term = 1.0, sum = 1.0;
+            for (int k = 1; k < 200; ++k) {
+                term *= y / (v + k);
+                sum += term;
+                if (term < 1e-17 * sum) break;
+            }
+            F = pdf * y / v * sum - target;
+        } else {
+            double term = 1.0, sum = 1.0;
+            for (int k = 1; k < v; ++k) { term *= y / k; sum += term; }
+            F = target - exp(-y) * sum;
+        }
+        const double d = F / pdf;
+        double step = d / (1.0 - 0.5 * d * ((v - 1) / y - 1.0));
+        if (!(step == step) || fabs(step) > 0.75 * y) step = copysign(0.75 * y, d);      // stay positive, bounded relative change
+        y -= step;
+        if (fabs(step) <= 2e-15 * y) break;
+    }
+    return y;
+}
+
+__global__ void __launch_bounds__(256)
+kfield_mnlt_kernel(const double* __restrict__ x, long long n, int v, double* __restrict__ y) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        y[i] = mnlt_int(x[i], v);
+}
+
+// coeff_acf_polyn (:121-139): per frame the three sums  S_n = sum exp(-x^2) H_n(x) g(x),  H_0 = 1, H_1 = 2x, H_2 = 4x^2 - 2.
+// sums: [frames][3], zero-initialised; grid (blocks, frames)
+__global__ void __launch_bounds__(256)
+kfield_coeff_sums_kernel(const double* __restrict__ x, const double* __restrict__ g, long long per_frame, double* __restrict__ sums) {
+    const int f = blockIdx.y;
+    const double* xf = x + static_cast<long long>(f) * per_frame;
+    const double* gf = g + static_cast<long long>(f) * per_frame;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < per_frame;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const double xv = xf[i], e = exp(-xv * xv) * gf[i];
+        s0 += e;
+        s1 += e * (2.0 * xv);
+        s2 += e * (4.0 * xv * xv - 2.0);
+    }
+    for (int off = 16; off >= 1; off >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+    }
+    __shared__ double sh[3][8];
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s0; sh[1][threadIdx.x >> 5] = s1; sh[2][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sh[threadIdx.x][w];
+        atomicAdd(sums + 3 * f + threadIdx.x, t);
+    }
+}
+
+// solve_acf_polyn (:141-164): out[f][i] = np.roots([a, b, 1 - acf[i]])[0] as (re, im), with [a, b, 1] = coeffs[f] (normalised):
+// the root of larger magnitude when the roots are real, the one with positive imaginary part otherwise.
+__global__ void __launch_bounds__(256)
+kfield_acf_root_kernel(const double* __restrict__ coeffs /* [frames][2] = a, b */, const double* __restrict__ acf, long long per_frame,
+                       double2* __restrict__ out) {
+    const int f = blockIdx.y;
+    const double a = coeffs[2 * f], b = coeffs[2 * f + 1];
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < per_frame;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const double c = 1.0 - acf[i];
+        const double disc = b * b - 4.0 * a * c;
+        const double s = sqrt(fabs(disc));
+        double2 r;
+        if (disc >= 0.0) { r.x = (-b - copysign(s, b)) / (2.0 * a); r.y = 0.0; }
+        else { r.x = -b / (2.0 * a); r.y = s / (2.0 * a); }
+        out[static_cast<long long>(f) * per_frame + i] = r;
+    }
+}
+
+// amplitude = | speckle * sqrt(texture) |  (:517-518), complex speckle, fp32 out
+__global__ void __launch_bounds__(256)
+kfield_amplitude_kernel(const double2* __restrict__ speckle, const double* __restrict__ texture, long long n, float* __restrict__ out) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const double2 z = speckle[i];
+        out[i] = static_cast<float>(hypot(z.x, z.y) * sqrt(texture[i]));
+    }
+}
+
 }  // namespace onet

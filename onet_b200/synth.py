@@ -2,7 +2,8 @@
 `Rayleigh_bg_Gaussian_EOT_generator_20230208.py`:
 
     get_rayleigh_frame(snr)            :219-249  ->  get_rayleigh_frames(n, snr, ...)   (n frames per call, on the device)
-    get_k_frame(snr)                   :178-217  ->  get_k_frames(n, snr, ...)          (compound-Gaussian K clutter, uncorrelated)
+    get_k_frame(snr)                   :178-217  ->  get_k_frames(n, snr, ...)          (correlated K field, or uncorrelated)
+    generate_K_distributed_noise (K_distributed_SeaClutter_Simulation_20210919.py:469-526) -> k_correlated_background
     add_gaussian_template_on_clutter_v3 :62-176  ->  add_gaussian_targets(frames, cx, cy, w, h, theta, snr)
     prepare_frames / prepare_data      :251-321  ->  prepare_data(...): the reference's dataset dictionary
                                                      {'<type>_imgs', '<type>_labels', 'psnr', 'desc'} (torch.save-able, read by
@@ -50,6 +51,75 @@ def k_background(n, h, w, seed=1981, nu=5, device="cuda", stream_id=0):
     out = torch.empty(n, h, w, dtype=torch.float32, device=dev)
     call("onet_synth_kclutter", ptr(out), out.numel(), int(nu), int(seed), int(stream_id), _stream(dev))
     return out
+
+
+_KFIELD_CONST = {}
+
+
+def _kfield_constants(size, v, dev):
+    """Per (size, v): the Gamma-field autocorrelation of eq. (69) of Tough & Ward as the reference samples it (:477-484) and the
+    square root of the speckle power spectrum |f|^-0.6 (:276-295), float64 on the device."""
+    key = (size, v, str(dev))
+    if key not in _KFIELD_CONST:
+        xs = np.linspace(10, size, num=size, endpoint=True)
+        XS, YS = np.meshgrid(xs, xs)
+        acf = 1 + np.exp(-(XS + YS) / 10) * np.cos(np.pi * YS / 8) / v
+        f = np.linspace(0.1, size / 10.0, num=size, endpoint=True)
+        Fx, Fy = np.meshgrid(f, f)
+        spec = np.sqrt(np.sqrt(Fx ** 2 + Fy ** 2) ** (-0.6))
+        _KFIELD_CONST[key] = (torch.from_numpy(acf).to(dev), torch.from_numpy(spec).to(dev))
+    return _KFIELD_CONST[key]
+
+
+def normal_white(n, h, w, seed=1981, device="cuda", stream_id=0):
+    """[n,h,w] float64 standard normal white noise (Philox + Box-Muller on the device)."""
+    dev = _need_cuda(device)
+    out = torch.empty(n, h, w, dtype=torch.float64, device=dev)
+    call("onet_synth_normal", ptr(out), out.numel(), int(seed), int(stream_id), _stream(dev))
+    return out
+
+
+def mnlt(x, v):
+    """`mnlt(x, v)` of the reference (:83-91) on the device: Gamma(shape v, scale 1) quantile of Phi(x); float64, integer v."""
+    if not x.is_cuda:
+        raise RuntimeError("onet_b200.synth has no CPU path")
+    x = x.contiguous().double()
+    y = torch.empty_like(x)
+    call("onet_kfield_mnlt", ptr(x), x.numel(), int(v), ptr(y), _stream(x.device))
+    return y
+
+
+def k_correlated_background(n, size, v=5, seed=1981, device="cuda", white=None, return_texture=False):
+    """n square fields of the reference's correlated K-distributed clutter, `generate_K_distributed_noise(size, size, v)`
+    (K_distributed_SeaClutter_Simulation_20210919.py:469-526), on the device: correlated Gamma texture (white noise -> measured
+    polynomial coefficients -> per-element quadratic root -> coloured Gaussian field -> mnlt) times a correlated complex speckle
+    field, amplitude as fp32 [n,size,size].  The element-wise stages are this library's kernels; the two FFT pairs go through
+    torch.fft (cuFFT) in complex128.  `white` = (texture noise, speckle noise), float64 [n,size,size], replays given draws
+    (tests use the reference's own); otherwise both are generated on the device from `seed`."""
+    dev = _need_cuda(device)
+    if white is None:
+        w1 = normal_white(n, size, size, seed=seed, device=dev, stream_id=0)
+        w2 = normal_white(n, size, size, seed=seed, device=dev, stream_id=1)
+    else:
+        w1, w2 = (t.to(dev).double().contiguous() for t in white)
+        assert w1.shape == (n, size, size) and w2.shape == (n, size, size)
+    st = _stream(dev)
+    acf, spec = _kfield_constants(size, v, dev)
+    per = size * size
+    g = mnlt(w1, v)
+    sums = torch.zeros(n, 3, dtype=torch.float64, device=dev)
+    call("onet_kfield_coeff_sums", ptr(w1), ptr(g), n, per, ptr(sums), st)
+    # alpha_n = S_n^2 / (pi n! 2^n), normalised by alpha_0 (:131-137, :488): [a, b] = [alpha_2, alpha_1] / alpha_0
+    alpha = sums ** 2 / (np.pi * torch.tensor([1.0, 2.0, 8.0], dtype=torch.float64, device=dev))
+    coeffs = torch.stack([alpha[:, 2] / alpha[:, 0], alpha[:, 1] / alpha[:, 0]], dim=1).contiguous()
+    roots = torch.empty(n, size, size, dtype=torch.complex128, device=dev)
+    call("onet_kfield_acf_root", ptr(coeffs), ptr(acf), n, per, ptr(roots), st)
+    gcn = torch.fft.ifft2(torch.fft.fft2(w1) * torch.sqrt(torch.fft.fft2(roots))).real.contiguous()     # :495-497
+    texture = mnlt(gcn, v)
+    speckle = torch.fft.ifft2(torch.fft.fft2(w2) * spec).contiguous()                                    # :287-296
+    amp = torch.empty(n, size, size, dtype=torch.float32, device=dev)
+    call("onet_kfield_amplitude", ptr(speckle), ptr(texture), n * per, ptr(amp), st)
+    return (amp, texture) if return_texture else amp
 
 
 def target_table(cx, cy, w, h, theta, img_h, img_w, host_threshold=False):
@@ -114,7 +184,13 @@ def draw_targets(n, img_sz, target_num=20, rng=None):
 
 
 def _frames(kind, n, snr, img_sz, target_num, seed, device, rng):
-    bg = (rayleigh_background if kind == "rayleigh" else k_background)(n, img_sz[0], img_sz[1], seed=seed, device=device)
+    if kind == "rayleigh":
+        bg = rayleigh_background(n, img_sz[0], img_sz[1], seed=seed, device=device)
+    elif kind == "kdist_correlated":
+        assert img_sz[0] == img_sz[1], "the reference's K field is square (its speckle field is size x size, :514)"
+        bg = k_correlated_background(n, img_sz[0], v=5, seed=seed, device=device)
+    else:
+        bg = k_background(n, img_sz[0], img_sz[1], seed=seed, device=device)
     rng = np.random.RandomState(seed) if rng is None else rng
     return add_gaussian_targets(bg, *draw_targets(n, img_sz, target_num, rng), snr)[:2]
 
@@ -124,9 +200,10 @@ def get_rayleigh_frames(n, snr=10, img_sz=(400, 400), target_num=20, seed=1981, 
     return _frames("rayleigh", n, snr, img_sz, target_num, seed, device, rng)
 
 
-def get_k_frames(n, snr=10, img_sz=(400, 400), target_num=20, seed=1981, device="cuda", rng=None):
-    """n frames of `get_k_frame(snr)` with the uncorrelated K-clutter background."""
-    return _frames("kdist", n, snr, img_sz, target_num, seed, device, rng)
+def get_k_frames(n, snr=10, img_sz=(400, 400), target_num=20, seed=1981, device="cuda", rng=None, correlated=True):
+    """n frames of `get_k_frame(snr)` (:178-217): the reference's correlated K field (gamma_shape 5) + 20 extended targets;
+    correlated=False uses the spatially uncorrelated compound-Gaussian background instead (one kernel, no FFT)."""
+    return _frames("kdist_correlated" if correlated else "kdist", n, snr, img_sz, target_num, seed, device, rng)
 
 
 def prepare_data(img_sz=(224, 224), bg_type="rayleigh", file_name=None, fnums=150, snrs=range(0, 11), seed=1981, device="cuda"):

@@ -227,3 +227,24 @@ def test_synth_oracle_matches_reference_golden(golden_dir):
         synth.target_table([[3.0]], [[64.0]], [[10.0]], [[18.0]], [[0.0]], 128, 128)
     with pytest.raises(ValueError):
         so.composite_frame(z["bg0"], [64.0], [64.0], [10.0], [18.0], [0.0], 13)         # snr outside the reference's table
+
+
+def test_kclutter_oracle_matches_reference_golden(golden_dir):
+    """oracle/kclutter_oracle.py against the unmodified reference's generate_K_distributed_noise on the reference's own
+    replayed draws (tests/golden/make_kclutter_golden.py), its mnlt() known answers, and the closed-form restatement of
+    np.roots(quadratic)[0] against np.roots itself."""
+    import os
+    from oracle import kclutter_oracle as ko
+    z = np.load(os.path.join(golden_dir, "kclutter.npz"))
+    for i in range(3):
+        size, v, _ = (int(t) for t in z[f"meta_{i}"])
+        amp, tex = ko.k_field(z[f"w1_{i}"], z[f"w2_{i}"], v)
+        assert np.allclose(amp, z[f"amp_{i}"], rtol=1e-11, atol=1e-12) and np.allclose(tex, z[f"tex_{i}"], rtol=1e-11, atol=1e-12)
+    for v in (1, 3, 5, 8):
+        assert np.allclose(ko.mnlt(z["mnlt_x"], v), z[f"mnlt_v{v}"], rtol=1e-13, atol=0)
+    rs = np.random.RandomState(0)
+    for _ in range(2000):
+        a, b, c = rs.uniform(0.01, 0.2), rs.uniform(0.01, 0.2) * rs.choice([-1, 1]), rs.uniform(-0.05, 0.05)
+        want = np.roots([a, b, c])[0]
+        got = ko.first_root(a, b, np.array([c]))[0]
+        assert abs(got - want) <= 1e-9 * max(1.0, abs(want)), (a, b, c, got, want)

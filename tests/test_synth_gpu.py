@@ -107,3 +107,35 @@ def test_dataset_and_checkpoint_formats(tmp_path):
     assert synth.load_checkpoint(net2, ck) == 17
     for (k, a), (_, b) in zip(net.state_dict().items(), net2.state_dict().items()):
         assert torch.equal(a, b), k
+
+
+def test_correlated_k_field_matches_reference_golden(golden_dir):
+    """onet_b200.synth.k_correlated_background on the reference's own replayed white-noise draws against the outputs of the
+    UNMODIFIED generate_K_distributed_noise (amplitude and Gamma texture; float64 pipeline, fp32 amplitude), the mnlt kernel
+    against the reference's known answers, and the device white noise against N(0,1)."""
+    from onet_b200 import synth
+    z = np.load(os.path.join(golden_dir, "kclutter.npz"))
+    for i in range(3):
+        size, v, _ = (int(t) for t in z[f"meta_{i}"])
+        w1, w2 = torch.from_numpy(z[f"w1_{i}"])[None], torch.from_numpy(z[f"w2_{i}"])[None]
+        amp, tex = synth.k_correlated_background(1, size, v=v, white=(w1, w2), return_texture=True)
+        amp, tex = amp[0].double().cpu().numpy(), tex[0].cpu().numpy()
+        assert np.abs(tex - z[f"tex_{i}"]).max() <= 1e-8 * np.abs(z[f"tex_{i}"]).max(), i
+        assert np.abs(amp - z[f"amp_{i}"]).max() <= 2e-7 * np.abs(z[f"amp_{i}"]).max(), i       # fp32 output
+    x = torch.from_numpy(z["mnlt_x"]).cuda()
+    for v in (1, 3, 5, 8):
+        got = synth.mnlt(x, v).cpu().numpy()
+        # the reference forms Phi(x) as 1 - erfc(x / sqrt 2) / 2 and loses digits in the upper tail; the kernel does not
+        assert np.abs(got / z[f"mnlt_v{v}"] - 1).max() < 1e-7, v
+    # batched: two frames at once == frame by frame
+    w = torch.randn(2, 2, 64, 64, dtype=torch.float64)
+    both = synth.k_correlated_background(2, 64, white=(w[0], w[1]))
+    one = synth.k_correlated_background(1, 64, white=(w[0, :1], w[1, :1]))
+    assert torch.allclose(both[:1], one, rtol=1e-6, atol=0)
+    g = synth.normal_white(4, 400, 400, seed=5).flatten()
+    assert torch.equal(g, synth.normal_white(4, 400, 400, seed=5).flatten())
+    assert abs(float(g.mean())) < 5e-3 and abs(float(g.var()) - 1.0) < 1e-2 and abs(float((g ** 4).mean()) - 3.0) < 5e-2
+    f, m = synth.get_k_frames(3, snr=6, seed=9)                     # the reference's setup: 400 x 400, 20 targets
+    assert f.shape == (3, 400, 400) and m.shape == (3, 400, 400) and bool(m.any()) and torch.isfinite(f).all()
+    e2 = float((synth.k_correlated_background(3, 400, seed=9) ** 2).mean())
+    assert 0.6 < e2 < 0.85, e2         # the unmodified reference at 400 x 400 (seed 9, 5.8 s on the CPU): 0.727
