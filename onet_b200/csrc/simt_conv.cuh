@@ -31,7 +31,10 @@ conv3x3_simt_kernel(const T* __restrict__ in, long long ldi, int ci_off, int N, 
                     double* __restrict__ stat_sum, double* __restrict__ stat_sq, int group_images) {
     __shared__ float As[16][64 + 4];
     __shared__ float Bs[16][64 + 4];
-    __shared__ float s_stat[2][2][64];   // [group][sum|sq][channel]
+    // [sum|sq][group][pixel-row thread ty][channel]: per-thread partial sums, folded over ty in a FIXED order.  (Shared-memory
+    // float atomics made the statistics - and through ReLU / max-pool switching the whole gradient of an ill-conditioned small
+    // case - depend on the order in which the threads arrived: FP32 verification mode must be reproducible.)
+    __shared__ float s_stat[2][2][16][64];
     const int tid = threadIdx.x;
     const long long M = static_cast<long long>(N) * H * W;
     const long long m0 = static_cast<long long>(blockIdx.x) * 64;
@@ -93,10 +96,7 @@ conv3x3_simt_kernel(const T* __restrict__ in, long long ldi, int ci_off, int N, 
     }
 
     const bool do_stats = stat_sum != nullptr;
-    if (do_stats) {
-        for (int i = tid; i < 2 * 2 * 64; i += 256) (&s_stat[0][0][0])[i] = 0.f;
-        __syncthreads();
-    }
+    float ps[2][4] = {}, pq[2][4] = {};      // this thread's sums / sums of squares per statistics group and channel j
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const long long m = m0 + ty * 4 + i;
@@ -111,19 +111,27 @@ conv3x3_simt_kernel(const T* __restrict__ in, long long ldi, int ci_off, int N, 
             out[m * ldo + co_off + co] = sv;
             if (do_stats) {
                 const float f = to_f<T>(sv);
-                atomicAdd(&s_stat[grp][0][tx * 4 + j], f);
-                atomicAdd(&s_stat[grp][1][tx * 4 + j], f * f);
+                if (grp == 0) { ps[0][j] += f; pq[0][j] = fmaf(f, f, pq[0][j]); }
+                else { ps[1][j] += f; pq[1][j] = fmaf(f, f, pq[1][j]); }
             }
         }
     }
     if (do_stats) {
-        __syncthreads();
-        for (int i = tid; i < 2 * 64; i += 256) {
-            const int g = i >> 6, c = i & 63;
-            if (co0 + c < Cout && (s_stat[g][1][c] != 0.f || s_stat[g][0][c] != 0.f)) {
-                atomicAdd(stat_sum + static_cast<long long>(g) * Cout + co0 + c, static_cast<double>(s_stat[g][0][c]));
-                atomicAdd(stat_sq + static_cast<long long>(g) * Cout + co0 + c, static_cast<double>(s_stat[g][1][c]));
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                s_stat[0][g][ty][tx * 4 + j] = ps[g][j];
+                s_stat[1][g][ty][tx * 4 + j] = pq[g][j];
             }
+        __syncthreads();
+        for (int i = tid; i < 2 * 2 * 64; i += 256) {
+            const int which = i >> 7, g = (i >> 6) & 1, c = i & 63;
+            float t = 0.f;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) t += s_stat[which][g][r][c];
+            if (co0 + c < Cout && t != 0.f)
+                atomicAdd((which == 0 ? stat_sum : stat_sq) + static_cast<long long>(g) * Cout + co0 + c, static_cast<double>(t));
         }
     }
 }
