@@ -163,6 +163,9 @@ def _family(name, a):
         fl = 2.0 * 9 * a[3] * a[4] * a[5] * a[6] * a[8]
         return ("conv3x3 fwd/dgrad (tcgen05 implicit GEMM)" if a[16] == 1 else "conv_first fwd (CUDA cores)"), fl, \
             f"{a[6]}->{a[8]} @{a[4]}x{a[5]} N={a[3]}"
+    if name == "onet_conv3x3_dgrad_bnred":      # dgrad with the previous layer's BatchNorm-backward reduce in its epilogue
+        return "conv3x3 fwd/dgrad (tcgen05 implicit GEMM)", 2.0 * 9 * a[3] * a[4] * a[5] * a[6] * a[8], \
+            f"{a[6]}->{a[8]} @{a[4]}x{a[5]} N={a[3]} +bnred"
     if name == "onet_conv3x3_wgrad":
         fl = 2.0 * 9 * a[6] * a[7] * a[8] * a[9] * a[10]
         return ("conv3x3 wgrad (tcgen05 split-K)" if a[13] == 1 else "conv_first wgrad (CUDA cores)"), fl, \
