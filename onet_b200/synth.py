@@ -206,23 +206,33 @@ def get_k_frames(n, snr=10, img_sz=(400, 400), target_num=20, seed=1981, device=
     return _frames("kdist_correlated" if correlated else "kdist", n, snr, img_sz, target_num, seed, device, rng)
 
 
+def assemble_dataset(per_snr, img_sz=(224, 224), bg_type="rayleigh"):
+    """The reference's dataset dictionary (prepare_data :288-321) from per-snr groups [(frames [n,1,H,W] in [0,1], masks [n,H,W],
+    snr), ...]: centre crop to img_sz (transforms.CenterCrop, :296), images float32 [N,1,h,w], labels float32 [N,h,w], one psnr
+    entry per frame.  Pure tensor bookkeeping on whatever device the groups live on; the result is on the CPU."""
+    imgs, labels, psnrs = [], [], []
+    for f, m, snr in per_snr:
+        top, left = int(round((f.shape[2] - img_sz[0]) / 2.0)), int(round((f.shape[3] - img_sz[1]) / 2.0))
+        imgs.append(f[:, :, top:top + img_sz[0], left:left + img_sz[1]].contiguous().float().cpu())
+        labels.append(m[:, top:top + img_sz[0], left:left + img_sz[1]].float().cpu())
+        psnrs.extend([snr] * f.shape[0])
+    n_per = per_snr[0][0].shape[0] if per_snr else 0
+    return {f"{bg_type}_imgs": torch.cat(imgs), f"{bg_type}_labels": torch.cat(labels), "psnr": psnrs,
+            "desc": f"{bg_type} clutter add 20 extended targets [pure fg higher than mu-2*simga] in each frame; "
+                    f"{n_per} frames per snr, synthesised on the GPU by onet_b200.synth"}
+
+
 def prepare_data(img_sz=(224, 224), bg_type="rayleigh", file_name=None, fnums=150, snrs=range(0, 11), seed=1981, device="cuda"):
     """The reference's dataset dictionary (prepare_data :288-321): per snr `fnums` frames of 400 x 400, every frame scaled to
     [0,1] by its own min / max (array_normal, :263), centre-cropped to img_sz, labels as float32.  Saved with torch.save when
     file_name is given — the file dataloader/simbg4onet_20230209.py:298-305 loads."""
     from .evaluate import normalize_per_frame
-    imgs, labels, psnrs = [], [], []
+    groups = []
     for k, snr in enumerate(snrs):
         get = get_rayleigh_frames if bg_type == "rayleigh" else get_k_frames
         f, m = get(fnums, snr=snr, seed=seed + 7919 * k, device=device)
-        f = normalize_per_frame(f.unsqueeze(1))
-        top, left = (f.shape[2] - img_sz[0]) // 2, (f.shape[3] - img_sz[1]) // 2
-        imgs.append(f[:, :, top:top + img_sz[0], left:left + img_sz[1]].contiguous())
-        labels.append(m[:, top:top + img_sz[0], left:left + img_sz[1]].float())
-        psnrs.extend([snr] * fnums)
-    data = {f"{bg_type}_imgs": torch.cat(imgs).cpu(), f"{bg_type}_labels": torch.cat(labels).cpu(), "psnr": psnrs,
-            "desc": f"{bg_type} clutter add 20 extended targets [pure fg higher than mu-2*simga] in each frame; "
-                    f"{fnums} frames per snr, synthesised on the GPU by onet_b200.synth"}
+        groups.append((normalize_per_frame(f.unsqueeze(1)), m, snr))
+    data = assemble_dataset(groups, img_sz, bg_type)
     if file_name is not None:
         torch.save(data, file_name)
     return data
