@@ -30,6 +30,21 @@ def plan_buckets(named_blocks, offsets):
     return buckets
 
 
+def cosine_warm_restarts_lr(epoch, base_lr=1e-4, T_0=300, T_mult=2, eta_min=1e-6):
+    """Learning rate of `torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(opt, T_0, T_mult, eta_min)` after `epoch` calls
+    of scheduler.step() — the schedule of Train_Onet_on_zy3_20240606.py:88-89, 125 (lr 1e-4, T_0 300, T_mult 2, eta_min 1e-6).
+    Use with `OnetTrainer.set_lr` once per epoch (the fused Adam reads the rate from device memory, also inside a graph)."""
+    import math
+    t, T_i = epoch, T_0
+    if T_mult == 1:
+        t = epoch % T_0
+    else:
+        while t >= T_i:
+            t -= T_i
+            T_i *= T_mult
+    return eta_min + (base_lr - eta_min) * (1 + math.cos(math.pi * t / T_i)) / 2
+
+
 class OnetTrainer:
     def __init__(self, onet, lr=5e-6, betas=(0.9, 0.999), eps=1e-8, process_group=None, overlap=True, graph=False):
         self.onet = onet

@@ -62,3 +62,20 @@ def test_serial_schedule_when_side_stream_is_off(monkeypatch):
     eng._flush_side()
     eng._join_side()
     assert log == [("call", "onet_conv3x3_wgrad", eng.stream), ("hook", "up4")]
+
+
+def test_cosine_warm_restarts_matches_torch_scheduler():
+    """onet_b200.trainer.cosine_warm_restarts_lr against torch's CosineAnnealingWarmRestarts stepped once per epoch, with the
+    ZY-3 script's settings (Train_Onet_on_zy3_20240606.py:88-89) and a short-period variant that crosses several restarts."""
+    import torch
+    from onet_b200.trainer import cosine_warm_restarts_lr
+    for base_lr, T_0, T_mult, eta_min, epochs in ((1e-4, 300, 2, 1e-6, 1000), (3e-4, 7, 2, 1e-5, 120), (1e-3, 5, 1, 0.0, 23)):
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.Adam([p], lr=base_lr)
+        sch = torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(opt, T_0=T_0, T_mult=T_mult, eta_min=eta_min)
+        for epoch in range(epochs):
+            want = opt.param_groups[0]["lr"]
+            got = cosine_warm_restarts_lr(epoch, base_lr, T_0, T_mult, eta_min)
+            assert abs(got - want) <= 1e-12 + 1e-9 * want, (epoch, got, want)
+            opt.step()
+            sch.step()
