@@ -1,5 +1,5 @@
 """Training-trajectory parity (-m gpu): OnetTrainer (zero_grad -> forward -> JSD loss -> backward -> fused Adam, every step
-through the CUDA kernels) against the CPU oracle driven by torch.optim.Adam — the reference's loop
+through the CUDA kernels) — and the reference's literal loop with torch.optim.Adam on this module's parameters — against the CPU oracle driven by torch.optim.Adam — the reference's loop
 (Train_Onet_on_simclutter_20250407.py:181, 209-218) — from identical weights on identical batches, over 12 optimizer steps.
 
 What is compared is the LOSS SEQUENCE: each step's loss depends on all previous updates, so a wrong gradient, a wrong Adam
@@ -13,7 +13,8 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("mode,graph,tol", [("fp32", False, 2e-4), ("bf16", False, 1e-2), ("bf16", True, 1e-2)])
+@pytest.mark.parametrize("mode,graph,tol", [("fp32", False, 2e-4), ("bf16", False, 1e-2), ("bf16", True, 1e-2),
+                                            ("fp32", "torch.optim", 2e-4), ("bf16", "torch.optim", 1e-2)])
 def test_loss_sequence_matches_oracle_training(mode, graph, tol):
     import onet_b200
     from onet_b200.trainer import OnetTrainer
@@ -43,8 +44,23 @@ def test_loss_sequence_matches_oracle_training(mode, graph, tol):
         sd["dwnu." + k] = v.clone()
     net.load_state_dict(sd)
     net = net.cuda()
-    tr = OnetTrainer(net, lr=lr, graph=graph)
-    got = [float(tr.step(xs[i % 3].cuda())) for i in range(steps)]
+    if graph == "torch.optim":
+        # the reference's own loop with the one-line import change: torch.optim.Adam on onet.parameters()
+        opt2 = torch.optim.Adam(net.parameters(), lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False)
+        got = []
+        for i in range(steps):
+            net.train()
+            net.zero_grad()
+            Lt, Vt, Ld, Vd, S = net(xs[i % 3].cuda())
+            St = S[:, 0, :, :].unsqueeze(dim=1)
+            Sd = S[:, 1, :, :].unsqueeze(dim=1)
+            loss = net.compute_loss(Lt, St, Ld, Sd)
+            loss.backward()
+            opt2.step()
+            got.append(loss.item())
+    else:
+        tr = OnetTrainer(net, lr=lr, graph=graph)
+        got = [float(tr.step(xs[i % 3].cuda())) for i in range(steps)]
     rel = [abs(a - b) / abs(b) for a, b in zip(got, ref)]
     print(f"{mode} graph={graph}: oracle {ref[0]:.5f} -> {ref[-1]:.5f}, here {got[0]:.5f} -> {got[-1]:.5f}, max rel {max(rel):.2e}")
     assert ref[-1] < ref[0]                      # the oracle's loss falls over these steps, so a frozen model would be caught
