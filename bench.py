@@ -351,7 +351,8 @@ def main():
             ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
             shapes = {k[1]: v for k, v in shape_t.items() if k[0] == top}
             roof = dict(bound="tensor", kernel=top, achieved=ach, peak=pk["bf16_sustained"], unit="TFLOP/s",
-                        frac=ach / pk["bf16_sustained"], traffic=None,
+                        frac=ach / pk["bf16_sustained"], frac_of_burst_peak=(ach / pk["bf16_burst"]) if pk.get("bf16_burst") else None,
+                        traffic=None,
                         peak_source=pk["src"] + ", sustained bf16 figure (kernel timed inside a long step; burst figure "
                                                 f"{pk['bf16_burst']})",
                         share_of_step=d["ms"] / total_ms, launches_per_step=d["calls"],
