@@ -248,3 +248,47 @@ def test_kclutter_oracle_matches_reference_golden(golden_dir):
         want = np.roots([a, b, c])[0]
         got = ko.first_root(a, b, np.array([c]))[0]
         assert abs(got - want) <= 1e-9 * max(1.0, abs(want)), (a, b, c, got, want)
+
+
+def test_numpy_restatement_anchors_the_aten_oracle():
+    """oracle/onet_numpy_oracle.py (plain numpy, float64, no torch ops) against the ATen-based oracle on a 1 x 32 x 48 batch of
+    two frames (ragged: exercises nothing divisible-by-16 specific) and a 40 x 24 one that goes through the F.pad branch:
+    forward maps and loss agree to fp32 rounding, and the ATen oracle's autograd gradient matches central finite differences
+    of the numpy loss on randomly chosen weights of every kind (first conv, deep conv, BatchNorm scale / shift, up-conv weight
+    and bias)."""
+    from oracle import onet_numpy_oracle as onp
+    for (b, h, w, seed) in ((2, 32, 48, 21), (1, 40, 24, 22)):
+        st = orc.perturb_bn_affine(orc.init_state(1, seed=seed), seed=seed + 1)
+        x = orc.rayleigh_frames(b, 1, h, w, seed=seed)
+        st64 = {k: v.double().numpy() for k, v in st.items() if v.dtype.is_floating_point}
+        ref = onp.onet_forward_loss(st64, x.numpy())
+        stc = {k: v.clone() for k, v in st.items()}
+        leaves = [k for k, v in stc.items() if v.dtype.is_floating_point and "running" not in k]
+        for k in leaves:
+            stc[k].requires_grad_(True)
+        Lt, Vt, Ld, Vd, S = orc.onet_forward(stc, x, training=True)
+        loss = orc.compute_loss(Lt, S[:, 0:1], Ld, S[:, 1:2])
+        rel = lambda a, bb: float(np.linalg.norm(a - bb) / np.linalg.norm(bb))
+        assert abs(float(loss) - ref["loss"]) <= 2e-5 * abs(ref["loss"]), (float(loss), ref["loss"])
+        assert rel(Lt.detach().numpy(), ref["Lt"]) < 1e-5 and rel(Vt.detach().numpy(), ref["Vt"]) < 1e-4
+        assert rel(S[:, 0:1].detach().numpy(), ref["St"]) < 1e-3
+        if seed != 21:
+            continue
+        loss.backward()
+        rs = np.random.RandomState(3)
+        picks = ["inc.double_conv.0.weight", "down4.maxpool_conv.1.double_conv.3.weight", "up1.up.weight", "up4.up.bias",
+                 "down2.maxpool_conv.1.double_conv.1.weight", "up3.conv.double_conv.4.bias", "up4.conv.double_conv.3.weight"]
+        for k in picks:
+            g = stc[k].grad.numpy().reshape(-1)
+            idx = int(np.argmax(np.abs(g))) if rs.rand() < 0.5 else int(rs.randint(g.size))
+            eps = 1e-4 * max(1.0, float(np.abs(st64[k]).max()))
+            fd = []
+            for sgn in (+1, -1):
+                pert = dict(st64)
+                arr = st64[k].copy().reshape(-1)
+                arr[idx] += sgn * eps
+                pert[k] = arr.reshape(st64[k].shape)
+                fd.append(onp.onet_forward_loss(pert, x.numpy())["loss"])
+            num = (fd[0] - fd[1]) / (2 * eps)
+            tol = 2e-2 * max(abs(num), float(np.abs(g).max()) * 1e-2)
+            assert abs(num - g[idx]) <= tol, (k, idx, num, g[idx])
