@@ -102,3 +102,27 @@ def test_driver_entry_points_and_tools_compile():
         py_compile.compile(os.path.join(ROOT, fn), doraise=True)
     ge = importlib.import_module("__graft_entry__")
     assert callable(ge.build) and callable(ge.smoke)
+
+
+def test_header_is_plain_c_and_links_from_a_c_program(lib_path, tmp_path):
+    """include/onet_b200.h must be consumable by a C compiler (C99, no C++-isms) and the library must link from plain C:
+    a tiny program takes the address of every declared entry point and calls onet_version() (no GPU needed)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not on PATH")
+    names = sorted(_prototypes())
+    src = tmp_path / "use_onet.c"
+    src.write_text('#include <stdio.h>\n#include "onet_b200.h"\nint main(void) {\n    const void* fns[] = {\n'
+                   + "".join(f"        (const void*)&{n},\n" for n in names)
+                   + '    };\n    printf("%d %d\\n", onet_version(), (int)(sizeof(fns) / sizeof(fns[0])));\n    return 0;\n}\n')
+    exe = tmp_path / "use_onet"
+    libdir = os.path.dirname(lib_path)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-Wno-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+           "-L", libdir, "-l:libonet_b200.so", f"-Wl,-rpath,{libdir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    ver, n = out.stdout.split()
+    assert int(ver) >= 100 and int(n) == len(names)
