@@ -6,6 +6,7 @@ python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 python __graft_entry__.py smoke 2>&1 | tail -2
 ONET_BENCH_DETAIL=gpurun_out/detail_v5.tsv python bench.py --steps 20 --warmup 3 > gpurun_out/bench_v5.json 2> gpurun_out/bench_v5.err
 echo "bench rc=$?"; tail -2 gpurun_out/bench_v5.err
+python tools/roofline_table.py gpurun_out/detail_v5.tsv > gpurun_out/per_layer_roofline_v5.md; tail -5 gpurun_out/per_layer_roofline_v5.md
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_v5.json 2> gpurun_out/bench_ref_v5.err; echo "ref rc=$?"; cut -c1-300 gpurun_out/bench_ref_v5.json
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -s 650 -c 240 --csv --log-file gpurun_out/launches_v5.csv \
