@@ -31,6 +31,7 @@ UNIT = "images/s"
 H = W = 256
 CIN = 1
 LR = 5e-6          # Train_Onet_on_simclutter_20250407.py:181
+EXTRA_MODES = [("fp32", 16)]      # (mode, frames per GPU) of the `modes` sub-record
 
 
 def _peaks():
@@ -136,19 +137,30 @@ def cpu_infer_baseline(threads):
     return 0.262144 / dt, dt
 
 
+def _config(batch, world, mode="bf16", workload="simclutter"):
+    """The `config` object of the JSON line; the reference arm reports the SAME object (it times a bounded sample of it)."""
+    prec = {"bf16": "bf16 operands, fp32 accumulate", "fp32": "FP32 verification mode (CUDA cores)",
+            "tf32": "tf32 tensor-core operands, fp32 storage and accumulate"}[mode]
+    return dict(workload=f"Onet(in_chns={CIN}, shared twin) fwd+bwd+JSD+Adam, batch {batch}/GPU of {CIN}x{H}x{W} "
+                         + ("K-distributed clutter frames (BASELINE configs[1])" if workload == "simclutter"
+                            else "synthetic multispectral patches (BASELINE configs[3] shape)") + "; " + prec,
+                per_gpu_batch=batch, global_batch=batch * world, image=[CIN, H, W], parallelism=f"dp{world}",
+                l2="working set (~19 GB of activations per step) is far larger than the 126 MB L2; inputs rotate over 4 batches")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    batch = 4
+    batch = 8          # BASELINE.json configs[0]: batch 8 of 1x256x256 frames on the CPU
     ips, sec = cpu_steps(batch, args.steps, args.warmup, threads)
-    sample = f"batch {batch} of 1x{H}x{W} K-clutter frames per step, {args.warmup} warm-up + {args.steps} timed steps"
+    sample = (f"each step = batch {batch} (BASELINE configs[0]) of the workload's {CIN}x{H}x{W} K-clutter frames, "
+              f"{args.warmup} warm-up + {args.steps} timed steps, oracle port on ATen CPU kernels; images/s is per image, the "
+              f"GPU arm runs {args.batch} frames per GPU and step")
     line = dict(impl="reference", metric=METRIC, value=ips, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f32", data="synthetic",
-                config=dict(workload=f"Onet(in_chns=1, shared twin) fwd+bwd+JSD+Adam, 1x{H}x{W} K-distributed clutter frames, "
-                                     f"CPU sample batch {batch}", per_gpu_batch=batch, image=[CIN, H, W]),
+                dtype="f32", data="synthetic", config=_config(args.batch, max(1, args.gpus), args.mode, args.workload),
                 cpu_baseline=dict(value=ips, unit=UNIT, cores=threads, kind="port", sample=sample),
                 e2e=dict(value=ips, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     _emit(line)
@@ -182,7 +194,7 @@ def _family(name, a):
     return name.replace("onet_", ""), 0.0, ""
 
 
-def profile_steps(trainer, x, nsteps, record=True):
+def profile_steps(trainer, x, nsteps, record=True, elem_bytes=2.0):
     """Per-call CUDA-event timing of `nsteps` more steps.  Every rank must run the steps (they contain the gradient
     all-reduce); only ranks with record=True keep the events.  Returns (by family, by kernel variant, by variant+shape)."""
     import torch
@@ -203,23 +215,133 @@ def profile_steps(trainer, x, nsteps, record=True):
                 ms = e0.elapsed_time(e1)
                 ints = [v for v in a if isinstance(v, int) and not isinstance(v, bool) and abs(v) < (1 << 40)]
                 f.write(f"{name}\t{kern}\t{fam_name}\t{ms:.4f}\t{(fl / (ms * 1e-3) / 1e12) if fl else 0:.1f}\t{ints}\n")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from roofline_table import work          # algorithmic HBM bytes of every call
     fam, kern_t, shape_t = {}, {}, {}
     for name, a, e0, e1, kern in prof:
         f, fl, shape = _family(name, a)
         ms = e0.elapsed_time(e1)
+        ints = [v for v in a if isinstance(v, int) and not isinstance(v, bool) and abs(v) < (1 << 40)]
+        desc, _, nbytes = work(name, ints, elem_bytes)
         if fl == 0.0:            # calls that launch several kernels (BatchNorm backward = reduce + apply + parameter gradient)
             kern = name.replace("onet_", "")
+            shape = desc
         for table, key in ((fam, f), (kern_t, kern), (shape_t, (kern, shape))):
-            d = table.setdefault(key, dict(ms=0.0, flops=0.0, calls=0))
+            d = table.setdefault(key, dict(ms=0.0, flops=0.0, calls=0, bytes=0.0))
             d["ms"] += ms
             d["flops"] += fl
+            d["bytes"] += nbytes
             d["calls"] += 1
     for table in (fam, kern_t, shape_t):
         for d in table.values():
             d["ms"] /= nsteps
             d["flops"] /= nsteps
+            d["bytes"] /= nsteps
             d["calls"] //= nsteps
     return fam, kern_t, shape_t
+
+
+# --------------------------------------------------------------------------------------------------
+# sub-records of the same JSON line: the other BASELINE configurations, measured in the same driver run
+# --------------------------------------------------------------------------------------------------
+def _timed_region(fn, steps, dev, world):
+    """CUDA-event time (ms, max over ranks) of `steps` calls of fn(i), barrier + synchronize on both sides."""
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def infer_record(dev, rank, world, steps=4, warmup=2, frames_per_gpu=2, size=2048, cpu_leg=True):
+    """BASELINE configs[4]: eval-mode inference on 1 x 2048 x 2048 radar frames, `frames_per_gpu` whole frames per rank and
+    step (halo tiling only splits a frame when there are fewer frames than ranks; tests/test_infer_gpu.py covers it), masks
+    as uint8.  `value`: frames resident in HBM; `e2e`: frames copied from pinned host memory on a copy stream one frame ahead
+    of the compute, every mask copied back (1 byte per pixel) while the next frame computes, host-synchronised per step."""
+    import torch
+    import onet_b200
+    from onet_b200 import _lib, synth
+    from onet_b200.evaluate import normalize_per_frame
+    from onet_b200.infer import TiledPredictor
+    torch.manual_seed(1981)
+    net = onet_b200.Onet(1, True, True, mode="bf16").to(dev)
+    pred = TiledPredictor.for_onet(net, tile=size, halo=96, max_batch=1)
+    f, _ = synth.get_rayleigh_frames(frames_per_gpu, snr=2, img_sz=(size, size), seed=7 + rank, device=dev)
+    frames = normalize_per_frame(f.unsqueeze(1))
+    host = frames.cpu().pin_memory()
+    for _ in range(warmup):
+        pred.predict_labels(frames)
+        pred.predict_labels(host)
+    l0 = _lib.launch_count()
+    ms_dev = _timed_region(lambda i: pred.predict_labels(frames), steps, dev, world)
+    launches = _lib.launch_count() - l0
+    ms_e2e = _timed_region(lambda i: pred.predict_labels(host), steps, dev, world)
+    mpix = world * frames_per_gpu * size * size / 1e6
+    pk = _peaks()
+    roof_mpix = pk["bf16_sustained"] * 1e12 / 2.935e6 / 1e6          # 2.935 MFLOP per pixel (SURVEY section 8d)
+    v = mpix * steps / (ms_dev * 1e-3)
+    rec = dict(metric="onet_infer_mpix_per_sec", value=v, unit="Mpix/s", n_gpus=world, steps=steps, warmup=warmup,
+               ms_per_step=ms_dev / steps, higher_is_better=True, scaling="weak", dtype="bf16", data="synthetic",
+               config=dict(workload=f"Onet eval-mode inference (BASELINE configs[4]), {frames_per_gpu} frames of 1x{size}x{size} "
+                                    f"Rayleigh clutter + targets per GPU and step, whole frames per rank, uint8 masks",
+                           frames_per_gpu=frames_per_gpu, size=size),
+               e2e=dict(value=mpix * steps / (ms_e2e * 1e-3), unit="Mpix/s", ms_per_step=ms_e2e / steps,
+                        h2d_bytes_per_step=frames_per_gpu * size * size * 4, d2h_bytes_per_step=frames_per_gpu * size * size),
+               gpu_launches=int(launches),
+               roofline=dict(bound="tensor", achieved=v / world * 2.935e6 / 1e6, peak=pk["bf16_sustained"], unit="TFLOP/s",
+                             frac=v / world / roof_mpix, roofline_mpix_per_gpu=roof_mpix,
+                             peak_source=pk["src"] + ", sustained bf16 figure (whole forward pass, 2.935 MFLOP per pixel)"))
+    if cpu_leg and rank == 0 and world == 1:
+        threads = os.cpu_count() or 1
+        mpix_cpu, dt = cpu_infer_baseline(threads)
+        rec["cpu_baseline"] = dict(value=mpix_cpu, unit="Mpix/s", cores=threads, kind="port",
+                                   sample=f"one 1x512x512 frame, eval-mode oracle forward ({dt:.2f} s)")
+    del pred, net, frames, f
+    torch.cuda.empty_cache()
+    return rec
+
+
+def train_record(dev, rank, world, cin, hw, batch, mode, steps, warmup, graph, workload):
+    """One more training configuration through the same trainer: (value, e2e) images/s, weak scaling."""
+    import torch
+    import onet_b200
+    from onet_b200.data import k_clutter_frames
+    from onet_b200.trainer import OnetTrainer
+    torch.manual_seed(1981)
+    net = onet_b200.Onet(cin, True, True, mode=mode).to(dev)
+    tr = OnetTrainer(net, lr=LR, graph=graph)
+    tr.broadcast_parameters(0)
+    host = [k_clutter_frames(batch, cin, hw, hw, seed=4000 + 97 * rank + i, n_targets=8).pin_memory() for i in range(2)]
+    res = [h.to(dev) for h in host]
+    for i in range(warmup):
+        tr.step(res[i % 2])
+    ms_dev = _timed_region(lambda i: tr.step(res[i % 2]), steps, dev, world)
+    loss = []
+    tr.step(host[0]).item()
+    ms_e2e = _timed_region(lambda i: loss.append(tr.step(host[i % 2]).item()), steps, dev, world)
+    imgs = world * batch * steps
+    rec = dict(metric=METRIC, value=imgs / (ms_dev * 1e-3), unit=UNIT, n_gpus=world, steps=steps, warmup=warmup,
+               ms_per_step=ms_dev / steps, higher_is_better=True, scaling="weak", dtype={"bf16": "bf16", "fp32": "f32", "tf32": "tf32"}[mode],
+               data="synthetic", config=dict(workload=workload, per_gpu_batch=batch, global_batch=batch * world, image=[cin, hw, hw],
+                                             parallelism=f"dp{world}", graph=bool(graph)),
+               e2e=dict(value=imgs / (ms_e2e * 1e-3), unit=UNIT, ms_per_step=ms_e2e / steps, h2d_bytes_per_step=batch * cin * hw * hw * 4,
+                        d2h_bytes_per_step=4),
+               peak_memory_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30, loss_last=loss[-1] if loss else None)
+    del tr, net, res
+    torch.cuda.empty_cache()
+    return rec
 
 
 _REAL_STDOUT = None
@@ -248,11 +370,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
-    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="simclutter", choices=["simclutter", "zy3"],
                     help="simclutter = BASELINE configs[1] (1x256x256, the headline); zy3 = configs[3] shape (3x224x224 patches)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying one CUDA graph per step")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the sub-records (inference configs[4], ZY-3 shape configs[3], verification modes) of the JSON line")
     args = ap.parse_args()
     global H, W, CIN
     if args.workload == "zy3":
@@ -331,9 +455,22 @@ def main():
     ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
-    fam, kern_t, shape_t = profile_steps(trainer, resident[0], 2, record=(rank == 0))
+    fam, kern_t, shape_t = profile_steps(trainer, resident[0], 2, record=(rank == 0), elem_bytes=2.0 if args.mode == "bf16" else 4.0)
     if world > 1:
         dist.barrier()
+
+    extra = {}
+    if not args.no_extra and args.workload == "simclutter" and args.mode == "bf16":
+        # the other BASELINE configurations in the same driver run (every rank takes part: they contain collectives)
+        extra["infer"] = infer_record(dev, rank, world, steps=4, warmup=2, cpu_leg=not args.no_cpu_baseline)
+        H, W, CIN = 224, 224, 3
+        extra["zy3"] = train_record(dev, rank, world, 3, 224, B, "bf16", min(args.steps, 10), 3, not args.no_graph,
+                                    _config(B, world, "bf16", "zy3")["workload"])
+        H, W, CIN = 256, 256, 1
+        # the modes that meet the north_star tolerances literally, beside the bf16 throughput mode (same step, same shape)
+        extra["modes"] = {}
+        for mode, mb in EXTRA_MODES:
+            extra["modes"][mode] = train_record(dev, rank, world, 1, 256, mb, mode, 2, 1, False, _config(mb, world, mode)["workload"])
 
     if rank == 0:
         pk = _peaks()
@@ -350,11 +487,13 @@ def main():
             d = gemm[top]
             ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
             shapes = {k[1]: v for k, v in shape_t.items() if k[0] == top}
-            roof = dict(bound="tensor", kernel=top, achieved=ach, peak=pk["bf16_sustained"], unit="TFLOP/s",
-                        frac=ach / pk["bf16_sustained"], frac_of_burst_peak=(ach / pk["bf16_burst"]) if pk.get("bf16_burst") else None,
+            # the per-kernel times come from an eager pass with CUDA events around every launch: each kernel runs alone,
+            # at burst clocks (their sum is below the replayed step) - so the denominator is the BURST figure
+            roof = dict(bound="tensor", kernel=top, achieved=ach, peak=pk["bf16_burst"], unit="TFLOP/s",
+                        frac=ach / pk["bf16_burst"], frac_of_sustained_peak=ach / pk["bf16_sustained"],
                         traffic=None,
-                        peak_source=pk["src"] + ", sustained bf16 figure (kernel timed inside a long step; burst figure "
-                                                f"{pk['bf16_burst']})",
+                        peak_source=pk["src"] + ", burst bf16 figure (kernel timed alone between CUDA events; sustained figure "
+                                                f"{pk['bf16_sustained']}, which the whole-step `step_tflops` is held against)",
                         share_of_step=d["ms"] / total_ms, launches_per_step=d["calls"],
                         flops_per_launch=d["flops"] / max(d["calls"], 1), ms_per_launch=d["ms"] / max(d["calls"], 1),
                         shapes={sh: dict(calls=v["calls"], ms_per_launch=round(v["ms"] / max(v["calls"], 1), 4),
@@ -380,6 +519,28 @@ def main():
             if famd:
                 roof["conv_fwd_dgrad_family"] = dict(tflops=famd["flops"] / (famd["ms"] * 1e-3) / 1e12, ms_per_step=famd["ms"],
                                                      launches_per_step=famd["calls"], share_of_step=famd["ms"] / total_ms)
+        # largest HBM-bound call family of the step (BatchNorm backward = reduce pass + apply pass + parameter gradients)
+        hbm = {k: d for k, d in kern_t.items() if d["flops"] == 0 and d["bytes"] > 0}
+        roof_hbm = None
+        if hbm:
+            topb = max(hbm, key=lambda k: hbm[k]["ms"])
+            d = hbm[topb]
+            achb = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+            shapes = {k[1]: v for k, v in shape_t.items() if k[0] == topb}
+            roof_hbm = dict(bound="hbm", kernel=topb, achieved=achb, peak=pk["hbm"], unit="GB/s", frac=achb / pk["hbm"], traffic=None,
+                            peak_source=pk["src"] + ", copy bandwidth", share_of_step=d["ms"] / total_ms, launches_per_step=d["calls"],
+                            bytes_per_launch=d["bytes"] / max(d["calls"], 1), ms_per_launch=d["ms"] / max(d["calls"], 1),
+                            note="algorithmic bytes: every operand read once per pass and the result written once "
+                                 "(tools/roofline_table.py::work)",
+                            shapes={sh: dict(calls=v["calls"], ms_per_launch=round(v["ms"] / max(v["calls"], 1), 4),
+                                             gbs=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 0)) for sh, v in
+                                    sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])})
+            for c in (roof or {}).get("ncu_captures", []):
+                if c.get("family") == topb:
+                    roof_hbm["traffic"] = c["dram_bytes"]
+                    roof_hbm["traffic_capture"] = dict(capture=c["capture"], algorithmic_bytes=c["algorithmic_bytes"],
+                                                       duration_us=c["duration_us"], kernel=c["kernel"])
+                    break
         per_kernel = {k: dict(ms_per_step=round(d["ms"], 3), share=round(d["ms"] / total_ms, 4), calls=d["calls"],
                               tflops=(round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 1) if d["flops"] else None))
                       for k, d in sorted(kern_t.items(), key=lambda kv: -kv[1]["ms"])}
@@ -389,25 +550,22 @@ def main():
         train_flops = sum(d["flops"] for d in fam.values())
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype="bf16" if args.mode == "bf16" else "f32", data="synthetic",
-                    config=dict(workload=f"Onet(in_chns={CIN}, shared twin) fwd+bwd+JSD+Adam, batch {B}/GPU of {CIN}x{H}x{W} "
-                                         + ("K-distributed clutter frames (BASELINE configs[1])" if args.workload == "simclutter"
-                                            else "synthetic multispectral patches (BASELINE configs[3] shape)")
-                                         + "; bf16 operands, fp32 accumulate",
-                                per_gpu_batch=B, global_batch=B * world, image=[CIN, H, W], parallelism=f"dp{world}",
-                                l2="working set (~19 GB of activations per step) is far larger than the 126 MB L2; "
-                                   "inputs rotate over 4 batches"),
+                    dtype={"bf16": "bf16", "fp32": "f32", "tf32": "tf32"}[args.mode], data="synthetic",
+                    config=_config(B, world, args.mode, args.workload),
                     e2e=dict(value=e2e_v, unit=UNIT, ms_per_step=ms_e2e / args.steps, h2d_bytes_per_step=B * CIN * H * W * 4,
                              d2h_bytes_per_step=4),
-                    gpu_launches=int(launches), clocks=clocks, roofline=roof, kernels=kernels, per_kernel=per_kernel,
+                    gpu_launches=int(launches), clocks=clocks, roofline=roof, roofline_hbm=roof_hbm, kernels=kernels,
+                    per_kernel=per_kernel,
                     step_tflops=train_flops / (ms_dev / args.steps * 1e-3) / 1e12 if fam else None,
+                    step_frac_of_sustained_peak=(train_flops / (ms_dev / args.steps * 1e-3) / 1e12 / pk["bf16_sustained"]) if fam else None,
                     loss_last=losses[-1] if losses else None)
+        line.update(extra)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            ips, sec = cpu_steps(4, 2, 1, threads)
+            ips, sec = cpu_steps(8, 2, 1, threads)
             line["cpu_baseline"] = dict(value=ips, unit=UNIT, cores=threads, kind="port",
-                                        sample=f"batch 4 of the same 1x{H}x{W} frames, 1 warm-up + 2 timed steps "
-                                               f"({sec:.1f} s/step), oracle port on ATen CPU kernels")
+                                        sample=f"batch 8 (BASELINE configs[0]) of the same {CIN}x{H}x{W} frames, 1 warm-up + 2 timed "
+                                               f"steps ({sec:.1f} s/step), oracle port on ATen CPU kernels")
         _emit(line)
     if world > 1:
         # a captured graph holds NCCL work; tear down in order and do not rely on interpreter-exit destructors

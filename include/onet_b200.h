@@ -41,6 +41,14 @@ const char* onet_last_kernel(void);
 const char* onet_last_error(void);
 int onet_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
+/* FP32 verification mode, reproducible gradients: registers (per device; NULL unregisters) a caller-owned fp32 workspace.
+ * While one is registered the CUDA-core weight-gradient kernels (onet_conv3x3_wgrad, onet_convT2x2_wgrad incl. its bias
+ * column sums; dtype ONET_F32, engine ONET_ENGINE_SIMT) write per-split partial sums into it and add them in split order,
+ * instead of accumulating with fp32 atomics; a call whose partials do not fit falls back to atomics.  The workspace must
+ * stay alive, and calls that use it must be ordered on one stream, until it is unregistered.  The reference's CPU
+ * convolution backward (ATen, torch>=1.7.0) is deterministic; this is what lets the fp32 parity tests run once. */
+int onet_set_splitk_workspace(float* ws, int64_t nfloats);
+
 /* X (B,Cin,H,W) fp32 NCHW -> twin NHWC batch [2B,H,W,Cin] = (X, clip(1-X+bias,0,1)).
  * Replaces Onet.forward's input handling, Onet_vanilla_20240606.py:175,180-181. */
 int onet_prep_input(const float* x, int B, int Cin, int H, int W, float bias, void* out, int dtype, void* stream);
@@ -157,6 +165,9 @@ int onet_head_bwd(const void* L, int64_t ldl, int offl, const void* Hf, int64_t 
 
 /* argmax of the 2-way softmax: 1 iff Vd > Vt (Onet.predict_label :193-202) */
 int onet_predict_label(const float* Vt, const float* Vd, int64_t n, int64_t* out, void* stream);
+/* the same decision as one byte per pixel: the mask format of the tiled inference path (onet_b200/infer.py), 8x fewer
+ * bytes over PCIe than the int64 argmax of the reference's predict_label */
+int onet_predict_label_u8(const float* Vt, const float* Vd, int64_t n, unsigned char* out, void* stream);
 
 /* Evaluation next to the path: counts[pred * 2 + gt] += 1 over n pixels, pred = (Vd > Vt) (predict_label :193-202), gt != 0
  * -> 1.  counts is a zero-initialised int64[4]; accuracy / mIoU / detection rate / false-alarm rate / target IoU of

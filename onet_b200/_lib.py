@@ -46,6 +46,7 @@ _p, _i, _i64, _f, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_f
 SIGNATURES = {
     "onet_version": [],
     "onet_device_info": [_p, _p, _p],
+    "onet_set_splitk_workspace": [_p, _i64],
     "onet_prep_input": [_p, _i, _i, _i, _i, _f, _p, _i, _p],
     "onet_pack_conv_weights": [_p, _i, _i, _p, _p, _i, _p],
     "onet_pack_convT_weights": [_p, _i, _i, _p, _p, _i, _p],
@@ -69,6 +70,7 @@ SIGNATURES = {
     "onet_head_fwd": [_p, _i64, _i, _p, _i64, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p],
     "onet_head_bwd": [_p, _i64, _i, _p, _i64, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
     "onet_predict_label": [_p, _p, _i64, _p, _p],
+    "onet_predict_label_u8": [_p, _p, _i64, _p, _p],
     "onet_eval_confusion": [_p, _p, _p, _i64, _p, _p],
     "onet_normalize_per_frame": [_p, _i, _i64, _p, _p, _p],
     "onet_synth_rayleigh": [_p, _i64, _f, _i64, _i, _p],
@@ -110,9 +112,14 @@ def lib():
 PROFILE = None   # set to a list to record (name, int args, start event, end event) of every call (bench.py)
 
 
-def call(name, *args):
-    """Invoke a C-ABI entry point; raise with the library's message on a non-zero status."""
+def call(name, *args, device=None):
+    """Invoke a C-ABI entry point; raise with the library's message on a non-zero status.  The library launches on the
+    CURRENT device: call sites outside `Onet._run_forward` / backward (which set it themselves) pass `device=`."""
     global LAUNCHES
+    if device is not None:
+        import torch
+        with torch.cuda.device(device):
+            return call(name, *args)
     if PROFILE is not None:
         import torch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

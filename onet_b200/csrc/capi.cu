@@ -120,15 +120,37 @@ static int make_up_map(CUtensorMap* m, const bf16* base, int C, int N, int H, in
     return make_map5(m, base, dims, st, box);
 }
 
-static int g_sm_count = 0;
+// Function attributes (dynamic shared-memory opt-in, carve-out), co-resident cluster counts and the SM count are properties of
+// ONE device: every cache below is indexed by the current device so that a process driving several GPUs stays correct.
+constexpr int kMaxDevices = 64;
+static int cur_dev() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+    return dev;
+}
 static int sm_count() {
-    if (g_sm_count == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sm_count <= 0) g_sm_count = 148;
+    static int count[kMaxDevices] = {};
+    const int dev = cur_dev();
+    if (count[dev] == 0) {
+        cudaDeviceGetAttribute(&count[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (count[dev] <= 0) count[dev] = 148;
     }
-    return g_sm_count;
+    return count[dev];
+}
+
+// Deterministic split-K (FP32 verification mode): when the caller has registered a workspace for the current device
+// (onet_set_splitk_workspace), the CUDA-core weight-gradient / column-sum kernels write one slab of partial sums per pixel
+// split and splitk_reduce_kernel adds the slabs in split order; without a (large enough) workspace they use fp32 atomics.
+static float* g_splitk_ws[kMaxDevices] = {};
+static long long g_splitk_floats[kMaxDevices] = {};
+static float* splitk_ws(long long floats_needed) {
+    const int dev = cur_dev();
+    return (g_splitk_ws[dev] != nullptr && floats_needed <= g_splitk_floats[dev]) ? g_splitk_ws[dev] : nullptr;
+}
+static int splitk_reduce(const float* partial, int splits, long long numel, float* dst, cudaStream_t st) {
+    const int grid = static_cast<int>(std::max(1LL, std::min<long long>((numel + 255) / 256, 148 * 8)));
+    splitk_reduce_kernel<<<grid, 256, 0, st>>>(partial, splits, numel, dst);
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -137,7 +159,8 @@ static int sm_count() {
 template <int BN>
 static int launch_px(const CUtensorMap& tA, const CUtensorMap& tB, const PxParams& p, cudaStream_t st) {
     using Cfg = PxCfg<BN>;
-    static bool attr_set = false;
+    static bool attr_set_[kMaxDevices] = {};
+    bool& attr_set = attr_set_[cur_dev()];
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tapgemm_px_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return fail("cudaFuncSetAttribute(px<%d>): %s", BN, cudaGetErrorString(e));
@@ -172,7 +195,8 @@ static void px_tiling(PxParams& p, int N, int H, int W, int group_images) {
 template <int BN>
 static int launch_halo_px(const CUtensorMap& tA, const CUtensorMap& tB, const PxParams& p, cudaStream_t st) {
     using Cfg = HaloCfg<BN>;
-    static bool attr_set = false;
+    static bool attr_set_[kMaxDevices] = {};
+    bool& attr_set = attr_set_[cur_dev()];
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_px_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return fail("cudaFuncSetAttribute(halo_px<%d>): %s", BN, cudaGetErrorString(e));
@@ -186,7 +210,8 @@ static int launch_halo_px(const CUtensorMap& tA, const CUtensorMap& tB, const Px
 template <int BN, bool RED = false>
 static int launch_halo_res_px(const CUtensorMap& tA, const CUtensorMap& tB, const PxParams& p, cudaStream_t st) {
     using Cfg = HaloResCfg<BN>;
-    static bool attr_set = false;
+    static bool attr_set_[kMaxDevices] = {};
+    bool& attr_set = attr_set_[cur_dev()];
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_res_px_kernel<BN, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return fail("cudaFuncSetAttribute(halo_res_px<%d>): %s", BN, cudaGetErrorString(e));
@@ -200,7 +225,8 @@ static int launch_halo_res_px(const CUtensorMap& tA, const CUtensorMap& tB, cons
 template <int BN, bool RED = false>
 static int launch_halo2_px(const CUtensorMap& tA, const CUtensorMap& tB, const PxParams& p, cudaStream_t st) {
     using Cfg = Halo2Cfg<BN>;
-    static int max_clusters = 0;
+    static int max_clusters_[kMaxDevices] = {};
+    int& max_clusters = max_clusters_[cur_dev()];
     if (max_clusters == 0) {
         cudaError_t e = cudaFuncSetAttribute(conv3x3_halo2_px_kernel<BN, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return fail("cudaFuncSetAttribute(halo2_px<%d>): %s", BN, cudaGetErrorString(e));
@@ -423,7 +449,8 @@ static int convT_dgrad_tc(const bf16* go, long long ldg, int goff, int N, int H,
 template <int BNW>
 static int launch_wg(const CUtensorMap& tG, const CUtensorMap& tI, const WgParams& p, cudaStream_t st) {
     using Cfg = WgCfg<BNW>;
-    static bool attr_set = false;
+    static bool attr_set_[kMaxDevices] = {};
+    bool& attr_set = attr_set_[cur_dev()];
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tapgemm_wg_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return fail("cudaFuncSetAttribute(wg<%d>): %s", BNW, cudaGetErrorString(e));
@@ -438,7 +465,8 @@ static int launch_wg(const CUtensorMap& tG, const CUtensorMap& tI, const WgParam
 template <int BNW>
 static int launch_wh(const CUtensorMap& tG, const CUtensorMap& tI, const WhParams& p, cudaStream_t st) {
     using Cfg = WhCfg<BNW>;
-    static bool attr_set = false;
+    static bool attr_set_[kMaxDevices] = {};
+    bool& attr_set = attr_set_[cur_dev()];
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(wgrad3x3_halo_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return fail("cudaFuncSetAttribute(wh<%d>): %s", BNW, cudaGetErrorString(e));
@@ -452,7 +480,8 @@ static int launch_wh(const CUtensorMap& tG, const CUtensorMap& tI, const WhParam
 // CTA-pair weight gradient (Mc, Nc multiples of 128)
 static int wgrad3x3_halo2_tc(const bf16* g, long long ldg, int goff, int Mc, const bf16* in, long long ldi, int ioff, int Nc,
                              int N, int H, int W, float* dw, cudaStream_t st) {
-    static int max_clusters = 0;
+    static int max_clusters_[kMaxDevices] = {};
+    int& max_clusters = max_clusters_[cur_dev()];
     if (max_clusters == 0) {
         cudaError_t e = cudaFuncSetAttribute(wgrad3x3_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Wh2Cfg::kSmemBytes);
         if (e != cudaSuccess) return fail("cudaFuncSetAttribute(wh2): %s", cudaGetErrorString(e));
@@ -638,6 +667,13 @@ int64_t onet_launch_count(void) { return g_launches; }
 const char* onet_last_kernel(void) { return g_last_kernel; }
 const char* onet_last_error(void) { return g_err; }
 
+int onet_set_splitk_workspace(float* ws, int64_t nfloats) {
+    const int dev = cur_dev();
+    g_splitk_ws[dev] = (ws != nullptr && nfloats > 0) ? ws : nullptr;
+    g_splitk_floats[dev] = g_splitk_ws[dev] ? nfloats : 0;
+    return 0;
+}
+
 int onet_device_info(int* smc, int* major, int* minor) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return fail("no CUDA device");
@@ -767,14 +803,21 @@ int onet_conv3x3_wgrad(const void* g, int64_t ldg, int g_off, const void* in, in
         const int lanes = Cin == 1 ? 32 : 8;       // column groups per block = 256 / (64 / CPT)
         const int wgb = (W / 4 + lanes - 1) / lanes, chunks = (H + ROWS - 1) / ROWS;
         const unsigned gx = static_cast<unsigned>(N) * chunks * wgb;
+        const long long numel = 64LL * 9 * Cin;
+        float* part = (dtype == ONET_F32) ? splitk_ws(static_cast<long long>(gx) * numel) : nullptr;
         if (dtype == ONET_F32) {
-            if (Cin == 1) conv_first_wgrad_rows_kernel<float, 1, 8, ROWS><<<gx, 256, 0, ST(stream)>>>(static_cast<const float*>(g), static_cast<const float*>(in), N, H, W, dw);
-            else conv_first_wgrad_rows_kernel<float, 3, 2, ROWS><<<gx, 256, 0, ST(stream)>>>(static_cast<const float*>(g), static_cast<const float*>(in), N, H, W, dw);
+            if (Cin == 1) conv_first_wgrad_rows_kernel<float, 1, 8, ROWS><<<gx, 256, 0, ST(stream)>>>(static_cast<const float*>(g), static_cast<const float*>(in), N, H, W, dw, part);
+            else conv_first_wgrad_rows_kernel<float, 3, 2, ROWS><<<gx, 256, 0, ST(stream)>>>(static_cast<const float*>(g), static_cast<const float*>(in), N, H, W, dw, part);
         } else {
-            if (Cin == 1) conv_first_wgrad_rows_kernel<bf16, 1, 8, ROWS><<<gx, 256, 0, ST(stream)>>>(static_cast<const bf16*>(g), static_cast<const bf16*>(in), N, H, W, dw);
-            else conv_first_wgrad_rows_kernel<bf16, 3, 2, ROWS><<<gx, 256, 0, ST(stream)>>>(static_cast<const bf16*>(g), static_cast<const bf16*>(in), N, H, W, dw);
+            if (Cin == 1) conv_first_wgrad_rows_kernel<bf16, 1, 8, ROWS><<<gx, 256, 0, ST(stream)>>>(static_cast<const bf16*>(g), static_cast<const bf16*>(in), N, H, W, dw, part);
+            else conv_first_wgrad_rows_kernel<bf16, 3, 2, ROWS><<<gx, 256, 0, ST(stream)>>>(static_cast<const bf16*>(g), static_cast<const bf16*>(in), N, H, W, dw, part);
         }
-        return check_launch("conv_first_wgrad");
+        if (check_launch("conv_first_wgrad")) return 1;
+        if (part != nullptr) {
+            splitk_reduce(part, static_cast<int>(gx), numel, dw, ST(stream));
+            return check_launch("splitk_reduce");
+        }
+        return 0;
     }
     const int K = 9 * Cin;
     const int bx = (Cout + 63) / 64, by = (K + 63) / 64;
@@ -783,13 +826,21 @@ int onet_conv3x3_wgrad(const void* g, int64_t ldg, int g_off, const void* in, in
     per = std::max<long long>(16, (per + 15) / 16 * 16);
     splits = static_cast<int>((M + per - 1) / per);
     dim3 grid(bx, by, splits);
+    const long long numel = 9LL * Cin * Cout;
+    // one split: a single add per address, already deterministic
+    float* part = (dtype == ONET_F32 && splits > 1) ? splitk_ws(static_cast<long long>(splits) * numel) : nullptr;
     if (dtype == ONET_F32)
         conv3x3_wgrad_simt_kernel<float><<<grid, 256, 0, ST(stream)>>>(static_cast<const float*>(g), ldg, g_off,
-                                                                       static_cast<const float*>(in), ldi, ci_off, N, H, W, Cin, Cout, dw, per);
+                                                                       static_cast<const float*>(in), ldi, ci_off, N, H, W, Cin, Cout, dw, per, part);
     else
         conv3x3_wgrad_simt_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(static_cast<const bf16*>(g), ldg, g_off,
-                                                                      static_cast<const bf16*>(in), ldi, ci_off, N, H, W, Cin, Cout, dw, per);
-    return check_launch("conv3x3_wgrad_simt");
+                                                                      static_cast<const bf16*>(in), ldi, ci_off, N, H, W, Cin, Cout, dw, per, part);
+    if (check_launch("conv3x3_wgrad_simt")) return 1;
+    if (part != nullptr) {
+        splitk_reduce(part, splits, numel, dw, ST(stream));
+        return check_launch("splitk_reduce");
+    }
+    return 0;
 }
 
 int onet_bn_finalize(const double* stat_sum, const double* stat_sq, int G, int C, double count, const float* gamma0,
@@ -854,7 +905,8 @@ static int bn_bwd_impl(const void* y, int N, int H, int W, int C, const float* s
     // The weight-gradient kernels of the previous layer run next to these kernels on a second stream (model.py): ask for the
     // largest shared-memory carve-out so that an SM already holding BatchNorm CTAs can still take a 171 KB wgrad CTA
     // (these kernels stream through L1 and do not need it).  ONET_BN_BWD_BLOCKS overrides the grid (A/B measurements).
-    static bool carveout_set = false;
+    static bool carveout_set_[kMaxDevices] = {};
+    bool& carveout_set = carveout_set_[cur_dev()];
     if (!carveout_set) {
         cudaFuncSetAttribute(bn_bwd_win_kernel<T, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(bn_bwd_win_kernel<T, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1027,11 +1079,16 @@ int onet_convT2x2_wgrad(const void* x, int64_t ldx, int xoff, const void* go, in
         // bias gradient = column sums of dO over the whole upsampled grid
         const int cpb = std::min(Co, 64);
         dim3 grid(static_cast<unsigned>(std::min<long long>(148 * 4, (4 * M + (256 / cpb) - 1) / (256 / cpb))), (Co + cpb - 1) / cpb);
+        float* part = (dtype == ONET_F32 && grid.x > 1) ? splitk_ws(static_cast<long long>(grid.x) * Co) : nullptr;
         if (dtype == ONET_F32)
-            colsum_kernel<float><<<grid, 256, 0, ST(stream)>>>(static_cast<const float*>(go), ldg, goff, 4 * M, Co, dbias, 2 * H, 2 * W, Ho, Wo);
+            colsum_kernel<float><<<grid, 256, 0, ST(stream)>>>(static_cast<const float*>(go), ldg, goff, 4 * M, Co, dbias, 2 * H, 2 * W, Ho, Wo, part);
         else
-            colsum_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(static_cast<const bf16*>(go), ldg, goff, 4 * M, Co, dbias, 2 * H, 2 * W, Ho, Wo);
+            colsum_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(static_cast<const bf16*>(go), ldg, goff, 4 * M, Co, dbias, 2 * H, 2 * W, Ho, Wo, part);
         if (check_launch("colsum")) return 1;
+        if (part != nullptr) {
+            splitk_reduce(part, static_cast<int>(grid.x), Co, dbias, ST(stream));
+            if (check_launch("splitk_reduce")) return 1;
+        }
     }
     if (engine == ONET_ENGINE_TC) {
         if (dtype != ONET_BF16) return fail("tc engine is bf16 only");
@@ -1044,13 +1101,19 @@ int onet_convT2x2_wgrad(const void* x, int64_t ldx, int xoff, const void* go, in
     const long long per = (M + splits - 1) / splits;
     splits = static_cast<int>((M + per - 1) / per);
     dim3 grid(static_cast<unsigned>((nthreads + 255) / 256), splits);
+    float* part = (dtype == ONET_F32 && splits > 1) ? splitk_ws(static_cast<long long>(splits) * nthreads) : nullptr;
     if (dtype == ONET_F32)
         convT2x2_wgrad_simt_kernel<float><<<grid, 256, 0, ST(stream)>>>(static_cast<const float*>(x), ldx, xoff,
-                                                                        static_cast<const float*>(go), ldg, goff, N, H, W, Cin, Co, dw, per, Ho, Wo);
+                                                                        static_cast<const float*>(go), ldg, goff, N, H, W, Cin, Co, dw, per, Ho, Wo, part);
     else
         convT2x2_wgrad_simt_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), ldx, xoff,
-                                                                       static_cast<const bf16*>(go), ldg, goff, N, H, W, Cin, Co, dw, per, Ho, Wo);
-    return check_launch("convT2x2_wgrad_simt");
+                                                                       static_cast<const bf16*>(go), ldg, goff, N, H, W, Cin, Co, dw, per, Ho, Wo, part);
+    if (check_launch("convT2x2_wgrad_simt")) return 1;
+    if (part != nullptr) {
+        splitk_reduce(part, splits, nthreads, dw, ST(stream));
+        return check_launch("splitk_reduce");
+    }
+    return 0;
 }
 
 }  // extern "C"
@@ -1111,6 +1174,12 @@ int onet_head_bwd(const void* L, int64_t ldl, int offl, const void* Hf, int64_t 
 int onet_predict_label(const float* Vt, const float* Vd, int64_t n, int64_t* out, void* stream) {
     predict_label_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(Vt, Vd, n, reinterpret_cast<long long*>(out));
     return check_launch("predict_label");
+}
+
+int onet_predict_label_u8(const float* Vt, const float* Vd, int64_t n, unsigned char* out, void* stream) {
+    if (n <= 0) return 0;
+    predict_label_u8_kernel<<<grid_for((n + 15) / 16, 256, 148 * 8), 256, 0, ST(stream)>>>(Vt, Vd, n, out);
+    return check_launch("predict_label_u8");
 }
 
 int onet_eval_confusion(const float* Vt, const float* Vd, const int64_t* gt, int64_t n, int64_t* counts, void* stream) {

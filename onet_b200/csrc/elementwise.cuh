@@ -540,6 +540,9 @@ __global__ void __launch_bounds__(256)
 head_fwd_kernel(const HeadArgs<T> a) {
     const long long npx = static_cast<long long>(a.B) * a.HW;
     const int sub = threadIdx.x & 7;
+    // the 8 threads of a pixel leave the loop together, the four pixel groups of a warp need not (B*H*W % 4 != 0):
+    // shuffle inside the group's own lanes only
+    const uint32_t gmask = 0xFFu << (threadIdx.x & 24);
     float lsum = 0.f;
     for (long long p = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 3; p < npx;
          p += (static_cast<long long>(gridDim.x) * blockDim.x) >> 3) {
@@ -559,10 +562,10 @@ head_fwd_kernel(const HeadArgs<T> a) {
         }
 #pragma unroll
         for (int o = 4; o >= 1; o >>= 1) {
-            vt += __shfl_xor_sync(0xffffffffu, vt, o);
-            vd += __shfl_xor_sync(0xffffffffu, vd, o);
-            sa += __shfl_xor_sync(0xffffffffu, sa, o);
-            sb += __shfl_xor_sync(0xffffffffu, sb, o);
+            vt += __shfl_xor_sync(gmask, vt, o);
+            vd += __shfl_xor_sync(gmask, vd, o);
+            sa += __shfl_xor_sync(gmask, sa, o);
+            sb += __shfl_xor_sync(gmask, sb, o);
         }
         if (sub == 0) {
             const float mx = fmaxf(vt, vd);
@@ -802,6 +805,31 @@ __global__ void predict_label_kernel(const float* __restrict__ Vt, const float* 
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x)
         out[i] = Vd[i] > Vt[i] ? 1 : 0;
+}
+
+// The same decision as one byte per pixel, 16 pixels per thread: the mask the tiled inference path copies back to the host
+// (8x fewer bytes than the reference's int64 argmax; widened on the host only when the caller asks for int64).
+__global__ void __launch_bounds__(256)
+predict_label_u8_kernel(const float* __restrict__ Vt, const float* __restrict__ Vd, long long n, unsigned char* __restrict__ out) {
+    const long long n16 = n >> 4;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const long long t0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const bool vec = ((reinterpret_cast<uintptr_t>(Vt) | reinterpret_cast<uintptr_t>(Vd) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (vec) {
+        for (long long i = t0; i < n16; i += stride) {
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(Vt) + 4 * i + k);
+                const float4 b = __ldg(reinterpret_cast<const float4*>(Vd) + 4 * i + k);
+                w[k] = (b.x > a.x ? 1u : 0u) | (b.y > a.y ? 1u << 8 : 0u) | (b.z > a.z ? 1u << 16 : 0u) | (b.w > a.w ? 1u << 24 : 0u);
+            }
+            reinterpret_cast<uint4*>(out)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        for (long long i = (n16 << 4) + t0; i < n; i += stride) out[i] = Vd[i] > Vt[i] ? 1 : 0;
+    } else {
+        for (long long i = t0; i < n; i += stride) out[i] = Vd[i] > Vt[i] ? 1 : 0;
+    }
 }
 
 // Evaluation step next to the path (test_simclutter, Train_Onet_on_simclutter_20250407.py:109-147): predicted label

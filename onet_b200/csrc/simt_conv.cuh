@@ -418,7 +418,8 @@ conv_first_fwd_rows_kernel(const T* __restrict__ in, int N, int H, int W, const 
 
 template <typename T, int CIN, int CPT, int ROWS>
 __global__ void __launch_bounds__(256, 2)
-conv_first_wgrad_rows_kernel(const T* __restrict__ g, const T* __restrict__ in, int N, int H, int W, float* __restrict__ dw) {
+conv_first_wgrad_rows_kernel(const T* __restrict__ g, const T* __restrict__ in, int N, int H, int W, float* __restrict__ dw,
+                             float* __restrict__ partial) {
     constexpr int K = 9 * CIN;
     constexpr int NG = 64 / CPT;            // channel groups
     constexpr int LANES = 256 / NG;         // column groups per block
@@ -477,19 +478,28 @@ conv_first_wgrad_rows_kernel(const T* __restrict__ g, const T* __restrict__ in, 
                 for (int c = 0; c < CIN; ++c) { x[0][cidx][c] = x[1][cidx][c]; x[1][cidx][c] = x[2][cidx][c]; }
         }
     }
-    // lanes of the same channel group inside a warp sit NG threads apart; then one shared-memory pass per block
+    // lanes of the same channel group inside a warp sit NG threads apart; the 8 warps then add into shared memory one
+    // after the other (a FIXED order: the result does not depend on scheduling, unlike shared-memory atomics)
 #pragma unroll
     for (int i = 0; i < CPT; ++i)
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            float v = acc[i][k];
-            for (int off = NG; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-            if ((threadIdx.x & 31) < NG) atomicAdd(&s_acc[(cg * CPT + i) * K + k], v);
+        for (int k = 0; k < K; ++k)
+            for (int off = NG; off < 32; off <<= 1) acc[i][k] += __shfl_xor_sync(0xffffffffu, acc[i][k], off);
+    for (int wp = 0; wp < 8; ++wp) {
+        if ((threadIdx.x >> 5) == wp && (threadIdx.x & 31) < NG) {
+#pragma unroll
+            for (int i = 0; i < CPT; ++i)
+#pragma unroll
+                for (int k = 0; k < K; ++k) s_acc[(cg * CPT + i) * K + k] += acc[i][k];
         }
-    __syncthreads();
+        __syncthreads();
+    }
     for (int i = threadIdx.x; i < 64 * K; i += 256) {
         const int co = i / K, k = i % K, tap = k / CIN, ci = k % CIN;
-        atomicAdd(dw + (static_cast<long long>(co) * CIN + ci) * 9 + tap, s_acc[i]);
+        const long long idx = (static_cast<long long>(co) * CIN + ci) * 9 + tap;
+        // deterministic mode: per-block partials, summed in block order by splitk_reduce_kernel
+        if (partial != nullptr) partial[static_cast<long long>(blockIdx.x) * (64 * K) + idx] = s_acc[i];
+        else atomicAdd(dw + idx, s_acc[i]);
     }
 }
 
@@ -502,7 +512,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 conv3x3_wgrad_simt_kernel(const T* __restrict__ g, long long ldg, int co_off, const T* __restrict__ in, long long ldi,
                           int ci_off, int N, int H, int W, int Cin, int Cout, float* __restrict__ dw,
-                          long long px_per_split) {
+                          long long px_per_split, float* __restrict__ partial) {
     __shared__ float Gs[16][64 + 4];
     __shared__ float Is[16][64 + 4];
     const int tid = threadIdx.x;
@@ -564,8 +574,22 @@ conv3x3_wgrad_simt_kernel(const T* __restrict__ g, long long ldg, int co_off, co
             const int k = k0 + tx * 4 + j;
             if (k >= K) continue;
             const int tap = k / Cin, ci = k % Cin;
-            atomicAdd(dw + (static_cast<long long>(co) * Cin + ci) * 9 + tap, acc[i][j]);
+            const long long idx = (static_cast<long long>(co) * Cin + ci) * 9 + tap;
+            // deterministic mode: one slab of partials per pixel split, summed in split order by splitk_reduce_kernel
+            if (partial != nullptr) partial[static_cast<long long>(blockIdx.z) * Cout * K + idx] = acc[i][j];
+            else atomicAdd(dw + idx, acc[i][j]);
         }
+    }
+}
+
+// dst[i] += sum_{s = 0 .. splits-1} partial[s * numel + i], in split order (deterministic split-K of the FP32 verification mode)
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long numel, float* __restrict__ dst) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < numel;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float t = 0.f;
+        for (int sp = 0; sp < splits; ++sp) t += partial[sp * numel + i];
+        dst[i] += t;
     }
 }
 
@@ -624,7 +648,8 @@ __global__ void convT2x2_dgrad_simt_kernel(const T* __restrict__ go, long long l
 template <typename T>
 __global__ void convT2x2_wgrad_simt_kernel(const T* __restrict__ x, long long ldx, int xoff, const T* __restrict__ go,
                                            long long ldg, int goff, int N, int H, int W, int Cin, int Co,
-                                           float* __restrict__ dw, long long px_per_split, int Ho, int Wo) {
+                                           float* __restrict__ dw, long long px_per_split, int Ho, int Wo,
+                                           float* __restrict__ partial) {
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<long long>(Cin) * Co * 4) return;
     const int tap = static_cast<int>(idx & 3);
@@ -641,14 +666,15 @@ __global__ void convT2x2_wgrad_simt_kernel(const T* __restrict__ x, long long ld
             go[((static_cast<long long>(n) * Ho + 2 * hh + (tap >> 1)) * Wo + 2 * ww + (tap & 1)) * ldg + goff + co]);
         acc = fmaf(xv, gv, acc);
     }
-    atomicAdd(dw + idx, acc);
+    if (partial != nullptr) partial[static_cast<long long>(blockIdx.y) * Cin * Co * 4 + idx] = acc;
+    else atomicAdd(dw + idx, acc);
 }
 
 // column sums over the valid [N, Hv, Wv] window of a [N, Ho, Wo, ld] buffer: out[c] += sum v[n,h,w, off + c]
 // (bias gradient of the transposed conv; the F.pad border of the concat buffer is excluded)
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ v, long long ld, int off, long long rows, int C, float* __restrict__ out,
-                              int Hv, int Wv, int Ho, int Wo) {
+                              int Hv, int Wv, int Ho, int Wo, float* __restrict__ partial) {
     // blockDim.x = 256: thread -> channel c = tid % cpb, row lane = tid / cpb
     const int cpb = min(C, 64);
     const int lanes = 256 / cpb;
@@ -667,7 +693,8 @@ __global__ void colsum_kernel(const T* __restrict__ v, long long ld, int off, lo
     if (rl == 0 && c < C) {
         float t = 0.f;
         for (int l = 0; l < lanes; ++l) t += s[l * cpb + threadIdx.x % cpb];
-        atomicAdd(out + c, t);
+        if (partial != nullptr) partial[static_cast<long long>(blockIdx.x) * C + c] = t;
+        else atomicAdd(out + c, t);
     }
 }
 

@@ -19,7 +19,7 @@ def confusion_counts(Vt, Vd, gt):
     Vt, Vd = Vt.contiguous().float(), Vd.contiguous().float()
     assert Vt.numel() == Vd.numel() == gt.numel()
     counts = torch.zeros(4, dtype=torch.long, device=Vt.device)
-    call("onet_eval_confusion", ptr(Vt), ptr(Vd), ptr(gt), Vt.numel(), ptr(counts), torch.cuda.current_stream(Vt.device).cuda_stream)
+    call("onet_eval_confusion", ptr(Vt), ptr(Vd), ptr(gt), Vt.numel(), ptr(counts), torch.cuda.current_stream(Vt.device).cuda_stream, device=Vt.device)
     return counts
 
 
@@ -68,13 +68,18 @@ def normalize_per_frame(x):
     nb, nc, h, w = x.shape
     out = torch.empty_like(x)
     work = torch.empty(2 * nb * nc, dtype=torch.int32, device=x.device)
-    call("onet_normalize_per_frame", ptr(x), nb * nc, h * w, ptr(work), ptr(out), torch.cuda.current_stream(x.device).cuda_stream)
+    call("onet_normalize_per_frame", ptr(x), nb * nc, h * w, ptr(work), ptr(out), torch.cuda.current_stream(x.device).cuda_stream, device=x.device)
     return out
 
 
-def _batch_metrics(Vt, Vd, label):
-    m = segmentation_metrics(confusion_counts(Vt, Vd, label), reassign=True)
-    return m, (m["acc"], m["miou"], m["dr"], m["far"], m["t_iou"])
+def _rows_from_counts(counts):
+    """[(acc, miou, dr, far, t_iou)] per batch from the stacked [n_batches, 4] confusion counts: ONE device -> host copy
+    for the whole evaluation loop (the reference syncs ~12 times per batch, Train_Onet_on_simclutter_20250407.py:109-147)."""
+    rows = []
+    for c in torch.stack(counts).tolist():
+        m = segmentation_metrics(c, reassign=True)
+        rows.append((m["acc"], m["miou"], m["dr"], m["far"], m["t_iou"]))
+    return rows
 
 
 def _device_of(config, onet):
@@ -89,12 +94,13 @@ def test_simclutter(str_txt, config, onet, test_loader, verbose=0, measure_snr=F
     (acc, miou, dr, far, tiou).  Plotting / saving of a random batch (`verbose`) is not part of the path."""
     import numpy as np
     onet.eval()
-    rows = []
+    counts = []
     dev = _device_of(config, onet)
     with torch.no_grad():
         for X, label, _ in test_loader:
-            _, Vt, _, Vd, _ = onet(X.to(dev))
-            rows.append(_batch_metrics(Vt, Vd, label.to(dev))[1])
+            _, Vt, _, Vd, _ = onet(X.to(dev, non_blocking=True))
+            counts.append(confusion_counts(Vt, Vd, label.to(dev, non_blocking=True)))      # stays on the device
+    rows = _rows_from_counts(counts)
     return tuple(float(v) for v in np.array(rows, dtype=np.float64).mean(axis=0))
 
 
@@ -107,17 +113,21 @@ def test_2nd_stage_simclutter(str_txt, config, onet, onet2nd, test_loader, verbo
     import numpy as np
     onet.eval()
     onet2nd.eval()
-    rows1, rows2 = [], []
+    counts1, counts2 = [], []
     dev = _device_of(config, onet)
     with torch.no_grad():
         for X1, label, _ in test_loader:
-            label = label.to(dev)
-            _, Vt1, _, Vd1, _ = onet(X1.to(dev))
-            m1, row1 = _batch_metrics(Vt1, Vd1, label)
-            rows1.append(row1)
-            X2 = normalize_per_frame(Vt1 if m1["flipped"] else Vd1)
+            label = label.to(dev, non_blocking=True)
+            _, Vt1, _, Vd1, _ = onet(X1.to(dev, non_blocking=True))
+            c1 = confusion_counts(Vt1, Vd1, label)
+            counts1.append(c1)
+            # re_assign_label flips the prediction when that raises the pixel accuracy (:410-453); the flip decides which
+            # response map is the foreground one - taken on the device, no host round trip inside the loop
+            flipped = (c1[0] + c1[3]) < (c1[2] + c1[1])
+            X2 = normalize_per_frame(torch.where(flipped, Vt1, Vd1))
             _, Vt2, _, Vd2, _ = onet2nd(X2)
-            rows2.append(_batch_metrics(Vt2, Vd2, label)[1])
+            counts2.append(confusion_counts(Vt2, Vd2, label))
+    rows1, rows2 = _rows_from_counts(counts1), _rows_from_counts(counts2)
     s1 = tuple(float(v) for v in np.array(rows1, dtype=np.float64).mean(axis=0))
     s2 = tuple(float(v) for v in np.array(rows2, dtype=np.float64).mean(axis=0))
     if return_all:

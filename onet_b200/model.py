@@ -47,6 +47,19 @@ _SIDE_STREAMS = {}
 _BNRED_MIN_C = int(os.environ.get("ONET_BNRED_MIN_C", "256"))
 
 
+# FP32 verification mode: split-K partial sums of the CUDA-core weight-gradient kernels go through this per-device workspace
+# and are added in a fixed order (onet_set_splitk_workspace), so that two runs give bit-identical gradients.
+_SPLITK_WS = {}
+_SPLITK_FLOATS = 16 << 20
+
+
+def _register_splitk_workspace(dev):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _SPLITK_WS:
+        _SPLITK_WS[key] = torch.empty(_SPLITK_FLOATS, dtype=torch.float32, device=dev)
+        call("onet_set_splitk_workspace", ptr(_SPLITK_WS[key]), _SPLITK_FLOATS, device=dev)
+
+
 def _side_stream(dev):
     key = dev.index if dev.index is not None else torch.cuda.current_device()
     if key not in _SIDE_STREAMS:
@@ -156,7 +169,8 @@ class UNet(nn.Module):
 
     def forward(self, x):
         eng = _Engine.for_unets([self], x, mode=getattr(self, "_mode", "bf16"), use_tc=getattr(self, "_use_tc", True))
-        rec = eng.forward_unet(x_is_twin=False, save=False, training_stats=self.training)
+        with torch.cuda.device(x.device):
+            rec = eng.forward_unet(x_is_twin=False, save=False, training_stats=self.training)
         B, H, W = x.shape[0], x.shape[2], x.shape[3]
         return _nchw_view(rec.cat0, B, H, W, 0, 64), _nchw_view(rec.Hf, B, H, W, 0, 64)
 
@@ -374,6 +388,11 @@ class _Engine:
             aff = torch.empty(4, G, cout, dtype=torch.float32, device=self.dev)
             call("onet_bn_eval_prepare", G, cout, ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var),
                  ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var), ptr(aff[2]), ptr(aff[3]), st)
+            if rec.save:
+                # differentiable eval-mode forward (frozen-BatchNorm fine-tuning, input saliency): the backward kernels read the
+                # running statistics where they read the batch statistics in training mode (a handful of C-element host-side ops)
+                aff[0] = bn.running_mean
+                aff[1] = torch.rsqrt(bn.running_var + 1e-5)
             if fused_eval:
                 # inference: BatchNorm(eval) + ReLU folded into the conv epilogue, written straight to its destination
                 call("onet_conv3x3_bn_relu_infer", ptr(src, self._img_off(src, n0) + off_src), ld_src, 0, n, h, w, cin, ptr(wf),
@@ -426,6 +445,8 @@ class _Engine:
         gradient must be ACCUMULATED into."""
         B, H, W, N2 = rec.B, rec.H, rec.W, rec.N2
         st = self.stream
+        if self.mode == "fp32":
+            _register_splitk_workspace(self.dev)
         # per-call event timing (bench.py's profile pass) records on the main stream only: keep that pass serial
         overlap = os.environ.get("ONET_NO_WGRAD_OVERLAP") is None and _lib.PROFILE is None
         self._side = _side_stream(self.dev) if overlap else None
@@ -539,7 +560,8 @@ class _Engine:
             sums = rec.sum_pool[rec.sum_off:rec.sum_off + 2 * G * cout]
             rec.sum_off += 2 * G * cout
         dY = self._empty(n, h, w, cout)
-        count = float(seg.group_images * h * w)
+        # eval-mode statistics are constants: the mean / projection terms of the BatchNorm backward vanish (1 / count = 0)
+        count = float(seg.group_images * h * w) if rec.training_stats else float("inf")
         self._flush_side()          # the previous layers' weight gradients run next to this BatchNorm backward
         if sv.get("prered") is not None:
             # the dgrad launch that produced g1 already reduced this layer's sums in its epilogue: apply pass only
@@ -724,7 +746,9 @@ class Onet(nn.Module):
 
     def forward(self, X):
         assert X.dim() == 4
-        if torch.is_grad_enabled() and self.training:
+        if torch.is_grad_enabled() and (self.training or any(p.requires_grad for p in self.parameters())):
+            # eval mode with autograd on (the reference's outputs are differentiable there too): BatchNorm uses and keeps its
+            # running statistics, the backward treats them as constants
             leaf = torch.zeros((), dtype=torch.float32, device=X.device, requires_grad=True)
             Lt, Vt, Ld, Vd, S, anchor = _OnetFn.apply(self, X, leaf)
             self._last = dict(Lt=Lt, Ld=Ld, S=S, anchor=anchor, rec=self._fwd_rec)
@@ -795,7 +819,7 @@ class Onet(nn.Module):
                 rec = l["rec"]
                 Y = torch.empty(rec.B, rec.H, rec.W, dtype=torch.long, device=S.device)
                 call("onet_predict_label", ptr(rec.Vt), ptr(rec.Vd), Y.numel(), ptr(Y),
-                     torch.cuda.current_stream(S.device).cuda_stream)
+                     torch.cuda.current_stream(S.device).cuda_stream, device=S.device)
                 return Y
             return torch.argmax(S, dim=1)
 

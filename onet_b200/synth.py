@@ -40,7 +40,7 @@ def rayleigh_background(n, h, w, seed=1981, sigma=1.0, device="cuda", stream_id=
     """[n,h,w] fp32 Rayleigh(sigma) amplitudes (reference :221, rayleigh.rvs(loc=0, scale=1))."""
     dev = _need_cuda(device)
     out = torch.empty(n, h, w, dtype=torch.float32, device=dev)
-    call("onet_synth_rayleigh", ptr(out), out.numel(), float(sigma), int(seed), int(stream_id), _stream(dev))
+    call("onet_synth_rayleigh", ptr(out), out.numel(), float(sigma), int(seed), int(stream_id), _stream(dev), device=dev)
     return out
 
 
@@ -49,7 +49,7 @@ def k_background(n, h, w, seed=1981, nu=5, device="cuda", stream_id=0):
     Rayleigh speckle x sqrt(Gamma(nu, 1/nu)) texture, spatially uncorrelated (see csrc/synth.cuh)."""
     dev = _need_cuda(device)
     out = torch.empty(n, h, w, dtype=torch.float32, device=dev)
-    call("onet_synth_kclutter", ptr(out), out.numel(), int(nu), int(seed), int(stream_id), _stream(dev))
+    call("onet_synth_kclutter", ptr(out), out.numel(), int(nu), int(seed), int(stream_id), _stream(dev), device=dev)
     return out
 
 
@@ -75,7 +75,7 @@ def normal_white(n, h, w, seed=1981, device="cuda", stream_id=0):
     """[n,h,w] float64 standard normal white noise (Philox + Box-Muller on the device)."""
     dev = _need_cuda(device)
     out = torch.empty(n, h, w, dtype=torch.float64, device=dev)
-    call("onet_synth_normal", ptr(out), out.numel(), int(seed), int(stream_id), _stream(dev))
+    call("onet_synth_normal", ptr(out), out.numel(), int(seed), int(stream_id), _stream(dev), device=dev)
     return out
 
 
@@ -85,7 +85,7 @@ def mnlt(x, v):
         raise RuntimeError("onet_b200.synth has no CPU path")
     x = x.contiguous().double()
     y = torch.empty_like(x)
-    call("onet_kfield_mnlt", ptr(x), x.numel(), int(v), ptr(y), _stream(x.device))
+    call("onet_kfield_mnlt", ptr(x), x.numel(), int(v), ptr(y), _stream(x.device), device=x.device)
     return y
 
 
@@ -108,17 +108,17 @@ def k_correlated_background(n, size, v=5, seed=1981, device="cuda", white=None, 
     per = size * size
     g = mnlt(w1, v)
     sums = torch.zeros(n, 3, dtype=torch.float64, device=dev)
-    call("onet_kfield_coeff_sums", ptr(w1), ptr(g), n, per, ptr(sums), st)
+    call("onet_kfield_coeff_sums", ptr(w1), ptr(g), n, per, ptr(sums), st, device=dev)
     # alpha_n = S_n^2 / (pi n! 2^n), normalised by alpha_0 (:131-137, :488): [a, b] = [alpha_2, alpha_1] / alpha_0
     alpha = sums ** 2 / (np.pi * torch.tensor([1.0, 2.0, 8.0], dtype=torch.float64, device=dev))
     coeffs = torch.stack([alpha[:, 2] / alpha[:, 0], alpha[:, 1] / alpha[:, 0]], dim=1).contiguous()
     roots = torch.empty(n, size, size, dtype=torch.complex128, device=dev)
-    call("onet_kfield_acf_root", ptr(coeffs), ptr(acf), n, per, ptr(roots), st)
+    call("onet_kfield_acf_root", ptr(coeffs), ptr(acf), n, per, ptr(roots), st, device=dev)
     gcn = torch.fft.ifft2(torch.fft.fft2(w1) * torch.sqrt(torch.fft.fft2(roots))).real.contiguous()     # :495-497
     texture = mnlt(gcn, v)
     speckle = torch.fft.ifft2(torch.fft.fft2(w2) * spec).contiguous()                                    # :287-296
     amp = torch.empty(n, size, size, dtype=torch.float32, device=dev)
-    call("onet_kfield_amplitude", ptr(speckle), ptr(texture), n * per, ptr(amp), st)
+    call("onet_kfield_amplitude", ptr(speckle), ptr(texture), n * per, ptr(amp), st, device=dev)
     return (amp, texture) if return_texture else amp
 
 
@@ -167,7 +167,7 @@ def add_gaussian_targets(frames, cx, cy, w, h, theta, snr):
     dtab = torch.from_numpy(tab.view(np.uint8).reshape(n, T * _TARGET_DTYPE.itemsize).copy()).to(frames.device)
     masks = torch.zeros(n, H, W, dtype=torch.uint8, device=frames.device)
     erc = torch.empty(n, dtype=torch.float32, device=frames.device)
-    call("onet_synth_add_targets", ptr(frames), ptr(masks), n, H, W, ptr(dtab), T, float(snr), ptr(erc), _stream(frames.device))
+    call("onet_synth_add_targets", ptr(frames), ptr(masks), n, H, W, ptr(dtab), T, float(snr), ptr(erc), _stream(frames.device), device=frames.device)
     return frames, masks.bool(), erc
 
 

@@ -128,10 +128,10 @@ class OnetTrainer:
         st = torch.cuda.current_stream(X.device).cuda_stream
         if adam_on_device:
             call("onet_adam_step_dev", ptr(self.flat), ptr(self.grads), ptr(self.m), ptr(self.v), self.flat.numel(),
-                 ptr(self._hyper), ptr(self._step_dev), 1.0 / self.world, st)
+                 ptr(self._hyper), ptr(self._step_dev), 1.0 / self.world, st, device=self.flat.device)
         else:
             call("onet_adam_step", ptr(self.flat), ptr(self.grads), ptr(self.m), ptr(self.v), self.flat.numel(), float(self.lr),
-                 float(self.betas[0]), float(self.betas[1]), float(self.eps), self.step_count + 1, 1.0 / self.world, st)
+                 float(self.betas[0]), float(self.betas[1]), float(self.eps), self.step_count + 1, 1.0 / self.world, st, device=self.flat.device)
         invalidate_packed_weights()
         return loss.detach()
 
@@ -169,6 +169,9 @@ class OnetTrainer:
                 self._capture(X)
             self._static_x.copy_(X, non_blocking=True)
             self._graph.replay()
+            # the replayed Adam kernel changed the weights through raw pointers: the packed operand copies the replay made
+            # BEFORE its update are stale for any eval / eager forward that follows (the next replay repacks by itself)
+            invalidate_packed_weights()
             self.step_count += 1
             return self._static_loss
         if X.device != dev:

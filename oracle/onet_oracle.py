@@ -38,6 +38,84 @@ ENCODER = [("down1", 64, 128), ("down2", 128, 256), ("down3", 256, 512), ("down4
 DECODER = [("up1", 1024, 512), ("up2", 512, 256), ("up3", 256, 128), ("up4", 128, 64)]
 
 
+# ----------------------------------------------------------------------------------------
+# reduced-precision emulation (checker for the bf16 / tf32 CUDA modes)
+# ----------------------------------------------------------------------------------------
+# The CUDA path's reduced-precision modes round at known points.  `emulate="bf16"` / `"tf32"` restates the SAME algorithm
+# with a rounding at exactly those points, in plain PyTorch on the CPU, so that the CUDA kernels can be held to it tightly
+# (what is left is fp32 accumulation order); against the FP32 reference the same modes are only held to the north_star
+# tolerances.  bf16 mode (onet_b200/csrc: conv epilogues, bn_relu_value, head_bwd_kernel, bn_bwd_*_kernel):
+#   forward : twin input, packed weights, every raw conv output Y, every post-ReLU activation and every up-conv output are
+#             stored as bf16; BatchNorm statistics are taken from the stored (rounded) Y; accumulation is fp32.
+#   backward: dL / dH from the head, every dY (BatchNorm backward) and every data gradient dX (conv / up-conv dgrad) are
+#             stored as bf16; weight / bias / BatchNorm parameter gradients stay fp32.
+# tf32 mode: storage is fp32 everywhere; only the tensor-core operands (activations, weights, output gradients of the 3x3
+#             and transposed convolutions except the first 1->64 / 3->64 layer, which runs on CUDA cores) lose their low 13
+#             mantissa bits (tcgen05.mma kind::tf32 reads the upper 19 bits of each fp32 operand: truncation).
+def _round_bf16(t):
+    return t.bfloat16().float()
+
+
+def _trunc_tf32(t):
+    return (t.contiguous().view(torch.int32) & -8192).view(torch.float32)
+
+
+class _Ste(torch.autograd.Function):
+    """y = f_fwd(x) in forward, g -> f_bwd(g) in backward (f = None: identity)."""
+
+    @staticmethod
+    def forward(ctx, x, f_fwd, f_bwd):
+        ctx.f_bwd = f_bwd
+        return x if f_fwd is None else f_fwd(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g if ctx.f_bwd is None else ctx.f_bwd(g)), None, None
+
+
+class _Policy:
+    """Where a mode rounds.  weight: a conv / up-conv weight operand; conv_in: the activation operand of a convolution
+    (its gradient is that convolution's data gradient); conv_out: a raw convolution output (its gradient is the dY the
+    convolution's backward kernels read); store: a stored activation; head_in: L / H as the head reads them."""
+
+    def __init__(self, mode):
+        assert mode in ("bf16", "tf32")
+        self.mode = mode
+
+    def image(self, t):
+        return _round_bf16(t) if self.mode == "bf16" else t
+
+    def weight(self, t, first=False):
+        if self.mode == "bf16":
+            return _Ste.apply(t, _round_bf16, None)
+        return t if first else _Ste.apply(t, _trunc_tf32, None)
+
+    def conv_in(self, t, first=False):
+        if self.mode == "bf16":
+            return _Ste.apply(t, None, _round_bf16)              # data gradient stored as bf16
+        return t if first else _Ste.apply(t, _trunc_tf32, None)   # operand truncation; data gradient stays fp32
+
+    def conv_out(self, t, first=False):
+        if self.mode == "bf16":
+            return _Ste.apply(t, _round_bf16, _round_bf16)       # Y stored as bf16, dY stored as bf16
+        return t if first else _Ste.apply(t, None, _trunc_tf32)   # dY is a tensor-core operand of dgrad and wgrad
+
+    def upconv_out(self, t):
+        if self.mode == "bf16":
+            return _Ste.apply(t, _round_bf16, None)              # bf16(acc + bias); its gradient is a slice of d(concat)
+        return _Ste.apply(t, None, _trunc_tf32)
+
+    def store(self, t):
+        return _Ste.apply(t, _round_bf16, None) if self.mode == "bf16" else t
+
+    def head_in(self, t):
+        return _Ste.apply(t, None, _round_bf16) if self.mode == "bf16" else t
+
+
+def _policy(emulate):
+    return None if emulate in (None, "fp32") else _Policy(emulate)
+
+
 def _dc_prefix(block):
     if block == "inc":
         return "inc.double_conv"
@@ -140,58 +218,98 @@ def _bn(st, prefix, x, training, taps=None):
     return y
 
 
-def double_conv(st, block, x, training, taps=None):
+def _bn_relu_emulated(st, prefix, y, training, q):
+    """BatchNorm + ReLU as the CUDA path evaluates it (bn_finalize_kernel + bn_relu_value, elementwise.cuh): statistics in
+    double from the stored Y, scale = gamma * invstd and shift = beta - mean * scale in fp32, act = relu(y * scale + shift),
+    stored in the mode's storage type.  Same function of y as `_bn` + relu up to fp32 rounding."""
+    w, b = st[f"{prefix}.weight"], st[f"{prefix}.bias"]
+    if training:
+        n = y.numel() // y.shape[1]
+        yd = y.double()
+        mean = yd.mean(dim=(0, 2, 3))
+        var = yd.var(dim=(0, 2, 3), unbiased=False)
+        with torch.no_grad():
+            rm, rv = st[f"{prefix}.running_mean"], st[f"{prefix}.running_var"]
+            rm.mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * mean.detach().float())
+            rv.mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * (var.detach() * (n / max(n - 1, 1))).float())
+            st[f"{prefix}.num_batches_tracked"] += 1
+        invstd = torch.rsqrt(var + BN_EPS).float()
+        mean = mean.float()
+    else:
+        mean = st[f"{prefix}.running_mean"]
+        invstd = torch.rsqrt(st[f"{prefix}.running_var"] + BN_EPS)
+    sc = w * invstd
+    sh = b - mean * sc
+    return q.store(torch.relu(y * sc[None, :, None, None] + sh[None, :, None, None]))
+
+
+def double_conv(st, block, x, training, taps=None, q=None):
     """Onet_vanilla_20240606.py:39-58: (conv3x3 pad 1 no bias -> BN -> ReLU) x 2."""
     p = _dc_prefix(block)
     for conv_i, bn_i in ((0, 1), (3, 4)):
-        x = F.conv2d(x, st[f"{p}.{conv_i}.weight"], None, padding=1)
+        if q is None:
+            x = F.conv2d(x, st[f"{p}.{conv_i}.weight"], None, padding=1)
+        else:
+            first = block == "inc" and conv_i == 0       # the 1 -> 64 / 3 -> 64 layer runs on CUDA cores in every mode
+            x = q.conv_out(F.conv2d(q.conv_in(x, first), q.weight(st[f"{p}.{conv_i}.weight"], first), None, padding=1), first)
         if taps is not None:
             taps[f"{p}.{conv_i}.raw"] = x
-        x = torch.relu(_bn(st, f"{p}.{bn_i}", x, training))
+        x = torch.relu(_bn(st, f"{p}.{bn_i}", x, training)) if q is None else _bn_relu_emulated(st, f"{p}.{bn_i}", x, training, q)
         if taps is not None:
             taps[f"{p}.{bn_i}.act"] = x
     return x
 
 
-def up_block(st, name, x1, x2, training, taps=None):
+def up_block(st, name, x1, x2, training, taps=None, q=None):
     """Onet_vanilla_20240606.py:75-101 (bilinear=False): ConvTranspose2d(C, C/2, 2, 2) with bias,
     zero-pad to the skip's size, cat([skip, up]) and DoubleConv."""
-    x1 = F.conv_transpose2d(x1, st[f"{name}.up.weight"], st[f"{name}.up.bias"], stride=2)
+    if q is None:
+        x1 = F.conv_transpose2d(x1, st[f"{name}.up.weight"], st[f"{name}.up.bias"], stride=2)
+    else:
+        x1 = q.upconv_out(F.conv_transpose2d(q.conv_in(x1), q.weight(st[f"{name}.up.weight"]), st[f"{name}.up.bias"], stride=2))
     dy = x2.shape[2] - x1.shape[2]
     dx = x2.shape[3] - x1.shape[3]
     x1 = F.pad(x1, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
     x = torch.cat([x2, x1], dim=1)
     if taps is not None:
         taps[f"{name}.cat"] = x
-    return double_conv(st, name, x, training, taps)
+    return double_conv(st, name, x, training, taps, q)
 
 
-def unet_forward(st, x, training=True, taps=None):
+def unet_forward(st, x, training=True, taps=None, q=None):
     """Onet_vanilla_20240606.py:142-153: returns (x1, y1) = (first-block output, last-block output)."""
-    x1 = double_conv(st, "inc", x, training, taps)
+    x1 = double_conv(st, "inc", x, training, taps, q)
     skips = [x1]
     h = x1
     for name, _, _ in ENCODER:
         h = F.max_pool2d(h, 2)
-        h = double_conv(st, name, h, training, taps)
+        h = double_conv(st, name, h, training, taps, q)
         skips.append(h)
     y = skips[-1]
     for i, (name, _, _) in enumerate(DECODER):
-        y = up_block(st, name, y, skips[3 - i], training, taps)
+        y = up_block(st, name, y, skips[3 - i], training, taps, q)
     return x1, y
 
 
-def onet_forward(st_top, x, training=True, st_dwn=None, bias=0.0, taps=None):
+def onet_forward(st_top, x, training=True, st_dwn=None, bias=0.0, taps=None, emulate=None):
     """Onet.forward, Onet_vanilla_20240606.py:174-191.  `st_dwn=None` is the weight-shared twin
     (`bshare=True`, :163-164): the SAME state (parameters and BN running buffers) is used for
-    both branches, top branch first."""
+    both branches, top branch first.  `emulate` = "bf16" / "tf32": the same algorithm with the CUDA path's
+    reduced-precision roundings (see `_Policy`); None = the reference's FP32 arithmetic."""
     st_dwn = st_top if st_dwn is None else st_dwn
+    q = _policy(emulate)
     tt = {} if taps is not None else None
     td = {} if taps is not None else None
-    Lt, Ht = unet_forward(st_top, x, training, tt)
-    Vt = (Lt * Ht).sum(dim=1, keepdim=True)
     Xd = torch.clip(1 - x + bias, 0, 1)
-    Ld, Hd = unet_forward(st_dwn, Xd, training, td)
+    if q is not None:
+        x, Xd = q.image(x), q.image(Xd)
+    Lt, Ht = unet_forward(st_top, x, training, tt, q)
+    if q is not None:        # the head's gradient w.r.t. L (both uses: V and the loss's channel sum) and H is stored rounded
+        Lt, Ht = q.head_in(Lt), q.head_in(Ht)
+    Vt = (Lt * Ht).sum(dim=1, keepdim=True)
+    Ld, Hd = unet_forward(st_dwn, Xd, training, td, q)
+    if q is not None:
+        Ld, Hd = q.head_in(Ld), q.head_in(Hd)
     Vd = (Ld * Hd).sum(dim=1, keepdim=True)
     S = torch.softmax(torch.cat([Vt, Vd], dim=1), dim=1)
     if taps is not None:
@@ -234,7 +352,7 @@ def predict_label(S):
     return torch.argmax(S, dim=1)
 
 
-def train_step_outputs(st, x, st_dwn=None):
+def train_step_outputs(st, x, st_dwn=None, emulate=None):
     """One reference training-step's forward + loss + backward (Train_Onet_on_simclutter_20250407.py:
     209-217) on a copy of `st` with autograd; returns (outputs dict, grads dict, new state)."""
     st = OrderedDict((k, v.clone()) for k, v in st.items())
@@ -246,7 +364,7 @@ def train_step_outputs(st, x, st_dwn=None):
         sd = OrderedDict((k, v.clone()) for k, v in st_dwn.items())
         for k in leaves:
             sd[k].requires_grad_(True)
-    Lt, Vt, Ld, Vd, S = onet_forward(st, x, True, sd)
+    Lt, Vt, Ld, Vd, S = onet_forward(st, x, True, sd, emulate=emulate)
     loss = compute_loss(Lt, S[:, 0:1], Ld, S[:, 1:2])
     loss.backward()
     grads = OrderedDict((k, st[k].grad.detach().clone()) for k in leaves)

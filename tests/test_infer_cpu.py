@@ -57,6 +57,8 @@ def test_tiled_equals_whole_frame_single_rank():
     # shows up as O(0.1))
     assert torch.allclose(Vt, vt, atol=2e-5, rtol=0) and torch.allclose(Vd, vd, atol=2e-5, rtol=0)
     assert float((lab != (vd > vt).squeeze(1).long()).float().mean()) < 1e-3
+    lab8 = TiledPredictor(fwd, tile=64, halo=96, max_batch=3).predict_labels(x)
+    assert lab8.dtype == torch.uint8 and torch.equal(lab8.long(), lab)
 
 
 def _worker(rank, world, port, q):
@@ -71,6 +73,14 @@ def _worker(rank, world, port, q):
         Vt, Vd, lab = TiledPredictor(fwd, tile=64, halo=96, max_batch=2).predict(x, rank=rank, world=world)
         assert torch.allclose(Vt, vt, atol=2e-5, rtol=0) and torch.allclose(Vd, vd, atol=2e-5, rtol=0)
         assert float((lab != (vd > vt).squeeze(1).long()).float().mean()) < 1e-3
+        # throughput entry point: uint8 masks, each rank only its own tiles; gather=True sums the one-byte masks
+        pred = TiledPredictor(fwd, tile=64, halo=96, max_batch=2)
+        mine = pred.predict_labels(x, rank=rank, world=world)
+        full = pred.predict_labels(x, rank=rank, world=world, gather=True)
+        assert mine.dtype == torch.uint8 and full.dtype == torch.uint8
+        assert float((full.long() != lab).float().mean()) < 1e-3
+        assert int(mine.sum()) < int(full.sum()) or int(full.sum()) == 0
+        assert bool(((mine == full) | (mine == 0)).all())
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, "ok"))

@@ -40,6 +40,11 @@ def _build(case_meta, mode, use_tc=True):
     return net.cuda(), st, st_d
 
 
+def _record(key, **values):
+    from parity_record import record
+    record(key, **values)
+
+
 def _rel(a, b):
     a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
@@ -67,33 +72,23 @@ def test_fp32_mode_matches_reference_golden(case, golden_dir):
     for name, t in (("Vt", Vt), ("Vd", Vd), ("S", S)):
         assert _rel(t, g[name]) < 2e-5, (name, _rel(t, g[name]))
     assert abs(float(Lt.float().double().norm()) - float(g["Lt.norm"])) <= 2e-5 * float(g["Lt.norm"])
-    # Gradients.  At random init the gradient of these tiny cases is ill-conditioned (module docstring): a 1e-7 change of a
-    # BatchNorm statistic switches ReLU / max-pool decisions and moves whole tensors by 1e-3 .. 2.5e-2.  The FP32 forward is
-    # therefore reproducible by construction (fixed-order statistics in conv3x3_simt_kernel; it once used shared-memory float
-    # atomics and this test saw 2-3 discrete outcomes per case, one of them above 2e-2).  What remains order-dependent are the
-    # fp32 atomics of the split-K weight-gradient kernels (~1e-9 of the gradient norm); the step is still repeated up to three
-    # times so that order noise can never be mistaken for a systematic error.
-    best = {}
-    for rep in range(3):
-        if rep:
-            _step(net, x)
-        errs = {}
-        for k, p in net.named_parameters():
-            gk = "grad." + k
-            if gk + ".full" in g:
-                errs[k] = _rel(p.grad, g[gk + ".full"])
-            else:
-                errs[k] = _rel(p.grad.reshape(-1)[::SAMPLE_STRIDE], g[gk + ".sample"])
-            best[k] = min(best.get(k, 1e9), errs[k])
-        assert np.median(list(errs.values())) < 5e-3, np.median(list(errs.values()))
-        if rep == 0:
-            first_state = {k: v.clone() for k, v in net.state_dict().items() if "running" in k or "num_batches" in k}
-        if max(best.values()) < 2e-2:
-            break
-    worst = max(best, key=best.get)
-    print(f"{case}: worst gradient rel-L2 {best[worst]:.2e} ({worst}), runs {rep + 1}")
-    assert best[worst] < 2e-2, (worst, best[worst])
-    net.load_state_dict({**net.state_dict(), **first_state})       # BatchNorm buffers as after ONE training step (golden)
+    # Gradients: ONE run.  The FP32 verification mode is reproducible by construction - fixed-order BatchNorm statistics in
+    # the forward kernels and fixed-order split-K sums in the weight-gradient kernels (onet_set_splitk_workspace) - so there is
+    # no order noise to average away (tests/test_parity_gpu.py::test_fp32_mode_is_reproducible checks bit-identity).
+    errs = {}
+    for k, p in net.named_parameters():
+        gk = "grad." + k
+        if gk + ".full" in g:
+            errs[k] = _rel(p.grad, g[gk + ".full"])
+        else:
+            errs[k] = _rel(p.grad.reshape(-1)[::SAMPLE_STRIDE], g[gk + ".sample"])
+    worst = max(errs, key=errs.get)
+    print(f"{case}: gradient rel-L2 median {np.median(list(errs.values())):.2e} worst {errs[worst]:.2e} ({worst})")
+    _record(f"fp32_vs_reference_golden[{case}]", loss_rel=abs(loss.item() - float(g["loss"])) / abs(float(g["loss"])),
+            grad_median=float(np.median(list(errs.values()))), grad_worst=errs[worst], grad_worst_tensor=worst)
+    assert np.median(list(errs.values())) < 5e-3, np.median(list(errs.values()))
+    assert errs[worst] < 2e-2, (worst, errs[worst])
+    # BatchNorm buffers after ONE training step
     for k, v in net.state_dict().items():
         if "running" in k:
             assert np.allclose(v.cpu().numpy(), g["buf." + k], rtol=1e-4, atol=1e-6), k
@@ -179,20 +174,8 @@ def test_generic_autograd_path_matches_fused():
     St, Sd = S[:, 0:1].clone(), S[:, 1:2].clone()      # clones defeat the fused fast path
     loss = net2.compute_loss(Lt, St, Ld, Sd)
     loss.backward()
-    # two fp32 runs differ by the order of the split-K atomics (ill-conditioned 32x32 case, see the golden test above):
-    # repeat the second run up to three times and keep the best agreement per tensor
-    best = {}
-    for rep in range(3):
-        if rep:
-            net2.zero_grad()
-            Lt, Vt, Ld, Vd, S = net2(x)
-            loss = net2.compute_loss(Lt, S[:, 0:1].clone(), Ld, S[:, 1:2].clone())
-            loss.backward()
-        for k, p in net2.named_parameters():
-            best[k] = min(best.get(k, 1e9), _rel(p.grad, fused[k]))
-        if max(best.values()) < 3e-2:
-            break
-    for k, e in best.items():
+    for k, p in net2.named_parameters():
+        e = _rel(p.grad, fused[k])
         assert e < 3e-2, (k, e)
 
 

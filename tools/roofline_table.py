@@ -15,9 +15,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def work(name, a):
-    """(description, flops, bytes) of one call from its integer arguments (pointers are not in the dump)."""
-    e = 2.0                                             # bytes per bf16 activation element
+def work(name, a, e=2.0):
+    """(description, flops, bytes) of one call from its integer arguments (pointers are not in the dump); e = bytes per
+    activation element (2 = bf16 mode, 4 = fp32 / tf32 modes)."""
     if name == "onet_conv3x3_fwd":
         ldi, _, n, h, w, ci, co = a[:7]
         return f"conv3x3 {ci}->{co} @{h}x{w}", 2.0 * 9 * n * h * w * ci * co, n * h * w * (ci + co) * e + 9 * ci * co * e
