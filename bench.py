@@ -31,7 +31,7 @@ UNIT = "images/s"
 H = W = 256
 CIN = 1
 LR = 5e-6          # Train_Onet_on_simclutter_20250407.py:181
-EXTRA_MODES = [("fp32", 16)]      # (mode, frames per GPU) of the `modes` sub-record
+EXTRA_MODES = [("tf32", 64), ("fp32", 16)]      # (mode, frames per GPU) of the `modes` sub-record
 
 
 def _peaks():

@@ -71,53 +71,56 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 5-D bf16 view (c, w, q, h, n) with 128-byte swizzle; strides in ELEMENTS for dims 1..4
+// 5-D view (c, w, q, h, n) with 128-byte swizzle; strides in ELEMENTS for dims 1..4; elem_bytes = 2 (bf16) or 4 (fp32, which
+// the tf32 kernels read as they are: the tensor core ignores the low 13 mantissa bits of each operand word)
 static int make_map5(CUtensorMap* m, const void* base, const uint64_t dims[5], const uint64_t strides_el[4],
-                     const uint32_t box[5]) {
+                     const uint32_t box[5], int elem_bytes) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
     cuuint64_t gd[5], gs[4];
     cuuint32_t bx[5], es[5];
     for (int i = 0; i < 5; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
-    for (int i = 0; i < 4; ++i) gs[i] = strides_el[i] * 2;
+    for (int i = 0; i < 4; ++i) gs[i] = strides_el[i] * elem_bytes;
     if (reinterpret_cast<uintptr_t>(base) % 16) return fail("tensor map base not 16-byte aligned");
     for (int i = 0; i < 4; ++i)
         if (gs[i] % 16) return fail("tensor map stride %d (%llu B) not a multiple of 16", i, (unsigned long long)gs[i]);
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gd, gs, bx, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5,
+                     const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(5d) failed with %d", static_cast<int>(r));
     return 0;
 }
 static int make_map2(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
-                     uint32_t box_outer) {
+                     uint32_t box_outer, int elem_bytes) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t gd[2] = {inner, outer}, gs[1] = {inner * 2};
+    cuuint64_t gd[2] = {inner, outer}, gs[1] = {inner * elem_bytes};
     cuuint32_t bx[2] = {box_inner, box_outer}, es[2] = {1, 1};
     if (reinterpret_cast<uintptr_t>(base) % 16 || gs[0] % 16) return fail("weight tensor map misaligned");
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gd, gs, bx, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                     const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(2d) failed with %d", static_cast<int>(r));
     return 0;
 }
 // plain NHWC activation view: (C, W, 1, H, N)
-static int make_act_map(CUtensorMap* m, const bf16* base, int C, int N, int H, int W, long long ld, const uint32_t box[5]) {
+template <typename T>
+static int make_act_map(CUtensorMap* m, const T* base, int C, int N, int H, int W, long long ld, const uint32_t box[5]) {
     const uint64_t dims[5] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), 1, static_cast<uint64_t>(H),
                               static_cast<uint64_t>(N)};
     const uint64_t st[4] = {static_cast<uint64_t>(ld), static_cast<uint64_t>(ld) * W, static_cast<uint64_t>(ld) * W,
                             static_cast<uint64_t>(ld) * W * H};
-    return make_map5(m, base, dims, st, box);
+    return make_map5(m, base, dims, st, box, static_cast<int>(sizeof(T)));
 }
 // fine grid [N,Ho,Wo,ld] (Ho >= 2H, Wo >= 2W) seen from the coarse grid: (c' = dx*ld + c, w, q = dy, h, n)
-static int make_up_map(CUtensorMap* m, const bf16* base, int C, int N, int H, int W, long long ld, const uint32_t box[5],
+template <typename T>
+static int make_up_map(CUtensorMap* m, const T* base, int C, int N, int H, int W, long long ld, const uint32_t box[5],
                        int Ho, int Wo) {
     const uint64_t dims[5] = {static_cast<uint64_t>(ld + C), static_cast<uint64_t>(W), 2, static_cast<uint64_t>(H),
                               static_cast<uint64_t>(N)};
     const uint64_t st[4] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(ld) * Wo,
                             static_cast<uint64_t>(ld) * 2 * Wo, static_cast<uint64_t>(ld) * Wo * Ho};
-    return make_map5(m, base, dims, st, box);
+    return make_map5(m, base, dims, st, box, static_cast<int>(sizeof(T)));
 }
 
 // Function attributes (dynamic shared-memory opt-in, carve-out), co-resident cluster counts and the SM count are properties of
@@ -156,20 +159,20 @@ static int splitk_reduce(const float* partial, int splits, long long numel, floa
 // ------------------------------------------------------------------------------------------------
 // pixel-major tcgen05 launcher
 // ------------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, class Op = OpBf16>
 static int launch_px(const CUtensorMap& tA, const CUtensorMap& tB, const PxParams& p, cudaStream_t st) {
     using Cfg = PxCfg<BN>;
     static bool attr_set_[kMaxDevices] = {};
     bool& attr_set = attr_set_[cur_dev()];
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tapgemm_px_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_px_kernel<BN, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return fail("cudaFuncSetAttribute(px<%d>): %s", BN, cudaGetErrorString(e));
         attr_set = true;
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     const int grid = std::min(tiles, sm_count());
-    tapgemm_px_kernel<BN><<<grid, kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, p);
-    return check_launch("tapgemm_px_kernel", BN);
+    tapgemm_px_kernel<BN, Op><<<grid, kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, p);
+    return check_launch(Op::kTf32 ? "tapgemm_px_kernel/tf32" : "tapgemm_px_kernel", BN);
 }
 
 // Fill the pixel tiling of PxParams; TN is restricted to divide `group_images` so that a tile never straddles
@@ -192,19 +195,19 @@ static void px_tiling(PxParams& p, int N, int H, int W, int group_images) {
     p.valid_rows = p.TW * p.TH * p.TN;
 }
 
-template <int BN>
+template <int BN, class Op = OpBf16>
 static int launch_halo_px(const CUtensorMap& tA, const CUtensorMap& tB, const PxParams& p, cudaStream_t st) {
     using Cfg = HaloCfg<BN>;
     static bool attr_set_[kMaxDevices] = {};
     bool& attr_set = attr_set_[cur_dev()];
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_px_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_px_kernel<BN, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return fail("cudaFuncSetAttribute(halo_px<%d>): %s", BN, cudaGetErrorString(e));
         attr_set = true;
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
-    conv3x3_halo_px_kernel<BN><<<std::min(tiles, sm_count()), kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, p);
-    return check_launch("conv3x3_halo_px_kernel", BN);
+    conv3x3_halo_px_kernel<BN, Op><<<std::min(tiles, sm_count()), kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, p);
+    return check_launch(Op::kTf32 ? "conv3x3_halo_px_kernel/tf32" : "conv3x3_halo_px_kernel", BN);
 }
 
 template <int BN, bool RED = false>
@@ -222,13 +225,13 @@ static int launch_halo_res_px(const CUtensorMap& tA, const CUtensorMap& tB, cons
 }
 
 // CTA-pair (cta_group::2) variant: grid = 2 x min(pair tiles, co-resident clusters)
-template <int BN, bool RED = false>
+template <int BN, bool RED = false, class Op = OpBf16>
 static int launch_halo2_px(const CUtensorMap& tA, const CUtensorMap& tB, const PxParams& p, cudaStream_t st) {
     using Cfg = Halo2Cfg<BN>;
     static int max_clusters_[kMaxDevices] = {};
     int& max_clusters = max_clusters_[cur_dev()];
     if (max_clusters == 0) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_halo2_px_kernel<BN, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_halo2_px_kernel<BN, RED, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return fail("cudaFuncSetAttribute(halo2_px<%d>): %s", BN, cudaGetErrorString(e));
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
@@ -241,7 +244,7 @@ static int launch_halo2_px(const CUtensorMap& tA, const CUtensorMap& tB, const P
         cfg.attrs = &at;
         cfg.numAttrs = 1;
         int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, conv3x3_halo2_px_kernel<BN, RED>, &cfg) != cudaSuccess || n <= 0) {
+        if (cudaOccupancyMaxActiveClusters(&n, conv3x3_halo2_px_kernel<BN, RED, Op>, &cfg) != cudaSuccess || n <= 0) {
             cudaGetLastError();
             n = sm_count() / 2;
         }
@@ -249,8 +252,8 @@ static int launch_halo2_px(const CUtensorMap& tA, const CUtensorMap& tB, const P
     }
     const int units = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
     const int grid = 2 * std::min(units, max_clusters);
-    conv3x3_halo2_px_kernel<BN, RED><<<grid, kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, p);
-    return check_launch(RED ? "conv3x3_halo2_px_kernel+bnred" : "conv3x3_halo2_px_kernel", BN);
+    conv3x3_halo2_px_kernel<BN, RED, Op><<<grid, kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, p);
+    return check_launch(RED ? "conv3x3_halo2_px_kernel+bnred" : (Op::kTf32 ? "conv3x3_halo2_px_kernel/tf32" : "conv3x3_halo2_px_kernel"), BN);
 }
 
 // Split-K factor for the weight-gradient kernels: minimise (waves x K-steps per unit + fixed per-unit epilogue cost).
@@ -305,11 +308,17 @@ static int conv3x3_tc_then_reduce(const bf16* in, long long ldi, int ci_off, int
                                   int Cout, bf16* out, long long ldo, int co_off, int group_images, cudaStream_t st,
                                   const BnRedArgs& red);
 
-static int conv3x3_tc(const bf16* in, long long ldi, int ci_off, int N, int H, int W, int Cin, const bf16* wp, int Cout,
-                      bf16* out, long long ldo, int co_off, double* ssum, double* ssq, int group_images, cudaStream_t st,
-                      const float* bn_scale = nullptr, const float* bn_shift = nullptr, const BnRedArgs* red = nullptr) {
+// Op = OpBf16: bf16 activations / packed weights; Op = OpTf32: fp32 activations / packed weights read as TF32 (no fused
+// BatchNorm-backward reduce, no weight-resident variant: its 9 taps x 2 K chunks would not fit in shared memory).
+template <class Op>
+static int conv3x3_tc(const typename Op::T* in, long long ldi, int ci_off, int N, int H, int W, int Cin, const typename Op::T* wp,
+                      int Cout, typename Op::T* out, long long ldo, int co_off, double* ssum, double* ssq, int group_images,
+                      cudaStream_t st, const float* bn_scale = nullptr, const float* bn_shift = nullptr, const BnRedArgs* red = nullptr) {
+    constexpr int KC = Op::kKC;
+    constexpr int EB = static_cast<int>(sizeof(typename Op::T));
     if (Cin % 64 || Cout % 64) return fail("tc conv needs Cin, Cout multiples of 64 (got %d, %d)", Cin, Cout);
     if (ldo % 8 || co_off % 8) return fail("tc conv output channel stride/offset must be multiples of 8");
+    if (Op::kTf32 && red) return fail("conv3x3_dgrad_bnred: bf16 path only");
     PxParams p;
     memset(&p, 0, sizeof(p));
     const int BN = pick_bn(Cout);
@@ -321,44 +330,50 @@ static int conv3x3_tc(const bf16* in, long long ldi, int ci_off, int N, int H, i
         p.num_m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
         p.valid_rows = 128;
         p.num_n_tiles = Cout / BN;
-        p.ntaps = 9; p.k_chunks = Cin / 64; p.cin = Cin;
+        p.ntaps = 9; p.k_chunks = Cin / KC; p.cin = Cin;
         p.epi_mode = EPI_STORE;
         p.out = out; p.ldo = ldo; p.out_coff = co_off;
         p.stat_sum = ssum; p.stat_sq = ssq; p.cout_total = Cout; p.stat_gstride = Cout; p.group_images = group_images > 0 ? group_images : N;
         p.scale = bn_scale; p.shift = bn_shift;
         apply_bnred(p, red, Cout);
         CUtensorMap tA, tB;
-        const uint32_t hbox[5] = {64, 8, 1, 18, 1};
+        const uint32_t hbox[5] = {KC, 8, 1, 18, 1};
         if (make_act_map(&tA, in + ci_off, Cin, N, H, W, ldi, hbox)) return 1;
         const char* min_kc_env = getenv("ONET_2CTA_MIN_KC");
         const int min_kc = min_kc_env ? atoi(min_kc_env) : 2;
-        if (p.num_m_tiles >= 2 && p.k_chunks >= min_kc && !getenv("ONET_NO_2CTA")) {
+        if (p.num_m_tiles >= 2 && Cin / 64 >= min_kc && !getenv("ONET_NO_2CTA")) {
             // CTA pairs: two pixel tiles per MMA, each CTA stages half of the weight tile
-            if (make_map2(&tB, wp, 9ULL * Cin, Cout, 64, BN / 2)) return 1;
-            if (red && BN == 256) return launch_halo2_px<256, true>(tA, tB, p, st);
-            if (red && BN == 128) return launch_halo2_px<128, true>(tA, tB, p, st);
-            if (red) return conv3x3_tc_then_reduce(in, ldi, ci_off, N, H, W, Cin, wp, Cout, out, ldo, co_off, group_images, st, *red);
-            if (BN == 256) return launch_halo2_px<256>(tA, tB, p, st);
-            if (BN == 128) return launch_halo2_px<128>(tA, tB, p, st);
-            return launch_halo2_px<64>(tA, tB, p, st);
+            if (make_map2(&tB, wp, 9ULL * Cin, Cout, KC, BN / 2, EB)) return 1;
+            if constexpr (!Op::kTf32) {
+                if (red && BN == 256) return launch_halo2_px<256, true>(tA, tB, p, st);
+                if (red && BN == 128) return launch_halo2_px<128, true>(tA, tB, p, st);
+                if (red) return conv3x3_tc_then_reduce(in, ldi, ci_off, N, H, W, Cin, wp, Cout, out, ldo, co_off, group_images, st, *red);
+            }
+            if (BN == 256) return launch_halo2_px<256, false, Op>(tA, tB, p, st);
+            if (BN == 128) return launch_halo2_px<128, false, Op>(tA, tB, p, st);
+            return launch_halo2_px<64, false, Op>(tA, tB, p, st);
         }
-        if (make_map2(&tB, wp, 9ULL * Cin, Cout, 64, BN)) return 1;
-        if (p.k_chunks == 1 && p.num_n_tiles == 1 && BN <= 128 && p.num_m_tiles >= 4 * sm_count() && !getenv("ONET_NO_BRES")) {
-            // Cin = 64, Cout <= 128, many tiles per CTA: weights stay resident in shared memory
-            if (red && BN == 64) return launch_halo_res_px<64, true>(tA, tB, p, st);
+        if (make_map2(&tB, wp, 9ULL * Cin, Cout, KC, BN, EB)) return 1;
+        if constexpr (!Op::kTf32) {
+            if (p.k_chunks == 1 && p.num_n_tiles == 1 && BN <= 128 && p.num_m_tiles >= 4 * sm_count() && !getenv("ONET_NO_BRES")) {
+                // Cin = 64, Cout <= 128, many tiles per CTA: weights stay resident in shared memory
+                if (red && BN == 64) return launch_halo_res_px<64, true>(tA, tB, p, st);
+                if (red) return conv3x3_tc_then_reduce(in, ldi, ci_off, N, H, W, Cin, wp, Cout, out, ldo, co_off, group_images, st, *red);
+                if (BN == 128) return launch_halo_res_px<128>(tA, tB, p, st);
+                return launch_halo_res_px<64>(tA, tB, p, st);
+            }
             if (red) return conv3x3_tc_then_reduce(in, ldi, ci_off, N, H, W, Cin, wp, Cout, out, ldo, co_off, group_images, st, *red);
-            if (BN == 128) return launch_halo_res_px<128>(tA, tB, p, st);
-            return launch_halo_res_px<64>(tA, tB, p, st);
         }
-        if (red) return conv3x3_tc_then_reduce(in, ldi, ci_off, N, H, W, Cin, wp, Cout, out, ldo, co_off, group_images, st, *red);
-        if (BN == 256) return launch_halo_px<256>(tA, tB, p, st);
-        if (BN == 128) return launch_halo_px<128>(tA, tB, p, st);
-        return launch_halo_px<64>(tA, tB, p, st);
+        if (BN == 256) return launch_halo_px<256, Op>(tA, tB, p, st);
+        if (BN == 128) return launch_halo_px<128, Op>(tA, tB, p, st);
+        return launch_halo_px<64, Op>(tA, tB, p, st);
     }
-    if (red) return conv3x3_tc_then_reduce(in, ldi, ci_off, N, H, W, Cin, wp, Cout, out, ldo, co_off, group_images, st, *red);
+    if constexpr (!Op::kTf32) {
+        if (red) return conv3x3_tc_then_reduce(in, ldi, ci_off, N, H, W, Cin, wp, Cout, out, ldo, co_off, group_images, st, *red);
+    }
     px_tiling(p, N, H, W, (ssum || bn_scale) ? group_images : 0);
     p.num_n_tiles = Cout / BN;
-    p.ntaps = 9; p.k_chunks = Cin / 64; p.cin = Cin;
+    p.ntaps = 9; p.k_chunks = Cin / KC; p.cin = Cin;
     // same accumulation order as the halo kernels (filter column outer, filter row inner): a pixel gets bit-identical
     // results whichever kernel variant its image size selects (tiled inference relies on it)
     for (int t = 0; t < 9; ++t) {
@@ -371,12 +386,12 @@ static int conv3x3_tc(const bf16* in, long long ldi, int ci_off, int N, int H, i
     p.stat_sum = ssum; p.stat_sq = ssq; p.cout_total = Cout; p.stat_gstride = Cout; p.group_images = group_images > 0 ? group_images : N;
     p.scale = bn_scale; p.shift = bn_shift;
     CUtensorMap tA, tB;
-    const uint32_t box[5] = {64, static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
+    const uint32_t box[5] = {KC, static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
     if (make_act_map(&tA, in + ci_off, Cin, N, H, W, ldi, box)) return 1;
-    if (make_map2(&tB, wp, 9ULL * Cin, Cout, 64, BN)) return 1;
-    if (BN == 256) return launch_px<256>(tA, tB, p, st);
-    if (BN == 128) return launch_px<128>(tA, tB, p, st);
-    return launch_px<64>(tA, tB, p, st);
+    if (make_map2(&tB, wp, 9ULL * Cin, Cout, KC, BN, EB)) return 1;
+    if (BN == 256) return launch_px<256, Op>(tA, tB, p, st);
+    if (BN == 128) return launch_px<128, Op>(tA, tB, p, st);
+    return launch_px<64, Op>(tA, tB, p, st);
 }
 
 // dgrad without a fused-reduce instantiation: the plain launch, then the standalone reduce pass over its output
@@ -384,13 +399,16 @@ static int conv3x3_tc_then_reduce(const bf16* in, long long ldi, int ci_off, int
                                   int Cout, bf16* out, long long ldo, int co_off, int group_images, cudaStream_t st,
                                   const BnRedArgs& red) {
     if (ldo != Cout || co_off != 0) return fail("conv3x3_dgrad_bnred: dense output required");
-    if (conv3x3_tc(in, ldi, ci_off, N, H, W, Cin, wp, Cout, out, ldo, co_off, nullptr, nullptr, group_images, st)) return 1;
+    if (conv3x3_tc<OpBf16>(in, ldi, ci_off, N, H, W, Cin, wp, Cout, out, ldo, co_off, nullptr, nullptr, group_images, st)) return 1;
     return bnred_standalone(red, out, N, H, W, Cout, group_images, st);
 }
 
 // convT fwd on tensor cores: D[px][(tap,co)] = X[px][:] . wf[(tap,co)][:], scatter epilogue
-static int convT_fwd_tc(const bf16* x, long long ldx, int xoff, int N, int H, int W, int Cin, const bf16* wf,
-                        const float* bias, int Co, bf16* out, long long ldo, int ooff, int Ho, int Wo, cudaStream_t st) {
+template <class Op>
+static int convT_fwd_tc(const typename Op::T* x, long long ldx, int xoff, int N, int H, int W, int Cin, const typename Op::T* wf,
+                        const float* bias, int Co, typename Op::T* out, long long ldo, int ooff, int Ho, int Wo, cudaStream_t st) {
+    constexpr int KC = Op::kKC;
+    constexpr int EB = static_cast<int>(sizeof(typename Op::T));
     if (Cin % 64 || Co % 64) return fail("tc convT needs Cin, Co multiples of 64 (got %d, %d)", Cin, Co);
     if (ldo % 8 || ooff % 8) return fail("tc convT output channel stride/offset must be multiples of 8");
     PxParams p;
@@ -398,7 +416,7 @@ static int convT_fwd_tc(const bf16* x, long long ldx, int xoff, int N, int H, in
     px_tiling(p, N, H, W, 0);
     const int BN = 256;                       // 4*Co is a multiple of 256; a tile spans one or more of the 2x2 positions
     p.num_n_tiles = 4 * Co / BN;
-    p.ntaps = 1; p.k_chunks = Cin / 64; p.cin = Cin;
+    p.ntaps = 1; p.k_chunks = Cin / KC; p.cin = Cin;
     p.taps[0] = make_int4(0, 0, 0, 0);
     p.tap_w[0] = 0;
     p.epi_mode = EPI_CONVT;
@@ -406,17 +424,18 @@ static int convT_fwd_tc(const bf16* x, long long ldx, int xoff, int N, int H, in
     p.bias = bias; p.co_per_tap = Co; p.cout_total = 4 * Co; p.stat_gstride = 4 * Co; p.group_images = N;
     p.Ho = Ho; p.Wo = Wo;
     CUtensorMap tA, tB;
-    const uint32_t box[5] = {64, static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
+    const uint32_t box[5] = {KC, static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
     if (make_act_map(&tA, x + xoff, Cin, N, H, W, ldx, box)) return 1;
-    if (make_map2(&tB, wf, Cin, 4ULL * Co, 64, BN)) return 1;
-    if (BN == 256) return launch_px<256>(tA, tB, p, st);
-    if (BN == 128) return launch_px<128>(tA, tB, p, st);
-    return launch_px<64>(tA, tB, p, st);
+    if (make_map2(&tB, wf, Cin, 4ULL * Co, KC, BN, EB)) return 1;
+    return launch_px<256, Op>(tA, tB, p, st);
 }
 
 // convT dgrad on tensor cores: dX[px][ci] = sum_{tap,co} dO[2px+tap][co] * wd[ci][(tap,co)]
-static int convT_dgrad_tc(const bf16* go, long long ldg, int goff, int N, int H, int W, int Cin, const bf16* wd, int Co,
-                          bf16* dx, long long ldd, int doff, int Ho, int Wo, cudaStream_t st) {
+template <class Op>
+static int convT_dgrad_tc(const typename Op::T* go, long long ldg, int goff, int N, int H, int W, int Cin, const typename Op::T* wd,
+                          int Co, typename Op::T* dx, long long ldd, int doff, int Ho, int Wo, cudaStream_t st) {
+    constexpr int KC = Op::kKC;
+    constexpr int EB = static_cast<int>(sizeof(typename Op::T));
     if (Cin % 64 || Co % 64) return fail("tc convT dgrad needs Cin, Co multiples of 64 (got %d, %d)", Cin, Co);
     if (ldd % 8 || doff % 8) return fail("tc convT dgrad output channel stride/offset must be multiples of 8");
     PxParams p;
@@ -424,7 +443,7 @@ static int convT_dgrad_tc(const bf16* go, long long ldg, int goff, int N, int H,
     px_tiling(p, N, H, W, 0);
     const int BN = pick_bn(Cin);
     p.num_n_tiles = Cin / BN;
-    p.ntaps = 4; p.k_chunks = Co / 64; p.cin = Co;
+    p.ntaps = 4; p.k_chunks = Co / KC; p.cin = Co;
     for (int t = 0; t < 4; ++t) {
         p.taps[t] = make_int4((t & 1) * static_cast<int>(ldg), 0, t >> 1, 0);
         p.tap_w[t] = t;
@@ -433,12 +452,12 @@ static int convT_dgrad_tc(const bf16* go, long long ldg, int goff, int N, int H,
     p.out = dx; p.ldo = ldd; p.out_coff = doff;
     p.cout_total = Cin; p.stat_gstride = Cin; p.group_images = N;
     CUtensorMap tA, tB;
-    const uint32_t box[5] = {64, static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
+    const uint32_t box[5] = {KC, static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
     if (make_up_map(&tA, go + goff, Co, N, H, W, ldg, box, Ho, Wo)) return 1;
-    if (make_map2(&tB, wd, 4ULL * Co, Cin, 64, BN)) return 1;
-    if (BN == 256) return launch_px<256>(tA, tB, p, st);
-    if (BN == 128) return launch_px<128>(tA, tB, p, st);
-    return launch_px<64>(tA, tB, p, st);
+    if (make_map2(&tB, wd, 4ULL * Co, Cin, KC, BN, EB)) return 1;
+    if (BN == 256) return launch_px<256, Op>(tA, tB, p, st);
+    if (BN == 128) return launch_px<128, Op>(tA, tB, p, st);
+    return launch_px<64, Op>(tA, tB, p, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -446,20 +465,20 @@ static int convT_dgrad_tc(const bf16* go, long long ldg, int goff, int N, int H,
 //   dW[m][n][t] (or transposed) = sum_px G[px (-) t][m] * In[px][n]
 //   g_is_up: the M-side operand lives on the 2x upsampled grid (transposed conv), taps = 2x2 positions.
 // ------------------------------------------------------------------------------------------------
-template <int BNW>
+template <int BNW, class Op = OpBf16>
 static int launch_wg(const CUtensorMap& tG, const CUtensorMap& tI, const WgParams& p, cudaStream_t st) {
-    using Cfg = WgCfg<BNW>;
+    using Cfg = WgCfg<BNW, Op>;
     static bool attr_set_[kMaxDevices] = {};
     bool& attr_set = attr_set_[cur_dev()];
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tapgemm_wg_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_wg_kernel<BNW, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return fail("cudaFuncSetAttribute(wg<%d>): %s", BNW, cudaGetErrorString(e));
         attr_set = true;
     }
     const int units = p.ngroups * p.num_m_tiles * p.num_n_tiles * p.ksplit;
     const int grid = std::min(units, sm_count());
-    tapgemm_wg_kernel<BNW><<<grid, 192, Cfg::kSmemBytes, st>>>(tG, tI, p);
-    return check_launch("tapgemm_wg_kernel", BNW);
+    tapgemm_wg_kernel<BNW, Op><<<grid, 192, Cfg::kSmemBytes, st>>>(tG, tI, p);
+    return check_launch(Op::kTf32 ? "tapgemm_wg_kernel/tf32" : "tapgemm_wg_kernel", BNW);
 }
 
 template <int BNW>
@@ -594,17 +613,23 @@ static int wgrad3x3_halo_tc(const bf16* g, long long ldg, int goff, int Mc, cons
     return launch_wh<64>(tG, tI, p, st);
 }
 
-static int wgrad_tc(const bf16* g, long long ldg, int goff, int Mc, bool g_is_up, const bf16* in, long long ldi, int ioff,
-                    int Nc, int N, int H, int W, int ntaps, float* dw, bool transposed, cudaStream_t st, int Ho = 0, int Wo = 0) {
+template <class Op>
+static int wgrad_tc(const typename Op::T* g, long long ldg, int goff, int Mc, bool g_is_up, const typename Op::T* in, long long ldi,
+                    int ioff, int Nc, int N, int H, int W, int ntaps, float* dw, bool transposed, cudaStream_t st, int Ho = 0,
+                    int Wo = 0) {
+    constexpr int KC = Op::kKC;
     if (Mc % 64 || Nc % 64) return fail("tc wgrad needs channel counts multiples of 64 (got %d, %d)", Mc, Nc);
-    if (!g_is_up && ntaps == 9 && !transposed && H >= 8 && W >= 8 && !getenv("ONET_NO_HALO"))
-        return wgrad3x3_halo_tc(g, ldg, goff, Mc, in, ldi, ioff, Nc, N, H, W, dw, st);
+    if constexpr (!Op::kTf32) {
+        if (!g_is_up && ntaps == 9 && !transposed && H >= 8 && W >= 8 && !getenv("ONET_NO_HALO"))
+            return wgrad3x3_halo_tc(g, ldg, goff, Mc, in, ldi, ioff, Nc, N, H, W, dw, st);
+    }
+    constexpr int SLAB = Op::kTf32 ? 32 : 64;         // pixels per K slab (WgCfg::kSlabPx)
     WgParams p;
     memset(&p, 0, sizeof(p));
     p.N = N; p.H = H; p.W = W;
     p.TW = std::min(p2floor(W), 8);
-    p.TH = std::min(p2floor(H), 64 / p.TW);
-    p.TN = 64 / (p.TW * p.TH);
+    p.TH = std::min(p2floor(H), SLAB / p.TW);
+    p.TN = SLAB / (p.TW * p.TH);
     p.tiles_w = (W + p.TW - 1) / p.TW;
     p.tiles_h = (H + p.TH - 1) / p.TH;
     p.tiles_n = (N + p.TN - 1) / p.TN;
@@ -647,12 +672,12 @@ static int wgrad_tc(const bf16* g, long long ldg, int goff, int Mc, bool g_is_up
     p.m_total = Mc; p.n_total = Nc; p.out_transposed = transposed ? 1 : 0;
     p.ks_slowest = getenv("ONET_WG_KS_FASTEST") ? 0 : 1;
     CUtensorMap tG, tI;
-    const uint32_t box[5] = {64, static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
+    const uint32_t box[5] = {KC, static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
     if (g_is_up) { if (make_up_map(&tG, g + goff, Mc, N, H, W, ldg, box, Ho, Wo)) return 1; }
     else { if (make_act_map(&tG, g + goff, Mc, N, H, W, ldg, box)) return 1; }
     if (make_act_map(&tI, in + ioff, Nc, N, H, W, ldi, box)) return 1;
-    if (BNW == 128) return launch_wg<128>(tG, tI, p, st);
-    return launch_wg<64>(tG, tI, p, st);
+    if (BNW == 128) return launch_wg<128, Op>(tG, tI, p, st);
+    return launch_wg<64, Op>(tG, tI, p, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -736,10 +761,12 @@ int onet_conv3x3_fwd(const void* in, int64_t ldi, int ci_off, int N, int H, int 
                      void* out, int64_t ldo, int co_off, double* stat_sum, double* stat_sq, int group_images,
                      int dtype, int engine, void* stream) {
     if (N <= 0 || H <= 0 || W <= 0) return fail("conv3x3_fwd: empty tensor");
-    if (engine == ONET_ENGINE_TC) {
-        if (dtype != ONET_BF16) return fail("tc engine is bf16 only");
-        return conv3x3_tc(static_cast<const bf16*>(in), ldi, ci_off, N, H, W, Cin, static_cast<const bf16*>(wp), Cout,
-                          static_cast<bf16*>(out), ldo, co_off, stat_sum, stat_sq, group_images, ST(stream));
+    if (engine == ONET_ENGINE_TC) {     // tensor cores: bf16 operands, or (dtype ONET_F32) fp32 operands read as TF32
+        if (dtype == ONET_F32)
+            return conv3x3_tc<OpTf32>(static_cast<const float*>(in), ldi, ci_off, N, H, W, Cin, static_cast<const float*>(wp), Cout,
+                                      static_cast<float*>(out), ldo, co_off, stat_sum, stat_sq, group_images, ST(stream));
+        return conv3x3_tc<OpBf16>(static_cast<const bf16*>(in), ldi, ci_off, N, H, W, Cin, static_cast<const bf16*>(wp), Cout,
+                                  static_cast<bf16*>(out), ldo, co_off, stat_sum, stat_sq, group_images, ST(stream));
     }
     const long long M = static_cast<long long>(N) * H * W;
     dim3 grid(static_cast<unsigned>((M + 63) / 64), (Cout + 63) / 64);
@@ -773,10 +800,13 @@ int onet_conv3x3_bn_relu_infer(const void* in, int64_t ldi, int ci_off, int N, i
                                const float* scale, const float* shift, int group_images, void* out, int64_t ldo, int co_off,
                                int dtype, int engine, void* stream) {
     if (N <= 0 || H <= 0 || W <= 0) return fail("conv3x3_bn_relu_infer: empty tensor");
-    if (engine != ONET_ENGINE_TC || dtype != ONET_BF16) return fail("conv3x3_bn_relu_infer: tensor-core engine, bf16 only");
+    if (engine != ONET_ENGINE_TC) return fail("conv3x3_bn_relu_infer: tensor-core engine only");
     if (scale == nullptr || shift == nullptr) return fail("conv3x3_bn_relu_infer: scale and shift are required");
-    return conv3x3_tc(static_cast<const bf16*>(in), ldi, ci_off, N, H, W, Cin, static_cast<const bf16*>(wp), Cout,
-                      static_cast<bf16*>(out), ldo, co_off, nullptr, nullptr, group_images, ST(stream), scale, shift);
+    if (dtype == ONET_F32)
+        return conv3x3_tc<OpTf32>(static_cast<const float*>(in), ldi, ci_off, N, H, W, Cin, static_cast<const float*>(wp), Cout,
+                                  static_cast<float*>(out), ldo, co_off, nullptr, nullptr, group_images, ST(stream), scale, shift);
+    return conv3x3_tc<OpBf16>(static_cast<const bf16*>(in), ldi, ci_off, N, H, W, Cin, static_cast<const bf16*>(wp), Cout,
+                              static_cast<bf16*>(out), ldo, co_off, nullptr, nullptr, group_images, ST(stream), scale, shift);
 }
 
 int onet_maxpool2x2(const void* in, int64_t ldi, int ioff, int N, int H, int W, int C, void* out, int dtype, void* stream) {
@@ -793,9 +823,11 @@ int onet_maxpool2x2(const void* in, int64_t ldi, int ioff, int N, int H, int W, 
 int onet_conv3x3_wgrad(const void* g, int64_t ldg, int g_off, const void* in, int64_t ldi, int ci_off, int N, int H,
                        int W, int Cin, int Cout, float* dw, int dtype, int engine, void* stream) {
     if (engine == ONET_ENGINE_TC) {
-        if (dtype != ONET_BF16) return fail("tc engine is bf16 only");
-        return wgrad_tc(static_cast<const bf16*>(g), ldg, g_off, Cout, false, static_cast<const bf16*>(in), ldi, ci_off, Cin,
-                        N, H, W, 9, dw, false, ST(stream));
+        if (dtype == ONET_F32)
+            return wgrad_tc<OpTf32>(static_cast<const float*>(g), ldg, g_off, Cout, false, static_cast<const float*>(in), ldi, ci_off,
+                                    Cin, N, H, W, 9, dw, false, ST(stream));
+        return wgrad_tc<OpBf16>(static_cast<const bf16*>(g), ldg, g_off, Cout, false, static_cast<const bf16*>(in), ldi, ci_off, Cin,
+                                N, H, W, 9, dw, false, ST(stream));
     }
     const long long M = static_cast<long long>(N) * H * W;
     if ((Cin == 1 || Cin == 3) && Cout == 64 && ldi == Cin && ci_off == 0 && ldg == 64 && g_off == 0 && W % 4 == 0) {
@@ -1008,8 +1040,8 @@ int onet_conv3x3_dgrad_bnred(const void* in, int64_t ldi, int ci_off, int N, int
     if (y_prev == nullptr || scale == nullptr || shift == nullptr || mean == nullptr || invstd == nullptr || sums == nullptr)
         return fail("conv3x3_dgrad_bnred: y_prev, scale, shift, mean, invstd and sums are required");
     BnRedArgs red{static_cast<const bf16*>(y_prev), scale, shift, mean, invstd, sums};
-    return conv3x3_tc(static_cast<const bf16*>(in), ldi, ci_off, N, H, W, Cin, static_cast<const bf16*>(wp), Cout,
-                      static_cast<bf16*>(out), Cout, 0, nullptr, nullptr, group_images, ST(stream), nullptr, nullptr, &red);
+    return conv3x3_tc<OpBf16>(static_cast<const bf16*>(in), ldi, ci_off, N, H, W, Cin, static_cast<const bf16*>(wp), Cout,
+                              static_cast<bf16*>(out), Cout, 0, nullptr, nullptr, group_images, ST(stream), nullptr, nullptr, &red);
 }
 
 int onet_convT2x2_fwd(const void* x, int64_t ldx, int xoff, int N, int H, int W, int Cin, const void* w,
@@ -1019,9 +1051,11 @@ int onet_convT2x2_fwd(const void* x, int64_t ldx, int xoff, int N, int H, int W,
     if (Wo == 0) Wo = 2 * W;
     if (Ho < 2 * H || Wo < 2 * W) return fail("convT2x2_fwd: output grid %dx%d smaller than 2H x 2W", Ho, Wo);
     if (engine == ONET_ENGINE_TC) {
-        if (dtype != ONET_BF16) return fail("tc engine is bf16 only");
-        return convT_fwd_tc(static_cast<const bf16*>(x), ldx, xoff, N, H, W, Cin, static_cast<const bf16*>(w), bias, Co,
-                            static_cast<bf16*>(out), ldo, ooff, Ho, Wo, ST(stream));
+        if (dtype == ONET_F32)
+            return convT_fwd_tc<OpTf32>(static_cast<const float*>(x), ldx, xoff, N, H, W, Cin, static_cast<const float*>(w), bias, Co,
+                                        static_cast<float*>(out), ldo, ooff, Ho, Wo, ST(stream));
+        return convT_fwd_tc<OpBf16>(static_cast<const bf16*>(x), ldx, xoff, N, H, W, Cin, static_cast<const bf16*>(w), bias, Co,
+                                    static_cast<bf16*>(out), ldo, ooff, Ho, Wo, ST(stream));
     }
     const long long total = 4LL * N * H * W * Co;
     if (dtype == ONET_F32)
@@ -1039,9 +1073,11 @@ int onet_convT2x2_dgrad(const void* go, int64_t ldg, int goff, int N, int H, int
     if (Wo == 0) Wo = 2 * W;
     if (Ho < 2 * H || Wo < 2 * W) return fail("convT2x2_dgrad: gradient grid %dx%d smaller than 2H x 2W", Ho, Wo);
     if (engine == ONET_ENGINE_TC) {
-        if (dtype != ONET_BF16) return fail("tc engine is bf16 only");
-        return convT_dgrad_tc(static_cast<const bf16*>(go), ldg, goff, N, H, W, Cin, static_cast<const bf16*>(w), Co,
-                              static_cast<bf16*>(dx), ldd, doff, Ho, Wo, ST(stream));
+        if (dtype == ONET_F32)
+            return convT_dgrad_tc<OpTf32>(static_cast<const float*>(go), ldg, goff, N, H, W, Cin, static_cast<const float*>(w), Co,
+                                          static_cast<float*>(dx), ldd, doff, Ho, Wo, ST(stream));
+        return convT_dgrad_tc<OpBf16>(static_cast<const bf16*>(go), ldg, goff, N, H, W, Cin, static_cast<const bf16*>(w), Co,
+                                      static_cast<bf16*>(dx), ldd, doff, Ho, Wo, ST(stream));
     }
     const long long total = static_cast<long long>(N) * H * W * Cin;
     if (dtype == ONET_F32)
@@ -1091,10 +1127,12 @@ int onet_convT2x2_wgrad(const void* x, int64_t ldx, int xoff, const void* go, in
         }
     }
     if (engine == ONET_ENGINE_TC) {
-        if (dtype != ONET_BF16) return fail("tc engine is bf16 only");
         // M-side = dO on the upsampled grid (m = co), N-side = X (n = ci); dW[ci][co][tap] -> transposed output
-        return wgrad_tc(static_cast<const bf16*>(go), ldg, goff, Co, true, static_cast<const bf16*>(x), ldx, xoff, Cin, N, H, W,
-                        4, dw, true, ST(stream), Ho, Wo);
+        if (dtype == ONET_F32)
+            return wgrad_tc<OpTf32>(static_cast<const float*>(go), ldg, goff, Co, true, static_cast<const float*>(x), ldx, xoff, Cin,
+                                    N, H, W, 4, dw, true, ST(stream), Ho, Wo);
+        return wgrad_tc<OpBf16>(static_cast<const bf16*>(go), ldg, goff, Co, true, static_cast<const bf16*>(x), ldx, xoff, Cin, N, H, W,
+                                4, dw, true, ST(stream), Ho, Wo);
     }
     const long long nthreads = 4LL * Cin * Co;
     int splits = static_cast<int>(std::max<long long>(1, std::min<long long>(M, (148LL * 2048) / std::max<long long>(1, nthreads))));

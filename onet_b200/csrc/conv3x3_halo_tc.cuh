@@ -18,7 +18,7 @@ namespace onet {
 
 template <int BN>
 struct HaloCfg {
-    static constexpr int kABytes = 144 * 128;                 // (16 + 2) rows x 8 pixels x 64 channels bf16
+    static constexpr int kABytes = 144 * 128;                 // (16 + 2) rows x 8 pixels x one 128-byte K chunk of channels
     static constexpr int kBBytes = BN * 128;
     static constexpr int kTapsPerB = (BN == 256) ? 1 : 3;     // vertical taps fetched per weight stage
     static constexpr int kSA = (BN == 64) ? 4 : 3;
@@ -29,10 +29,11 @@ struct HaloCfg {
     static constexpr int kSmemBytes = kSA * kABytes + kSB * kBStageBytes + kAuxBytes + 1024;
 };
 
-template <int BN>
+template <int BN, class Op = OpBf16>
 __global__ void __launch_bounds__(kPxThreads, 1)
 conv3x3_halo_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PxParams p) {
     using Cfg = HaloCfg<BN>;
+    constexpr int KC = Op::kKC;
     constexpr int SA = Cfg::kSA, SB = Cfg::kSB;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -75,7 +76,7 @@ conv3x3_halo_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     for (int kw = 0; kw < 3; ++kw) {
                         mbar_wait(bar_emptyA + 8 * sa, pa ^ 1);
                         mbar_expect_tx(bar_fullA + 8 * sa, Cfg::kABytes);
-                        tma_load_5d(ringA + sa * Cfg::kABytes, &tmA, bar_fullA + 8 * sa, kc * 64, w0 + kw - 1, 0, h0 - 1, nt);
+                        tma_load_5d(ringA + sa * Cfg::kABytes, &tmA, bar_fullA + 8 * sa, kc * KC, w0 + kw - 1, 0, h0 - 1, nt);
                         if (++sa == SA) { sa = 0; pa ^= 1; }
                         for (int kh = 0; kh < 3; kh += TPB) {
                             mbar_wait(bar_emptyB + 8 * sb, pb ^ 1);
@@ -83,7 +84,7 @@ conv3x3_halo_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
                             for (int j = 0; j < TPB; ++j)
                                 tma_load_2d(ringB + sb * Cfg::kBStageBytes + j * Cfg::kBBytes, &tmB, bar_fullB + 8 * sb,
-                                            ((kh + j) * 3 + kw) * p.cin + kc * 64, co0);
+                                            ((kh + j) * 3 + kw) * p.cin + kc * KC, co0);
                             if (++sb == SB) { sb = 0; pb ^= 1; }
                         }
                     }
@@ -93,7 +94,7 @@ conv3x3_halo_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     } else if (warp == 1) {
         // one elected thread runs the whole issue loop (no per-iteration warp convergence, no uniform-datapath loops)
         if (elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+            constexpr uint32_t idesc = umma_idesc<Op>(128, BN, 0, 0);
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0;
             int it = 0;
@@ -117,7 +118,7 @@ conv3x3_halo_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                                 const uint64_t db = umma_smem_desc(ringB + sb * Cfg::kBStageBytes + j * Cfg::kBBytes, 16, 1024);
 #pragma unroll
                                 for (int kk = 0; kk < 4; ++kk) {
-                                    umma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, accumulate);
+                                    umma<Op>(d_tmem, da + 2 * kk, db + 2 * kk, idesc, accumulate);
                                     accumulate = 1;
                                 }
                             }
@@ -144,8 +145,8 @@ conv3x3_halo_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
-            px_store_epilogue<BN>(p, tile % p.num_m_tiles, tile / p.num_m_tiles, acc, tmem_base, q, ew, lane, s_part,
-                                  bar_tempty + 8 * acc, false, sacc);
+            px_store_epilogue<BN, false, Op>(p, tile % p.num_m_tiles, tile / p.num_m_tiles, acc, tmem_base, q, ew, lane, s_part,
+                                             bar_tempty + 8 * acc, false, sacc);
         }
         px_stat_flush<BN>(p, sacc, ew, lane, s_part);
     }
@@ -306,10 +307,11 @@ struct Halo2Cfg {
     static constexpr int kSmemBytes = kSA * kABytes + kSB * kBStageBytes + kAuxBytes + 1024;
 };
 
-template <int BN, bool RED = false>
+template <int BN, bool RED = false, class Op = OpBf16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPxThreads, 1)
 conv3x3_halo2_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PxParams p) {
     using Cfg = Halo2Cfg<BN>;
+    constexpr int KC = Op::kKC;
     constexpr int SA = Cfg::kSA, SB = Cfg::kSB, TPB = Cfg::kTapsPerB;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -358,7 +360,7 @@ conv3x3_halo2_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                     for (int kw = 0; kw < 3; ++kw) {
                         mbar_wait(bar_emptyA + 8 * sa, pa ^ 1);
                         if (rank == 0) mbar_expect_tx(bar_fullA + 8 * sa, 2 * Cfg::kABytes);
-                        tma_load_5d_2cta(ringA + sa * Cfg::kABytes, &tmA, lead_fullA + 8 * sa, kc * 64, w0 + kw - 1, 0, h0 - 1, nt);
+                        tma_load_5d_2cta(ringA + sa * Cfg::kABytes, &tmA, lead_fullA + 8 * sa, kc * KC, w0 + kw - 1, 0, h0 - 1, nt);
                         if (++sa == SA) { sa = 0; pa ^= 1; }
                         for (int kh = 0; kh < 3; kh += TPB) {
                             mbar_wait(bar_emptyB + 8 * sb, pb ^ 1);
@@ -366,7 +368,7 @@ conv3x3_halo2_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 #pragma unroll
                             for (int j = 0; j < TPB; ++j)
                                 tma_load_2d_2cta(ringB + sb * Cfg::kBStageBytes + j * Cfg::kBHalfBytes, &tmB, lead_fullB + 8 * sb,
-                                                 ((kh + j) * 3 + kw) * p.cin + kc * 64, co0);
+                                                 ((kh + j) * 3 + kw) * p.cin + kc * KC, co0);
                             if (++sb == SB) { sb = 0; pb ^= 1; }
                         }
                     }
@@ -375,7 +377,7 @@ conv3x3_halo2_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         }
     } else if (warp == 1) {
         if (rank == 0 && elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
+            constexpr uint32_t idesc = umma_idesc<Op>(256, BN, 0, 0);
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0;
             int it = 0;
@@ -399,7 +401,7 @@ conv3x3_halo2_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                                 const uint64_t db = umma_smem_desc(ringB + sb * Cfg::kBStageBytes + j * Cfg::kBHalfBytes, 16, 1024);
 #pragma unroll
                                 for (int kk = 0; kk < 4; ++kk) {
-                                    umma_bf16_2cta(d_tmem, da + 2 * kk, db + 2 * kk, idesc, accumulate);
+                                    umma_2cta<Op>(d_tmem, da + 2 * kk, db + 2 * kk, idesc, accumulate);
                                     accumulate = 1;
                                 }
                             }
@@ -433,7 +435,7 @@ conv3x3_halo2_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             if (m_tile < p.num_m_tiles) {
-                px_store_epilogue<BN, RED>(p, m_tile, n_tile, acc, tmem_base, q, ew, lane, s_part, lead_tempty + 8 * acc, true, sacc);
+                px_store_epilogue<BN, RED, Op>(p, m_tile, n_tile, acc, tmem_base, q, ew, lane, s_part, lead_tempty + 8 * acc, true, sacc);
             } else {           // padding tile of an odd tile count: nothing to store
                 tc_fence_before();
                 __syncwarp();

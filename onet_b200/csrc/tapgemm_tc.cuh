@@ -1,7 +1,7 @@
 // tcgen05 / TMEM / TMA "tap-GEMM" kernels for sm_100a: the tensor-core engine behind the 3x3 convolutions
 // (fwd, dgrad, wgrad) and the 2x2/stride-2 transposed convolutions (fwd, dgrad, wgrad) of the Onet U-Nets.
 //
-// Activations are NHWC bf16.  Every operand tile is fetched by TMA from a 5-D view (c, w, q, h, n) of an
+// Activations are NHWC, bf16 (OpBf16) or fp32 read as TF32 (OpTf32, tc_common.cuh).  Every operand tile is fetched by TMA from a 5-D view (c, w, q, h, n) of an
 // activation tensor with the 128-byte swizzle, so a "tap" (a filter offset) is nothing but a coordinate
 // offset of the box; out-of-bounds rows are zero-filled by the TMA unit, which implements the conv padding.
 //
@@ -32,12 +32,12 @@ struct PxParams {
     int tiles_w, tiles_h, tiles_n;
     int num_m_tiles, num_n_tiles;
     int valid_rows;            // TW*TH*TN
-    int ntaps, k_chunks, cin;  // K = ntaps * cin, cin = 64 * k_chunks
+    int ntaps, k_chunks, cin;  // K = ntaps * cin, cin = Op::kKC * k_chunks (one K chunk = 128 bytes of channels)
     int4 taps[kMaxTaps];       // coordinate offsets (dc, dw, dq, dh) of each tap in the 5-D input view
     int tap_w[kMaxTaps];       // index of each tap in the packed weight tensor (K coordinate = tap_w * cin + channel)
     // epilogue
     int epi_mode;
-    __nv_bfloat16* out;        // EPI_STORE: [N,H,W,ldo]; EPI_CONVT: [N,2H,2W,ldo]
+    void* out;                 // EPI_STORE: [N,H,W,ldo]; EPI_CONVT: [N,2H,2W,ldo]; elements of Op::T
     long long ldo;             // channels per pixel of the output buffer
     int out_coff;              // first output channel inside the buffer
     double* stat_sum;          // [groups][cout_total] or nullptr
@@ -193,10 +193,12 @@ __device__ __forceinline__ void px_red_prefetch(const PxParams& p, int m_tile, i
 
 // Store epilogue of the pixel-major kernels: raw bf16 output + BatchNorm partial sums.
 // `arrive_bar`: the accumulator-drained barrier; `remote`: it is a shared::cluster address in the peer (leader) CTA.
-template <int BN, bool RED = false>
+template <int BN, bool RED = false, class Op = OpBf16>
 __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile, int n_tile, int acc, uint32_t tmem_base, int q,
                                                   int ew, int lane, float* s_part, uint32_t arrive_bar, bool remote,
                                                   PxStatAcc& sacc) {
+    static_assert(!(RED && Op::kTf32), "the fused BatchNorm-backward reduce exists for the bf16 kernels only");
+    using OT = typename Op::T;
     // ew = 0 .. kPxEpiWarps-1; warps ew and ew+4 share TMEM lane quarter q and split the 32-column chunks
     const int half = ew >> 2;
     const int row = q * 32 + lane;
@@ -205,7 +207,7 @@ __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile,
     const int w = wt * p.TW + w_l, h = ht * p.TH + h_l, n = nt * p.TN + n_l, co0 = n_tile * BN;
     const bool valid = (row < p.valid_rows) && (w < p.W) && (h < p.H) && (n < p.N);
     const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-    __nv_bfloat16* orow = p.out + ((static_cast<long long>(n) * p.H + h) * p.W + w) * p.ldo + p.out_coff + co0;
+    OT* orow = static_cast<OT*>(p.out) + ((static_cast<long long>(n) * p.H + h) * p.W + w) * p.ldo + p.out_coff + co0;
     const bool do_stats = p.stat_sum != nullptr;
     // per-row running sums (no per-tile cross-lane traffic): 64-column tiles always; 128-column tiles when only column
     // sums are wanted (rs / rq then hold this warp's two chunks)
@@ -235,28 +237,43 @@ __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile,
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float4 sc = __ldg(sc4 + j), sh = __ldg(sh4 + j);
-                pk[2 * j] = pack_bf16x2(fmaxf(fmaf(__uint_as_float(r[4 * j]), sc.x, sh.x), 0.f),
-                                        fmaxf(fmaf(__uint_as_float(r[4 * j + 1]), sc.y, sh.y), 0.f));
-                pk[2 * j + 1] = pack_bf16x2(fmaxf(fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z), 0.f),
-                                            fmaxf(fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w), 0.f));
+                r[4 * j] = __float_as_uint(fmaxf(fmaf(__uint_as_float(r[4 * j]), sc.x, sh.x), 0.f));
+                r[4 * j + 1] = __float_as_uint(fmaxf(fmaf(__uint_as_float(r[4 * j + 1]), sc.y, sh.y), 0.f));
+                r[4 * j + 2] = __float_as_uint(fmaxf(fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z), 0.f));
+                r[4 * j + 3] = __float_as_uint(fmaxf(fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w), 0.f));
+            }
+        }
+        if constexpr (Op::kTf32) {     // fp32 storage: 128 bytes per pixel and chunk, stored as they are
+            if (valid) {
+                uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
             }
         } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-        }
-        if (valid) {
-            uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
+            if (valid) {
+                uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            }
         }
         if (do_stats) {
             float v[32], s2[32];
+            if constexpr (Op::kTf32) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
-                const float lo = valid ? __low2float(b) : 0.f, hi = valid ? __high2float(b) : 0.f;
-                v[2 * j] = lo; v[2 * j + 1] = hi;
-                s2[2 * j] = lo * lo; s2[2 * j + 1] = hi * hi;
+                for (int j = 0; j < 32; ++j) {
+                    v[j] = valid ? __uint_as_float(r[j]) : 0.f;
+                    s2[j] = v[j] * v[j];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {     // statistics of the values as stored (bf16-rounded)
+                    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
+                    const float lo = valid ? __low2float(b) : 0.f, hi = valid ? __high2float(b) : 0.f;
+                    v[2 * j] = lo; v[2 * j + 1] = hi;
+                    s2[2 * j] = lo * lo; s2[2 * j + 1] = hi * hi;
+                }
             }
             if (RED) {      // BatchNorm-backward reduce of the previous layer: v = dz, s2 = dz * (y - mean) * invstd
                 const int grp = min((nt * p.TN) / p.group_images, 1);
@@ -340,9 +357,11 @@ __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile,
     }
 }
 
-template <int BN>
+template <int BN, class Op = OpBf16>
 __global__ void __launch_bounds__(kPxThreads, 1)
 tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PxParams p) {
+    using OT = typename Op::T;
+    constexpr int KC = Op::kKC;
     using Cfg = PxCfg<BN>;
     constexpr int STAGES = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -399,8 +418,8 @@ tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         const uint32_t fb = bar_full + 8 * stage;
                         mbar_expect_tx(fb, a_tx + Cfg::kBBytes);
                         const int4 tp = p.taps[t];
-                        tma_load_5d(sA, &tmA, fb, tp.x + kc * 64, w0 + tp.y, tp.z, h0 + tp.w, n0);
-                        tma_load_2d(sB, &tmB, fb, p.tap_w[t] * p.cin + kc * 64, co0);
+                        tma_load_5d(sA, &tmA, fb, tp.x + kc * KC, w0 + tp.y, tp.z, h0 + tp.w, n0);
+                        tma_load_2d(sB, &tmB, fb, p.tap_w[t] * p.cin + kc * KC, co0);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -409,7 +428,7 @@ tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (one elected thread)
         if (elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+            constexpr uint32_t idesc = umma_idesc<Op>(128, BN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -425,8 +444,8 @@ tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     const uint32_t sA = base + stage * Cfg::kStageBytes, sB = sA + Cfg::kABytes;
                     const uint64_t da = umma_smem_desc(sA, 16, 1024), db = umma_smem_desc(sB, 16, 1024);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)   // 4 x (K = 16 bf16 = 32 B) inside the 128-B swizzle row
-                        umma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0);
+                    for (int kk = 0; kk < 4; ++kk)   // 4 x (32 B of K: 16 bf16 / 8 tf32) inside the 128-B swizzle row
+                        umma<Op>(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0);
                     umma_commit(bar_empty + 8 * stage);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -459,7 +478,7 @@ tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 
             if (p.epi_mode == EPI_STORE) {
-                px_store_epilogue<BN>(p, m_tile, n_tile, acc, tmem_base, q, ew, lane, s_part, bar_tempty + 8 * acc, false, sacc);
+                px_store_epilogue<BN, false, Op>(p, m_tile, n_tile, acc, tmem_base, q, ew, lane, s_part, bar_tempty + 8 * acc, false, sacc);
             } else {
                 // EPI_CONVT: column = (tap, co); scatter to the 2x upsampled grid, add bias.  A tile may span several
                 // taps (BN up to 4 * co_per_tap); every 32-column chunk lies inside one tap (co_per_tap % 32 == 0).
@@ -474,19 +493,29 @@ tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         const int colg = co0 + (ch + u) * 32;
                         const int tap = colg / p.co_per_tap, cbase = colg % p.co_per_tap;
                         const int dy = tap >> 1, dx = tap & 1;
-                        __nv_bfloat16* dst16 = p.out +
-                                               ((static_cast<long long>(n) * p.Ho + (2 * h + dy)) * p.Wo + (2 * w + dx)) * p.ldo +
-                                               p.out_coff + cbase;
+                        OT* dstT = static_cast<OT*>(p.out) +
+                                   ((static_cast<long long>(n) * p.Ho + (2 * h + dy)) * p.Wo + (2 * w + dx)) * p.ldo + p.out_coff + cbase;
                         const float4* bias4 = reinterpret_cast<const float4*>(p.bias + cbase);
                         if (valid) {
-                            uint4* dst = reinterpret_cast<uint4*>(dst16);
+                            uint4* dst = reinterpret_cast<uint4*>(dstT);
+                            if constexpr (Op::kTf32) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float4 b0 = __ldg(bias4 + 2 * j), b1 = __ldg(bias4 + 2 * j + 1);
-                                dst[j] = make_uint4(pack_bf16x2(__uint_as_float(r[u][j * 8 + 0]) + b0.x, __uint_as_float(r[u][j * 8 + 1]) + b0.y),
-                                                    pack_bf16x2(__uint_as_float(r[u][j * 8 + 2]) + b0.z, __uint_as_float(r[u][j * 8 + 3]) + b0.w),
-                                                    pack_bf16x2(__uint_as_float(r[u][j * 8 + 4]) + b1.x, __uint_as_float(r[u][j * 8 + 5]) + b1.y),
-                                                    pack_bf16x2(__uint_as_float(r[u][j * 8 + 6]) + b1.z, __uint_as_float(r[u][j * 8 + 7]) + b1.w));
+                                for (int j = 0; j < 8; ++j) {
+                                    const float4 b0 = __ldg(bias4 + j);
+                                    dst[j] = make_uint4(__float_as_uint(__uint_as_float(r[u][j * 4 + 0]) + b0.x),
+                                                        __float_as_uint(__uint_as_float(r[u][j * 4 + 1]) + b0.y),
+                                                        __float_as_uint(__uint_as_float(r[u][j * 4 + 2]) + b0.z),
+                                                        __float_as_uint(__uint_as_float(r[u][j * 4 + 3]) + b0.w));
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float4 b0 = __ldg(bias4 + 2 * j), b1 = __ldg(bias4 + 2 * j + 1);
+                                    dst[j] = make_uint4(pack_bf16x2(__uint_as_float(r[u][j * 8 + 0]) + b0.x, __uint_as_float(r[u][j * 8 + 1]) + b0.y),
+                                                        pack_bf16x2(__uint_as_float(r[u][j * 8 + 2]) + b0.z, __uint_as_float(r[u][j * 8 + 3]) + b0.w),
+                                                        pack_bf16x2(__uint_as_float(r[u][j * 8 + 4]) + b1.x, __uint_as_float(r[u][j * 8 + 5]) + b1.y),
+                                                        pack_bf16x2(__uint_as_float(r[u][j * 8 + 6]) + b1.z, __uint_as_float(r[u][j * 8 + 7]) + b1.w));
+                                }
                             }
                         }
                     }
@@ -530,7 +559,7 @@ struct WgGroup {          // one work-unit type: up to 3 accumulators, each M=12
 
 struct WgParams {
     int N, H, W;                         // pixel grid that is reduced over
-    int TW, TH, TN;                      // pixel slab = TW*TH*TN = 64 pixels
+    int TW, TH, TN;                      // pixel slab = TW*TH*TN = 64 pixels (bf16) / 32 pixels (tf32)
     int tiles_w, tiles_h, tiles_n, num_px_tiles;
     int ksplit, px_tiles_per_split;
     int ngroups, num_m_tiles, num_n_tiles;
@@ -544,21 +573,32 @@ struct WgParams {
     int ks_slowest;
 };
 
-template <int BNW>
+// One operand "box" = one pixel slab x one 128-byte row of channels: 64 pixels x 64 bf16 channels (8 KB), or - fp32 operands
+// read as TF32 - 32 pixels x 32 channels (4 KB; the slab is halved so that three stages of N-side + 3 accumulators x M = 128
+// still fit in shared memory).  An M = 128 accumulator is made of 128 / kKC boxes, LBO = one box apart.
+template <int BNW, class Op = OpBf16>
 struct WgCfg {
-    static constexpr int kNBytes = (BNW / 64) * 8192;            // N-side (unshifted) operand per stage
-    static constexpr int kMBytes = kWgMaxAcc * 2 * 8192;          // M-side: up to 3 acc x 2 blocks
+    static constexpr int kSlabPx = Op::kTf32 ? 32 : 64;
+    static constexpr int kBoxBytes = kSlabPx * 128;
+    static constexpr int kBoxesPerHalf = 64 / Op::kKC;            // boxes per 64-channel half of an accumulator's M operand
+    static constexpr int kNBoxes = BNW / Op::kKC;
+    static constexpr int kNBytes = kNBoxes * kBoxBytes;          // N-side (unshifted) operand per stage
+    static constexpr int kAccBytes = 2 * kBoxesPerHalf * kBoxBytes;
+    static constexpr int kMBytes = kWgMaxAcc * kAccBytes;         // M-side: up to 3 accumulators x (2 x 64 channels)
     static constexpr int kStageBytes = kNBytes + kMBytes;
-    static constexpr int kStages = (BNW == 128) ? 3 : 3;
+    static constexpr int kStages = 3;
+    static constexpr int kKSteps = 4;                             // MMAs per slab: 64 px / K16 (bf16), 32 px / K8 (tf32)
+    static constexpr int kKStepUnits = (Op::kTf32 ? 1024 : 2048) / 16;   // descriptor advance per MMA, in 16-byte units
     static constexpr int kTmemCols = 512;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 1024;
 };
 
-template <int BNW>
+template <int BNW, class Op = OpBf16>
 __global__ void __launch_bounds__(192, 1)
 tapgemm_wg_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmI, const WgParams p) {
-    using Cfg = WgCfg<BNW>;
+    using Cfg = WgCfg<BNW, Op>;
     constexpr int STAGES = Cfg::kStages;
+    constexpr int KC = Op::kKC, BOX = Cfg::kBoxBytes, BPH = Cfg::kBoxesPerHalf;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -605,8 +645,8 @@ tapgemm_wg_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                 const int px_begin = ks * p.px_tiles_per_split;
                 const int px_end = min(px_begin + p.px_tiles_per_split, p.num_px_tiles);
                 int nboxes = 0;
-                for (int a = 0; a < grp.nacc; ++a) nboxes += (grp.tapB[a] >= 0) ? 2 : 1;
-                const uint32_t tx = static_cast<uint32_t>(nboxes) * 8192u + Cfg::kNBytes;
+                for (int a = 0; a < grp.nacc; ++a) nboxes += (grp.tapB[a] >= 0) ? 2 * BPH : BPH;
+                const uint32_t tx = static_cast<uint32_t>(nboxes) * BOX + Cfg::kNBytes;
                 for (int pt = px_begin; pt < px_end; ++pt) {
                     const int wt = pt % p.tiles_w, ht = (pt / p.tiles_w) % p.tiles_h, nn = pt / (p.tiles_w * p.tiles_h);
                     const int w0 = wt * p.TW, h0 = ht * p.TH, nimg0 = nn * p.TN;
@@ -615,14 +655,19 @@ tapgemm_wg_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                     const uint32_t fb = bar_full + 8 * stage;
                     mbar_expect_tx(fb, tx);
 #pragma unroll
-                    for (int b = 0; b < BNW / 64; ++b) tma_load_5d(sN + b * 8192, &tmI, fb, n0 + b * 64, w0, 0, h0, nimg0);
+                    for (int b = 0; b < Cfg::kNBoxes; ++b) tma_load_5d(sN + b * BOX, &tmI, fb, n0 + b * KC, w0, 0, h0, nimg0);
                     for (int a = 0; a < grp.nacc; ++a) {
                         const int4 ta = p.taps[grp.tapA[a]];
-                        tma_load_5d(sM + (2 * a) * 8192, &tmG, fb, m0 + grp.offA[a] + ta.x, w0 + ta.y, ta.z, h0 + ta.w, nimg0);
+#pragma unroll
+                        for (int b = 0; b < BPH; ++b)
+                            tma_load_5d(sM + a * Cfg::kAccBytes + b * BOX, &tmG, fb, m0 + grp.offA[a] + b * KC + ta.x, w0 + ta.y, ta.z,
+                                        h0 + ta.w, nimg0);
                         if (grp.tapB[a] >= 0) {
                             const int4 tb = p.taps[grp.tapB[a]];
-                            tma_load_5d(sM + (2 * a + 1) * 8192, &tmG, fb, m0 + grp.offB[a] + tb.x, w0 + tb.y, tb.z,
-                                        h0 + tb.w, nimg0);
+#pragma unroll
+                            for (int b = 0; b < BPH; ++b)
+                                tma_load_5d(sM + a * Cfg::kAccBytes + (BPH + b) * BOX, &tmG, fb, m0 + grp.offB[a] + b * KC + tb.x,
+                                            w0 + tb.y, tb.z, h0 + tb.w, nimg0);
                         }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -631,7 +676,7 @@ tapgemm_wg_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         }
     } else if (warp == 1) {
         if (elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(128, BNW, 1, 1);   // both operands MN-major
+            constexpr uint32_t idesc = umma_idesc<Op>(128, BNW, 1, 1);   // both operands MN-major
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -648,12 +693,13 @@ tapgemm_wg_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
                     const uint32_t sN = base + stage * Cfg::kStageBytes, sM = sN + Cfg::kNBytes;
-                    const uint64_t db = umma_smem_desc(sN, 8192, 1024);
+                    const uint64_t db = umma_smem_desc(sN, BOX, 1024);
                     for (int a = 0; a < nacc; ++a) {
-                        const uint64_t da = umma_smem_desc(sM + a * 16384, 8192, 1024);
+                        const uint64_t da = umma_smem_desc(sM + a * Cfg::kAccBytes, BOX, 1024);
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)   // 4 x 16 pixels; 16 pixel rows = 2048 B
-                            umma_bf16(tmem_base + a * BNW, da + 128 * kk, db + 128 * kk, idesc, (pt > px_begin) || kk);
+                        for (int kk = 0; kk < Cfg::kKSteps; ++kk)   // 16 pixel rows = 2048 B (bf16) / 8 pixel rows = 1024 B (tf32) per MMA
+                            umma<Op>(tmem_base + a * BNW, da + Cfg::kKStepUnits * kk, db + Cfg::kKStepUnits * kk, idesc,
+                                     (pt > px_begin) || kk);
                     }
                     umma_commit(bar_empty + 8 * stage);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }

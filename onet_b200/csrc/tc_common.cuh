@@ -112,6 +112,17 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// The same with fp32 operands read as TF32 (the tensor core uses the upper 19 bits of every operand word: sign, 8-bit
+// exponent, 10-bit mantissa; the low 13 mantissa bits are ignored) - K = 8 per instruction, still 32 bytes of K per row.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // Arrive on an mbarrier once all previously issued MMAs of this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -205,6 +216,15 @@ __device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a,
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_tf32_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrive (once all previously issued MMAs completed) on the mbarrier at the same offset in BOTH CTAs of the pair
 __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
@@ -234,6 +254,39 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, u
                                                        uint32_t b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) |
            ((M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ operand kinds of the tensor-core kernels
+// Every kernel is written in BYTES: a K chunk is one 128-byte swizzle row per pixel / output channel, an MMA consumes 32 bytes
+// of K.  The operand kind only decides how many channels that is, the instruction kind and the storage type of the epilogue.
+//   OpBf16: bf16 storage and operands (64 channels per chunk, K = 16 per MMA)   - the throughput mode
+//   OpTf32: fp32 storage, operands read as TF32 (32 channels per chunk, K = 8 per MMA) - the tolerance-meeting fast mode
+struct OpBf16 {
+    using T = __nv_bfloat16;
+    static constexpr int kKC = 64;               // channels per 128-byte K chunk
+    static constexpr uint32_t kFmt = 1;          // idesc a_format / b_format: BF16
+    static constexpr bool kTf32 = false;
+};
+struct OpTf32 {
+    using T = float;
+    static constexpr int kKC = 32;
+    static constexpr uint32_t kFmt = 2;          // TF32
+    static constexpr bool kTf32 = true;
+};
+template <class Op>
+__host__ __device__ constexpr uint32_t umma_idesc(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {
+    return (1u << 4) | (Op::kFmt << 7) | (Op::kFmt << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) |
+           ((M >> 4) << 24);
+}
+template <class Op>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (Op::kTf32) umma_tf32(tmem_d, desc_a, desc_b, idesc, accumulate);
+    else umma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);
+}
+template <class Op>
+__device__ __forceinline__ void umma_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (Op::kTf32) umma_tf32_2cta(tmem_d, desc_a, desc_b, idesc, accumulate);
+    else umma_bf16_2cta(tmem_d, desc_a, desc_b, idesc, accumulate);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -31,7 +31,9 @@ from ._lib import BF16, ENGINE_SIMT, ENGINE_TC, F32, call, ptr
 _ENC = [("down1", 64, 128), ("down2", 128, 256), ("down3", 256, 512), ("down4", 512, 1024)]
 _DEC = [("up1", 1024, 512), ("up2", 512, 256), ("up3", 256, 128), ("up4", 128, 64)]
 
-_DTYPES = {"fp32": (F32, torch.float32), "bf16": (BF16, torch.bfloat16)}
+# mode -> (C-ABI dtype, torch storage dtype).  "tf32": fp32 storage everywhere, the tcgen05 kernels read the fp32 operands as
+# TF32 (C-ABI: dtype ONET_F32 with engine ONET_ENGINE_TC) - the fast mode that meets the north_star tolerances literally.
+_DTYPES = {"fp32": (F32, torch.float32), "bf16": (BF16, torch.bfloat16), "tf32": (F32, torch.float32)}
 
 _PACK_GEN = [0]
 
@@ -205,7 +207,7 @@ class _Engine:
             raise ValueError(f"mode must be one of {list(_DTYPES)}")
         self.mode = mode
         self.dt, self.tdt = _DTYPES[mode]
-        self.use_tc = bool(use_tc) and mode == "bf16"
+        self.use_tc = bool(use_tc) and mode in ("bf16", "tf32")
         self.segments = segments
         self.x = x
         self.dev = x.device
@@ -445,7 +447,7 @@ class _Engine:
         gradient must be ACCUMULATED into."""
         B, H, W, N2 = rec.B, rec.H, rec.W, rec.N2
         st = self.stream
-        if self.mode == "fp32":
+        if self.mode in ("fp32", "tf32"):       # (tf32: the first layer's weight gradient runs on the CUDA-core kernels)
             _register_splitk_workspace(self.dev)
         # per-call event timing (bench.py's profile pass) records on the main stream only: keep that pass serial
         overlap = os.environ.get("ONET_NO_WGRAD_OVERLAP") is None and _lib.PROFILE is None
@@ -584,7 +586,7 @@ class _Engine:
         _, wd = self._packed(conv, "conv")
         dX = self._empty(n, h, w, cin)
         prev = rec.saved.get((si, li - 1)) if (li & 1) else None
-        if (prev is not None and eng == ENGINE_TC and colsum is None and prev["cout"] == cin and prev["h"] == h
+        if (prev is not None and eng == ENGINE_TC and self.mode == "bf16" and colsum is None and prev["cout"] == cin and prev["h"] == h
                 and cin >= _BNRED_MIN_C and os.environ.get("ONET_NO_BNRED_FUSION") is None):
             # second conv of a DoubleConv: its data gradient is the gradient w.r.t. the first conv's activation - reduce the
             # first conv's BatchNorm-backward sums in this launch's epilogue (saves one pass over (Y, g) in HBM)
@@ -673,8 +675,9 @@ class _FusedJsdFn(torch.autograd.Function):
 
 class Onet(nn.Module):
     def __init__(self, in_chns=1, binit=False, bshare=True, mode="bf16", use_tc=True):
-        """`mode`: "bf16" (bf16 storage/operands, fp32 accumulate — the throughput mode) or "fp32" (FP32
-        verification mode on CUDA cores).  `use_tc=False` forces the CUDA-core kernels in bf16 mode too."""
+        """`mode`: "bf16" (bf16 storage/operands, fp32 accumulate - the throughput mode), "tf32" (fp32 storage, tensor-core
+        operands read as TF32, fp32 accumulate - the fast mode inside the north_star tolerances) or "fp32" (FP32
+        verification mode on CUDA cores).  `use_tc=False` forces the CUDA-core kernels in the bf16 / tf32 modes too."""
         super().__init__()
         self.topu = UNet(n_channels=in_chns, n_classes=1, bilinear=False, binit=binit)
         if bshare:

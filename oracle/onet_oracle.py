@@ -243,7 +243,21 @@ def _bn_relu_emulated(st, prefix, y, training, q):
     return q.store(torch.relu(y * sc[None, :, None, None] + sh[None, :, None, None]))
 
 
-def double_conv(st, block, x, training, taps=None, q=None):
+def _forced(x, force, key, taps):
+    """Teacher forcing: the VALUE of x becomes force[key] (the tensor another implementation stored at this point) while the
+    gradient still flows through x's own graph; taps[key + ".own"] keeps what this implementation computed from the forced
+    inputs.  With every raw convolution output and up-conv output forced, all data-dependent decisions of the forward pass
+    (BatchNorm statistics, ReLU masks, max-pool arg-max) are the other implementation's, so the backward pass is compared as
+    the LINEAR map it is - free of the network's ill-conditioning at random init (a 1e-6 relative perturbation of the forward
+    moves the free-running gradient by 3e-3, bf16 rounding flips by 0.2)."""
+    if force is None or key not in force:
+        return x
+    if taps is not None:
+        taps[key + ".own"] = x.detach()
+    return x + (force[key].to(x.dtype) - x).detach()
+
+
+def double_conv(st, block, x, training, taps=None, q=None, force=None):
     """Onet_vanilla_20240606.py:39-58: (conv3x3 pad 1 no bias -> BN -> ReLU) x 2."""
     p = _dc_prefix(block)
     for conv_i, bn_i in ((0, 1), (3, 4)):
@@ -252,6 +266,7 @@ def double_conv(st, block, x, training, taps=None, q=None):
         else:
             first = block == "inc" and conv_i == 0       # the 1 -> 64 / 3 -> 64 layer runs on CUDA cores in every mode
             x = q.conv_out(F.conv2d(q.conv_in(x, first), q.weight(st[f"{p}.{conv_i}.weight"], first), None, padding=1), first)
+        x = _forced(x, force, f"{p}.{conv_i}.raw", taps)
         if taps is not None:
             taps[f"{p}.{conv_i}.raw"] = x
         x = torch.relu(_bn(st, f"{p}.{bn_i}", x, training)) if q is None else _bn_relu_emulated(st, f"{p}.{bn_i}", x, training, q)
@@ -260,42 +275,46 @@ def double_conv(st, block, x, training, taps=None, q=None):
     return x
 
 
-def up_block(st, name, x1, x2, training, taps=None, q=None):
+def up_block(st, name, x1, x2, training, taps=None, q=None, force=None):
     """Onet_vanilla_20240606.py:75-101 (bilinear=False): ConvTranspose2d(C, C/2, 2, 2) with bias,
     zero-pad to the skip's size, cat([skip, up]) and DoubleConv."""
     if q is None:
         x1 = F.conv_transpose2d(x1, st[f"{name}.up.weight"], st[f"{name}.up.bias"], stride=2)
     else:
         x1 = q.upconv_out(F.conv_transpose2d(q.conv_in(x1), q.weight(st[f"{name}.up.weight"]), st[f"{name}.up.bias"], stride=2))
+    x1 = _forced(x1, force, f"{name}.up.out", taps)
+    if taps is not None:
+        taps[f"{name}.up.out"] = x1
     dy = x2.shape[2] - x1.shape[2]
     dx = x2.shape[3] - x1.shape[3]
     x1 = F.pad(x1, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
     x = torch.cat([x2, x1], dim=1)
     if taps is not None:
         taps[f"{name}.cat"] = x
-    return double_conv(st, name, x, training, taps, q)
+    return double_conv(st, name, x, training, taps, q, force)
 
 
-def unet_forward(st, x, training=True, taps=None, q=None):
+def unet_forward(st, x, training=True, taps=None, q=None, force=None):
     """Onet_vanilla_20240606.py:142-153: returns (x1, y1) = (first-block output, last-block output)."""
-    x1 = double_conv(st, "inc", x, training, taps, q)
+    x1 = double_conv(st, "inc", x, training, taps, q, force)
     skips = [x1]
     h = x1
     for name, _, _ in ENCODER:
         h = F.max_pool2d(h, 2)
-        h = double_conv(st, name, h, training, taps, q)
+        h = double_conv(st, name, h, training, taps, q, force)
         skips.append(h)
     y = skips[-1]
     for i, (name, _, _) in enumerate(DECODER):
-        y = up_block(st, name, y, skips[3 - i], training, taps, q)
+        y = up_block(st, name, y, skips[3 - i], training, taps, q, force)
     return x1, y
 
 
-def onet_forward(st_top, x, training=True, st_dwn=None, bias=0.0, taps=None, emulate=None):
+def onet_forward(st_top, x, training=True, st_dwn=None, bias=0.0, taps=None, emulate=None, force=None):
     """Onet.forward, Onet_vanilla_20240606.py:174-191.  `st_dwn=None` is the weight-shared twin
     (`bshare=True`, :163-164): the SAME state (parameters and BN running buffers) is used for
     both branches, top branch first.  `emulate` = "bf16" / "tf32": the same algorithm with the CUDA path's
-    reduced-precision roundings (see `_Policy`); None = the reference's FP32 arithmetic."""
+    reduced-precision roundings (see `_Policy`); None = the reference's FP32 arithmetic.  `force` = {"top": {...}, "dwn": {...}}
+    of tensors keyed like `taps` ("<prefix>.<conv>.raw", "<up block>.up.out"): teacher forcing, see `_forced`."""
     st_dwn = st_top if st_dwn is None else st_dwn
     q = _policy(emulate)
     tt = {} if taps is not None else None
@@ -303,11 +322,12 @@ def onet_forward(st_top, x, training=True, st_dwn=None, bias=0.0, taps=None, emu
     Xd = torch.clip(1 - x + bias, 0, 1)
     if q is not None:
         x, Xd = q.image(x), q.image(Xd)
-    Lt, Ht = unet_forward(st_top, x, training, tt, q)
+    ft, fd = (None, None) if force is None else (force.get("top"), force.get("dwn"))
+    Lt, Ht = unet_forward(st_top, x, training, tt, q, ft)
     if q is not None:        # the head's gradient w.r.t. L (both uses: V and the loss's channel sum) and H is stored rounded
         Lt, Ht = q.head_in(Lt), q.head_in(Ht)
     Vt = (Lt * Ht).sum(dim=1, keepdim=True)
-    Ld, Hd = unet_forward(st_dwn, Xd, training, td, q)
+    Ld, Hd = unet_forward(st_dwn, Xd, training, td, q, fd)
     if q is not None:
         Ld, Hd = q.head_in(Ld), q.head_in(Hd)
     Vd = (Ld * Hd).sum(dim=1, keepdim=True)
@@ -352,7 +372,7 @@ def predict_label(S):
     return torch.argmax(S, dim=1)
 
 
-def train_step_outputs(st, x, st_dwn=None, emulate=None):
+def train_step_outputs(st, x, st_dwn=None, emulate=None, force=None, taps=None):
     """One reference training-step's forward + loss + backward (Train_Onet_on_simclutter_20250407.py:
     209-217) on a copy of `st` with autograd; returns (outputs dict, grads dict, new state)."""
     st = OrderedDict((k, v.clone()) for k, v in st.items())
@@ -364,7 +384,7 @@ def train_step_outputs(st, x, st_dwn=None, emulate=None):
         sd = OrderedDict((k, v.clone()) for k, v in st_dwn.items())
         for k in leaves:
             sd[k].requires_grad_(True)
-    Lt, Vt, Ld, Vd, S = onet_forward(st, x, True, sd, emulate=emulate)
+    Lt, Vt, Ld, Vd, S = onet_forward(st, x, True, sd, emulate=emulate, force=force, taps=taps)
     loss = compute_loss(Lt, S[:, 0:1], Ld, S[:, 1:2])
     loss.backward()
     grads = OrderedDict((k, st[k].grad.detach().clone()) for k in leaves)

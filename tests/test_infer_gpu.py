@@ -7,7 +7,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "tf32"])
 def test_tiled_inference_is_bit_identical_to_whole_frame(mode):
     import onet_b200
     from onet_b200.data import rayleigh_target_frames

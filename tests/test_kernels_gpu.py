@@ -82,6 +82,75 @@ def test_conv3x3_tc_fwd(n, h, w, cin, cout):
     assert err < 4e-3, err
 
 
+def _tf32t(t):
+    """fp32 -> tf32 by truncation (the low 13 mantissa bits cleared): exactly representable tensor-core operands"""
+    return (t.contiguous().view(torch.int32) & -8192).view(torch.float32)
+
+
+def _tf32r(t):
+    """fp32 -> tf32 by round-to-nearest (ties away), cvt.rna.tf32.f32"""
+    return ((t.contiguous().view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+
+
+TF32_SHAPES = [(2, 16, 16, 64, 64), (4, 16, 16, 128, 256), (2, 32, 32, 64, 128), (8, 4, 4, 256, 256), (4, 2, 2, 128, 64),
+               (2, 24, 40, 128, 64), (1, 19, 21, 64, 128), (3, 48, 40, 64, 256), (5, 32, 16, 128, 128), (2, 16, 16, 256, 256),
+               (3, 8, 24, 128, 384), (2, 64, 64, 64, 64)]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", TF32_SHAPES)
+def test_conv3x3_tf32_fwd_dgrad_wgrad(n, h, w, cin, cout):
+    """tcgen05 kind::tf32 kernels (C-ABI: dtype ONET_F32 + engine ONET_ENGINE_TC) on tf32-exact inputs: products are exact in
+    fp32, so only the accumulation order differs from the FP32 torch op."""
+    U = _imports()
+    torch.manual_seed(11)
+    x = _tf32t(torch.randn(n, cin, h, w, device="cuda"))
+    wt = _tf32t(torch.randn(cout, cin, 3, 3, device="cuda") * (2.0 / (9 * cin)) ** 0.5)
+    wf, wd = U.pack_conv(wt, U.F32)
+    g = max(n // 2, 1)
+    y, st = U.conv3x3(U.to_nhwc(x, torch.float32), wf, cout, U.F32, U.ENGINE_TC, group_images=g, stats=True)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x, wt, padding=1)
+    err = U.rel_l2(U.from_nhwc(y), ref)
+    assert err < 2e-6, err
+    yf = U.from_nhwc(y).double()
+    assert torch.allclose(st[0, 0], yf[:g].sum(dim=(0, 2, 3)), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(st[1, 0], (yf[:g] ** 2).sum(dim=(0, 2, 3)), rtol=1e-5, atol=1e-3)
+    if n > g:
+        assert torch.allclose(st[0, 1], yf[g:].sum(dim=(0, 2, 3)), rtol=1e-5, atol=1e-3)
+    gy = _tf32t(torch.randn(n, cout, h, w, device="cuda"))
+    dx, _ = U.conv3x3(U.to_nhwc(gy, torch.float32), wd, cin, U.F32, U.ENGINE_TC)
+    dref = torch.nn.grad.conv2d_input(x.shape, wt, gy, padding=1)
+    err = U.rel_l2(U.from_nhwc(dx), dref)
+    assert err < 2e-6, err
+    dw = U.conv3x3_wgrad(U.to_nhwc(gy, torch.float32), U.to_nhwc(x, torch.float32), U.F32, U.ENGINE_TC)
+    torch.cuda.synchronize()
+    wref = torch.nn.grad.conv2d_weight(x, (cout, cin, 3, 3), gy, padding=1)
+    err = U.rel_l2(dw, wref)
+    assert err < 1e-5, err
+
+
+def test_tf32_operand_semantics():
+    """What the tensor core does with fp32 operands that are NOT tf32-exact: the oracle's tf32 emulation (`_Policy`, truncation
+    of the low 13 mantissa bits) must be the arithmetic of the hardware.  Compares one convolution on full-precision random
+    inputs with the FP32 op on truncated and on round-to-nearest operands; records both and requires the truncation model."""
+    U = _imports()
+    from parity_record import record
+    torch.manual_seed(12)
+    n, h, w, cin, cout = 2, 32, 32, 128, 128
+    x = torch.randn(n, cin, h, w, device="cuda")
+    wt = torch.randn(cout, cin, 3, 3, device="cuda") * (2.0 / (9 * cin)) ** 0.5
+    wf, _ = U.pack_conv(wt, U.F32)
+    y, _ = U.conv3x3(U.to_nhwc(x, torch.float32), wf, cout, U.F32, U.ENGINE_TC)
+    got = U.from_nhwc(y)
+    e_trunc = U.rel_l2(got, F.conv2d(_tf32t(x), _tf32t(wt), padding=1))
+    e_rna = U.rel_l2(got, F.conv2d(_tf32r(x), _tf32r(wt), padding=1))
+    e_fp32 = U.rel_l2(got, F.conv2d(x, wt, padding=1))
+    print(f"tf32 operands: vs truncated {e_trunc:.2e}, vs round-to-nearest {e_rna:.2e}, vs full fp32 {e_fp32:.2e}")
+    record("tf32_operand_semantics", vs_truncated=e_trunc, vs_round_to_nearest=e_rna, vs_fp32=e_fp32)
+    assert e_fp32 < 2e-3
+    assert e_trunc < 2e-6, (e_trunc, e_rna)
+
+
 def test_conv3x3_tc_strided_input():
     """input taken from channels [64,128) of a wider (concat-like) buffer"""
     U = _imports()
@@ -109,7 +178,7 @@ def test_conv3x3_tc_wgrad(n, h, w, cin, cout):
 
 
 @pytest.mark.parametrize("pad", [(0, 0), (1, 1), (1, 0)])
-@pytest.mark.parametrize("engine_name", ["simt_fp32", "simt_bf16", "tc"])
+@pytest.mark.parametrize("engine_name", ["simt_fp32", "simt_bf16", "tc", "tc_tf32"])
 @pytest.mark.parametrize("n,h,w,cin", [(2, 4, 4, 128), (3, 8, 8, 256), (2, 16, 16, 128), (4, 2, 2, 1024)])
 def test_convT2x2(engine_name, n, h, w, cin, pad):
     """ConvTranspose2d(C, C/2, 2, 2) + bias written into the up half of a concat buffer whose fine grid is
@@ -117,9 +186,10 @@ def test_convT2x2(engine_name, n, h, w, cin, pad):
     and zero-fills the last row / column; backward ignores the border."""
     U = _imports()
     call, ptr = U.call, U.ptr
-    dt, eng = {"simt_fp32": (U.F32, U.ENGINE_SIMT), "simt_bf16": (U.BF16, U.ENGINE_SIMT), "tc": (U.BF16, U.ENGINE_TC)}[engine_name]
+    dt, eng = {"simt_fp32": (U.F32, U.ENGINE_SIMT), "simt_bf16": (U.BF16, U.ENGINE_SIMT), "tc": (U.BF16, U.ENGINE_TC),
+               "tc_tf32": (U.F32, U.ENGINE_TC)}[engine_name]
     tdt = U.TDT[dt]
-    rnd = (lambda t: t) if dt == U.F32 else _bf16r
+    rnd = _tf32t if engine_name == "tc_tf32" else ((lambda t: t) if dt == U.F32 else _bf16r)
     ph, pw = pad
     ho, wo = 2 * h + ph, 2 * w + pw
     co = cin // 2

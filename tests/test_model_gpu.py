@@ -179,7 +179,7 @@ def test_generic_autograd_path_matches_fused():
         assert e < 3e-2, (k, e)
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "tf32"])
 def test_graph_replayed_step_matches_eager_step(mode):
     """OnetTrainer(graph=True) — one captured CUDA graph replayed per step, Adam step count and lr in device memory —
     against the eager trainer: same losses, same parameter trajectory, same BatchNorm buffers after 4 steps (the
