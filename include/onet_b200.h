@@ -73,9 +73,25 @@ int onet_conv3x3_fwd(const void* in, int64_t ldi, int ci_off, int N, int H, int 
                      void* out, int64_t ldo, int co_off, double* stat_sum, double* stat_sq, int group_images,
                      int dtype, int engine, void* stream);
 
+/* The FIRST convolution of each U-Net (in_chns 1 or 3 -> 64 at full resolution, Onet_vanilla_20240606.py:111,47-49) without
+ * materialising its raw output: 64 outputs per pixel are recomputed from the 3 x 3 x in_chns patch wherever they are needed
+ * (x [N,H,W,Cin] dense, wp = packed wf [64][9][Cin], W % 4 == 0).  Results are those of onet_conv3x3_fwd + onet_bn_relu_apply
+ * (bit for bit) and of onet_bn_relu_bwd + onet_conv3x3_wgrad (same expressions, sums in a different order):
+ *   onet_first_conv_stats   : BatchNorm partial sums of conv(x) as stored (rounded to dtype) -> onet_bn_finalize
+ *   onet_first_conv_bn_relu : out [N,H,W,64] = relu(conv(x) * scale + shift)   (training: batch statistics; eval: running)
+ *   onet_first_conv_bwd     : g [N,H,W,64] = gradient w.r.t. out; reduces the BatchNorm-backward sums (sums: zeroed double
+ *                             [G][2][64]), forms dY in registers and accumulates dw [64][Cin][3][3] (+ dgamma / dbeta). */
+int onet_first_conv_stats(const void* x, int N, int H, int W, int Cin, const void* wp, double* stat_sum, double* stat_sq,
+                          int group_images, int dtype, void* stream);
+int onet_first_conv_bn_relu(const void* x, int N, int H, int W, int Cin, const void* wp, const float* scale, const float* shift,
+                            int group_images, void* out, int dtype, void* stream);
+int onet_first_conv_bwd(const void* x, int N, int H, int W, int Cin, const void* wp, const float* scale, const float* shift,
+                        const float* mean, const float* invstd, int group_images, const void* g, double* sums, double count,
+                        float* dw, float* dgamma0, float* dbeta0, float* dgamma1, float* dbeta1, int dtype, void* stream);
+
 /* Inference: the same convolution with BatchNorm(eval) + ReLU folded into the epilogue, out = relu(conv * scale + shift)
  * (scale / shift [G][Cout] from onet_bn_eval_prepare), written straight to its destination (e.g. a concat-buffer slice):
- * nn.Conv2d + nn.BatchNorm2d(eval) + nn.ReLU, Onet_vanilla_20240606.py:47-53.  Tensor-core engine, bf16 only. */
+ * nn.Conv2d + nn.BatchNorm2d(eval) + nn.ReLU, Onet_vanilla_20240606.py:47-53.  Tensor-core engine (bf16, or fp32 storage with tf32 operands). */
 int onet_conv3x3_bn_relu_infer(const void* in, int64_t ldi, int ci_off, int N, int H, int W, int Cin, const void* wp, int Cout,
                                const float* scale, const float* shift, int group_images, void* out, int64_t ldo, int co_off,
                                int dtype, int engine, void* stream);
@@ -103,14 +119,16 @@ int onet_bn_eval_prepare(int G, int C, const float* gamma0, const float* beta0, 
  * pool != NULL, the 2x2 max-pooled map [N,H/2,W/2,C] in the same pass (nn.ReLU :49,53 + nn.MaxPool2d(2) :67
  * + the skip half of torch.cat :100).  Nothing else is saved: the backward pass recomputes the window arg-max. */
 int onet_bn_relu_apply(const void* y, int N, int H, int W, int C, const float* scale, const float* shift,
-                       int group_images, void* out, int64_t ldo, int ooff, void* pool, int dtype, void* stream);
+                       int group_images, void* out, int64_t ldo, int ooff, void* pool, void* pool_arg, int dtype, void* stream);
 
 /* Backward of BN -> ReLU (-> skip / max-pool): gradient sources g1 (+ optional g2, optional pooled gp routed to
- * the first maximum of each 2x2 window, recomputed from y), produces dy [N,H,W,C] and accumulates dgamma/dbeta.
+ * the first maximum of each 2x2 window: read from gp_arg, the uint16 [N,H/2,W/2,C/8] arg-max words (2 bits per channel)
+ * onet_bn_relu_apply wrote into its pool_arg, or recomputed from y when gp_arg is NULL), produces dy [N,H,W,C] and
+ * accumulates dgamma/dbeta.
  * `sums` is a zero-initialised [G][2][C] double workspace. */
 int onet_bn_relu_bwd(const void* y, int N, int H, int W, int C, const float* scale, const float* shift,
                      const float* mean, const float* invstd, int group_images, const void* g1, int64_t ld1, int off1,
-                     const void* g2, int64_t ld2, int off2, const void* gp, double* sums, double count,
+                     const void* g2, int64_t ld2, int off2, const void* gp, const void* gp_arg, double* sums, double count,
                      void* dy, float* dgamma0, float* dbeta0, float* dgamma1, float* dbeta1, int dtype, void* stream);
 
 /* Backward fusion (tcgen05 bf16 path): the 3x3 data gradient whose OUTPUT is the gradient g w.r.t. the post-ReLU activation
@@ -162,6 +180,24 @@ int onet_head_fwd(const void* L, int64_t ldl, int offl, const void* Hf, int64_t 
 int onet_head_bwd(const void* L, int64_t ldl, int offl, const void* Hf, int64_t ldh, int offh, int B, int H, int W,
                   const float* Vt, const float* Vd, const float* a, const float* b, const float* gscale,
                   const float* gVt, const float* gVd, const float* gS, void* dL, void* dH, int dtype, void* stream);
+
+/* The same head with the LAST layer's BatchNorm + ReLU folded in: Y is that layer's raw conv output [2B,H,W,ldy], the head
+ * applies h = relu(y * hscale + hshift) per branch itself (top / down constants, [64] each), so the separate BatchNorm pass
+ * over the global feature and the tensor it would write do not exist.  Backward counterpart: onet_head_bwd_scalars (the
+ * per-pixel part of onet_head_bwd: gv[0..B*H*W) = dV of the top branch, gv[B*H*W..) of the down branch, gab = the gradient of the
+ * loss's channel sums, same layout) followed by onet_bn_relu_bwd_head: the last layer's BatchNorm backward whose incoming
+ * gradient is formed on the fly as g = gv * L (never stored) and whose reduce pass also writes dL = gv * relu(bn(y)) + gab.
+ * Results are those of onet_head_bwd + onet_bn_relu_bwd bit for bit up to the order of the sums. */
+int onet_head_fwd_bn(const void* L, int64_t ldl, int offl, const void* Y, int64_t ldy, int offy, int B, int H, int W,
+                     const float* hscale_t, const float* hshift_t, const float* hscale_d, const float* hshift_d,
+                     float* Vt, float* Vd, float* S, float* a_out, float* b_out, double* loss_acc, int dtype, void* stream);
+int onet_head_bwd_scalars(const float* Vt, const float* Vd, const float* a_in, const float* b_in, const float* gscale,
+                          const float* gVt, const float* gVd, const float* gS, int B, int H, int W, float* gv, float* gab,
+                          void* stream);
+int onet_bn_relu_bwd_head(const void* y, int N, int H, int W, int C, const float* scale, const float* shift, const float* mean,
+                          const float* invstd, int group_images, const void* L, int64_t ldl, int offl, const float* gv,
+                          const float* gab, void* dL, double* sums, double count, void* dy, float* dgamma0, float* dbeta0,
+                          float* dgamma1, float* dbeta1, int dtype, void* stream);
 
 /* argmax of the 2-way softmax: 1 iff Vd > Vt (Onet.predict_label :193-202) */
 int onet_predict_label(const float* Vt, const float* Vd, int64_t n, int64_t* out, void* stream);

@@ -52,13 +52,16 @@ SIGNATURES = {
     "onet_pack_convT_weights": [_p, _i, _i, _p, _p, _i, _p],
     "onet_pack_all_weights": [_i, _p, _p, _p, _p, _p, _p, _i, _p],
     "onet_conv3x3_fwd": [_p, _i64, _i, _i, _i, _i, _i, _p, _i, _p, _i64, _i, _p, _p, _i, _i, _i, _p],
+    "onet_first_conv_stats": [_p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p],
+    "onet_first_conv_bn_relu": [_p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p],
+    "onet_first_conv_bwd": [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p, _d, _p, _p, _p, _p, _p, _i, _p],
     "onet_conv3x3_bn_relu_infer": [_p, _i64, _i, _i, _i, _i, _i, _p, _i, _p, _p, _i, _p, _i64, _i, _i, _i, _p],
     "onet_maxpool2x2": [_p, _i64, _i, _i, _i, _i, _i, _p, _i, _p],
     "onet_conv3x3_wgrad": [_p, _i64, _i, _p, _i64, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p],
     "onet_bn_finalize": [_p, _p, _i, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p],
     "onet_bn_eval_prepare": [_i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
-    "onet_bn_relu_apply": [_p, _i, _i, _i, _i, _p, _p, _i, _p, _i64, _i, _p, _i, _p],
-    "onet_bn_relu_bwd": [_p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _i64, _i, _p, _i64, _i, _p, _p, _d, _p,
+    "onet_bn_relu_apply": [_p, _i, _i, _i, _i, _p, _p, _i, _p, _i64, _i, _p, _p, _i, _p],
+    "onet_bn_relu_bwd": [_p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _i64, _i, _p, _i64, _i, _p, _p, _p, _d, _p,
                          _p, _p, _p, _p, _i, _p],
     "onet_conv3x3_dgrad_bnred": [_p, _i64, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "onet_bn_relu_bwd_apply": [_p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _i64, _i, _p, _d, _p, _p, _p, _p, _p, _i, _p],
@@ -69,6 +72,9 @@ SIGNATURES = {
     "onet_add_colsums": [_p, _i, _p, _p],
     "onet_head_fwd": [_p, _i64, _i, _p, _i64, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p],
     "onet_head_bwd": [_p, _i64, _i, _p, _i64, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
+    "onet_head_fwd_bn": [_p, _i64, _i, _p, _i64, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
+    "onet_head_bwd_scalars": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p],
+    "onet_bn_relu_bwd_head": [_p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _i64, _i, _p, _p, _p, _p, _d, _p, _p, _p, _p, _p, _i, _p],
     "onet_predict_label": [_p, _p, _i64, _p, _p],
     "onet_predict_label_u8": [_p, _p, _i64, _p, _p],
     "onet_eval_confusion": [_p, _p, _p, _i64, _p, _p],

@@ -10,6 +10,7 @@
 
 #include "../../include/onet_b200.h"
 #include "elementwise.cuh"
+#include "first_layer.cuh"
 #include "simt_conv.cuh"
 #include "synth.cuh"
 #include "tapgemm_tc.cuh"
@@ -74,7 +75,7 @@ static EncodeTiledFn get_encode() {
 // 5-D view (c, w, q, h, n) with 128-byte swizzle; strides in ELEMENTS for dims 1..4; elem_bytes = 2 (bf16) or 4 (fp32, which
 // the tf32 kernels read as they are: the tensor core ignores the low 13 mantissa bits of each operand word)
 static int make_map5(CUtensorMap* m, const void* base, const uint64_t dims[5], const uint64_t strides_el[4],
-                     const uint32_t box[5], int elem_bytes) {
+                     const uint32_t box[5], int elem_bytes, bool mn_major = false) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
     cuuint64_t gd[5], gs[4];
@@ -84,8 +85,11 @@ static int make_map5(CUtensorMap* m, const void* base, const uint64_t dims[5], c
     if (reinterpret_cast<uintptr_t>(base) % 16) return fail("tensor map base not 16-byte aligned");
     for (int i = 0; i < 4; ++i)
         if (gs[i] % 16) return fail("tensor map stride %d (%llu B) not a multiple of 16", i, (unsigned long long)gs[i]);
+    // MN-major (weight-gradient) operands of 32-bit elements must sit in shared memory in the "128-byte swizzle, 32-byte atom"
+    // pattern (tc_common.cuh, umma_smem_desc); everything else uses the plain 128-byte swizzle
+    const CUtensorMapSwizzle sw = (mn_major && elem_bytes == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
     CUresult r = enc(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5,
-                     const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(5d) failed with %d", static_cast<int>(r));
     return 0;
@@ -105,22 +109,23 @@ static int make_map2(CUtensorMap* m, const void* base, uint64_t inner, uint64_t 
 }
 // plain NHWC activation view: (C, W, 1, H, N)
 template <typename T>
-static int make_act_map(CUtensorMap* m, const T* base, int C, int N, int H, int W, long long ld, const uint32_t box[5]) {
+static int make_act_map(CUtensorMap* m, const T* base, int C, int N, int H, int W, long long ld, const uint32_t box[5],
+                        bool mn_major = false) {
     const uint64_t dims[5] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), 1, static_cast<uint64_t>(H),
                               static_cast<uint64_t>(N)};
     const uint64_t st[4] = {static_cast<uint64_t>(ld), static_cast<uint64_t>(ld) * W, static_cast<uint64_t>(ld) * W,
                             static_cast<uint64_t>(ld) * W * H};
-    return make_map5(m, base, dims, st, box, static_cast<int>(sizeof(T)));
+    return make_map5(m, base, dims, st, box, static_cast<int>(sizeof(T)), mn_major);
 }
 // fine grid [N,Ho,Wo,ld] (Ho >= 2H, Wo >= 2W) seen from the coarse grid: (c' = dx*ld + c, w, q = dy, h, n)
 template <typename T>
 static int make_up_map(CUtensorMap* m, const T* base, int C, int N, int H, int W, long long ld, const uint32_t box[5],
-                       int Ho, int Wo) {
+                       int Ho, int Wo, bool mn_major = false) {
     const uint64_t dims[5] = {static_cast<uint64_t>(ld + C), static_cast<uint64_t>(W), 2, static_cast<uint64_t>(H),
                               static_cast<uint64_t>(N)};
     const uint64_t st[4] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(ld) * Wo,
                             static_cast<uint64_t>(ld) * 2 * Wo, static_cast<uint64_t>(ld) * Wo * Ho};
-    return make_map5(m, base, dims, st, box, static_cast<int>(sizeof(T)));
+    return make_map5(m, base, dims, st, box, static_cast<int>(sizeof(T)), mn_major);
 }
 
 // Function attributes (dynamic shared-memory opt-in, carve-out), co-resident cluster counts and the SM count are properties of
@@ -673,9 +678,9 @@ static int wgrad_tc(const typename Op::T* g, long long ldg, int goff, int Mc, bo
     p.ks_slowest = getenv("ONET_WG_KS_FASTEST") ? 0 : 1;
     CUtensorMap tG, tI;
     const uint32_t box[5] = {KC, static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
-    if (g_is_up) { if (make_up_map(&tG, g + goff, Mc, N, H, W, ldg, box, Ho, Wo)) return 1; }
-    else { if (make_act_map(&tG, g + goff, Mc, N, H, W, ldg, box)) return 1; }
-    if (make_act_map(&tI, in + ioff, Nc, N, H, W, ldi, box)) return 1;
+    if (g_is_up) { if (make_up_map(&tG, g + goff, Mc, N, H, W, ldg, box, Ho, Wo, true)) return 1; }
+    else { if (make_act_map(&tG, g + goff, Mc, N, H, W, ldg, box, true)) return 1; }
+    if (make_act_map(&tI, in + ioff, Nc, N, H, W, ldi, box, true)) return 1;
     if (BNW == 128) return launch_wg<128, Op>(tG, tI, p, st);
     return launch_wg<64, Op>(tG, tI, p, st);
 }
@@ -796,6 +801,87 @@ int onet_conv3x3_fwd(const void* in, int64_t ldi, int ci_off, int N, int H, int 
     return check_launch("conv3x3_simt");
 }
 
+// ---- first convolution of the U-Net without materialising its output (first_layer.cuh)
+static int first_layer_check(const char* what, int N, int H, int W, int Cin) {
+    if (N <= 0 || H <= 0 || W <= 0) return fail("%s: empty tensor", what);
+    if (Cin != 1 && Cin != 3) return fail("%s: in_chns must be 1 or 3 (got %d)", what, Cin);
+    if (W % 4) return fail("%s: width must be a multiple of 4 (got %d); use onet_conv3x3_fwd + onet_bn_relu_apply", what, W);
+    return 0;
+}
+
+int onet_first_conv_stats(const void* x, int N, int H, int W, int Cin, const void* wp, double* stat_sum, double* stat_sq,
+                          int group_images, int dtype, void* stream) {
+    if (first_layer_check("first_conv_stats", N, H, W, Cin)) return 1;
+    if (stat_sum == nullptr || stat_sq == nullptr) return fail("first_conv_stats: stat_sum and stat_sq are required");
+    constexpr int ROWS = 32;
+    const int wgb = (W / 4 + 31) / 32, chunks = (H + ROWS - 1) / ROWS;
+    const unsigned fg = static_cast<unsigned>(N) * chunks * wgb;
+    const int gi = group_images > 0 ? group_images : N;
+#define ONET_FIRST_FWD(TT, CC, MODE, OUT)                                                                                          \
+    first_conv_fwd_kernel<TT, CC, ROWS, MODE><<<fg, 256, 0, ST(stream)>>>(static_cast<const TT*>(x), N, H, W, static_cast<const TT*>(wp), \
+                                                                          stat_sum, stat_sq, scale_, shift_, gi, static_cast<TT*>(OUT))
+    const float* scale_ = nullptr;
+    const float* shift_ = nullptr;
+    if (dtype == ONET_F32) { if (Cin == 1) ONET_FIRST_FWD(float, 1, FIRST_STATS, nullptr); else ONET_FIRST_FWD(float, 3, FIRST_STATS, nullptr); }
+    else { if (Cin == 1) ONET_FIRST_FWD(bf16, 1, FIRST_STATS, nullptr); else ONET_FIRST_FWD(bf16, 3, FIRST_STATS, nullptr); }
+    return check_launch("first_conv_stats");
+}
+
+int onet_first_conv_bn_relu(const void* x, int N, int H, int W, int Cin, const void* wp, const float* scale, const float* shift,
+                            int group_images, void* out, int dtype, void* stream) {
+    if (first_layer_check("first_conv_bn_relu", N, H, W, Cin)) return 1;
+    if (scale == nullptr || shift == nullptr || out == nullptr) return fail("first_conv_bn_relu: scale, shift and out are required");
+    constexpr int ROWS = 32;
+    const int wgb = (W / 4 + 31) / 32, chunks = (H + ROWS - 1) / ROWS;
+    const unsigned fg = static_cast<unsigned>(N) * chunks * wgb;
+    const int gi = group_images > 0 ? group_images : N;
+    double* stat_sum = nullptr;
+    double* stat_sq = nullptr;
+    const float* scale_ = scale;
+    const float* shift_ = shift;
+    if (dtype == ONET_F32) { if (Cin == 1) ONET_FIRST_FWD(float, 1, FIRST_APPLY, out); else ONET_FIRST_FWD(float, 3, FIRST_APPLY, out); }
+    else { if (Cin == 1) ONET_FIRST_FWD(bf16, 1, FIRST_APPLY, out); else ONET_FIRST_FWD(bf16, 3, FIRST_APPLY, out); }
+#undef ONET_FIRST_FWD
+    return check_launch("first_conv_bn_relu");
+}
+
+int onet_first_conv_bwd(const void* x, int N, int H, int W, int Cin, const void* wp, const float* scale, const float* shift,
+                        const float* mean, const float* invstd, int group_images, const void* g, double* sums, double count,
+                        float* dw, float* dgamma0, float* dbeta0, float* dgamma1, float* dbeta1, int dtype, void* stream) {
+    if (first_layer_check("first_conv_bwd", N, H, W, Cin)) return 1;
+    if (g == nullptr || sums == nullptr || dw == nullptr) return fail("first_conv_bwd: g, sums and dw are required");
+    constexpr int ROWS = 32;
+    FirstBwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.N = N; a.H = H; a.W = W; a.group_images = group_images > 0 ? group_images : N;
+    a.scale = scale; a.shift = shift; a.mean = mean; a.invstd = invstd;
+    a.sums = sums; a.count = count; a.dw = dw;
+    const int G = std::min(2, (N + a.group_images - 1) / a.group_images);
+    const int lanes = Cin == 1 ? 16 : 4;                    // column groups per block = 256 / (64 / CPT)
+    const int wgb = (W / 4 + lanes - 1) / lanes, chunks = (H + ROWS - 1) / ROWS;
+    const unsigned gx = static_cast<unsigned>(N) * chunks * wgb;
+    const long long numel = 64LL * 9 * Cin;
+    a.partial = (dtype == ONET_F32) ? splitk_ws(static_cast<long long>(gx) * numel) : nullptr;
+#define ONET_FIRST_BWD(KERNEL, TT, CC, CPT)                                                                                       \
+    KERNEL<TT, CC, CPT, ROWS><<<gx, 256, 0, ST(stream)>>>(static_cast<const TT*>(x), static_cast<const TT*>(wp), static_cast<const TT*>(g), a)
+    if (dtype == ONET_F32) { if (Cin == 1) ONET_FIRST_BWD(first_conv_bwd_reduce_kernel, float, 1, 4); else ONET_FIRST_BWD(first_conv_bwd_reduce_kernel, float, 3, 1); }
+    else { if (Cin == 1) ONET_FIRST_BWD(first_conv_bwd_reduce_kernel, bf16, 1, 4); else ONET_FIRST_BWD(first_conv_bwd_reduce_kernel, bf16, 3, 1); }
+    if (check_launch("first_conv_bwd_reduce")) return 1;
+    if (dtype == ONET_F32) { if (Cin == 1) ONET_FIRST_BWD(first_conv_bwd_wgrad_kernel, float, 1, 4); else ONET_FIRST_BWD(first_conv_bwd_wgrad_kernel, float, 3, 1); }
+    else { if (Cin == 1) ONET_FIRST_BWD(first_conv_bwd_wgrad_kernel, bf16, 1, 4); else ONET_FIRST_BWD(first_conv_bwd_wgrad_kernel, bf16, 3, 1); }
+#undef ONET_FIRST_BWD
+    if (check_launch("first_conv_bwd_wgrad")) return 1;
+    if (a.partial != nullptr) {
+        splitk_reduce(a.partial, static_cast<int>(gx), numel, dw, ST(stream));
+        if (check_launch("splitk_reduce")) return 1;
+    }
+    if (dgamma0 != nullptr) {
+        bn_param_grad_kernel<<<1, 64, 0, ST(stream)>>>(sums, G, 64, dgamma0, dbeta0, dgamma1 ? dgamma1 : dgamma0, dbeta1 ? dbeta1 : dbeta0);
+        if (check_launch("bn_param_grad")) return 1;
+    }
+    return 0;
+}
+
 int onet_conv3x3_bn_relu_infer(const void* in, int64_t ldi, int ci_off, int N, int H, int W, int Cin, const void* wp, int Cout,
                                const float* scale, const float* shift, int group_images, void* out, int64_t ldo, int co_off,
                                int dtype, int engine, void* stream) {
@@ -902,7 +988,7 @@ int onet_bn_eval_prepare(int G, int C, const float* gamma0, const float* beta0, 
 }
 
 int onet_bn_relu_apply(const void* y, int N, int H, int W, int C, const float* scale, const float* shift,
-                       int group_images, void* out, int64_t ldo, int ooff, void* pool, int dtype, void* stream) {
+                       int group_images, void* out, int64_t ldo, int ooff, void* pool, void* pool_arg, int dtype, void* stream) {
     if (C % 8 || ldo % 8 || ooff % 8) return fail("bn_relu_apply: channel counts/offsets must be multiples of 8");
     const long long total = static_cast<long long>(N) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
     const int gi = group_images > 0 ? group_images : N;
@@ -910,10 +996,12 @@ int onet_bn_relu_apply(const void* y, int N, int H, int W, int C, const float* s
     const int grid = grid_for((total + UNR - 1) / UNR, 256, 148 * 24);
     if (dtype == ONET_F32)
         bn_relu_apply_kernel<float, UNR><<<grid, 256, 0, ST(stream)>>>(
-            static_cast<const float*>(y), N, H, W, C, scale, shift, gi, static_cast<float*>(out), ldo, ooff, static_cast<float*>(pool));
+            static_cast<const float*>(y), N, H, W, C, scale, shift, gi, static_cast<float*>(out), ldo, ooff, static_cast<float*>(pool),
+            static_cast<unsigned short*>(pool_arg));
     else
         bn_relu_apply_kernel<bf16, UNR><<<grid, 256, 0, ST(stream)>>>(
-            static_cast<const bf16*>(y), N, H, W, C, scale, shift, gi, static_cast<bf16*>(out), ldo, ooff, static_cast<bf16*>(pool));
+            static_cast<const bf16*>(y), N, H, W, C, scale, shift, gi, static_cast<bf16*>(out), ldo, ooff, static_cast<bf16*>(pool),
+            static_cast<unsigned short*>(pool_arg));
     return check_launch("bn_relu_apply");
 }
 
@@ -922,15 +1010,18 @@ int onet_bn_relu_apply(const void* y, int N, int H, int W, int C, const float* s
 template <typename T>
 static int bn_bwd_impl(const void* y, int N, int H, int W, int C, const float* scale, const float* shift, const float* mean,
                        const float* invstd, int group_images, const void* g1, int64_t ld1, int off1, const void* g2,
-                       int64_t ld2, int off2, const void* gp, double* sums, double count, void* dy,
-                       float* dgamma0, float* dbeta0, float* dgamma1, float* dbeta1, cudaStream_t st, bool prereduced = false) {
+                       int64_t ld2, int off2, const void* gp, const void* gp_arg, double* sums, double count, void* dy,
+                       float* dgamma0, float* dbeta0, float* dgamma1, float* dbeta1, cudaStream_t st, bool prereduced = false,
+                       const float* g1_scale = nullptr, const float* dl_add = nullptr, void* dl_out = nullptr) {
     BnBwdArgs<T> a;
+    a.g1_scale = g1_scale; a.dl_add = dl_add; a.dl_out = static_cast<T*>(dl_out);
     a.y = static_cast<const T*>(y); a.N = N; a.H = H; a.W = W; a.C = C;
     a.scale = scale; a.shift = shift; a.mean = mean; a.invstd = invstd;
     a.group_images = group_images > 0 ? group_images : N;
     a.g1 = static_cast<const T*>(g1); a.ld1 = ld1; a.off1 = off1;
     a.g2 = static_cast<const T*>(g2); a.ld2 = ld2; a.off2 = off2;
     a.gp = static_cast<const T*>(gp);
+    a.gp_arg = static_cast<const unsigned short*>(gp_arg);
     a.sums = sums; a.count = count; a.dy = static_cast<T*>(dy);
     const int G = std::min(2, (N + a.group_images - 1) / a.group_images);
     const int OC = C / 8, lanes = std::max(1, 256 / OC);
@@ -1005,7 +1096,7 @@ extern "C" {
 
 int onet_bn_relu_bwd(const void* y, int N, int H, int W, int C, const float* scale, const float* shift,
                      const float* mean, const float* invstd, int group_images, const void* g1, int64_t ld1, int off1,
-                     const void* g2, int64_t ld2, int off2, const void* gp, double* sums, double count,
+                     const void* g2, int64_t ld2, int off2, const void* gp, const void* gp_arg, double* sums, double count,
                      void* dy, float* dgamma0, float* dbeta0, float* dgamma1, float* dbeta1, int dtype, void* stream) {
     if (static_cast<long long>(N) * H * W >= (1LL << 31)) return fail("bn_relu_bwd: more than 2^31 pixels");
     if (C % 8 || C > 2048) return fail("bn_relu_bwd: C must be a multiple of 8 and <= 2048");
@@ -1013,10 +1104,24 @@ int onet_bn_relu_bwd(const void* y, int N, int H, int W, int C, const float* sca
     if (gp != nullptr && C > 1024) return fail("bn_relu_bwd: the pooled variant supports C <= 1024");
     if (g1 == nullptr) return fail("bn_relu_bwd: g1 is required");
     if (dtype == ONET_F32)
-        return bn_bwd_impl<float>(y, N, H, W, C, scale, shift, mean, invstd, group_images, g1, ld1, off1, g2, ld2, off2, gp,
+        return bn_bwd_impl<float>(y, N, H, W, C, scale, shift, mean, invstd, group_images, g1, ld1, off1, g2, ld2, off2, gp, gp_arg,
                                   sums, count, dy, dgamma0, dbeta0, dgamma1, dbeta1, ST(stream));
-    return bn_bwd_impl<bf16>(y, N, H, W, C, scale, shift, mean, invstd, group_images, g1, ld1, off1, g2, ld2, off2, gp,
+    return bn_bwd_impl<bf16>(y, N, H, W, C, scale, shift, mean, invstd, group_images, g1, ld1, off1, g2, ld2, off2, gp, gp_arg,
                              sums, count, dy, dgamma0, dbeta0, dgamma1, dbeta1, ST(stream));
+}
+
+int onet_bn_relu_bwd_head(const void* y, int N, int H, int W, int C, const float* scale, const float* shift, const float* mean,
+                          const float* invstd, int group_images, const void* L, int64_t ldl, int offl, const float* gv,
+                          const float* gab, void* dL, double* sums, double count, void* dy, float* dgamma0, float* dbeta0,
+                          float* dgamma1, float* dbeta1, int dtype, void* stream) {
+    if (static_cast<long long>(N) * H * W >= (1LL << 31)) return fail("bn_relu_bwd_head: more than 2^31 pixels");
+    if (C % 8 || C > 2048 || 256 % (C / 8) != 0) return fail("bn_relu_bwd_head: C must be a multiple of 8 with C/8 dividing 256");
+    if (L == nullptr || gv == nullptr || gab == nullptr || dL == nullptr) return fail("bn_relu_bwd_head: L, gv, gab and dL are required");
+    if (dtype == ONET_F32)
+        return bn_bwd_impl<float>(y, N, H, W, C, scale, shift, mean, invstd, group_images, L, ldl, offl, nullptr, 0, 0, nullptr, nullptr,
+                                  sums, count, dy, dgamma0, dbeta0, dgamma1, dbeta1, ST(stream), false, gv, gab, dL);
+    return bn_bwd_impl<bf16>(y, N, H, W, C, scale, shift, mean, invstd, group_images, L, ldl, offl, nullptr, 0, 0, nullptr, nullptr,
+                             sums, count, dy, dgamma0, dbeta0, dgamma1, dbeta1, ST(stream), false, gv, gab, dL);
 }
 
 int onet_bn_relu_bwd_apply(const void* y, int N, int H, int W, int C, const float* scale, const float* shift,
@@ -1027,9 +1132,9 @@ int onet_bn_relu_bwd_apply(const void* y, int N, int H, int W, int C, const floa
     if (C % 8 || C > 2048 || 256 % (C / 8) != 0) return fail("bn_relu_bwd_apply: C must be a multiple of 8 with C/8 dividing 256");
     if (g1 == nullptr || sums == nullptr) return fail("bn_relu_bwd_apply: g1 and sums are required");
     if (dtype == ONET_F32)
-        return bn_bwd_impl<float>(y, N, H, W, C, scale, shift, mean, invstd, group_images, g1, ld1, off1, nullptr, 0, 0, nullptr,
+        return bn_bwd_impl<float>(y, N, H, W, C, scale, shift, mean, invstd, group_images, g1, ld1, off1, nullptr, 0, 0, nullptr, nullptr,
                                   sums, count, dy, dgamma0, dbeta0, dgamma1, dbeta1, ST(stream), true);
-    return bn_bwd_impl<bf16>(y, N, H, W, C, scale, shift, mean, invstd, group_images, g1, ld1, off1, nullptr, 0, 0, nullptr,
+    return bn_bwd_impl<bf16>(y, N, H, W, C, scale, shift, mean, invstd, group_images, g1, ld1, off1, nullptr, 0, 0, nullptr, nullptr,
                              sums, count, dy, dgamma0, dbeta0, dgamma1, dbeta1, ST(stream), true);
 }
 
@@ -1184,6 +1289,40 @@ int onet_head_fwd(const void* L, int64_t ldl, int offl, const void* Hf, int64_t 
         head_fwd_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(a);
     }
     return check_launch("head_fwd");
+}
+
+int onet_head_fwd_bn(const void* L, int64_t ldl, int offl, const void* Y, int64_t ldy, int offy, int B, int H, int W,
+                     const float* hscale_t, const float* hshift_t, const float* hscale_d, const float* hshift_d,
+                     float* Vt, float* Vd, float* S, float* a_out, float* b_out, double* loss_acc, int dtype, void* stream) {
+    if (ldl % 8 || offl % 8 || ldy % 8 || offy % 8) return fail("head: channel strides/offsets must be multiples of 8");
+    if (!hscale_t || !hshift_t || !hscale_d || !hshift_d) return fail("head_fwd_bn: the four scale / shift vectors are required");
+    const long long npx = static_cast<long long>(B) * H * W;
+    const int grid = grid_for(npx * 8, 256, 148 * 8);
+    if (dtype == ONET_F32) {
+        HeadArgs<float> a;
+        fill_head(a, L, ldl, offl, Y, ldy, offy, B, H, W);
+        a.Vt = Vt; a.Vd = Vd; a.S = S; a.a = a_out; a.b = b_out; a.loss_acc = loss_acc;
+        a.hsc_t = hscale_t; a.hsh_t = hshift_t; a.hsc_d = hscale_d; a.hsh_d = hshift_d;
+        head_fwd_kernel<float><<<grid, 256, 0, ST(stream)>>>(a);
+    } else {
+        HeadArgs<bf16> a;
+        fill_head(a, L, ldl, offl, Y, ldy, offy, B, H, W);
+        a.Vt = Vt; a.Vd = Vd; a.S = S; a.a = a_out; a.b = b_out; a.loss_acc = loss_acc;
+        a.hsc_t = hscale_t; a.hsh_t = hshift_t; a.hsc_d = hscale_d; a.hsh_d = hshift_d;
+        head_fwd_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(a);
+    }
+    return check_launch("head_fwd+bn");
+}
+
+int onet_head_bwd_scalars(const float* Vt, const float* Vd, const float* a_in, const float* b_in, const float* gscale,
+                          const float* gVt, const float* gVd, const float* gS, int B, int H, int W, float* gv, float* gab,
+                          void* stream) {
+    const long long npx = static_cast<long long>(B) * H * W;
+    if (npx <= 0) return 0;
+    if (gv == nullptr || gab == nullptr) return fail("head_bwd_scalars: gv and gab are required");
+    head_bwd_scalars_kernel<<<grid_for(npx, 256, 148 * 8), 256, 0, ST(stream)>>>(Vt, Vd, a_in, b_in, gscale, gVt, gVd, gS, npx,
+                                                                               static_cast<long long>(H) * W, gv, gab);
+    return check_launch("head_bwd_scalars");
 }
 
 int onet_head_bwd(const void* L, int64_t ldl, int offl, const void* Hf, int64_t ldh, int offh, int B, int H, int W,

@@ -136,11 +136,15 @@ __device__ __forceinline__ float bn_relu_value(float y, float sc, float sh) {
     return round_to<T>(fmaxf(fmaf(y, sc, sh), 0.f));
 }
 
+// ReLU mask of the backward pass: the stored activation round(max(y * sc + sh, 0)) is > 0 exactly when the fp32 pre-activation
+// is (rounding to bf16 keeps the sign and, with fp32's exponent range, never flushes a positive value to zero)
+__device__ __forceinline__ bool relu_open(float y, float sc, float sh) { return fmaf(y, sc, sh) > 0.f; }
+
 template <typename T, int UNR>
 __global__ void __launch_bounds__(256, 3)
 bn_relu_apply_kernel(const T* __restrict__ y, int N, int H, int W, int C, const float* __restrict__ scale,
                      const float* __restrict__ shift, int group_images, T* __restrict__ out, long long ldo, int ooff,
-                     T* __restrict__ pool) {
+                     T* __restrict__ pool, unsigned short* __restrict__ pool_arg) {
     const int OC = C >> 3, H2 = (H + 1) >> 1, W2 = (W + 1) >> 1, HP = H >> 1, WP = W >> 1;
     const long long total = static_cast<long long>(N) * H2 * W2 * OC;
     const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -172,7 +176,8 @@ bn_relu_apply_kernel(const T* __restrict__ y, int N, int H, int W, int C, const 
             load8<float>(scale + g * C + oc * 8, sc);
             load8<float>(shift + g * C + oc * 8, sh);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) mx[i] = 0.f;            // post-ReLU values are >= 0
+            for (int i = 0; i < 8; ++i) mx[i] = -1.f;           // post-ReLU values are >= 0: position 0 always enters
+            uint32_t best = 0;                                  // first maximum of the window per channel, 2 bits each
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
                 const int h = 2 * h2_[u] + (d >> 1), w = 2 * w2_[u] + (d & 1);
@@ -182,13 +187,18 @@ bn_relu_apply_kernel(const T* __restrict__ y, int N, int H, int W, int C, const 
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         v[i] = bn_relu_value<T>(v[i], sc[i], sh[i]);
-                        mx[i] = fmaxf(mx[i], v[i]);
+                        if (v[i] > mx[i]) { mx[i] = v[i]; best = (best & ~(3u << (2 * i))) | (static_cast<uint32_t>(d) << (2 * i)); }
                     }
                     store8<T>(out + ((static_cast<long long>(n) * H + h) * W + w) * ldo + ooff + oc * 8, v);
                 }
             }
-            if (pool != nullptr && h2_[u] < HP && w2_[u] < WP)
-                store8<T>(pool + ((static_cast<long long>(n) * HP + h2_[u]) * WP + w2_[u]) * C + oc * 8, mx);
+            if (pool != nullptr && h2_[u] < HP && w2_[u] < WP) {
+                const long long pw = (static_cast<long long>(n) * HP + h2_[u]) * WP + w2_[u];
+                store8<T>(pool + pw * C + oc * 8, mx);
+                // the routing of the pooled gradient, kept for the backward pass: 2 bytes per 32 activations instead of
+                // recomputing 32 BatchNorm + ReLU + rounding + compare chains there
+                if (pool_arg != nullptr) pool_arg[pw * OC + oc] = static_cast<unsigned short>(best);
+            }
         }
     }
 }
@@ -211,6 +221,13 @@ struct BnBwdArgs {
     const T* g1; long long ld1; int off1;
     const T* g2; long long ld2; int off2;
     const T* gp;                                 // [N,H/2,W/2,C] or nullptr
+    const unsigned short* gp_arg;                // [N,H/2,W/2,C/8] arg-max bits written by bn_relu_apply_kernel, or nullptr (recompute)
+    // Last layer of the U-Net fused with the head backward (bn_bwd_px_kernel only): the incoming gradient is not a stored
+    // tensor but g[p][c] = round(g1[p][c] * g1_scale[p]) with g1 = the local feature L and g1_scale = the per-pixel dV of
+    // the head (head_bwd_scalars_kernel); the reduce pass also writes dL[p][c] = g1_scale[p] * relu(bn(y))[p][c] + dl_add[p].
+    const float* g1_scale;                       // [N*H*W] or nullptr
+    const float* dl_add;                         // [N*H*W]
+    T* dl_out;                                   // [N,H,W,C] or nullptr
     double* sums;                                // [G][2][C]
     double count;                                // elements per channel per group
     T* dy;                                       // [N,H,W,C]
@@ -290,9 +307,21 @@ bn_bwd_px_kernel(const BnBwdArgs<T> a) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) gg[i] += g2v[i];
                 }
+                if (a.g1_scale != nullptr) {       // head-fused last layer: g = dV * L, dL = dV * H + d(a) with H = relu(bn(y))
+                    const float gs = __ldg(a.g1_scale + q);
+                    if (!APPLY && a.dl_out != nullptr) {
+                        const float ga = __ldg(a.dl_add + q);
+                        float dl[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) dl[i] = fmaf(gs, bn_relu_value<T>(y[i], sc[i], sh[i]), ga);
+                        store8<T>(a.dl_out + q * a.C + oc * 8, dl);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) gg[i] = round_to<T>(gs * gg[i]);      // what a stored dH would hold
+                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float dz = bn_relu_value<T>(y[i], sc[i], sh[i]) > 0.f ? gg[i] : 0.f;
+                    const float dz = relu_open(y[i], sc[i], sh[i]) ? gg[i] : 0.f;
                     const float yc = y[i] - mu[i];
                     if (APPLY) {
                         o[i] = fmaf(sc[i], dz, -fmaf(yc, k2[i], k1[i]));
@@ -369,7 +398,9 @@ bn_bwd_win_kernel(const BnBwdArgs<T> a) {
             rp = pooled ? ldraw<T>(a.gp + ((static_cast<long long>(n) * HP + h2) * WP + w2) * a.C + oc * 8) : zero_raw<T>();
             // first maximum of the window per channel (2 bits each), exactly as the forward pass pooled it
             uint32_t best = 0;
-            {
+            if (a.gp_arg != nullptr) {
+                if (pooled) best = __ldg(a.gp_arg + ((static_cast<long long>(n) * HP + h2) * WP + w2) * OC + oc);
+            } else {
                 float mx[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) mx[i] = -1.f;
@@ -402,7 +433,7 @@ bn_bwd_win_kernel(const BnBwdArgs<T> a) {
                 for (int i = 0; i < 8; ++i) {
                     const bool is_best = pooled && ((best >> (2 * i)) & 3u) == static_cast<uint32_t>(d);
                     const float gsum = gg[i] + (is_best ? gpv[i] : 0.f);
-                    const float dz = bn_relu_value<T>(y[i], sc[i], sh[i]) > 0.f ? gsum : 0.f;
+                    const float dz = relu_open(y[i], sc[i], sh[i]) ? gsum : 0.f;
                     const float yc = y[i] - mu[i];
                     if (APPLY) {
                         o[i] = fmaf(sc[i], dz, -fmaf(yc, k2[i], k1[i]));
@@ -533,7 +564,60 @@ struct HeadArgs {
     const float* gscale;                     // upstream d(loss) scalar (device) or nullptr (=> no fused loss grad)
     const float* gVt; const float* gVd; const float* gS;   // optional external gradients, fp32
     T* dL; T* dH;                            // [2B,H,W,64] dense
+    // Fused with the last layer's BatchNorm + ReLU: Hf then points to that layer's RAW conv output and the head applies
+    // h = relu(hf * scale + shift) itself (top / down branch constants, [64] each); nullptr = Hf holds the activation.
+    const float* hsc_t; const float* hsh_t; const float* hsc_d; const float* hsh_d;
 };
+
+// head backward, per-pixel part only: dV of both branches (gv[0 .. npx) top, gv[npx .. 2 npx) down) and the gradient of the
+// loss's channel sums (gab, same layout) - everything head_bwd_kernel computes before it touches L and H.
+__device__ __forceinline__ void head_pixel_grads(const float* __restrict__ Vt, const float* __restrict__ Vd, const float* __restrict__ ain,
+                                                 const float* __restrict__ bin, const float* gscale, const float* gVt, const float* gVd,
+                                                 const float* gS, long long p, long long npx, long long HW, float& g_vt, float& g_vd,
+                                                 float& g_a, float& g_b) {
+    const float gsv = gscale != nullptr ? *gscale : 0.f;
+    const float cc = gsv / (2.f * static_cast<float>(npx));
+    const float vt = Vt[p], vd = Vd[p], sa = ain[p], sb = bin[p];
+    const float mx = fmaxf(vt, vd);
+    const float et = expf(vt - mx), ed = expf(vd - mx);
+    const float inv = 1.f / (et + ed);
+    const float st = et * inv, sd = ed * inv;
+    float g_st = 0.f, g_sd = 0.f;
+    g_a = 0.f; g_b = 0.f;
+    if (gscale != nullptr) {
+        float v, d1, d2, d3, d4;
+        sp_ref(-sa * st, v, d1);
+        sp_ref(sa * sd, v, d2);
+        sp_ref(-sb * sd, v, d3);
+        sp_ref(sb * st, v, d4);
+        g_a = (-st * d1 + sd * d2) * cc;
+        g_b = (-sd * d3 + st * d4) * cc;
+        g_st = (-sa * d1 + sb * d4) * cc;
+        g_sd = (sa * d2 - sb * d3) * cc;
+    }
+    if (gS != nullptr) {
+        const long long n = p / HW, hw = p % HW;
+        g_st += gS[(n * 2 + 0) * HW + hw];
+        g_sd += gS[(n * 2 + 1) * HW + hw];
+    }
+    const float gsm = st * sd * (g_st - g_sd);          // softmax backward
+    g_vt = gsm; g_vd = -gsm;
+    if (gVt != nullptr) g_vt += gVt[p];
+    if (gVd != nullptr) g_vd += gVd[p];
+}
+
+__global__ void __launch_bounds__(256)
+head_bwd_scalars_kernel(const float* __restrict__ Vt, const float* __restrict__ Vd, const float* __restrict__ ain,
+                        const float* __restrict__ bin, const float* gscale, const float* gVt, const float* gVd, const float* gS,
+                        long long npx, long long HW, float* __restrict__ gv, float* __restrict__ gab) {
+    for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < npx;
+         p += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float g_vt, g_vd, g_a, g_b;
+        head_pixel_grads(Vt, Vd, ain, bin, gscale, gVt, gVd, gS, p, npx, HW, g_vt, g_vd, g_a, g_b);
+        gv[p] = g_vt; gv[p + npx] = g_vd;
+        gab[p] = g_a; gab[p + npx] = g_b;
+    }
+}
 
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -543,6 +627,13 @@ head_fwd_kernel(const HeadArgs<T> a) {
     // the 8 threads of a pixel leave the loop together, the four pixel groups of a warp need not (B*H*W % 4 != 0):
     // shuffle inside the group's own lanes only
     const uint32_t gmask = 0xFFu << (threadIdx.x & 24);
+    float hsc_t[8], hsh_t[8], hsc_d[8], hsh_d[8];
+    if (a.hsc_t != nullptr) {
+        load8<float>(a.hsc_t + sub * 8, hsc_t);
+        load8<float>(a.hsh_t + sub * 8, hsh_t);
+        load8<float>(a.hsc_d + sub * 8, hsc_d);
+        load8<float>(a.hsh_d + sub * 8, hsh_d);
+    }
     float lsum = 0.f;
     for (long long p = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 3; p < npx;
          p += (static_cast<long long>(gridDim.x) * blockDim.x) >> 3) {
@@ -552,6 +643,13 @@ head_fwd_kernel(const HeadArgs<T> a) {
         load8<T>(a.Hf + p * a.ldh + a.offh + sub * 8, ht);
         load8<T>(a.L + pd * a.ldl + a.offl + sub * 8, ld);
         load8<T>(a.Hf + pd * a.ldh + a.offh + sub * 8, hd);
+        if (a.hsc_t != nullptr) {        // Hf is the last layer's raw conv output: BatchNorm + ReLU here, no separate pass
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                ht[i] = bn_relu_value<T>(ht[i], hsc_t[i], hsh_t[i]);
+                hd[i] = bn_relu_value<T>(hd[i], hsc_d[i], hsh_d[i]);
+            }
+        }
         float vt = 0.f, vd = 0.f, sa = 0.f, sb = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {

@@ -299,9 +299,8 @@ __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile,
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         const float y = __uint_as_float((e & 1) ? (yw[e >> 1] & 0xffff0000u) : (yw[e >> 1] << 16));
-                        // the stored post-ReLU activation is bf16(max(y * sc + sh, 0)) (bn_relu_value, elementwise.cuh)
-                        const float act = __bfloat162float(__float2bfloat16(fmaxf(fmaf(y, sc[e], sh[e]), 0.f)));
-                        const float dz = act > 0.f ? v[8 * j4 + e] : 0.f;
+                        // ReLU mask = sign of the pre-activation (relu_open, elementwise.cuh)
+                        const float dz = fmaf(y, sc[e], sh[e]) > 0.f ? v[8 * j4 + e] : 0.f;
                         v[8 * j4 + e] = dz;
                         s2[8 * j4 + e] = dz * ((y - mu[e]) * is[e]);
                     }
@@ -693,9 +692,13 @@ tapgemm_wg_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
                     const uint32_t sN = base + stage * Cfg::kStageBytes, sM = sN + Cfg::kNBytes;
-                    const uint64_t db = umma_smem_desc(sN, BOX, 1024);
+                    // MN-major operands: bf16 = 128-byte swizzle over 8 pixel rows; tf32 = 128-byte swizzle with 32-byte atoms over
+                    // 4 pixel rows (the only MN-major layout the tensor core accepts for 32-bit elements)
+                    constexpr uint32_t LT = Op::kTf32 ? kUmmaSwizzle128BAtom32B : kUmmaSwizzle128B;
+                    constexpr uint32_t SBO = Op::kTf32 ? 512 : 1024;
+                    const uint64_t db = umma_smem_desc(sN, BOX, SBO, LT);
                     for (int a = 0; a < nacc; ++a) {
-                        const uint64_t da = umma_smem_desc(sM + a * Cfg::kAccBytes, BOX, 1024);
+                        const uint64_t da = umma_smem_desc(sM + a * Cfg::kAccBytes, BOX, SBO, LT);
 #pragma unroll
                         for (int kk = 0; kk < Cfg::kKSteps; ++kk)   // 16 pixel rows = 2048 B (bf16) / 8 pixel rows = 1024 B (tf32) per MMA
                             umma<Op>(tmem_base + a * BNW, da + Cfg::kKStepUnits * kk, db + Cfg::kKStepUnits * kk, idesc,

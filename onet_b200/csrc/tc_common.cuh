@@ -238,13 +238,19 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
 //   K-major tile  (rows = M/N index, 128 B of K per row):  SBO = 1024 B between 8-row groups, LBO unused.
 //   MN-major tile (rows = K index, 128 B of M/N per row):  SBO = 1024 B between 8-row (K) groups,
 //                                                          LBO = bytes between 64-element M/N blocks.
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   MN-major tile of 32-bit (TF32) elements: the only legal layout is layout_type 1, "128-byte swizzle with 32-byte atoms"
+//   (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 128 B (32 M/N elements), the swizzle repeats every 4 rows (K),
+//   SBO = bytes between 4-row groups (512), LBO = bytes between 32-element M/N blocks.
+constexpr uint32_t kUmmaSwizzle128B = 2;
+constexpr uint32_t kUmmaSwizzle128BAtom32B = 1;
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type = kUmmaSwizzle128B) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
     d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= static_cast<uint64_t>(1) << 46;   // version = 1 (Blackwell)
-    d |= static_cast<uint64_t>(2) << 61;   // SWIZZLE_128B
+    d |= static_cast<uint64_t>(layout_type) << 61;
     return d;
 }
 // Instruction descriptor for kind::f16 with BF16 A/B and FP32 accumulate.

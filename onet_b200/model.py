@@ -317,6 +317,10 @@ class _Engine:
         rec.mid = {}      # dense activations after the first conv of each block, and decoder block outputs
         rec.saved = {}    # per (segment index, layer index): dict(Y, stats)
         rec.training_stats, rec.save = training_stats, save
+        # head fusion (training forward of the twin network): see _conv_bn_relu / head_forward
+        rec.y_last, rec.head_aff = None, []
+        if x_is_twin and save and os.environ.get("ONET_NO_HEAD_FUSION") is None:
+            rec.y_last = self._empty(N2, H, W, 64)
         nseg_groups = sum(seg.groups for seg in self.segments)
         rec.stat_pool = torch.zeros(2 * 5888 * nseg_groups, dtype=torch.float64, device=self.dev) if training_stats else None
         rec.stat_off = 0
@@ -372,8 +376,17 @@ class _Engine:
         eng = self._engine_for(cin, cout)
         G = seg.groups
         st = self.stream
+        if (li == 0 and cin in (1, 3) and cout == 64 and w % 4 == 0 and pool is None and ld_src == cin and off_src == 0
+                and ld_dst == 64 and off_dst == 0 and os.environ.get("ONET_NO_FIRST_RECOMPUTE") is None):
+            return self._first_conv_bn_relu(rec, si, seg, li, conv, bn, wf, src, n0, n, h, w, cin, dst)
         fused_eval = (not rec.training_stats) and eng == ENGINE_TC and not rec.save
-        Y = None if fused_eval else self._empty(n, h, w, cout)
+        # last layer of the twin forward with backward to follow: its BatchNorm + ReLU is applied by the head kernel, and its
+        # raw output lives in ONE [2B,H,W,64] buffer across the segments (the head indexes both branches)
+        head_fused = getattr(rec, "y_last", None) is not None and li == 17
+        if head_fused:
+            Y = rec.y_last[n0:n0 + n]
+        else:
+            Y = None if fused_eval else self._empty(n, h, w, cout)
         if rec.training_stats:
             stats = rec.stat_pool[rec.stat_off:rec.stat_off + 2 * G * cout].view(2, G, cout)
             rec.stat_off += 2 * G * cout
@@ -406,11 +419,43 @@ class _Engine:
                 return
             call("onet_conv3x3_fwd", ptr(src, self._img_off(src, n0) + off_src), ld_src, 0, n, h, w, cin, ptr(wf), cout,
                  ptr(Y), cout, 0, None, None, seg.group_images, self.dt, eng, st)
-        call("onet_bn_relu_apply", ptr(Y), n, h, w, cout, ptr(aff[2]), ptr(aff[3]), seg.group_images,
-             ptr(dst, self._img_off(dst, n0) + off_dst), ld_dst, 0,
-             ptr(pool, self._img_off(pool, n0)) if pool is not None else None, self.dt, st)
+        # with a pooled output kept for backward: the window arg-max (2 bits per channel) is stored, not recomputed there
+        parg = torch.empty(n, h // 2, w // 2, cout // 8, dtype=torch.int16, device=self.dev) if (pool is not None and rec.save) else None
+        if head_fused:
+            rec.head_aff.append((n0, n, aff))
+        else:
+            call("onet_bn_relu_apply", ptr(Y), n, h, w, cout, ptr(aff[2]), ptr(aff[3]), seg.group_images,
+                 ptr(dst, self._img_off(dst, n0) + off_dst), ld_dst, 0,
+                 ptr(pool, self._img_off(pool, n0)) if pool is not None else None, ptr(parg), self.dt, st)
         if rec.save:
-            rec.saved[(si, li)] = dict(Y=Y, aff=aff, src=(src, ld_src, off_src), h=h, w=w, cin=cin, cout=cout)
+            rec.saved[(si, li)] = dict(Y=Y, aff=aff, src=(src, ld_src, off_src), h=h, w=w, cin=cin, cout=cout, parg=parg)
+
+    def _first_conv_bn_relu(self, rec, si, seg, li, conv, bn, wf, src, n0, n, h, w, cin, dst):
+        """First convolution of a U-Net (reference :111,47-49) WITHOUT materialising its 64-channel raw output: the statistics
+        pass and the BatchNorm + ReLU pass both recompute it from the input patch (csrc/first_layer.cuh); backward does the same
+        (`onet_first_conv_bwd`).  Same results as the generic conv -> BatchNorm path, 3.2 GB less HBM traffic per step at B = 64."""
+        G, st = seg.groups, self.stream
+        x = ptr(src, self._img_off(src, n0))
+        aff = torch.empty(4, G, 64, dtype=torch.float32, device=self.dev)   # mean, invstd, scale, shift
+        if rec.training_stats:
+            stats = rec.stat_pool[rec.stat_off:rec.stat_off + 2 * G * 64].view(2, G, 64)
+            rec.stat_off += 2 * G * 64
+            call("onet_first_conv_stats", x, n, h, w, cin, ptr(wf), ptr(stats[0]), ptr(stats[1]), seg.group_images, self.dt, st)
+            call("onet_bn_finalize", ptr(stats[0]), ptr(stats[1]), G, 64, float(seg.group_images * h * w),
+                 ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var),
+                 ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var),
+                 float(bn.momentum), ptr(aff[0]), ptr(aff[1]), ptr(aff[2]), ptr(aff[3]), st)
+            rec.nbt.append((bn.num_batches_tracked, G))
+        else:
+            call("onet_bn_eval_prepare", G, 64, ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var),
+                 ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var), ptr(aff[2]), ptr(aff[3]), st)
+            if rec.save:
+                aff[0] = bn.running_mean
+                aff[1] = torch.rsqrt(bn.running_var + 1e-5)
+        call("onet_first_conv_bn_relu", x, n, h, w, cin, ptr(wf), ptr(aff[2]), ptr(aff[3]), seg.group_images,
+             ptr(dst, self._img_off(dst, n0)), self.dt, st)
+        if rec.save:
+            rec.saved[(si, li)] = dict(Y=None, aff=aff, src=(src, cin, 0), h=h, w=w, cin=cin, cout=64, first=True, wf=wf)
 
     def _upconv(self, seg, up, x, cx, n0, n, h, w, cat, ld_cat, off_cat, ho, wo):
         """x [n,h,w,cin] -> channels [off_cat, off_cat+co) of the concat buffer [n,ho,wo,ld_cat]; ho - 2h, wo - 2w in {0,1}:
@@ -438,6 +483,16 @@ class _Engine:
         rec.a = torch.empty(B, H, W, dtype=f32, device=self.dev)
         rec.b = torch.empty(B, H, W, dtype=f32, device=self.dev)
         rec.loss_acc = torch.zeros((), dtype=torch.float64, device=self.dev)
+        if rec.y_last is not None:
+            # the global feature H = relu(bn(y_last)) is formed inside the head kernel (per-branch BatchNorm constants)
+            st_, sh_ = {}, {}
+            for n0, n, aff in rec.head_aff:           # shared twin: one segment, groups 0 / 1; otherwise one segment per branch
+                for gi in range(aff.shape[1]):
+                    st_[n0 + gi * (n // aff.shape[1])] = aff[2][gi]
+                    sh_[n0 + gi * (n // aff.shape[1])] = aff[3][gi]
+            call("onet_head_fwd_bn", ptr(rec.cat0), 128, 0, ptr(rec.y_last), 64, 0, B, H, W, ptr(st_[0]), ptr(sh_[0]), ptr(st_[B]),
+                 ptr(sh_[B]), ptr(rec.Vt), ptr(rec.Vd), ptr(rec.S), ptr(rec.a), ptr(rec.b), ptr(rec.loss_acc), self.dt, self.stream)
+            return
         call("onet_head_fwd", ptr(rec.cat0), 128, 0, ptr(rec.Hf), 64, 0, B, H, W, ptr(rec.Vt), ptr(rec.Vd), ptr(rec.S),
              ptr(rec.a), ptr(rec.b), ptr(rec.loss_acc), self.dt, self.stream)
 
@@ -455,12 +510,26 @@ class _Engine:
         self._deferred, self._inflight, self._hooks_deferred, self._hooks_ready = [], [], [], []
         self._after_block = after_block
         dL = self._empty(N2, H, W, 64)
-        dH = self._empty(N2, H, W, 64)
-        call("onet_head_bwd", ptr(rec.cat0), 128, 0, ptr(rec.Hf), 64, 0, B, H, W, ptr(rec.Vt), ptr(rec.Vd), ptr(rec.a),
-             ptr(rec.b), ptr(gscale), ptr(gVt), ptr(gVd), ptr(gS), ptr(dL), ptr(dH), self.dt, st)
-        for g_ext, n0 in ((gLt, 0), (gLd, B)):
-            if g_ext is not None:   # external gradient w.r.t. the returned local features (generic autograd path)
-                dL[n0:n0 + B].add_(g_ext.permute(0, 2, 3, 1).to(self.tdt))
+        head_fused = rec.y_last is not None
+        if head_fused:
+            # only the per-pixel part of the head backward runs here; dH = dV * L is formed on the fly by the last layer's
+            # BatchNorm backward, whose reduce pass also writes dL (onet_bn_relu_bwd_head)
+            dH = None
+            gv = torch.empty(N2 * H * W, dtype=torch.float32, device=self.dev)
+            gab = torch.empty(N2 * H * W, dtype=torch.float32, device=self.dev)
+            call("onet_head_bwd_scalars", ptr(rec.Vt), ptr(rec.Vd), ptr(rec.a), ptr(rec.b), ptr(gscale), ptr(gVt), ptr(gVd), ptr(gS),
+                 B, H, W, ptr(gv), ptr(gab), st)
+        else:
+            dH = self._empty(N2, H, W, 64)
+            call("onet_head_bwd", ptr(rec.cat0), 128, 0, ptr(rec.Hf), 64, 0, B, H, W, ptr(rec.Vt), ptr(rec.Vd), ptr(rec.a),
+                 ptr(rec.b), ptr(gscale), ptr(gVt), ptr(gVd), ptr(gS), ptr(dL), ptr(dH), self.dt, st)
+
+        def add_external(lo, hi):   # external gradient w.r.t. the returned local features (generic autograd path)
+            for g_ext, m0 in ((gLt, 0), (gLd, B)):
+                if g_ext is not None and lo <= m0 and m0 + B <= hi:
+                    dL[m0:m0 + B].add_(g_ext.permute(0, 2, 3, 1).to(self.tdt))
+        if not head_fused:
+            add_external(0, N2)
         cs = [64, 128, 256, 512, 1024]
         hs, ws = rec.hs, rec.ws
         rec.sum_pool = torch.zeros(2 * 5888 * sum(seg.groups for seg in self.segments), dtype=torch.float64, device=self.dev)
@@ -470,18 +539,23 @@ class _Engine:
             ups = seg.unet.up_layers()
             n0, n = seg.n0, seg.n
 
-            def bwd(li, g1, ld1, off1, g2=None, ld2=0, off2=0, gp=None, need_dgrad=True, colsum=None):
+            def bwd(li, g1, ld1, off1, g2=None, ld2=0, off2=0, gp=None, need_dgrad=True, colsum=None, head=None):
                 return self._conv_bn_relu_bwd(rec, si, seg, li, layers[li][1], layers[li][2], n0, n, g1, ld1, off1, g2,
-                                              ld2, off2, gp, need_dgrad, grad_of, colsum)
+                                              ld2, off2, gp, need_dgrad, grad_of, colsum, head)
 
             # decoder, top (level 0) to bottom (level 3): layer indices 10+2j, 11+2j for j = 0..3 (k = 3-j)
-            g_out = dH[n0:n0 + n]            # gradient w.r.t. the block output at level k
+            g_out = None if head_fused else dH[n0:n0 + n]            # gradient w.r.t. the block output at level k
             dcat = [None] * 4
             for k in range(4):
                 j = 3 - k
                 li = 10 + 2 * j
                 c = cs[k]
-                d_mid = bwd(li + 1, g_out, c, 0)                       # -> grad wrt mid activation [n,h,w,c]
+                if k == 0 and head_fused:
+                    px0 = n0 * H * W
+                    d_mid = bwd(li + 1, rec.cat0[n0:n0 + n], 128, 0, head=(gv[px0:], gab[px0:], dL[n0:n0 + n]))
+                    add_external(n0, n0 + n)
+                else:
+                    d_mid = bwd(li + 1, g_out, c, 0)                   # -> grad wrt mid activation [n,h,w,c]
                 # grad wrt concat buffer [n,h,w,2c]; its column sums (up half = the up-conv's bias gradient) come
                 # out of the same kernel's epilogue
                 colsum = torch.zeros(2, 2 * c, dtype=torch.float64, device=self.dev)
@@ -552,12 +626,26 @@ class _Engine:
             self._hooks_deferred.append((unet, block))
 
     def _conv_bn_relu_bwd(self, rec, si, seg, li, conv, bn, n0, n, g1, ld1, off1, g2, ld2, off2, gp, need_dgrad, grad_of,
-                          colsum=None):
+                          colsum=None, head=None):
         """g1/g2/gp are SEGMENT-LOCAL tensors (first image = image n0 of the batch)."""
         sv = rec.saved[(si, li)]
         Y, aff, h, w, cin, cout = sv["Y"], sv["aff"], sv["h"], sv["w"], sv["cin"], sv["cout"]
         G = seg.groups
         st = self.stream
+        if sv.get("first"):
+            # first convolution: BatchNorm backward + weight gradient with y and dY recomputed / kept in registers
+            assert g2 is None and gp is None and ld1 == 64 and off1 == 0 and not need_dgrad
+            sums = rec.sum_pool[rec.sum_off:rec.sum_off + 2 * G * 64]
+            rec.sum_off += 2 * G * 64
+            count = float(seg.group_images * h * w) if rec.training_stats else float("inf")
+            src = sv["src"][0]
+            # the last call of a U-Net's backward: queued behind the deferred weight gradients on the same (side) stream - it
+            # shares the deterministic split-K workspace of the FP32 mode with them, which must be used from ONE stream
+            self._wgrad((g1, src, sums), "onet_first_conv_bwd", ptr(src, self._img_off(src, n0)), n, h, w, cin, ptr(sv["wf"]),
+                        ptr(aff[2]), ptr(aff[3]), ptr(aff[0]), ptr(aff[1]), seg.group_images, ptr(g1), ptr(sums), count,
+                        ptr(grad_of(conv.weight)), ptr(grad_of(bn.weight)), ptr(grad_of(bn.bias)), ptr(grad_of(bn.weight)),
+                        ptr(grad_of(bn.bias)), self.dt)
+            return None
         if sv.get("prered") is None:
             sums = rec.sum_pool[rec.sum_off:rec.sum_off + 2 * G * cout]
             rec.sum_off += 2 * G * cout
@@ -565,7 +653,14 @@ class _Engine:
         # eval-mode statistics are constants: the mean / projection terms of the BatchNorm backward vanish (1 / count = 0)
         count = float(seg.group_images * h * w) if rec.training_stats else float("inf")
         self._flush_side()          # the previous layers' weight gradients run next to this BatchNorm backward
-        if sv.get("prered") is not None:
+        if head is not None:
+            # last layer, fused with the head backward: g1 is the local feature L, the gradient is dV * L (head = (dV, d(a), dL))
+            assert g2 is None and gp is None
+            gv, gab, dL = head
+            call("onet_bn_relu_bwd_head", ptr(Y), n, h, w, cout, ptr(aff[2]), ptr(aff[3]), ptr(aff[0]), ptr(aff[1]),
+                 seg.group_images, ptr(g1, off1), ld1, 0, ptr(gv), ptr(gab), ptr(dL), ptr(sums), count, ptr(dY),
+                 ptr(grad_of(bn.weight)), ptr(grad_of(bn.bias)), ptr(grad_of(bn.weight)), ptr(grad_of(bn.bias)), self.dt, st)
+        elif sv.get("prered") is not None:
             # the dgrad launch that produced g1 already reduced this layer's sums in its epilogue: apply pass only
             assert g2 is None and gp is None and ld1 == cout and off1 == 0
             call("onet_bn_relu_bwd_apply", ptr(Y), n, h, w, cout, ptr(aff[2]), ptr(aff[3]), ptr(aff[0]), ptr(aff[1]),
@@ -574,7 +669,7 @@ class _Engine:
         else:
             call("onet_bn_relu_bwd", ptr(Y), n, h, w, cout, ptr(aff[2]), ptr(aff[3]), ptr(aff[0]), ptr(aff[1]),
                  seg.group_images, ptr(g1, off1), ld1, 0, ptr(g2, off2) if g2 is not None else None, ld2, 0,
-                 ptr(gp) if gp is not None else None, ptr(sums), count, ptr(dY),
+                 ptr(gp) if gp is not None else None, ptr(sv.get("parg")) if gp is not None else None, ptr(sums), count, ptr(dY),
                  ptr(grad_of(bn.weight)), ptr(grad_of(bn.bias)), ptr(grad_of(bn.weight)), ptr(grad_of(bn.bias)), self.dt, st)
         self._join_side()
         eng = self._engine_for(cin, cout)

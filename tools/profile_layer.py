@@ -72,8 +72,9 @@ def make_runner(kind, n, h, w, cin, cout):
         ldo = out.shape[-1]
         pl = torch.empty(n, h // 2, w // 2, c, device=dev, dtype=bf) if pool else None
         byts = elems * (2 + 2) + (elems / 4 * 2 if pool else 0)
+        parg = torch.empty(n, h // 2, w // 2, c // 8, device=dev, dtype=torch.int16) if pool else None
         return (lambda: call("onet_bn_relu_apply", ptr(y), n, h, w, c, ptr(aff[2]), ptr(aff[3]), g, ptr(out), ldo, 0, ptr(pl),
-                             U.BF16, st())), 0.0, byts
+                             ptr(parg), U.BF16, st())), 0.0, byts
     g1 = torch.randn(n, h, w, 2 * c if pool else c, device=dev).to(bf)
     ld1 = g1.shape[-1]
     g2 = torch.randn(n, h, w, c, device=dev).to(bf) if kind.endswith("_g2") else None
@@ -83,13 +84,14 @@ def make_runner(kind, n, h, w, cin, cout):
     dgam = torch.zeros(c, device=dev)
     dbet = torch.zeros(c, device=dev)
     count = float(g * h * w)
+    parg = torch.randint(0, 1 << 15, (n, h // 2, w // 2, c // 8), device=dev, dtype=torch.int16) if pool else None
     # algorithmic bytes: y + g1 (+ g2) read once each, pooled gradient + argmax bytes once, dy written once
     byts = elems * (2 + 2 + 2) + (elems * 2 if g2 is not None else 0) + (elems / 4 * 2 if pool else 0)
 
     def run():
         sums.zero_()
         call("onet_bn_relu_bwd", ptr(y), n, h, w, c, ptr(aff[2]), ptr(aff[3]), ptr(aff[0]), ptr(aff[1]), g, ptr(g1), ld1, 0,
-             ptr(g2), c, 0, ptr(gp), ptr(sums), count, ptr(dy), ptr(dgam), ptr(dbet), ptr(dgam), ptr(dbet), U.BF16, st())
+             ptr(g2), c, 0, ptr(gp), ptr(parg), ptr(sums), count, ptr(dy), ptr(dgam), ptr(dbet), ptr(dgam), ptr(dbet), U.BF16, st())
     return run, 0.0, byts
 
 

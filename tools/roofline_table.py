@@ -36,6 +36,15 @@ def work(name, a, e=2.0):
     if name == "onet_convT2x2_wgrad":
         _, _, _, _, n, h, w, ci, co = a[:9]
         return f"up-conv wgrad {ci}->{co} @{h}x{w}", 2.0 * 4 * n * h * w * ci * co, n * h * w * (ci + 4 * co) * e
+    if name == "onet_first_conv_stats":
+        n, h, w, ci = a[:4]
+        return f"first conv {ci}->64 @{h}x{w}: statistics (recomputed)", 0.0, n * h * w * ci * e
+    if name == "onet_first_conv_bn_relu":
+        n, h, w, ci = a[:4]
+        return f"first conv {ci}->64 @{h}x{w}: conv + BN + ReLU", 0.0, n * h * w * (ci + 64) * e
+    if name == "onet_first_conv_bwd":
+        n, h, w, ci = a[:4]
+        return f"first conv {ci}->64 @{h}x{w}: BN backward + wgrad (recomputed)", 0.0, n * h * w * 2 * (ci + 64) * e
     if name == "onet_bn_relu_apply":
         n, h, w, c, _, ldo = a[:6]
         pooled = ldo == 2 * c
@@ -48,6 +57,15 @@ def work(name, a, e=2.0):
     if name == "onet_bn_relu_bwd_apply":
         n, h, w, c = a[:4]
         return f"BN+ReLU backward (apply only) C={c} @{h}x{w}", 0.0, n * h * w * c * 3 * e
+    if name == "onet_head_fwd_bn":
+        b, h, w = a[4:7]
+        return f"head + JSD loss (+ last BN + ReLU) @{h}x{w}", 0.0, b * h * w * (4 * 64 * e + 24)
+    if name == "onet_head_bwd_scalars":
+        b, h, w = a[:3]
+        return f"head backward, per-pixel part @{h}x{w}", 0.0, b * h * w * 32.0
+    if name == "onet_bn_relu_bwd_head":
+        n, h, w, c = a[:4]
+        return f"last BN+ReLU backward fused with head backward C={c} @{h}x{w}", 0.0, n * h * w * c * 6 * e
     if name == "onet_head_fwd":
         b, h, w = a[4:7]
         return f"head + JSD loss @{h}x{w}", 0.0, b * h * w * (4 * 64 * e + 24)
