@@ -454,6 +454,7 @@ def main():
     e2e_step(0)
     ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    peak_mem_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
 
     fam, kern_t, shape_t = profile_steps(trainer, resident[0], 2, record=(rank == 0), elem_bytes=2.0 if args.mode == "bf16" else 4.0)
     if world > 1:
@@ -558,7 +559,7 @@ def main():
                     per_kernel=per_kernel,
                     step_tflops=train_flops / (ms_dev / args.steps * 1e-3) / 1e12 if fam else None,
                     step_frac_of_sustained_peak=(train_flops / (ms_dev / args.steps * 1e-3) / 1e12 / pk["bf16_sustained"]) if fam else None,
-                    loss_last=losses[-1] if losses else None)
+                    peak_memory_gb=peak_mem_gb, loss_last=losses[-1] if losses else None)
         line.update(extra)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

@@ -286,6 +286,7 @@ bn_bwd_px_kernel(const BnBwdArgs<T> a) {
         const long long stride = static_cast<long long>(gridDim.x) * LANES;
         for (long long p = p_begin + blockIdx.x * static_cast<long long>(LANES) + ln; p < p_end; p += stride * UNROLL) {
             Raw8<T> ry[UNROLL], rg1[UNROLL], rg2[has_g2 ? UNROLL : 1];
+            float gsr[UNROLL], gar[UNROLL];          // head-fused last layer: per-pixel scalars, loaded with the tensors
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const long long q = p + u * stride;
@@ -293,6 +294,10 @@ bn_bwd_px_kernel(const BnBwdArgs<T> a) {
                 ry[u] = ok ? ldraw<T>(a.y + q * a.C + oc * 8) : zero_raw<T>();
                 rg1[u] = ok ? ldraw<T>(a.g1 + q * a.ld1 + a.off1 + oc * 8) : zero_raw<T>();
                 if (has_g2) rg2[has_g2 ? u : 0] = ok ? ldraw<T>(a.g2 + q * a.ld2 + a.off2 + oc * 8) : zero_raw<T>();
+                if (a.g1_scale != nullptr) {
+                    gsr[u] = ok ? __ldg(a.g1_scale + q) : 0.f;
+                    gar[u] = (ok && !APPLY && a.dl_out != nullptr) ? __ldg(a.dl_add + q) : 0.f;
+                }
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
@@ -308,9 +313,9 @@ bn_bwd_px_kernel(const BnBwdArgs<T> a) {
                     for (int i = 0; i < 8; ++i) gg[i] += g2v[i];
                 }
                 if (a.g1_scale != nullptr) {       // head-fused last layer: g = dV * L, dL = dV * H + d(a) with H = relu(bn(y))
-                    const float gs = __ldg(a.g1_scale + q);
+                    const float gs = gsr[u];
                     if (!APPLY && a.dl_out != nullptr) {
-                        const float ga = __ldg(a.dl_add + q);
+                        const float ga = gar[u];
                         float dl[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) dl[i] = fmaf(gs, bn_relu_value<T>(y[i], sc[i], sh[i]), ga);
@@ -665,25 +670,25 @@ head_fwd_kernel(const HeadArgs<T> a) {
             sa += __shfl_xor_sync(gmask, sa, o);
             sb += __shfl_xor_sync(gmask, sb, o);
         }
-        if (sub == 0) {
-            const float mx = fmaxf(vt, vd);
-            const float et = expf(vt - mx), ed = expf(vd - mx);
-            const float inv = 1.f / (et + ed);
-            const float st = et * inv, sd = ed * inv;
-            const long long n = p / a.HW, hw = p % a.HW;
-            a.Vt[p] = vt;
-            a.Vd[p] = vd;
-            a.S[(n * 2 + 0) * a.HW + hw] = st;
-            a.S[(n * 2 + 1) * a.HW + hw] = sd;
-            a.a[p] = sa;
-            a.b[p] = sb;
-            float v1, v2, v3, v4, d;
-            sp_ref(-sa * st, v1, d);
-            sp_ref(sa * sd, v2, d);
-            sp_ref(-sb * sd, v3, d);
-            sp_ref(sb * st, v4, d);
-            lsum += (v1 + v2) + (v3 + v4);
+        // every lane of the pixel holds the four sums: the softmax is evaluated redundantly, the four softplus terms and the six
+        // stores are spread over the pixel's lanes (one lane doing all of it left 7 of 8 lanes idle through ~100 instructions)
+        const float mx = fmaxf(vt, vd);
+        const float et = expf(vt - mx), ed = expf(vd - mx);
+        const float inv = 1.f / (et + ed);
+        const float st = et * inv, sd = ed * inv;
+        if (sub < 4) {
+            const float xarg = sub == 0 ? -sa * st : (sub == 1 ? sa * sd : (sub == 2 ? -sb * sd : sb * st));
+            float v, d;
+            sp_ref(xarg, v, d);
+            lsum += v;
         }
+        const long long n = p / a.HW, hw = p % a.HW;
+        if (sub == 0) a.Vt[p] = vt;
+        else if (sub == 1) a.Vd[p] = vd;
+        else if (sub == 2) a.S[(n * 2 + 0) * a.HW + hw] = st;
+        else if (sub == 3) a.S[(n * 2 + 1) * a.HW + hw] = sd;
+        else if (sub == 4) a.a[p] = sa;
+        else if (sub == 5) a.b[p] = sb;
     }
     __shared__ float s_l[256];
     s_l[threadIdx.x] = lsum;
