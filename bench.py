@@ -375,6 +375,7 @@ def main():
     ap.add_argument("--workload", default="simclutter", choices=["simclutter", "zy3"],
                     help="simclutter = BASELINE configs[1] (1x256x256, the headline); zy3 = configs[3] shape (3x224x224 patches)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying one CUDA graph per step")
+    ap.add_argument("--no-profile", action="store_true", help="skip the eager per-kernel timing pass (no `roofline` objects)")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the sub-records (inference configs[4], ZY-3 shape configs[3], verification modes) of the JSON line")
     args = ap.parse_args()
@@ -456,7 +457,13 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     peak_mem_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
 
-    fam, kern_t, shape_t = profile_steps(trainer, resident[0], 2, record=(rank == 0), elem_bytes=2.0 if args.mode == "bf16" else 4.0)
+    # per-kernel pass (eager, events around every call).  It allocates a second set of activations next to the captured graph's
+    # private pool: skipped when that would not fit (e.g. 256 frames per GPU) - the line then carries no per-kernel roofline
+    free_b, total_b = torch.cuda.mem_get_info(dev)
+    if args.no_profile or (trainer.use_graph and peak_mem_gb * 2 ** 30 * 1.2 > free_b):
+        fam, kern_t, shape_t = {}, {}, {}
+    else:
+        fam, kern_t, shape_t = profile_steps(trainer, resident[0], 2, record=(rank == 0), elem_bytes=2.0 if args.mode == "bf16" else 4.0)
     if world > 1:
         dist.barrier()
 
@@ -477,7 +484,7 @@ def main():
         pk = _peaks()
         value = world * B * args.steps / (ms_dev / 1e3)
         e2e_v = world * B * args.steps / (ms_e2e / 1e3)
-        total_ms = sum(d["ms"] for d in fam.values())
+        total_ms = sum(d["ms"] for d in fam.values()) or 1.0
         # dominant kernel = the kernel variant (one __global__ function) with the most time in the step; its launches
         # have different layer shapes, so achieved = sum of algorithmic FLOPs / sum of CUDA-event times = the
         # per-launch average of both.
@@ -549,6 +556,8 @@ def main():
                            tflops=(round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 1) if d["flops"] else None))
                    for k, d in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
         train_flops = sum(d["flops"] for d in fam.values())
+        if not fam:          # no per-kernel pass: the algorithmic figure of SURVEY.md section 8d (per image, twin network)
+            train_flops = (576.90e9 if args.workload == "simclutter" else 442.15e9) * B
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype={"bf16": "bf16", "fp32": "f32", "tf32": "tf32"}[args.mode], data="synthetic",
@@ -557,8 +566,8 @@ def main():
                              d2h_bytes_per_step=4),
                     gpu_launches=int(launches), clocks=clocks, roofline=roof, roofline_hbm=roof_hbm, kernels=kernels,
                     per_kernel=per_kernel,
-                    step_tflops=train_flops / (ms_dev / args.steps * 1e-3) / 1e12 if fam else None,
-                    step_frac_of_sustained_peak=(train_flops / (ms_dev / args.steps * 1e-3) / 1e12 / pk["bf16_sustained"]) if fam else None,
+                    step_tflops=train_flops / (ms_dev / args.steps * 1e-3) / 1e12,
+                    step_frac_of_sustained_peak=train_flops / (ms_dev / args.steps * 1e-3) / 1e12 / pk["bf16_sustained"],
                     peak_memory_gb=peak_mem_gb, loss_last=losses[-1] if losses else None)
         line.update(extra)
         if world == 1 and not args.no_cpu_baseline:

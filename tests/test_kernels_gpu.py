@@ -376,8 +376,9 @@ def test_bn_relu_fwd_bwd(dt_name, n, h, w, c, pool):
         assert torch.equal(dy2, dy)
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 8, 12), (1, 17, 17), (3, 5, 7)])     # 289 and 105 pixels: B*H*W % 4 != 0
 @pytest.mark.parametrize("dt_name", ["fp32", "bf16"])
-def test_head_fwd_bwd_vs_numpy_oracle(dt_name):
+def test_head_fwd_bwd_vs_numpy_oracle(dt_name, B, H, W):
     U = _imports()
     from oracle import onet_oracle as orc
     call, ptr = U.call, U.ptr
@@ -385,7 +386,6 @@ def test_head_fwd_bwd_vs_numpy_oracle(dt_name):
     tdt = U.TDT[dt]
     rnd = (lambda t: t) if dt == U.F32 else _bf16r
     torch.manual_seed(6)
-    B, H, W = 2, 8, 12
     # local features up to ~1.5 so that a = sum_p L_p reaches the |x| > 37 and > 18 softplus branches
     Lt, Ht, Ld, Hd = [rnd(torch.rand(B, 64, H, W, device="cuda") * s) for s in (1.5, 0.05, 1.2, 0.05)]
     cat0 = torch.zeros(2 * B, H, W, 128, dtype=tdt, device="cuda")
@@ -413,6 +413,39 @@ def test_head_fwd_bwd_vs_numpy_oracle(dt_name):
     tol = 2e-5 if dt == U.F32 else 4e-3
     for got, key in ((dL[:B], "dLt"), (dH[:B], "dHt"), (dL[B:], "dLd"), (dH[B:], "dHd")):
         assert U.rel_l2(got.float().permute(0, 3, 1, 2).cpu(), torch.from_numpy(r[key])) < tol, key
+    # the fused form: the head applies the last layer's BatchNorm + ReLU itself (onet_head_fwd_bn) and the per-pixel part of the
+    # backward (onet_head_bwd_scalars) reproduces the dV / d(a) that onet_head_bwd folds into dL and dH
+    Y = rnd(torch.randn(2 * B, H, W, 64, device="cuda")).to(tdt)
+    sc = 0.5 + torch.rand(2, 64, device="cuda")
+    sh = 0.2 * torch.randn(2, 64, device="cuda")
+    Hb = torch.empty_like(Y)
+    call("onet_bn_relu_apply", ptr(Y), 2 * B, H, W, 64, ptr(sc), ptr(sh), B, ptr(Hb), 64, 0, None, None, dt, U.stream())
+    outs = []
+    for fused in (False, True):
+        o = [torch.empty(B, 1, H, W, **f32), torch.empty(B, 1, H, W, **f32), torch.empty(B, 2, H, W, **f32), torch.empty(B, H, W, **f32),
+             torch.empty(B, H, W, **f32), torch.zeros((), dtype=torch.float64, device="cuda")]
+        if fused:
+            call("onet_head_fwd_bn", ptr(cat0), 128, 0, ptr(Y), 64, 0, B, H, W, ptr(sc[0]), ptr(sh[0]), ptr(sc[1]), ptr(sh[1]),
+                 *[ptr(t) for t in o], dt, U.stream())
+        else:
+            call("onet_head_fwd", ptr(cat0), 128, 0, ptr(Hb), 64, 0, B, H, W, *[ptr(t) for t in o], dt, U.stream())
+        outs.append(o)
+    for t0, t1 in zip(outs[0][:5], outs[1][:5]):
+        assert torch.equal(t0, t1)
+    assert abs(float(outs[0][5]) - float(outs[1][5])) <= 1e-9 * abs(float(outs[0][5]))      # block sums meet in double atomics
+    Vt2, Vd2, _, a2, b2, _ = outs[1]
+    dL2, dH2 = torch.empty_like(dL), torch.empty_like(dH)
+    call("onet_head_bwd", ptr(cat0), 128, 0, ptr(Hb), 64, 0, B, H, W, ptr(Vt2), ptr(Vd2), ptr(a2), ptr(b2), ptr(gscale), None,
+         None, None, ptr(dL2), ptr(dH2), dt, U.stream())
+    gv = torch.empty(2 * n, **f32)
+    gab = torch.empty(2 * n, **f32)
+    call("onet_head_bwd_scalars", ptr(Vt2), ptr(Vd2), ptr(a2), ptr(b2), ptr(gscale), None, None, None, B, H, W, ptr(gv), ptr(gab),
+         U.stream())
+    Lall = cat0[..., :64].float()
+    dH_from_scalars = (gv.view(2 * B, H, W, 1) * Lall).to(tdt)
+    dL_from_scalars = (gv.view(2 * B, H, W, 1) * Hb.float() + gab.view(2 * B, H, W, 1)).to(tdt)
+    assert U.rel_l2(dH_from_scalars.float(), dH2.float()) < (1e-6 if dt == U.F32 else 3e-3)
+    assert U.rel_l2(dL_from_scalars.float(), dL2.float()) < (1e-6 if dt == U.F32 else 3e-3)
 
 
 def test_adam_kernel_matches_torch():

@@ -1,7 +1,8 @@
 """Run ONE kernel family of the Onet path repeatedly (for ncu captures and quick timing).
 
     python tools/profile_layer.py KIND N H W Cin Cout [iters]
-KIND: fwd (conv + BN partial statistics) | dgrad (conv, no statistics) | wgrad | convT | convT_dgrad | convT_wgrad |
+KIND: fwd (conv + BN partial statistics) | dgrad (conv, no statistics) | wgrad | fwd_tf32 | dgrad_tf32 | wgrad_tf32 |
+      convT | convT_dgrad | convT_wgrad |
       bnapply | bnapply_pool | bnbwd | bnbwd_pool | bnbwd_pool_g2   (the BN kinds use C = Cout; Cin is ignored)
 Prints the CUDA-event time per launch and the achieved TFLOP/s (convolutions) or GB/s of algorithmic bytes (BN kinds)."""
 import os
@@ -27,6 +28,18 @@ def make_runner(kind, n, h, w, cin, cout):
         if kind == "first_fwd":
             return (lambda: U.conv3x3(x, wf, cout, U.BF16, U.ENGINE_SIMT, group_images=max(n // 2, 1), stats=True)), 0.0, byts
         return (lambda: U.conv3x3_wgrad(gy, x, U.BF16, U.ENGINE_SIMT)), 0.0, byts
+    if kind in ("fwd_tf32", "dgrad_tf32", "wgrad_tf32"):        # tcgen05 kind::tf32 kernels: fp32 storage (C-ABI: ONET_F32 + ONET_ENGINE_TC)
+        x = torch.randn(n, h, w, cin, device=dev)
+        wt = torch.randn(cout, cin, 3, 3, device=dev) * 0.05
+        wf, wd = U.pack_conv(wt, U.F32)
+        gy = torch.randn(n, h, w, cout, device=dev)
+        flops = 2.0 * 9 * n * h * w * cin * cout
+        byts = 4.0 * n * h * w * (cin + cout)
+        if kind == "fwd_tf32":
+            return (lambda: U.conv3x3(x, wf, cout, U.F32, U.ENGINE_TC, group_images=max(n // 2, 1), stats=True)), flops, byts
+        if kind == "dgrad_tf32":
+            return (lambda: U.conv3x3(x, wf, cout, U.F32, U.ENGINE_TC, stats=False)), flops, byts
+        return (lambda: U.conv3x3_wgrad(gy, x, U.F32, U.ENGINE_TC)), flops, byts
     if kind in ("fwd", "dgrad", "wgrad"):
         x = torch.randn(n, h, w, cin, device=dev).to(bf)
         wt = torch.randn(cout, cin, 3, 3, device=dev) * 0.05
