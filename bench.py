@@ -513,8 +513,12 @@ def main():
                 if "ncu_traffic" in fn and fn.endswith(".json"):
                     caps = json.load(open(os.path.join(ROOT, "profiles", fn)))      # the newest round's file wins
                     cap_file = fn
+            def _norm(k):        # "conv3x3_halo2_px_kernel<256, 0, OpBf16>" (ncu) and "conv3x3_halo2_px_kernel<256>" (library) -> same key
+                base, _, targs = k.replace(" ", "").partition("<")
+                first = targs.split(",")[0].rstrip(">")
+                return base.replace("/tf32", ""), (first if first.isdigit() else ""), ("Tf32" in k or "/tf32" in k)
             for c in caps:
-                if c["kernel"].replace(" ", "") == top.replace(" ", ""):
+                if _norm(c["kernel"]) == _norm(top):
                     roof["traffic"] = c["dram_bytes"]
                     roof["traffic_capture"] = dict(file="profiles/" + cap_file, capture=c["capture"],
                                                    algorithmic_bytes=c["algorithmic_bytes"], duration_us=c["duration_us"],
