@@ -292,3 +292,45 @@ def test_numpy_restatement_anchors_the_aten_oracle():
             num = (fd[0] - fd[1]) / (2 * eps)
             tol = 2e-2 * max(abs(num), float(np.abs(g).max()) * 1e-2)
             assert abs(num - g[idx]) <= tol, (k, idx, num, g[idx])
+
+
+def test_reduced_precision_restatements_and_teacher_forcing():
+    """oracle.onet_forward(emulate=..., force=...) — the checker of the bf16 / tf32 CUDA modes (tests/test_parity_gpu.py):
+    rounding happens where the policy says, the tf32 model is truncation, teacher forcing with a run's own taps reproduces that run
+    exactly, and forcing another run's conv outputs makes the forward decisions (hence the activations) that run's."""
+    import torch
+    from oracle import onet_oracle as orc
+    st = orc.perturb_bn_affine(orc.init_state(1, seed=3), seed=103)
+    x = orc.rayleigh_frames(2, 1, 32, 32, seed=3)
+    bf = lambda t: t.bfloat16().float()
+    t = torch.tensor([1.0 + 2.0 ** -11, -3.1415927, 1e-30, 65504.0])
+    tt = orc._trunc_tf32(t)
+    assert torch.equal(tt.view(torch.int32) & 0x1FFF, torch.zeros(4, dtype=torch.int32)) and float(tt[0]) == 1.0 and abs(float(tt[1])) < abs(float(t[1]))
+    outs, grads, taps = {}, {}, {}
+    for mode in (None, "tf32", "bf16"):
+        taps[mode] = {}
+        outs[mode], grads[mode], _ = orc.train_step_outputs(st, x, emulate=mode, taps=taps[mode])
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    # precision ladder against the FP32 run
+    assert rel(outs["tf32"]["Vt"], outs[None]["Vt"]) < 5e-3 < 5 * rel(outs["bf16"]["Vt"], outs[None]["Vt"])
+    # bf16 policy: stored conv outputs and activations are bf16 values; tf32 policy: storage stays fp32
+    for key, v in taps["bf16"]["top"].items():
+        if key.endswith(".raw") or key.endswith(".act") or key.endswith(".up.out"):
+            assert torch.equal(bf(v.detach()), v.detach()), key
+    raw = taps["tf32"]["top"]["down1.maxpool_conv.1.double_conv.0.raw"].detach()
+    assert not torch.equal(bf(raw), raw)
+    # teacher forcing with the run's own stored outputs: the identical run
+    for mode in ("bf16", "tf32"):
+        force = {b: {k: v.detach() for k, v in taps[mode][b].items() if k.endswith(".raw") or k.endswith(".up.out")} for b in ("top", "dwn")}
+        assert len(force["top"]) == 22
+        o2, g2, _ = orc.train_step_outputs(st, x, emulate=mode, force=force)
+        assert float(o2["loss"]) == float(outs[mode]["loss"])
+        assert max(rel(g2[k], grads[mode][k]) for k in g2) == 0.0
+    # forcing the bf16 run's conv outputs into the FP32 oracle: its activations become the bf16 run's (up to the activation
+    # rounding the FP32 oracle does not do), and `.own` keeps what the FP32 oracle computed from the forced inputs
+    force = {b: {k: v.detach() for k, v in taps["bf16"][b].items() if k.endswith(".raw") or k.endswith(".up.out")} for b in ("top", "dwn")}
+    t3 = {}
+    o3, _, _ = orc.train_step_outputs(st, x, emulate=None, force=force, taps=t3)
+    assert rel(o3["Vt"], outs["bf16"]["Vt"]) < 0.2 * rel(outs[None]["Vt"], outs["bf16"]["Vt"])
+    own = t3["top"]["inc.double_conv.3.raw.own"]
+    assert 0 < rel(own, force["top"]["inc.double_conv.3.raw"]) < 1e-2
