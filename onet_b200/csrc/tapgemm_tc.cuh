@@ -487,6 +487,55 @@ tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     tmem_ld_32x32(t_addr + ch * 32, r[0]);
                     tmem_ld_32x32(t_addr + ch * 32 + 32, r[1]);
                     tmem_ld_wait();
+                    if constexpr (!Op::kTf32) {
+                        if (p.TW >= 8 && (p.co_per_tap & 63) == 0) {
+                            // Full-line stores.  A thread owns one pixel; written directly, every 16-byte store of a warp would go to a
+                            // different 128-byte line (32 LSU wavefronts per instruction: the scatter was LSU-bound at ~3 TB/s).  The two
+                            // chunks are the 64 channels = 128 contiguous bytes of ONE fine pixel: transpose the 8 x 16-byte pieces across
+                            // the 8 lanes that hold 8 consecutive pixels of a tile row, so that 8 consecutive lanes write one whole line.
+                            const int colg = co0 + ch * 32;
+                            const int tap = colg / p.co_per_tap, cbase = colg % p.co_per_tap;
+                            const int dy = tap >> 1, dx = tap & 1;
+                            const float4* bias4 = reinterpret_cast<const float4*>(p.bias + cbase);
+                            uint4 qv[8];
+#pragma unroll
+                            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float4 b0 = __ldg(bias4 + 8 * u + 2 * j), b1 = __ldg(bias4 + 8 * u + 2 * j + 1);
+                                    qv[4 * u + j] =
+                                        make_uint4(pack_bf16x2(__uint_as_float(r[u][j * 8 + 0]) + b0.x, __uint_as_float(r[u][j * 8 + 1]) + b0.y),
+                                                   pack_bf16x2(__uint_as_float(r[u][j * 8 + 2]) + b0.z, __uint_as_float(r[u][j * 8 + 3]) + b0.w),
+                                                   pack_bf16x2(__uint_as_float(r[u][j * 8 + 4]) + b1.x, __uint_as_float(r[u][j * 8 + 5]) + b1.y),
+                                                   pack_bf16x2(__uint_as_float(r[u][j * 8 + 6]) + b1.z, __uint_as_float(r[u][j * 8 + 7]) + b1.w));
+                                }
+                            const int jl = lane & 7;
+#pragma unroll
+                            for (int b = 1; b < 8; b <<= 1) {          // 8 x 8 transpose of 16-byte pieces inside each group of 8 lanes
+                                const bool up = (jl & b) != 0;
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    if (e & b) continue;
+                                    const uint4 send = up ? qv[e] : qv[e | b];
+                                    uint4 recv;
+                                    recv.x = __shfl_xor_sync(0xffffffffu, send.x, b);
+                                    recv.y = __shfl_xor_sync(0xffffffffu, send.y, b);
+                                    recv.z = __shfl_xor_sync(0xffffffffu, send.z, b);
+                                    recv.w = __shfl_xor_sync(0xffffffffu, send.w, b);
+                                    if (up) qv[e] = recv; else qv[e | b] = recv;
+                                }
+                            }
+                            // now qv[i] = piece jl of pixel (w - jl + i): lanes jl = 0..7 of a group cover that pixel's 128 bytes
+                            const bool vrow = (row < p.valid_rows) && (h < p.H) && (n < p.N);       // uniform inside the group of 8 lanes
+                            const int wb = w - jl;
+                            __nv_bfloat16* lbase = static_cast<__nv_bfloat16*>(p.out) +
+                                                   ((static_cast<long long>(n) * p.Ho + (2 * h + dy)) * p.Wo + (2 * wb + dx)) * p.ldo + p.out_coff + cbase;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                if (vrow && wb + i < p.W) reinterpret_cast<uint4*>(lbase + static_cast<long long>(i) * 2 * p.ldo)[jl] = qv[i];
+                            continue;
+                        }
+                    }
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
                         const int colg = co0 + (ch + u) * 32;

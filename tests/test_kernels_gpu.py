@@ -242,7 +242,8 @@ def test_conv3x3_tc_wgrad(n, h, w, cin, cout):
 
 @pytest.mark.parametrize("pad", [(0, 0), (1, 1), (1, 0)])
 @pytest.mark.parametrize("engine_name", ["simt_fp32", "simt_bf16", "tc", "tc_tf32"])
-@pytest.mark.parametrize("n,h,w,cin", [(2, 4, 4, 128), (3, 8, 8, 256), (2, 16, 16, 128), (4, 2, 2, 1024)])
+@pytest.mark.parametrize("n,h,w,cin", [(2, 4, 4, 128), (3, 8, 8, 256), (2, 16, 16, 128), (4, 2, 2, 1024),
+                                       (2, 20, 24, 128), (1, 32, 48, 256)])     # partial 16 x 8 tiles: the full-line store path
 def test_convT2x2(engine_name, n, h, w, cin, pad):
     """ConvTranspose2d(C, C/2, 2, 2) + bias written into the up half of a concat buffer whose fine grid is
     (2h + ph) x (2w + pw): the reference's F.pad (Onet_vanilla_20240606.py:92-96) for odd skip sizes puts the map at (0,0)
