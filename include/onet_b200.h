@@ -80,14 +80,20 @@ int onet_conv3x3_fwd(const void* in, int64_t ldi, int ci_off, int N, int H, int 
  *   onet_first_conv_stats   : BatchNorm partial sums of conv(x) as stored (rounded to dtype) -> onet_bn_finalize
  *   onet_first_conv_bn_relu : out [N,H,W,64] = relu(conv(x) * scale + shift)   (training: batch statistics; eval: running)
  *   onet_first_conv_bwd     : g [N,H,W,64] = gradient w.r.t. out; reduces the BatchNorm-backward sums (sums: zeroed double
- *                             [G][2][64]), forms dY in registers and accumulates dw [64][Cin][3][3] (+ dgamma / dbeta). */
-int onet_first_conv_stats(const void* x, int N, int H, int W, int Cin, const void* wp, double* stat_sum, double* stat_sq,
-                          int group_images, int dtype, void* stream);
+ *                             [G][2][64]), forms dY in registers and accumulates dw [64][Cin][3][3] (+ dgamma / dbeta).
+ * in_chns = 1 with `gram` (zeroed double [G][90] = patch moments S[9], G[9][9] per statistics group): the conv output is linear
+ * in the 3 x 3 patch, so the statistics are w.S and w^T G w (no pass over 64 channels), and the backward is ONE pass over g
+ * (s1, s2 and A[c][k] = sum dz v[k] into `acc_a`, zeroed float [G][64][9]) followed by a closed-form assembly of dW from A, S, G;
+ * y is then used unrounded everywhere (round_y = 0 in onet_first_conv_bn_relu).  gram = NULL (or in_chns = 3): the two-pass form
+ * whose values are those of the stored path (round_y = 1). */
+int onet_first_conv_stats(const void* x, int N, int H, int W, int Cin, const void* wp, double* gram, double* stat_sum,
+                          double* stat_sq, int group_images, int dtype, void* stream);
 int onet_first_conv_bn_relu(const void* x, int N, int H, int W, int Cin, const void* wp, const float* scale, const float* shift,
-                            int group_images, void* out, int dtype, void* stream);
+                            int group_images, void* out, int round_y, int dtype, void* stream);
 int onet_first_conv_bwd(const void* x, int N, int H, int W, int Cin, const void* wp, const float* scale, const float* shift,
-                        const float* mean, const float* invstd, int group_images, const void* g, double* sums, double count,
-                        float* dw, float* dgamma0, float* dbeta0, float* dgamma1, float* dbeta1, int dtype, void* stream);
+                        const float* mean, const float* invstd, int group_images, const void* g, const double* gram, float* acc_a,
+                        double* sums, double count, float* dw, float* dgamma0, float* dbeta0, float* dgamma1, float* dbeta1,
+                        int dtype, void* stream);
 
 /* Inference: the same convolution with BatchNorm(eval) + ReLU folded into the epilogue, out = relu(conv * scale + shift)
  * (scale / shift [G][Cout] from onet_bn_eval_prepare), written straight to its destination (e.g. a concat-buffer slice):

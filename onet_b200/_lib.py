@@ -52,9 +52,9 @@ SIGNATURES = {
     "onet_pack_convT_weights": [_p, _i, _i, _p, _p, _i, _p],
     "onet_pack_all_weights": [_i, _p, _p, _p, _p, _p, _p, _i, _p],
     "onet_conv3x3_fwd": [_p, _i64, _i, _i, _i, _i, _i, _p, _i, _p, _i64, _i, _p, _p, _i, _i, _i, _p],
-    "onet_first_conv_stats": [_p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p],
-    "onet_first_conv_bn_relu": [_p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p],
-    "onet_first_conv_bwd": [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p, _d, _p, _p, _p, _p, _p, _i, _p],
+    "onet_first_conv_stats": [_p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p],
+    "onet_first_conv_bn_relu": [_p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _i, _p],
+    "onet_first_conv_bwd": [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _d, _p, _p, _p, _p, _p, _i, _p],
     "onet_conv3x3_bn_relu_infer": [_p, _i64, _i, _i, _i, _i, _i, _p, _i, _p, _p, _i, _p, _i64, _i, _i, _i, _p],
     "onet_maxpool2x2": [_p, _i64, _i, _i, _i, _i, _i, _p, _i, _p],
     "onet_conv3x3_wgrad": [_p, _i64, _i, _p, _i64, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p],

@@ -809,26 +809,41 @@ static int first_layer_check(const char* what, int N, int H, int W, int Cin) {
     return 0;
 }
 
-int onet_first_conv_stats(const void* x, int N, int H, int W, int Cin, const void* wp, double* stat_sum, double* stat_sq,
-                          int group_images, int dtype, void* stream) {
+int onet_first_conv_stats(const void* x, int N, int H, int W, int Cin, const void* wp, double* gram, double* stat_sum,
+                          double* stat_sq, int group_images, int dtype, void* stream) {
     if (first_layer_check("first_conv_stats", N, H, W, Cin)) return 1;
     if (stat_sum == nullptr || stat_sq == nullptr) return fail("first_conv_stats: stat_sum and stat_sq are required");
     constexpr int ROWS = 32;
-    const int wgb = (W / 4 + 31) / 32, chunks = (H + ROWS - 1) / ROWS;
-    const unsigned fg = static_cast<unsigned>(N) * chunks * wgb;
     const int gi = group_images > 0 ? group_images : N;
-#define ONET_FIRST_FWD(TT, CC, MODE, OUT)                                                                                          \
-    first_conv_fwd_kernel<TT, CC, ROWS, MODE><<<fg, 256, 0, ST(stream)>>>(static_cast<const TT*>(x), N, H, W, static_cast<const TT*>(wp), \
-                                                                          stat_sum, stat_sq, scale_, shift_, gi, static_cast<TT*>(OUT))
+    const int chunks = (H + ROWS - 1) / ROWS;
+    if (Cin == 1 && gram != nullptr) {
+        // closed form: patch moments S, G per statistics group, then sum y = w.S, sum y^2 = w^T G w (first_layer.cuh)
+        const int G = std::min(2, (N + gi - 1) / gi);
+        const int WG = W / 4;
+        const int threads = WG <= 64 ? 64 : (WG <= 128 ? 128 : 256);
+        const int wgb = (WG + 255) / 256;
+        const unsigned fg = static_cast<unsigned>(N) * chunks * wgb;
+        if (dtype == ONET_F32) first_gram_kernel<float, ROWS><<<fg, threads, 0, ST(stream)>>>(static_cast<const float*>(x), N, H, W, gi, gram);
+        else first_gram_kernel<bf16, ROWS><<<fg, threads, 0, ST(stream)>>>(static_cast<const bf16*>(x), N, H, W, gi, gram);
+        if (check_launch("first_gram")) return 1;
+        if (dtype == ONET_F32) first_stats_from_gram_kernel<float><<<G, 64, 0, ST(stream)>>>(static_cast<const float*>(wp), gram, G, stat_sum, stat_sq);
+        else first_stats_from_gram_kernel<bf16><<<G, 64, 0, ST(stream)>>>(static_cast<const bf16*>(wp), gram, G, stat_sum, stat_sq);
+        return check_launch("first_stats_from_gram");
+    }
+    const int wgb = (W / 4 + 31) / 32;
+    const unsigned fg = static_cast<unsigned>(N) * chunks * wgb;
+#define ONET_FIRST_FWD(TT, CC, MODE, RND, OUT)                                                                                     \
+    first_conv_fwd_kernel<TT, CC, ROWS, MODE, RND><<<fg, 256, 0, ST(stream)>>>(static_cast<const TT*>(x), N, H, W, static_cast<const TT*>(wp), \
+                                                                               stat_sum, stat_sq, scale_, shift_, gi, static_cast<TT*>(OUT))
     const float* scale_ = nullptr;
     const float* shift_ = nullptr;
-    if (dtype == ONET_F32) { if (Cin == 1) ONET_FIRST_FWD(float, 1, FIRST_STATS, nullptr); else ONET_FIRST_FWD(float, 3, FIRST_STATS, nullptr); }
-    else { if (Cin == 1) ONET_FIRST_FWD(bf16, 1, FIRST_STATS, nullptr); else ONET_FIRST_FWD(bf16, 3, FIRST_STATS, nullptr); }
+    if (dtype == ONET_F32) { if (Cin == 1) ONET_FIRST_FWD(float, 1, FIRST_STATS, true, nullptr); else ONET_FIRST_FWD(float, 3, FIRST_STATS, true, nullptr); }
+    else { if (Cin == 1) ONET_FIRST_FWD(bf16, 1, FIRST_STATS, true, nullptr); else ONET_FIRST_FWD(bf16, 3, FIRST_STATS, true, nullptr); }
     return check_launch("first_conv_stats");
 }
 
 int onet_first_conv_bn_relu(const void* x, int N, int H, int W, int Cin, const void* wp, const float* scale, const float* shift,
-                            int group_images, void* out, int dtype, void* stream) {
+                            int group_images, void* out, int round_y, int dtype, void* stream) {
     if (first_layer_check("first_conv_bn_relu", N, H, W, Cin)) return 1;
     if (scale == nullptr || shift == nullptr || out == nullptr) return fail("first_conv_bn_relu: scale, shift and out are required");
     constexpr int ROWS = 32;
@@ -839,18 +854,62 @@ int onet_first_conv_bn_relu(const void* x, int N, int H, int W, int Cin, const v
     double* stat_sq = nullptr;
     const float* scale_ = scale;
     const float* shift_ = shift;
-    if (dtype == ONET_F32) { if (Cin == 1) ONET_FIRST_FWD(float, 1, FIRST_APPLY, out); else ONET_FIRST_FWD(float, 3, FIRST_APPLY, out); }
-    else { if (Cin == 1) ONET_FIRST_FWD(bf16, 1, FIRST_APPLY, out); else ONET_FIRST_FWD(bf16, 3, FIRST_APPLY, out); }
+    if (dtype == ONET_F32) {        // fp32 storage: rounding is the identity
+        if (Cin == 1) ONET_FIRST_FWD(float, 1, FIRST_APPLY, false, out); else ONET_FIRST_FWD(float, 3, FIRST_APPLY, false, out);
+    } else if (round_y) {
+        if (Cin == 1) ONET_FIRST_FWD(bf16, 1, FIRST_APPLY, true, out); else ONET_FIRST_FWD(bf16, 3, FIRST_APPLY, true, out);
+    } else {
+        if (Cin == 1) ONET_FIRST_FWD(bf16, 1, FIRST_APPLY, false, out); else ONET_FIRST_FWD(bf16, 3, FIRST_APPLY, false, out);
+    }
 #undef ONET_FIRST_FWD
     return check_launch("first_conv_bn_relu");
 }
 
 int onet_first_conv_bwd(const void* x, int N, int H, int W, int Cin, const void* wp, const float* scale, const float* shift,
-                        const float* mean, const float* invstd, int group_images, const void* g, double* sums, double count,
-                        float* dw, float* dgamma0, float* dbeta0, float* dgamma1, float* dbeta1, int dtype, void* stream) {
+                        const float* mean, const float* invstd, int group_images, const void* g, const double* gram, float* acc_a,
+                        double* sums, double count, float* dw, float* dgamma0, float* dbeta0, float* dgamma1, float* dbeta1,
+                        int dtype, void* stream) {
     if (first_layer_check("first_conv_bwd", N, H, W, Cin)) return 1;
     if (g == nullptr || sums == nullptr || dw == nullptr) return fail("first_conv_bwd: g, sums and dw are required");
     constexpr int ROWS = 32;
+    if (Cin == 1 && gram != nullptr) {
+        // single pass over g + closed-form assembly from the patch moments of the forward pass (first_layer.cuh)
+        if (acc_a == nullptr) return fail("first_conv_bwd: acc_a (zeroed float [G][64][9]) is required with gram");
+        FirstFusedArgs fa;
+        memset(&fa, 0, sizeof(fa));
+        fa.N = N; fa.H = H; fa.W = W; fa.group_images = group_images > 0 ? group_images : N;
+        fa.scale = scale; fa.shift = shift; fa.mean = mean; fa.invstd = invstd; fa.sums = sums; fa.acc_a = acc_a;
+        const int G = std::min(2, (N + fa.group_images - 1) / fa.group_images);
+        const int lanes = 16, wgb = (W / 4 + lanes - 1) / lanes, chunks = (H + ROWS - 1) / ROWS;
+        const unsigned gx = static_cast<unsigned>(N) * chunks * wgb;
+        const long long numel = 64LL * 9;
+        fa.partial = (dtype == ONET_F32) ? splitk_ws(static_cast<long long>(gx) * numel) : nullptr;
+        if (dtype == ONET_F32)
+            first_conv_bwd_fused_kernel<float, 4, ROWS><<<gx, 256, 0, ST(stream)>>>(static_cast<const float*>(x), static_cast<const float*>(wp), static_cast<const float*>(g), fa);
+        else
+            first_conv_bwd_fused_kernel<bf16, 4, ROWS><<<gx, 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), static_cast<const bf16*>(wp), static_cast<const bf16*>(g), fa);
+        if (check_launch("first_conv_bwd_fused")) return 1;
+        if (fa.partial != nullptr) {       // deterministic: per-block partials added in block order, group by group
+            const long long per_img = static_cast<long long>(chunks) * wgb;
+            const long long b0 = std::min<long long>(fa.group_images, N) * per_img;
+            splitk_reduce(fa.partial, static_cast<int>(b0), numel, acc_a, ST(stream));
+            if (check_launch("splitk_reduce")) return 1;
+            if (G > 1) {
+                splitk_reduce(fa.partial + b0 * numel, static_cast<int>(gx - b0), numel, acc_a + numel, ST(stream));
+                if (check_launch("splitk_reduce")) return 1;
+            }
+        }
+        if (dtype == ONET_F32)
+            first_bwd_assemble_kernel<float><<<(64 * 9 + 127) / 128, 128, 0, ST(stream)>>>(static_cast<const float*>(wp), gram, acc_a, sums, scale, mean, invstd, G, count, dw);
+        else
+            first_bwd_assemble_kernel<bf16><<<(64 * 9 + 127) / 128, 128, 0, ST(stream)>>>(static_cast<const bf16*>(wp), gram, acc_a, sums, scale, mean, invstd, G, count, dw);
+        if (check_launch("first_bwd_assemble")) return 1;
+        if (dgamma0 != nullptr) {
+            bn_param_grad_kernel<<<1, 64, 0, ST(stream)>>>(sums, G, 64, dgamma0, dbeta0, dgamma1 ? dgamma1 : dgamma0, dbeta1 ? dbeta1 : dbeta0);
+            if (check_launch("bn_param_grad")) return 1;
+        }
+        return 0;
+    }
     FirstBwdArgs a;
     memset(&a, 0, sizeof(a));
     a.N = N; a.H = H; a.W = W; a.group_images = group_images > 0 ? group_images : N;

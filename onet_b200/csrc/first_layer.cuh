@@ -21,7 +21,10 @@ namespace onet {
 
 enum FirstMode : int { FIRST_STATS = 0, FIRST_APPLY = 1 };
 
-template <typename T, int CIN, int ROWS, int MODE>
+// ROUND_Y: the recomputed conv output is rounded to the storage type before use (what a stored Y would hold: in_chns = 3, whose
+// statistics come from the same rounded values); in_chns = 1 uses the fp32 value everywhere - its statistics are analytic
+// (first_gram_kernel) and nothing of this layer's output or output gradient is ever stored, so there is nothing to round.
+template <typename T, int CIN, int ROWS, int MODE, bool ROUND_Y = true>
 __global__ void __launch_bounds__(256, CIN == 1 ? 3 : 2)
 first_conv_fwd_kernel(const T* __restrict__ in, int N, int H, int W, const T* __restrict__ wp, double* __restrict__ stat_sum,
                       double* __restrict__ stat_sq, const float* __restrict__ scale, const float* __restrict__ shift,
@@ -73,7 +76,7 @@ first_conv_fwd_kernel(const T* __restrict__ in, int N, int H, int W, const T* __
                 float o[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float f = round_to<T>(acc[j][i]);          // the value a stored Y would hold
+                    const float f = ROUND_Y ? round_to<T>(acc[j][i]) : acc[j][i];          // the value a stored Y would hold
                     if (MODE == FIRST_STATS) {
                         a1[i] += f;
                         a2[i] = fmaf(f, f, a2[i]);
@@ -333,6 +336,245 @@ first_conv_bwd_wgrad_kernel(const T* __restrict__ in, const T* __restrict__ wp, 
         if (a.partial != nullptr) a.partial[static_cast<long long>(blockIdx.x) * (64 * K) + idx] = s_acc[i];
         else atomicAdd(a.dw + idx, s_acc[i]);
     }
+}
+
+
+// =====================================================================================================
+// in_chns = 1: statistics and the "y-dependent" part of the weight gradient in closed form.
+//
+// The conv output is LINEAR in the 9-pixel patch v_p:  y[p][c] = w_c . v_p.  With the patch moments of a statistics group,
+//     S[k] = sum_p v_p[k],      G[k][k'] = sum_p v_p[k] v_p[k']            (9 + 81 numbers, first_gram_kernel)
+// the BatchNorm statistics need no pass over the 64-channel tensor:  sum_p y = w_c . S,  sum_p y^2 = w_c^T G w_c.
+// Backward: dY = sc dz - k1 - k2 (y - mu)  (k1 = sc s1/n, k2 = sc invstd s2/n) gives
+//     dW[c][k] = sum_p dY[p][c] v_p[k] = sc A[c][k] - k1 S[k] - k2 ((G w_c)[k] - mu S[k]),   A[c][k] = sum_p dz[p][c] v_p[k],
+// so ONE pass over g (first_conv_bwd_fused_kernel: recompute y for the ReLU mask, accumulate s1, s2 and A) replaces the reduce pass
+// + the weight-gradient pass, and neither y nor dY is rounded or stored anywhere.
+// =====================================================================================================
+constexpr int kGramK = 9;
+constexpr int kGramSize = kGramK + kGramK * kGramK;      // S[9] then G[9][9], doubles, per statistics group
+
+template <typename T, int ROWS>
+__global__ void __launch_bounds__(256, 3)
+first_gram_kernel(const T* __restrict__ in, int N, int H, int W, int group_images, double* __restrict__ gram) {
+    constexpr int NACC = kGramK + kGramK * (kGramK + 1) / 2;      // S + upper triangle of G = 54
+    __shared__ float s_red[8][NACC];
+    const int WG = W >> 2, wgb = (WG + 255) >> 8, chunks = (H + ROWS - 1) / ROWS;
+    int b = blockIdx.x;
+    const int wg = (b % wgb) * 256 + threadIdx.x; b /= wgb;
+    const int h0 = (b % chunks) * ROWS;
+    const int n = b / chunks;
+    const int h1 = min(H, h0 + ROWS);
+    const int w0 = wg * 4;
+    const long long nb = static_cast<long long>(n) * H * W;
+    const int grp = min(n / group_images, 1);
+    float acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+    if (wg < WG) {
+        float x[3][6][1];
+        load_row6<T, 1>(in, nb, h0 - 1, w0, H, W, x[0]);
+        load_row6<T, 1>(in, nb, h0, w0, H, W, x[1]);
+        for (int h = h0; h < h1; ++h) {
+            load_row6<T, 1>(in, nb, h + 1, w0, H, W, x[2]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float v[kGramK];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) v[t] = x[t / 3][j + t % 3][0];
+                int o = kGramK;
+#pragma unroll
+                for (int k = 0; k < kGramK; ++k) {
+                    acc[k] += v[k];
+#pragma unroll
+                    for (int k2 = k; k2 < kGramK; ++k2) { acc[o] = fmaf(v[k], v[k2], acc[o]); ++o; }
+                }
+            }
+#pragma unroll
+            for (int cidx = 0; cidx < 6; ++cidx) { x[0][cidx][0] = x[1][cidx][0]; x[1][cidx][0] = x[2][cidx][0]; }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) {
+        float v = acc[i];
+        for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NACC) {
+        float t = 0.f;
+        for (int wv = 0; wv < static_cast<int>(blockDim.x >> 5); ++wv) t += s_red[wv][threadIdx.x];       // fixed order inside the block
+        // expand the triangle index into (k, k2) and add to both symmetric entries
+        int i = threadIdx.x;
+        double* dst = gram + static_cast<long long>(grp) * kGramSize;
+        if (i < kGramK) {
+            atomicAdd(dst + i, static_cast<double>(t));
+        } else {
+            i -= kGramK;
+            int k = 0;
+            while (i >= kGramK - k) { i -= kGramK - k; ++k; }
+            const int k2 = k + i;
+            atomicAdd(dst + kGramK + k * kGramK + k2, static_cast<double>(t));
+            if (k2 != k) atomicAdd(dst + kGramK + k2 * kGramK + k, static_cast<double>(t));
+        }
+    }
+}
+
+// stat_sum[g][c] = w_c . S_g,  stat_sq[g][c] = w_c^T G_g w_c   (the sums onet_bn_finalize expects); one thread per (g, c)
+template <typename T>
+__global__ void first_stats_from_gram_kernel(const T* __restrict__ wp, const double* __restrict__ gram, int G,
+                                             double* __restrict__ stat_sum, double* __restrict__ stat_sq) {
+    const int c = threadIdx.x, g = blockIdx.x;
+    if (c >= 64 || g >= G) return;
+    const double* S = gram + static_cast<long long>(g) * kGramSize;
+    const double* Gm = S + kGramK;
+    double w[kGramK];
+#pragma unroll
+    for (int k = 0; k < kGramK; ++k) w[k] = static_cast<double>(to_f<T>(wp[c * kGramK + k]));
+    double s = 0.0, q = 0.0;
+#pragma unroll
+    for (int k = 0; k < kGramK; ++k) {
+        s += w[k] * S[k];
+        double r = 0.0;
+#pragma unroll
+        for (int k2 = 0; k2 < kGramK; ++k2) r += Gm[k * kGramK + k2] * w[k2];
+        q += w[k] * r;
+    }
+    stat_sum[g * 64 + c] = s;
+    stat_sq[g * 64 + c] = q;
+}
+
+struct FirstFusedArgs {
+    int N, H, W, group_images;
+    const float* scale; const float* shift; const float* mean; const float* invstd;   // [G][64]
+    double* sums;                                                                     // [G][2][64]
+    float* acc_a;                                                                     // A [G][64][9] (atomics), or
+    float* partial;                                                                   // per-block partials [blocks][64*9] (deterministic mode)
+};
+
+// One backward pass over g (in_chns = 1): s1 = sum dz, s2 = sum dz (y - mu) invstd, A[c][k] = sum dz v[k].
+template <typename T, int CPT, int ROWS>
+__global__ void __launch_bounds__(256, 2)
+first_conv_bwd_fused_kernel(const T* __restrict__ in, const T* __restrict__ wp, const T* __restrict__ g, const FirstFusedArgs a) {
+    constexpr int CIN = 1, K = 9;
+    constexpr int NG = 64 / CPT, LANES = 256 / NG;
+    __shared__ float ws[K][64];
+    __shared__ float s_acc[64 * K];
+    __shared__ float s_red[2][64];
+    for (int i = threadIdx.x; i < K * 64; i += 256) ws[i % K][i / K] = to_f<T>(wp[i]);
+    for (int i = threadIdx.x; i < 64 * K; i += 256) s_acc[i] = 0.f;
+    if (threadIdx.x < 128) s_red[threadIdx.x >> 6][threadIdx.x & 63] = 0.f;
+    __syncthreads();
+    const int H = a.H, W = a.W;
+    const int cg = threadIdx.x % NG, ln = threadIdx.x / NG;
+    const int WG = W >> 2, wgb = (WG + LANES - 1) / LANES, chunks = (H + ROWS - 1) / ROWS;
+    int b = blockIdx.x;
+    const int wg = (b % wgb) * LANES + ln; b /= wgb;
+    const int h0 = (b % chunks) * ROWS;
+    const int n = b / chunks;
+    const int h1 = min(H, h0 + ROWS);
+    const int w0 = wg * 4;
+    const long long nb = static_cast<long long>(n) * H * W;
+    const int grp = min(n / a.group_images, 1);
+    float sc[CPT], sh[CPT], mu[CPT], acc1[CPT], acc2[CPT];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+        const int c = grp * 64 + cg * CPT + i;
+        sc[i] = a.scale[c]; sh[i] = a.shift[c]; mu[i] = a.mean[c];
+        acc1[i] = 0.f; acc2[i] = 0.f;
+    }
+    float acc[CPT][K];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i)
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[i][k] = 0.f;
+    if (wg < WG) {
+        float x[3][6][CIN];
+        load_row6<T, CIN>(in, nb, h0 - 1, w0, H, W, x[0]);
+        load_row6<T, CIN>(in, nb, h0, w0, H, W, x[1]);
+        for (int h = h0; h < h1; ++h) {
+            load_row6<T, CIN>(in, nb, h + 1, w0, H, W, x[2]);
+            const long long p0 = nb + static_cast<long long>(h) * W + w0;
+            float gv[4][CPT];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) first_load_g<T, CPT>(g, p0 + j, cg, gv[j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < CPT; ++i) {
+                    float y = 0.f;
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) y = fmaf(x[t / 3][j + t % 3][0], ws[t][cg * CPT + i], y);
+                    const float dz = relu_open(y, sc[i], sh[i]) ? gv[j][i] : 0.f;
+                    acc1[i] += dz;
+                    acc2[i] = fmaf(dz, y - mu[i], acc2[i]);
+                    gv[j][i] = dz;
+                }
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int i = 0; i < CPT; ++i) acc[i][t] = fmaf(gv[j][i], x[t / 3][j + t % 3][0], acc[i][t]);
+#pragma unroll
+            for (int cidx = 0; cidx < 6; ++cidx) { x[0][cidx][0] = x[1][cidx][0]; x[1][cidx][0] = x[2][cidx][0]; }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+        float v1 = acc1[i], v2 = acc2[i] * a.invstd[grp * 64 + cg * CPT + i];
+        for (int off = NG; off < 32; off <<= 1) {
+            v1 += __shfl_xor_sync(0xffffffffu, v1, off);
+            v2 += __shfl_xor_sync(0xffffffffu, v2, off);
+        }
+        acc1[i] = v1; acc2[i] = v2;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            for (int off = NG; off < 32; off <<= 1) acc[i][k] += __shfl_xor_sync(0xffffffffu, acc[i][k], off);
+    }
+    for (int wp_ = 0; wp_ < 8; ++wp_) {          // warps add one after the other: fixed order
+        if ((threadIdx.x >> 5) == wp_ && (threadIdx.x & 31) < NG) {
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) {
+                s_red[0][cg * CPT + i] += acc1[i];
+                s_red[1][cg * CPT + i] += acc2[i];
+#pragma unroll
+                for (int k = 0; k < K; ++k) s_acc[(cg * CPT + i) * K + k] += acc[i][k];
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 128) {
+        const int stat = threadIdx.x >> 6, c = threadIdx.x & 63;
+        atomicAdd(a.sums + (static_cast<long long>(grp) * 2 + stat) * 64 + c, static_cast<double>(s_red[stat][c]));
+    }
+    for (int i = threadIdx.x; i < 64 * K; i += 256) {
+        if (a.partial != nullptr) a.partial[static_cast<long long>(blockIdx.x) * (64 * K) + i] = s_acc[i];
+        else atomicAdd(a.acc_a + static_cast<long long>(grp) * 64 * K + i, s_acc[i]);
+    }
+}
+
+// dW[c][k] += sum_g [ sc A_g[c][k] - k1 S_g[k] - k2 ((G_g w_c)[k] - mu S_g[k]) ];  one thread per (c, k)
+template <typename T>
+__global__ void first_bwd_assemble_kernel(const T* __restrict__ wp, const double* __restrict__ gram, const float* __restrict__ acc_a,
+                                          const double* __restrict__ sums, const float* __restrict__ scale, const float* __restrict__ mean,
+                                          const float* __restrict__ invstd, int G, double count, float* __restrict__ dw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 64 * kGramK) return;
+    const int c = i / kGramK, k = i % kGramK;
+    const double inv_n = 1.0 / count;            // 0 for eval-mode statistics (count = inf): the mean / projection terms vanish
+    double t = 0.0;
+    for (int g = 0; g < G; ++g) {
+        const double* S = gram + static_cast<long long>(g) * kGramSize;
+        const double* Gm = S + kGramK;
+        const double sc = scale[g * 64 + c], mu = mean[g * 64 + c], is = invstd[g * 64 + c];
+        const double k1 = sc * sums[(g * 2 + 0) * 64 + c] * inv_n;
+        const double k2 = sc * is * sums[(g * 2 + 1) * 64 + c] * inv_n;
+        double gw = 0.0;
+#pragma unroll
+        for (int k2i = 0; k2i < kGramK; ++k2i) gw += Gm[k * kGramK + k2i] * static_cast<double>(to_f<T>(wp[c * kGramK + k2i]));
+        t += sc * static_cast<double>(acc_a[(static_cast<long long>(g) * 64 + c) * kGramK + k]) - k1 * S[k] - k2 * (gw - mu * S[k]);
+    }
+    dw[i] += static_cast<float>(t);       // dw is [64][1][3][3]: index c * 9 + tap
 }
 
 }  // namespace onet

@@ -437,10 +437,16 @@ class _Engine:
         G, st = seg.groups, self.stream
         x = ptr(src, self._img_off(src, n0))
         aff = torch.empty(4, G, 64, dtype=torch.float32, device=self.dev)   # mean, invstd, scale, shift
+        # in_chns = 1: the conv output is linear in the 3 x 3 patch, so the patch moments (S[9], G[9][9] per statistics group) give
+        # the BatchNorm statistics in closed form and, in backward, the y-dependent part of the weight gradient
+        # (csrc/first_layer.cuh); y is then never rounded.  ONET_NO_FIRST_GRAM=1: the two-pass form (also used for in_chns = 3).
+        use_gram = cin == 1 and os.environ.get("ONET_NO_FIRST_GRAM") is None
+        gram = torch.zeros(G, 90, dtype=torch.float64, device=self.dev) if use_gram and (rec.training_stats or rec.save) else None
         if rec.training_stats:
             stats = rec.stat_pool[rec.stat_off:rec.stat_off + 2 * G * 64].view(2, G, 64)
             rec.stat_off += 2 * G * 64
-            call("onet_first_conv_stats", x, n, h, w, cin, ptr(wf), ptr(stats[0]), ptr(stats[1]), seg.group_images, self.dt, st)
+            call("onet_first_conv_stats", x, n, h, w, cin, ptr(wf), ptr(gram), ptr(stats[0]), ptr(stats[1]), seg.group_images,
+                 self.dt, st)
             call("onet_bn_finalize", ptr(stats[0]), ptr(stats[1]), G, 64, float(seg.group_images * h * w),
                  ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var),
                  ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var),
@@ -452,10 +458,15 @@ class _Engine:
             if rec.save:
                 aff[0] = bn.running_mean
                 aff[1] = torch.rsqrt(bn.running_var + 1e-5)
+        if gram is not None and not rec.training_stats:       # eval-mode forward with backward to follow: moments only
+            scratch = torch.empty(2, G, 64, dtype=torch.float64, device=self.dev)
+            call("onet_first_conv_stats", x, n, h, w, cin, ptr(wf), ptr(gram), ptr(scratch[0]), ptr(scratch[1]), seg.group_images,
+                 self.dt, st)
+        round_y = 0 if use_gram else 1
         call("onet_first_conv_bn_relu", x, n, h, w, cin, ptr(wf), ptr(aff[2]), ptr(aff[3]), seg.group_images,
-             ptr(dst, self._img_off(dst, n0)), self.dt, st)
+             ptr(dst, self._img_off(dst, n0)), round_y, self.dt, st)
         if rec.save:
-            rec.saved[(si, li)] = dict(Y=None, aff=aff, src=(src, cin, 0), h=h, w=w, cin=cin, cout=64, first=True, wf=wf)
+            rec.saved[(si, li)] = dict(Y=None, aff=aff, src=(src, cin, 0), h=h, w=w, cin=cin, cout=64, first=True, wf=wf, gram=gram)
 
     def _upconv(self, seg, up, x, cx, n0, n, h, w, cat, ld_cat, off_cat, ho, wo):
         """x [n,h,w,cin] -> channels [off_cat, off_cat+co) of the concat buffer [n,ho,wo,ld_cat]; ho - 2h, wo - 2w in {0,1}:
@@ -641,8 +652,11 @@ class _Engine:
             src = sv["src"][0]
             # the last call of a U-Net's backward: queued behind the deferred weight gradients on the same (side) stream - it
             # shares the deterministic split-K workspace of the FP32 mode with them, which must be used from ONE stream
-            self._wgrad((g1, src, sums), "onet_first_conv_bwd", ptr(src, self._img_off(src, n0)), n, h, w, cin, ptr(sv["wf"]),
-                        ptr(aff[2]), ptr(aff[3]), ptr(aff[0]), ptr(aff[1]), seg.group_images, ptr(g1), ptr(sums), count,
+            gram = sv.get("gram")
+            acc_a = torch.zeros(G, 64, 9, dtype=torch.float32, device=self.dev) if gram is not None else None
+            self._wgrad((g1, src, sums, acc_a), "onet_first_conv_bwd", ptr(src, self._img_off(src, n0)), n, h, w, cin, ptr(sv["wf"]),
+                        ptr(aff[2]), ptr(aff[3]), ptr(aff[0]), ptr(aff[1]), seg.group_images, ptr(g1), ptr(gram), ptr(acc_a),
+                        ptr(sums), count,
                         ptr(grad_of(conv.weight)), ptr(grad_of(bn.weight)), ptr(grad_of(bn.bias)), ptr(grad_of(bn.weight)),
                         ptr(grad_of(bn.bias)), self.dt)
             return None

@@ -117,11 +117,11 @@ def test_first_layer_recompute_matches_stored_path(dt_name, n, h, w, cin):
     call("onet_bn_relu_apply", ptr(y), n, h, w, 64, ptr(aff_ref[2]), ptr(aff_ref[3]), g, ptr(act_ref), 64, 0, None, None, dt, U.stream())
     # recompute path
     st = torch.zeros(2, 2, 64, dtype=torch.float64, device="cuda")
-    call("onet_first_conv_stats", ptr(xn), n, h, w, cin, ptr(wf), ptr(st[0]), ptr(st[1]), g, dt, U.stream())
+    call("onet_first_conv_stats", ptr(xn), n, h, w, cin, ptr(wf), None, ptr(st[0]), ptr(st[1]), g, dt, U.stream())
     assert torch.allclose(st, st_ref, rtol=1e-12, atol=1e-9)
     aff = finalize(st)
     act = torch.empty_like(act_ref)
-    call("onet_first_conv_bn_relu", ptr(xn), n, h, w, cin, ptr(wf), ptr(aff_ref[2]), ptr(aff_ref[3]), g, ptr(act), dt, U.stream())
+    call("onet_first_conv_bn_relu", ptr(xn), n, h, w, cin, ptr(wf), ptr(aff_ref[2]), ptr(aff_ref[3]), g, ptr(act), 1, dt, U.stream())
     assert torch.equal(act, act_ref)
     assert torch.allclose(aff, aff_ref, rtol=1e-6, atol=1e-7)
     # backward
@@ -137,12 +137,48 @@ def test_first_layer_recompute_matches_stored_path(dt_name, n, h, w, cin):
     dw = torch.zeros(64, cin, 3, 3, device="cuda")
     dgam, dbet = torch.zeros(64, device="cuda"), torch.zeros(64, device="cuda")
     call("onet_first_conv_bwd", ptr(xn), n, h, w, cin, ptr(wf), ptr(aff_ref[2]), ptr(aff_ref[3]), ptr(aff_ref[0]), ptr(aff_ref[1]), g,
-         ptr(gn), ptr(sums), count, ptr(dw), ptr(dgam), ptr(dbet), ptr(dgam), ptr(dbet), dt, U.stream())
+         ptr(gn), None, None, ptr(sums), count, ptr(dw), ptr(dgam), ptr(dbet), ptr(dgam), ptr(dbet), dt, U.stream())
     torch.cuda.synchronize()
     assert torch.allclose(sums, sums_ref, rtol=1e-5, atol=1e-4)
     assert U.rel_l2(dgam, dgam_ref) < 1e-5 and U.rel_l2(dbet, dbet_ref) < 1e-5
     # bf16: a 1e-7 difference of a sum can flip the bf16 rounding of single dY elements
     assert U.rel_l2(dw, dw_ref) < (1e-5 if dt == U.F32 else 2e-3), U.rel_l2(dw, dw_ref)
+    if cin != 1:
+        return
+    # in_chns = 1, closed form: statistics from the patch moments, ONE backward pass + assembly; y and dY unrounded, so against
+    # the stored bf16 path only up to the rounding it does (and exactly the same quantities in fp32)
+    gram = torch.zeros(2, 90, dtype=torch.float64, device="cuda")
+    st2 = torch.zeros(2, 2, 64, dtype=torch.float64, device="cuda")
+    call("onet_first_conv_stats", ptr(xn), n, h, w, cin, ptr(wf), ptr(gram), ptr(st2[0]), ptr(st2[1]), g, dt, U.stream())
+    yf = F.conv2d(x, wt, padding=1).double()              # unrounded conv output (operands are exact in the storage type)
+    for gi, sl in enumerate((slice(0, g), slice(g, n))):
+        assert torch.allclose(st2[0, gi], yf[sl].sum(dim=(0, 2, 3)), rtol=1e-6, atol=1e-4)
+        assert torch.allclose(st2[1, gi], (yf[sl] ** 2).sum(dim=(0, 2, 3)), rtol=1e-6, atol=1e-4)
+    aff2 = finalize(st2)
+    act2 = torch.empty_like(act_ref)
+    call("onet_first_conv_bn_relu", ptr(xn), n, h, w, cin, ptr(wf), ptr(aff2[2]), ptr(aff2[3]), g, ptr(act2), 0, dt, U.stream())
+    act2_ref = torch.relu(yf.float() * torch.repeat_interleave(aff2[2], torch.tensor([g, n - g], device="cuda"), dim=0)[:, :, None, None]
+                          + torch.repeat_interleave(aff2[3], torch.tensor([g, n - g], device="cuda"), dim=0)[:, :, None, None])
+    assert U.rel_l2(U.from_nhwc(act2), act2_ref) < (1e-6 if dt == U.F32 else 3e-3)
+    sums2 = torch.zeros_like(sums_ref)
+    dw2 = torch.zeros(64, cin, 3, 3, device="cuda")
+    acc_a = torch.zeros(2, 64, 9, device="cuda")
+    dgam2, dbet2 = torch.zeros(64, device="cuda"), torch.zeros(64, device="cuda")
+    call("onet_first_conv_bwd", ptr(xn), n, h, w, cin, ptr(wf), ptr(aff2[2]), ptr(aff2[3]), ptr(aff2[0]), ptr(aff2[1]), g,
+         ptr(gn), ptr(gram), ptr(acc_a), ptr(sums2), count, ptr(dw2), ptr(dgam2), ptr(dbet2), ptr(dgam2), ptr(dbet2), dt, U.stream())
+    # torch reference of the same layer: conv -> BatchNorm (batch statistics per group) -> ReLU, gradient gr
+    xr = x.clone()
+    wr = wt.clone().requires_grad_(True)
+    gam, bet = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    out = []
+    for sl in (slice(0, g), slice(g, n)):
+        yy = F.conv2d(xr[sl], wr, padding=1)
+        out.append(torch.relu(F.batch_norm(yy, None, None, gam, bet, training=True, eps=1e-5)))
+    (torch.cat(out) * gr).sum().backward()
+    torch.cuda.synchronize()
+    tol = 2e-5 if dt == U.F32 else 2e-3
+    assert U.rel_l2(dw2, wr.grad) < tol, U.rel_l2(dw2, wr.grad)
+    assert U.rel_l2(dgam2, gam.grad) < tol and U.rel_l2(dbet2, bet.grad) < tol
 
 
 def _tf32t(t):

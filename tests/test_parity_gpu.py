@@ -78,7 +78,9 @@ def _cuda_taps(net, B):
     for li, key in enumerate(names):
         sv = rec.saved[(0, li)]
         Y = sv["Y"]
-        if Y is None:        # first convolution: its raw output is never stored (csrc/first_layer.cuh) - the stored-path kernel gives it
+        if Y is None and sv.get("gram") is not None:
+            continue         # in_chns = 1: y is recomputed in fp32 from the patch and never rounded - the oracle's own value is the same
+        if Y is None:        # first convolution (two-pass form): its raw output is not stored - the stored-path kernel gives it
             import gpu_util as U
             src = sv["src"][0]
             dt = U.BF16 if src.dtype == torch.bfloat16 else U.F32

@@ -44,7 +44,8 @@ def work(name, a, e=2.0):
         return f"first conv {ci}->64 @{h}x{w}: conv + BN + ReLU", 0.0, n * h * w * (ci + 64) * e
     if name == "onet_first_conv_bwd":
         n, h, w, ci = a[:4]
-        return f"first conv {ci}->64 @{h}x{w}: BN backward + wgrad (recomputed)", 0.0, n * h * w * 2 * (ci + 64) * e
+        # algorithmic minimum: one pass over g and x (what the in_chns = 1 closed-form path does; the two-pass form reads them twice)
+        return f"first conv {ci}->64 @{h}x{w}: BN backward + wgrad (recomputed)", 0.0, n * h * w * (ci + 64) * e
     if name == "onet_bn_relu_apply":
         n, h, w, c, _, ldo = a[:6]
         pooled = ldo == 2 * c

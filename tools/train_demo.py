@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--lr", type=float, default=5e-6)          # Train_Onet_on_simclutter_20250407.py:181
     ap.add_argument("--out", default=None, help="write a reference-format checkpoint here")
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "tf32", "fp32"])
     args = ap.parse_args()
     import onet_b200
     import onet_b200.evaluate as oev
@@ -54,7 +55,7 @@ def main():
     test_loader = [(imgs[te_idx[i:i + B]], labels[te_idx[i:i + B]].long(), snrs[te_idx[i:i + B]]) for i in range(0, len(te_idx), B)]
     cfg = types.SimpleNamespace(device=dev)
 
-    net = onet_b200.Onet(1, True, True, mode="bf16").to(dev)
+    net = onet_b200.Onet(1, True, True, mode=args.mode).to(dev)
     trainer = OnetTrainer(net, lr=args.lr, graph=True)
     before = oev.test_simclutter("before", cfg, net, test_loader, verbose=0)
     train_x = imgs[tr_idx].pin_memory()
@@ -74,7 +75,7 @@ def main():
     if args.out:
         synth.save_checkpoint(net, args.epochs - 1, args.out)
     names = ("acc", "miou", "dr", "far", "tiou")
-    print(json.dumps(dict(frames=n, train_frames=len(tr_idx), test_frames=len(te_idx), snr=args.snr, batch=B, lr=args.lr,
+    print(json.dumps(dict(mode=args.mode, frames=n, train_frames=len(tr_idx), test_frames=len(te_idx), snr=args.snr, batch=B, lr=args.lr,
                           epochs=args.epochs, steps=steps, synth_seconds=round(t_synth, 3), train_seconds=round(t_train, 3),
                           train_images_per_s=round(steps * B / t_train, 1), loss_per_epoch=[round(v, 5) for v in loss_epochs],
                           before=dict(zip(names, (round(v, 4) for v in before))),
