@@ -11,6 +11,7 @@
 #include "../../include/onet_b200.h"
 #include "elementwise.cuh"
 #include "first_layer.cuh"
+#include "first_layer_mma.cuh"
 #include "simt_conv.cuh"
 #include "synth.cuh"
 #include "tapgemm_tc.cuh"
@@ -802,6 +803,12 @@ int onet_conv3x3_fwd(const void* in, int64_t ldi, int ci_off, int N, int H, int 
 }
 
 // ---- first convolution of the U-Net without materialising its output (first_layer.cuh)
+// ONET_NO_FIRST_MMA=1: A/B switch back to the CUDA-core form of the 1-channel bf16 first conv (first_layer.cuh)
+static bool first_mma_disabled() {
+    static const bool off = getenv("ONET_NO_FIRST_MMA") != nullptr;
+    return off;
+}
+
 static int first_layer_check(const char* what, int N, int H, int W, int Cin) {
     if (N <= 0 || H <= 0 || W <= 0) return fail("%s: empty tensor", what);
     if (Cin != 1 && Cin != 3) return fail("%s: in_chns must be 1 or 3 (got %d)", what, Cin);
@@ -858,6 +865,11 @@ int onet_first_conv_bn_relu(const void* x, int N, int H, int W, int Cin, const v
         if (Cin == 1) ONET_FIRST_FWD(float, 1, FIRST_APPLY, false, out); else ONET_FIRST_FWD(float, 3, FIRST_APPLY, false, out);
     } else if (round_y) {
         if (Cin == 1) ONET_FIRST_FWD(bf16, 1, FIRST_APPLY, true, out); else ONET_FIRST_FWD(bf16, 3, FIRST_APPLY, true, out);
+    } else if (Cin == 1 && !first_mma_disabled()) {
+        // unrounded y, one input channel: warp-level tensor-core form (first_layer_mma.cuh), any width
+        const unsigned mg = static_cast<unsigned>(N) * ((H + kFmRows - 1) / kFmRows) * ((W + kFmCols - 1) / kFmCols);
+        first_mma_fwd_kernel<<<mg, 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), N, H, W, static_cast<const bf16*>(wp), scale, shift, gi,
+                                                         static_cast<bf16*>(out));
     } else {
         if (Cin == 1) ONET_FIRST_FWD(bf16, 1, FIRST_APPLY, false, out); else ONET_FIRST_FWD(bf16, 3, FIRST_APPLY, false, out);
     }
@@ -884,11 +896,19 @@ int onet_first_conv_bwd(const void* x, int N, int H, int W, int Cin, const void*
         const unsigned gx = static_cast<unsigned>(N) * chunks * wgb;
         const long long numel = 64LL * 9;
         fa.partial = (dtype == ONET_F32) ? splitk_ws(static_cast<long long>(gx) * numel) : nullptr;
-        if (dtype == ONET_F32)
+        const bool mma = dtype != ONET_F32 && !first_mma_disabled();
+        if (dtype == ONET_F32) {
             first_conv_bwd_fused_kernel<float, 4, ROWS><<<gx, 256, 0, ST(stream)>>>(static_cast<const float*>(x), static_cast<const float*>(wp), static_cast<const float*>(g), fa);
-        else
+            if (check_launch("first_conv_bwd_fused")) return 1;
+        } else if (!mma) {
             first_conv_bwd_fused_kernel<bf16, 4, ROWS><<<gx, 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), static_cast<const bf16*>(wp), static_cast<const bf16*>(g), fa);
-        if (check_launch("first_conv_bwd_fused")) return 1;
+            if (check_launch("first_conv_bwd_fused")) return 1;
+        } else {
+            // bf16: A and s1 by warp-level MMAs, s2 derived from A in the assembly kernel (first_layer_mma.cuh)
+            const unsigned mg = static_cast<unsigned>(N) * ((H + kFmRows - 1) / kFmRows) * ((W + kFmCols - 1) / kFmCols);
+            first_mma_bwd_kernel<<<mg, 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), static_cast<const bf16*>(wp), static_cast<const bf16*>(g), fa);
+            if (check_launch("first_mma_bwd")) return 1;
+        }
         if (fa.partial != nullptr) {       // deterministic: per-block partials added in block order, group by group
             const long long per_img = static_cast<long long>(chunks) * wgb;
             const long long b0 = std::min<long long>(fa.group_images, N) * per_img;
@@ -900,9 +920,9 @@ int onet_first_conv_bwd(const void* x, int N, int H, int W, int Cin, const void*
             }
         }
         if (dtype == ONET_F32)
-            first_bwd_assemble_kernel<float><<<(64 * 9 + 127) / 128, 128, 0, ST(stream)>>>(static_cast<const float*>(wp), gram, acc_a, sums, scale, mean, invstd, G, count, dw);
+            first_bwd_assemble_kernel<float><<<(64 * 9 + 127) / 128, 128, 0, ST(stream)>>>(static_cast<const float*>(wp), gram, acc_a, sums, scale, mean, invstd, G, count, dw, 0);
         else
-            first_bwd_assemble_kernel<bf16><<<(64 * 9 + 127) / 128, 128, 0, ST(stream)>>>(static_cast<const bf16*>(wp), gram, acc_a, sums, scale, mean, invstd, G, count, dw);
+            first_bwd_assemble_kernel<bf16><<<(64 * 9 + 127) / 128, 128, 0, ST(stream)>>>(static_cast<const bf16*>(wp), gram, acc_a, sums, scale, mean, invstd, G, count, dw, mma ? 1 : 0);
         if (check_launch("first_bwd_assemble")) return 1;
         if (dgamma0 != nullptr) {
             bn_param_grad_kernel<<<1, 64, 0, ST(stream)>>>(sums, G, 64, dgamma0, dbeta0, dgamma1 ? dgamma1 : dgamma0, dbeta1 ? dbeta1 : dbeta0);

@@ -553,11 +553,13 @@ first_conv_bwd_fused_kernel(const T* __restrict__ in, const T* __restrict__ wp, 
     }
 }
 
-// dW[c][k] += sum_g [ sc A_g[c][k] - k1 S_g[k] - k2 ((G_g w_c)[k] - mu S_g[k]) ];  one thread per (c, k)
+// dW[c][k] += sum_g [ sc A_g[c][k] - k1 S_g[k] - k2 ((G_g w_c)[k] - mu S_g[k]) ];  one thread per (c, k).
+// derive_s2: sums[g][1][c] = sum dz (y - mu) invstd is not given but follows from A (y = w_c . v):  invstd (w_c . A_g[c][:] - mu s1);
+// every thread of channel c evaluates it for itself and the k == 0 thread stores it for bn_param_grad_kernel.
 template <typename T>
 __global__ void first_bwd_assemble_kernel(const T* __restrict__ wp, const double* __restrict__ gram, const float* __restrict__ acc_a,
-                                          const double* __restrict__ sums, const float* __restrict__ scale, const float* __restrict__ mean,
-                                          const float* __restrict__ invstd, int G, double count, float* __restrict__ dw) {
+                                          double* __restrict__ sums, const float* __restrict__ scale, const float* __restrict__ mean,
+                                          const float* __restrict__ invstd, int G, double count, float* __restrict__ dw, int derive_s2) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 64 * kGramK) return;
     const int c = i / kGramK, k = i % kGramK;
@@ -567,12 +569,23 @@ __global__ void first_bwd_assemble_kernel(const T* __restrict__ wp, const double
         const double* S = gram + static_cast<long long>(g) * kGramSize;
         const double* Gm = S + kGramK;
         const double sc = scale[g * 64 + c], mu = mean[g * 64 + c], is = invstd[g * 64 + c];
+        const float* Ac = acc_a + (static_cast<long long>(g) * 64 + c) * kGramK;
+        double s2;
+        if (derive_s2) {
+            double wa = 0.0;
+#pragma unroll
+            for (int k2i = 0; k2i < kGramK; ++k2i) wa += static_cast<double>(to_f<T>(wp[c * kGramK + k2i])) * static_cast<double>(Ac[k2i]);
+            s2 = is * (wa - mu * sums[(g * 2 + 0) * 64 + c]);
+            if (k == 0) sums[(g * 2 + 1) * 64 + c] = s2;
+        } else {
+            s2 = sums[(g * 2 + 1) * 64 + c];
+        }
         const double k1 = sc * sums[(g * 2 + 0) * 64 + c] * inv_n;
-        const double k2 = sc * is * sums[(g * 2 + 1) * 64 + c] * inv_n;
+        const double k2 = sc * is * s2 * inv_n;
         double gw = 0.0;
 #pragma unroll
         for (int k2i = 0; k2i < kGramK; ++k2i) gw += Gm[k * kGramK + k2i] * static_cast<double>(to_f<T>(wp[c * kGramK + k2i]));
-        t += sc * static_cast<double>(acc_a[(static_cast<long long>(g) * 64 + c) * kGramK + k]) - k1 * S[k] - k2 * (gw - mu * S[k]);
+        t += sc * static_cast<double>(Ac[k]) - k1 * S[k] - k2 * (gw - mu * S[k]);
     }
     dw[i] += static_cast<float>(t);       // dw is [64][1][3][3]: index c * 9 + tap
 }

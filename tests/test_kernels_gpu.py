@@ -83,7 +83,7 @@ def test_conv3x3_tc_fwd(n, h, w, cin, cout):
 
 
 @pytest.mark.parametrize("dt_name", ["fp32", "bf16"])
-@pytest.mark.parametrize("n,h,w,cin", [(4, 32, 32, 1), (2, 40, 24, 3), (6, 16, 132, 1), (2, 67, 20, 1)])
+@pytest.mark.parametrize("n,h,w,cin", [(4, 32, 32, 1), (2, 40, 24, 3), (6, 16, 132, 1), (2, 67, 20, 1), (2, 35, 520, 1), (4, 16, 256, 1)])
 def test_first_layer_recompute_matches_stored_path(dt_name, n, h, w, cin):
     """csrc/first_layer.cuh (the first convolution without materialising Y / dY) against the stored path of the same library:
     conv_first_fwd -> bn_finalize -> bn_relu_apply and bn_relu_bwd -> conv_first_wgrad.  Forward: bit-identical activations,
@@ -151,15 +151,23 @@ def test_first_layer_recompute_matches_stored_path(dt_name, n, h, w, cin):
     st2 = torch.zeros(2, 2, 64, dtype=torch.float64, device="cuda")
     call("onet_first_conv_stats", ptr(xn), n, h, w, cin, ptr(wf), ptr(gram), ptr(st2[0]), ptr(st2[1]), g, dt, U.stream())
     yf = F.conv2d(x, wt, padding=1).double()              # unrounded conv output (operands are exact in the storage type)
-    for gi, sl in enumerate((slice(0, g), slice(g, n))):
-        assert torch.allclose(st2[0, gi], yf[sl].sum(dim=(0, 2, 3)), rtol=1e-6, atol=1e-4)
-        assert torch.allclose(st2[1, gi], (yf[sl] ** 2).sum(dim=(0, 2, 3)), rtol=1e-6, atol=1e-4)
+    ya = F.conv2d(x, wt.abs(), padding=1).double()        # the un-cancelled magnitude: the patch moments are fp32 sums per block,
+    for gi, sl in enumerate((slice(0, g), slice(g, n))):  # so the error is relative to sum |w|.v, not to the cancelled sum w.v
+        assert ((st2[0, gi] - yf[sl].sum(dim=(0, 2, 3))).abs() <= 2e-6 * ya[sl].sum(dim=(0, 2, 3)) + 1e-4).all()
+        assert ((st2[1, gi] - (yf[sl] ** 2).sum(dim=(0, 2, 3))).abs() <= 2e-6 * (ya[sl] ** 2).sum(dim=(0, 2, 3)) + 1e-4).all()
     aff2 = finalize(st2)
     act2 = torch.empty_like(act_ref)
     call("onet_first_conv_bn_relu", ptr(xn), n, h, w, cin, ptr(wf), ptr(aff2[2]), ptr(aff2[3]), g, ptr(act2), 0, dt, U.stream())
     act2_ref = torch.relu(yf.float() * torch.repeat_interleave(aff2[2], torch.tensor([g, n - g], device="cuda"), dim=0)[:, :, None, None]
                           + torch.repeat_interleave(aff2[3], torch.tensor([g, n - g], device="cuda"), dim=0)[:, :, None, None])
     assert U.rel_l2(U.from_nhwc(act2), act2_ref) < (1e-6 if dt == U.F32 else 3e-3)
+    if dt == U.BF16:
+        # warp-level tensor-core form (first_layer_mma.cuh): products exact, fp32 accumulation -> the bf16 results are the rounded
+        # reference except where a 1e-7 difference crosses a rounding boundary (then by one bf16 step)
+        got, want = U.from_nhwc(act2), _bf16r(act2_ref)
+        diff = got != want
+        assert diff.float().mean().item() < 1e-3, diff.float().mean().item()
+        assert ((got - want).abs() <= want.abs() * 2.0 ** -7 + 1e-5).all()      # near zero: y * sc + sh cancels
     sums2 = torch.zeros_like(sums_ref)
     dw2 = torch.zeros(64, cin, 3, 3, device="cuda")
     acc_a = torch.zeros(2, 64, 9, device="cuda")
