@@ -79,9 +79,13 @@ struct PxCfg {
 struct PxStatAcc {
     double s0, q0, s1, q1;
     int n_tile;
-    // BN == 64 only: per-ROW (per-thread) running sums of this warp's 32 columns, folded across lanes only when the
-    // statistics group changes and at the end - the per-tile shuffle butterfly (124 warp shuffles per tile through the
-    // shared-memory crossbar the MMAs and TMA also use) made the forward 64-channel layers 0.25 ms slower than dgrad
+    // Per-ROW (per-thread) running sums of this warp's columns, folded across lanes only when the statistics group changes and
+    // at the end: a per-tile shuffle butterfly costs 124 warp shuffles per 32-column chunk, and shuffles go through the
+    // shared-memory crossbar that the MMAs and TMA saturate (they made the forward 64 -> 128 layer 53 % slower than its dgrad
+    // form).  BN = 64: one chunk per warp, 32 columns per thread.  BN = 128 / 256 (2 / 4 chunks per warp; bf16): before
+    // accumulating, lane pairs (quads) swap halves (quarters) of the PACKED bf16 words of a chunk - 8 (16) shuffles - so a thread
+    // holds 2 (4) rows x 16 (8) columns and 32 accumulators per statistic cover all of the warp's chunks:
+    //   rs / rq [cc * (32 >> STEPS) + i]  =  chunk cc, column 16 (lane & 1) + 8 ((lane >> 1) & 1) [STEPS = 2] + i
     float rs[32], rq[32];
     int grp, pending;
     __device__ __forceinline__ void reset(int nt) { s0 = q0 = s1 = q1 = 0.0; n_tile = nt; }
@@ -91,6 +95,53 @@ struct PxStatAcc {
         pending = 0;
     }
 };
+
+template <int BN> struct PxRowAcc {
+    // lane-exchange steps; -1: no row form.  (256-column tiles could use 2 steps - px_rowacc_packed<2, .> - but the four-way
+    // chunk dispatch spills in the 168-register kernels, and their statistics cost 3 % at most: they keep the per-tile butterfly.)
+    static constexpr int kSteps = BN == 64 ? 0 : (BN == 128 ? 1 : -1);
+    static constexpr int kChunks = BN >= 64 ? BN / 64 : 1;                                   // 32-column chunks per epilogue warp
+    static constexpr int kVals = kSteps >= 0 ? (32 >> kSteps) : 32;                          // running sums per chunk and statistic
+};
+
+__device__ __forceinline__ void px_acc_word(uint32_t w, float& s_lo, float& s_hi, float& q_lo, float& q_hi) {
+    const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
+    s_lo += lo; s_hi += hi;
+    q_lo = fmaf(lo, lo, q_lo); q_hi = fmaf(hi, hi, q_hi);
+}
+
+// Chunk CC of a warp: pk = the 16 packed bf16 words (32 columns) of this thread's row, as stored.
+template <int STEPS, int CC>
+__device__ __forceinline__ void px_rowacc_packed(const uint32_t (&pk)[16], bool valid, int lane, PxStatAcc& a) {
+    constexpr int V = 32 >> STEPS;
+    uint32_t k[8], r[8];
+    const bool b1 = (lane & 1) != 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t lo = valid ? pk[j] : 0u, hi = valid ? pk[8 + j] : 0u;
+        k[j] = b1 ? hi : lo;
+        r[j] = __shfl_xor_sync(0xffffffffu, b1 ? lo : hi, 1);
+    }
+    if constexpr (STEPS == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            px_acc_word(k[j], a.rs[CC * V + 2 * j], a.rs[CC * V + 2 * j + 1], a.rq[CC * V + 2 * j], a.rq[CC * V + 2 * j + 1]);
+            px_acc_word(r[j], a.rs[CC * V + 2 * j], a.rs[CC * V + 2 * j + 1], a.rq[CC * V + 2 * j], a.rq[CC * V + 2 * j + 1]);
+        }
+    } else {
+        const bool b2 = (lane & 2) != 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t k2 = b2 ? k[4 + j] : k[j], r2 = b2 ? r[4 + j] : r[j];
+            const uint32_t k3 = __shfl_xor_sync(0xffffffffu, b2 ? k[j] : k[4 + j], 2);
+            const uint32_t r3 = __shfl_xor_sync(0xffffffffu, b2 ? r[j] : r[4 + j], 2);
+            px_acc_word(k2, a.rs[CC * V + 2 * j], a.rs[CC * V + 2 * j + 1], a.rq[CC * V + 2 * j], a.rq[CC * V + 2 * j + 1]);
+            px_acc_word(r2, a.rs[CC * V + 2 * j], a.rs[CC * V + 2 * j + 1], a.rq[CC * V + 2 * j], a.rq[CC * V + 2 * j + 1]);
+            px_acc_word(k3, a.rs[CC * V + 2 * j], a.rs[CC * V + 2 * j + 1], a.rq[CC * V + 2 * j], a.rq[CC * V + 2 * j + 1]);
+            px_acc_word(r3, a.rs[CC * V + 2 * j], a.rs[CC * V + 2 * j + 1], a.rq[CC * V + 2 * j], a.rq[CC * V + 2 * j + 1]);
+        }
+    }
+}
 
 // transposing butterfly: on return lane j holds in v[0] / s2[0] the sum over the warp's 32 lanes of element j
 __device__ __forceinline__ void px_butterfly(float (&v)[32], float (&s2)[32], int lane) {
@@ -123,20 +174,24 @@ __device__ __forceinline__ void px_butterfly1(float (&v)[32], int lane) {     //
 }
 
 // Fold the per-row running sums into the per-column fp64 accumulators of the owner threads.  Collective over the
-// kPxEpiWarps epilogue warps (named barrier 1).  BN == 64: rs / rq = sums / sums of squares of this warp's chunk;
-// BN == 128 (sums only): rs / rq = sums of this warp's chunks `half` and `half + 2`.
+// kPxEpiWarps epilogue warps (named barrier 1).  Rare: when the statistics group or the n-tile changes and at the end.
 template <int BN>
 __device__ __forceinline__ void px_stat_fold_rows(PxStatAcc& a, int q, int ew, int lane, float* s_part) {
+    using RA = PxRowAcc<BN>;
     const int half = ew >> 2;
-    px_butterfly(a.rs, a.rq, lane);
-    if (BN == 64) {
-        s_part[(q * 2 + 0) * BN + half * 32 + lane] = a.rs[0];
-        s_part[(q * 2 + 1) * BN + half * 32 + lane] = a.rq[0];
-    } else {
-        s_part[(q * 2 + 0) * BN + half * 32 + lane] = a.rs[0];
-        s_part[(q * 2 + 0) * BN + (half + 2) * 32 + lane] = a.rq[0];
-        s_part[(q * 2 + 1) * BN + half * 32 + lane] = 0.f;
-        s_part[(q * 2 + 1) * BN + (half + 2) * 32 + lane] = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < RA::kChunks; ++cc) {
+        float v[32], s2[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {       // this lane's columns of the chunk, zero elsewhere (PxStatAcc layout)
+            const bool own = (RA::kSteps < 1 || ((i >> 4) & 1) == (lane & 1)) && (RA::kSteps < 2 || ((i >> 3) & 1) == ((lane >> 1) & 1));
+            v[i] = own ? a.rs[cc * RA::kVals + (i & (RA::kVals - 1))] : 0.f;
+            s2[i] = own ? a.rq[cc * RA::kVals + (i & (RA::kVals - 1))] : 0.f;
+        }
+        px_butterfly(v, s2, lane);
+        const int ch = half + cc * (kPxEpiWarps / 4);
+        s_part[(q * 2 + 0) * BN + ch * 32 + lane] = v[0];
+        s_part[(q * 2 + 1) * BN + ch * 32 + lane] = s2[0];
     }
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kPxEpiWarps) : "memory");
     const int c = ew * 32 + lane;
@@ -155,7 +210,9 @@ __device__ __forceinline__ void px_stat_fold_rows(PxStatAcc& a, int q, int ew, i
 }
 template <int BN>
 __device__ __forceinline__ void px_stat_flush(const PxParams& p, PxStatAcc& a, int ew, int lane, float* s_part) {
-    if ((BN == 64 || BN == 128) && p.stat_sum != nullptr && a.pending) px_stat_fold_rows<(BN == 64 ? 64 : 128)>(a, (ew & 3), ew, lane, s_part);
+    if constexpr (PxRowAcc<BN>::kSteps >= 0) {
+        if (p.stat_sum != nullptr && a.pending) px_stat_fold_rows<BN>(a, (ew & 3), ew, lane, s_part);
+    }
     const int c = ew * 32 + lane;
     if (a.n_tile >= 0 && c < BN && p.stat_sum != nullptr) {
         const long long col = static_cast<long long>(a.n_tile) * BN + c;
@@ -209,9 +266,9 @@ __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile,
     const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
     OT* orow = static_cast<OT*>(p.out) + ((static_cast<long long>(n) * p.H + h) * p.W + w) * p.ldo + p.out_coff + co0;
     const bool do_stats = p.stat_sum != nullptr;
-    // per-row running sums (no per-tile cross-lane traffic): 64-column tiles always; 128-column tiles when only column
-    // sums are wanted (rs / rq then hold this warp's two chunks)
-    const bool rowacc = do_stats && (BN == 64 || (BN == 128 && p.stat_sq == nullptr));
+    // per-row running sums (PxStatAcc): 64-column tiles always; 128- and 256-column bf16 tiles after a packed lane exchange
+    constexpr bool kPackedAcc = !Op::kTf32 && !RED && PxRowAcc<BN>::kSteps >= 1;
+    const bool rowacc = do_stats && (BN == 64 || kPackedAcc);
     if (rowacc) {      // (collective) fold the running row sums when the statistics group or n-tile changes
         const int grp = min((nt * p.TN) / p.group_images, 1);
         if (sacc.n_tile != n_tile) {
@@ -258,7 +315,20 @@ __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile,
                 for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
             }
         }
-        if (do_stats) {
+        if constexpr (kPackedAcc) {
+            if (do_stats) {
+                const int cc = (ch - half) / (kPxEpiWarps / 4);      // warp-uniform
+                if constexpr (PxRowAcc<BN>::kSteps == 1) {
+                    if (cc == 0) px_rowacc_packed<1, 0>(pk, valid, lane, sacc);
+                    else px_rowacc_packed<1, 1>(pk, valid, lane, sacc);
+                } else {
+                    if (cc == 0) px_rowacc_packed<2, 0>(pk, valid, lane, sacc);
+                    else if (cc == 1) px_rowacc_packed<2, 1>(pk, valid, lane, sacc);
+                    else if (cc == 2) px_rowacc_packed<2, 2>(pk, valid, lane, sacc);
+                    else px_rowacc_packed<2, 3>(pk, valid, lane, sacc);
+                }
+            }
+        } else if (do_stats) {
             float v[32], s2[32];
             if constexpr (Op::kTf32) {
 #pragma unroll
@@ -309,14 +379,6 @@ __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile,
             if (BN == 64) {          // one chunk per warp: keep per-row running sums, no cross-lane traffic per tile
 #pragma unroll
                 for (int j = 0; j < 32; ++j) { sacc.rs[j] += v[j]; sacc.rq[j] += s2[j]; }
-            } else if (rowacc) {     // BN == 128, sums only: rs = this warp's first chunk, rq = its second chunk
-                if (ch < 2) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) sacc.rs[j] += v[j];
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) sacc.rq[j] += v[j];
-                }
             } else if (p.stat_sq != nullptr) {
                 px_butterfly(v, s2, lane);
                 s_part[(q * 2 + 0) * BN + ch * 32 + lane] = v[0];
