@@ -177,7 +177,9 @@ static int launch_px(const CUtensorMap& tA, const CUtensorMap& tB, const PxParam
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     const int grid = std::min(tiles, sm_count());
-    tapgemm_px_kernel<BN, Op><<<grid, kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, p);
+    PxParams pf = p;
+    px_set_fastdiv(pf);
+    tapgemm_px_kernel<BN, Op><<<grid, kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, pf);
     return check_launch(Op::kTf32 ? "tapgemm_px_kernel/tf32" : "tapgemm_px_kernel", BN);
 }
 
@@ -212,7 +214,9 @@ static int launch_halo_px(const CUtensorMap& tA, const CUtensorMap& tB, const Px
         attr_set = true;
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
-    conv3x3_halo_px_kernel<BN, Op><<<std::min(tiles, sm_count()), kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, p);
+    PxParams pf = p;
+    px_set_fastdiv(pf);
+    conv3x3_halo_px_kernel<BN, Op><<<std::min(tiles, sm_count()), kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, pf);
     return check_launch(Op::kTf32 ? "conv3x3_halo_px_kernel/tf32" : "conv3x3_halo_px_kernel", BN);
 }
 
@@ -226,7 +230,9 @@ static int launch_halo_res_px(const CUtensorMap& tA, const CUtensorMap& tB, cons
         if (e != cudaSuccess) return fail("cudaFuncSetAttribute(halo_res_px<%d>): %s", BN, cudaGetErrorString(e));
         attr_set = true;
     }
-    conv3x3_halo_res_px_kernel<BN, RED><<<std::min(p.num_m_tiles, sm_count()), kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, p);
+    PxParams pf = p;
+    px_set_fastdiv(pf);
+    conv3x3_halo_res_px_kernel<BN, RED><<<std::min(p.num_m_tiles, sm_count()), kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, pf);
     return check_launch(RED ? "conv3x3_halo_res_px_kernel+bnred" : "conv3x3_halo_res_px_kernel", BN);
 }
 
@@ -258,7 +264,9 @@ static int launch_halo2_px(const CUtensorMap& tA, const CUtensorMap& tB, const P
     }
     const int units = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
     const int grid = 2 * std::min(units, max_clusters);
-    conv3x3_halo2_px_kernel<BN, RED, Op><<<grid, kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, p);
+    PxParams pf = p;
+    px_set_fastdiv(pf);
+    conv3x3_halo2_px_kernel<BN, RED, Op><<<grid, kPxThreads, Cfg::kSmemBytes, st>>>(tA, tB, pf);
     return check_launch(RED ? "conv3x3_halo2_px_kernel+bnred" : (Op::kTf32 ? "conv3x3_halo2_px_kernel/tf32" : "conv3x3_halo2_px_kernel"), BN);
 }
 

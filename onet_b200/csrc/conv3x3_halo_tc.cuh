@@ -69,8 +69,9 @@ conv3x3_halo_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
-                const int wt = m_tile % p.tiles_w, ht = (m_tile / p.tiles_w) % p.tiles_h, nt = m_tile / (p.tiles_w * p.tiles_h);
+                const int n_tile = fd_div(tile, p.fd_m), m_tile = tile - n_tile * p.num_m_tiles;
+                int wt, ht, nt;
+                px_tile_coord(p, m_tile, wt, ht, nt);
                 const int w0 = wt * 8, h0 = ht * 16, co0 = n_tile * BN;
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
                     for (int kw = 0; kw < 3; ++kw) {
@@ -143,10 +144,11 @@ conv3x3_halo_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
+            const int n_tile = fd_div(tile, p.fd_m), m_tile = tile - n_tile * p.num_m_tiles;
+            const PxRowCoord rc = px_row_coord(p, m_tile, q, lane);
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
-            px_store_epilogue<BN, false, Op>(p, tile % p.num_m_tiles, tile / p.num_m_tiles, acc, tmem_base, q, ew, lane, s_part,
-                                             bar_tempty + 8 * acc, false, sacc);
+            px_store_epilogue<BN, false, Op>(p, rc, n_tile, acc, tmem_base, q, ew, lane, s_part, bar_tempty + 8 * acc, false, sacc);
         }
         px_stat_flush<BN>(p, sacc, ew, lane, s_part);
     }
@@ -215,7 +217,8 @@ conv3x3_halo_res_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             int sa = 0;
             uint32_t pa = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int wt = tile % p.tiles_w, ht = (tile / p.tiles_w) % p.tiles_h, nt = tile / (p.tiles_w * p.tiles_h);
+                int wt, ht, nt;
+                px_tile_coord(p, tile, wt, ht, nt);
                 const int w0 = wt * 8, h0 = ht * 16;
                 for (int kw = 0; kw < 3; ++kw) {
                     mbar_wait(bar_emptyA + 8 * sa, pa ^ 1);
@@ -272,9 +275,10 @@ conv3x3_halo_res_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             if (RED && tile + static_cast<int>(gridDim.x) < num_tiles) px_red_prefetch<BN>(p, tile + gridDim.x, 0, q, ew, lane);
+            const PxRowCoord rc = px_row_coord(p, tile, q, lane);
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
-            px_store_epilogue<BN, RED>(p, tile, 0, acc, tmem_base, q, ew, lane, s_part, bar_tempty + 8 * acc, false, sacc);
+            px_store_epilogue<BN, RED>(p, rc, 0, acc, tmem_base, q, ew, lane, s_part, bar_tempty + 8 * acc, false, sacc);
         }
         px_stat_flush<BN>(p, sacc, ew, lane, s_part);
     }
@@ -352,9 +356,10 @@ conv3x3_halo2_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0;
             for (int unit = pair; unit < num_units; unit += npairs) {
-                const int m_tile = 2 * (unit % num_pair_m) + static_cast<int>(rank), n_tile = unit / num_pair_m;
+                const int n_tile = fd_div(unit, p.fd_pm), m_tile = 2 * (unit - n_tile * num_pair_m) + static_cast<int>(rank);
                 // an m_tile == num_m_tiles (odd tile count) decodes to image index N: every row is out of bounds -> zeros
-                const int wt = m_tile % p.tiles_w, ht = (m_tile / p.tiles_w) % p.tiles_h, nt = m_tile / (p.tiles_w * p.tiles_h);
+                int wt, ht, nt;
+                px_tile_coord(p, m_tile, wt, ht, nt);
                 const int w0 = wt * 8, h0 = ht * 16, co0 = n_tile * BN + static_cast<int>(rank) * (BN / 2);
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
                     for (int kw = 0; kw < 3; ++kw) {
@@ -425,17 +430,20 @@ conv3x3_halo2_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         sacc.grp = 0;
         int it = 0;
         if (RED && pair < num_units)
-            px_red_prefetch<BN>(p, 2 * (pair % num_pair_m) + static_cast<int>(rank), pair / num_pair_m, q, ew, lane);
+            px_red_prefetch<BN>(p, 2 * (pair - fd_div(pair, p.fd_pm) * num_pair_m) + static_cast<int>(rank), fd_div(pair, p.fd_pm), q, ew, lane);
         for (int unit = pair; unit < num_units; unit += npairs, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int m_tile = 2 * (unit % num_pair_m) + static_cast<int>(rank), n_tile = unit / num_pair_m;
-            if (RED && unit + npairs < num_units)
-                px_red_prefetch<BN>(p, 2 * ((unit + npairs) % num_pair_m) + static_cast<int>(rank), (unit + npairs) / num_pair_m, q, ew, lane);
+            const int n_tile = fd_div(unit, p.fd_pm), m_tile = 2 * (unit - n_tile * num_pair_m) + static_cast<int>(rank);
+            if (RED && unit + npairs < num_units) {
+                const int nn = fd_div(unit + npairs, p.fd_pm);
+                px_red_prefetch<BN>(p, 2 * (unit + npairs - nn * num_pair_m) + static_cast<int>(rank), nn, q, ew, lane);
+            }
+            const PxRowCoord rc = px_row_coord(p, min(m_tile, p.num_m_tiles - 1), q, lane);
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             if (m_tile < p.num_m_tiles) {
-                px_store_epilogue<BN, RED, Op>(p, m_tile, n_tile, acc, tmem_base, q, ew, lane, s_part, lead_tempty + 8 * acc, true, sacc);
+                px_store_epilogue<BN, RED, Op>(p, rc, n_tile, acc, tmem_base, q, ew, lane, s_part, lead_tempty + 8 * acc, true, sacc);
             } else {           // padding tile of an odd tile count: nothing to store
                 tc_fence_before();
                 __syncwarp();

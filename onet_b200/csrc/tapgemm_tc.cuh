@@ -22,6 +22,24 @@ namespace onet {
 
 constexpr int kMaxTaps = 9;
 
+// n / d for 0 <= n < 2^31 by multiply-high (the tile-index decompositions of the persistent kernels: a runtime integer division
+// is ~25 dependent instructions, and the epilogue warps did four of them per tile)
+struct FastDiv { uint32_t d, mul, shr; };
+inline FastDiv make_fastdiv(int d) {
+    FastDiv f;
+    f.d = static_cast<uint32_t>(d > 0 ? d : 1);
+    if (f.d == 1u) { f.mul = 0u; f.shr = 0u; return f; }
+    uint32_t lg = 0;
+    while ((1ull << lg) < f.d) ++lg;
+    const uint32_t pw = 31u + lg;
+    f.mul = static_cast<uint32_t>(((1ull << pw) + f.d - 1ull) / f.d);
+    f.shr = pw - 32u;
+    return f;
+}
+__device__ __forceinline__ int fd_div(int n, const FastDiv& f) {
+    return f.d == 1u ? n : static_cast<int>(__umulhi(static_cast<uint32_t>(n), f.mul) >> f.shr);
+}
+
 enum EpiMode : int { EPI_STORE = 0, EPI_CONVT = 1 };
 // (EPI_STORE with PxParams::scale != nullptr = inference: BatchNorm(eval) + ReLU folded into the store)
 
@@ -31,6 +49,7 @@ struct PxParams {
     int TW, TH, TN, log_tw, log_th;
     int tiles_w, tiles_h, tiles_n;
     int num_m_tiles, num_n_tiles;
+    FastDiv fd_w, fd_wh, fd_m, fd_pm;   // / tiles_w, / (tiles_w * tiles_h), / num_m_tiles, / ceil(num_m_tiles / 2); px_set_fastdiv()
     int valid_rows;            // TW*TH*TN
     int ntaps, k_chunks, cin;  // K = ntaps * cin, cin = Op::kKC * k_chunks (one K chunk = 128 bytes of channels)
     int4 taps[kMaxTaps];       // coordinate offsets (dc, dw, dq, dh) of each tap in the 5-D input view
@@ -60,6 +79,38 @@ struct PxParams {
     int co_per_tap;            // EPI_CONVT: output channels per 2x2 position
     int Ho, Wo;                // EPI_CONVT: height / width of the fine grid the buffer holds (>= 2H, 2W; F.pad border beyond)
 };
+
+inline void px_set_fastdiv(PxParams& p) {
+    p.fd_w = make_fastdiv(p.tiles_w);
+    p.fd_wh = make_fastdiv(p.tiles_w * p.tiles_h);
+    p.fd_m = make_fastdiv(p.num_m_tiles);
+    p.fd_pm = make_fastdiv((p.num_m_tiles + 1) >> 1);
+}
+
+// Output pixel of an epilogue thread (TMEM lane quarter q, lane) in pixel tile m_tile.  Computed BEFORE the wait for the tile's
+// accumulator so that it is off the accumulator-drain path.
+struct PxRowCoord {
+    int n, h, w, nt;
+    bool valid;
+};
+__device__ __forceinline__ void px_tile_coord(const PxParams& p, int m_tile, int& wt, int& ht, int& nt) {
+    nt = fd_div(m_tile, p.fd_wh);
+    const int rem = m_tile - nt * (p.tiles_w * p.tiles_h);
+    ht = fd_div(rem, p.fd_w);
+    wt = rem - ht * p.tiles_w;
+}
+__device__ __forceinline__ PxRowCoord px_row_coord(const PxParams& p, int m_tile, int q, int lane) {
+    const int row = q * 32 + lane;
+    const int w_l = row & (p.TW - 1), h_l = (row >> p.log_tw) & (p.TH - 1), n_l = row >> (p.log_tw + p.log_th);
+    int wt, ht, nt;
+    px_tile_coord(p, m_tile, wt, ht, nt);
+    PxRowCoord c;
+    c.w = wt * p.TW + w_l; c.h = ht * p.TH + h_l; c.n = nt * p.TN + n_l; c.nt = nt;
+    c.valid = (row < p.valid_rows) && (c.w < p.W) && (c.h < p.H) && (c.n < p.N);
+    return c;
+}
+// statistics group of pixel tile nt (at most two groups: the twin branches; a tile never straddles them)
+__device__ __forceinline__ int px_group(const PxParams& p, int nt) { return (nt * p.TN >= p.group_images) ? 1 : 0; }
 
 template <int BN>
 struct PxCfg {
@@ -235,12 +286,9 @@ template <int BN>
 __device__ __forceinline__ void px_red_prefetch(const PxParams& p, int m_tile, int n_tile, int q, int ew, int lane) {
     if (m_tile >= p.num_m_tiles) return;
     const int half = ew >> 2;
-    const int row = q * 32 + lane;
-    const int w_l = row & (p.TW - 1), h_l = (row >> p.log_tw) & (p.TH - 1), n_l = row >> (p.log_tw + p.log_th);
-    const int wt = m_tile % p.tiles_w, ht = (m_tile / p.tiles_w) % p.tiles_h, nt = m_tile / (p.tiles_w * p.tiles_h);
-    const int w = wt * p.TW + w_l, h = ht * p.TH + h_l, n = nt * p.TN + n_l;
-    if (!((row < p.valid_rows) && (w < p.W) && (h < p.H) && (n < p.N))) return;
-    const __nv_bfloat16* yrow = p.red_y + ((static_cast<long long>(n) * p.H + h) * p.W + w) * p.cout_total + n_tile * BN;
+    const PxRowCoord rc = px_row_coord(p, m_tile, q, lane);
+    if (!rc.valid) return;
+    const __nv_bfloat16* yrow = p.red_y + ((static_cast<long long>(rc.n) * p.H + rc.h) * p.W + rc.w) * p.cout_total + n_tile * BN;
 #pragma unroll
     for (int ch = half; ch < BN / 32; ch += kPxEpiWarps / 4) {
         if (BN == 64) asm volatile("prefetch.global.L1 [%0];" ::"l"(yrow + ch * 32));
@@ -249,28 +297,31 @@ __device__ __forceinline__ void px_red_prefetch(const PxParams& p, int m_tile, i
 }
 
 // Store epilogue of the pixel-major kernels: raw bf16 output + BatchNorm partial sums.
-// `arrive_bar`: the accumulator-drained barrier; `remote`: it is a shared::cluster address in the peer (leader) CTA.
+// `rc`: this thread's output pixel (px_row_coord, computed before the accumulator wait); `arrive_bar`: the accumulator-drained
+// barrier; `remote`: it is a shared::cluster address in the peer (leader) CTA.
+// bf16 tiles of up to 128 columns release the accumulator as soon as this warp's columns are in registers (packed to bf16) and do
+// the stores and the statistics afterwards: with 64 input channels a tile's MMAs take about as long as its epilogue, and an
+// accumulator held through the whole epilogue stalled the MMA warp (forward 64 -> 64 was 14 % slower than its dgrad form).
 template <int BN, bool RED = false, class Op = OpBf16>
-__device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile, int n_tile, int acc, uint32_t tmem_base, int q,
+__device__ __forceinline__ void px_store_epilogue(const PxParams& p, const PxRowCoord& rc, int n_tile, int acc, uint32_t tmem_base, int q,
                                                   int ew, int lane, float* s_part, uint32_t arrive_bar, bool remote,
                                                   PxStatAcc& sacc) {
     static_assert(!(RED && Op::kTf32), "the fused BatchNorm-backward reduce exists for the bf16 kernels only");
     using OT = typename Op::T;
     // ew = 0 .. kPxEpiWarps-1; warps ew and ew+4 share TMEM lane quarter q and split the 32-column chunks
     const int half = ew >> 2;
-    const int row = q * 32 + lane;
-    const int w_l = row & (p.TW - 1), h_l = (row >> p.log_tw) & (p.TH - 1), n_l = row >> (p.log_tw + p.log_th);
-    const int wt = m_tile % p.tiles_w, ht = (m_tile / p.tiles_w) % p.tiles_h, nt = m_tile / (p.tiles_w * p.tiles_h);
-    const int w = wt * p.TW + w_l, h = ht * p.TH + h_l, n = nt * p.TN + n_l, co0 = n_tile * BN;
-    const bool valid = (row < p.valid_rows) && (w < p.W) && (h < p.H) && (n < p.N);
+    const int n = rc.n, h = rc.h, w = rc.w, nt = rc.nt, co0 = n_tile * BN;
+    const bool valid = rc.valid;
     const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
     OT* orow = static_cast<OT*>(p.out) + ((static_cast<long long>(n) * p.H + h) * p.W + w) * p.ldo + p.out_coff + co0;
     const bool do_stats = p.stat_sum != nullptr;
-    // per-row running sums (PxStatAcc): 64-column tiles always; 128- and 256-column bf16 tiles after a packed lane exchange
+    const int grp = px_group(p, nt);
+    // per-row running sums (PxStatAcc): 64-column tiles always; 128-column bf16 tiles after a packed lane exchange
     constexpr bool kPackedAcc = !Op::kTf32 && !RED && PxRowAcc<BN>::kSteps >= 1;
+    constexpr int kChunksPerWarp = BN >= 64 ? BN / 64 : 1;
+    constexpr bool kEarlyRelease = !Op::kTf32 && BN >= 64 && kChunksPerWarp <= 2;
     const bool rowacc = do_stats && (BN == 64 || kPackedAcc);
     if (rowacc) {      // (collective) fold the running row sums when the statistics group or n-tile changes
-        const int grp = min((nt * p.TN) / p.group_images, 1);
         if (sacc.n_tile != n_tile) {
             px_stat_flush<BN>(p, sacc, ew, lane, s_part);
             sacc.reset(n_tile);
@@ -281,14 +332,19 @@ __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile,
         }
         sacc.pending = 1;
     }
-#pragma unroll 1
-    for (int ch = half; ch < BN / 32; ch += kPxEpiWarps / 4) {
-        uint32_t r[32];
+    auto release = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+            if (remote) mbar_arrive_cluster(arrive_bar);
+            else mbar_arrive(arrive_bar);
+        }
+    };
+    // accumulator chunk -> registers (inference: BatchNorm(eval) + ReLU applied), bf16: packed as stored
+    auto load_chunk = [&](int ch, uint32_t (&r)[32], uint32_t (&pk)[16]) {
         tmem_ld_32x32(t_addr + ch * 32, r);
         tmem_ld_wait();
-        uint32_t pk[16];
         if (p.scale != nullptr) {      // inference: y = relu(acc * scale[c] + shift[c])
-            const int grp = min((nt * p.TN) / p.group_images, 1);
             const float4* sc4 = reinterpret_cast<const float4*>(p.scale + static_cast<long long>(grp) * p.cout_total + co0 + ch * 32);
             const float4* sh4 = reinterpret_cast<const float4*>(p.shift + static_cast<long long>(grp) * p.cout_total + co0 + ch * 32);
 #pragma unroll
@@ -300,6 +356,13 @@ __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile,
                 r[4 * j + 3] = __float_as_uint(fmaxf(fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w), 0.f));
             }
         }
+        if constexpr (!Op::kTf32) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+        }
+    };
+    // store + statistics of one chunk (r: fp32 values, used by the tf32 kernels only; pk: packed bf16)
+    auto finish_chunk = [&](int ch, const uint32_t* r, const uint32_t (&pk)[16]) {
         if constexpr (Op::kTf32) {     // fp32 storage: 128 bytes per pixel and chunk, stored as they are
             if (valid) {
                 uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
@@ -307,8 +370,6 @@ __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile,
                 for (int j = 0; j < 8; ++j) dst[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
             }
         } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
             if (valid) {
                 uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
 #pragma unroll
@@ -318,15 +379,8 @@ __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile,
         if constexpr (kPackedAcc) {
             if (do_stats) {
                 const int cc = (ch - half) / (kPxEpiWarps / 4);      // warp-uniform
-                if constexpr (PxRowAcc<BN>::kSteps == 1) {
-                    if (cc == 0) px_rowacc_packed<1, 0>(pk, valid, lane, sacc);
-                    else px_rowacc_packed<1, 1>(pk, valid, lane, sacc);
-                } else {
-                    if (cc == 0) px_rowacc_packed<2, 0>(pk, valid, lane, sacc);
-                    else if (cc == 1) px_rowacc_packed<2, 1>(pk, valid, lane, sacc);
-                    else if (cc == 2) px_rowacc_packed<2, 2>(pk, valid, lane, sacc);
-                    else px_rowacc_packed<2, 3>(pk, valid, lane, sacc);
-                }
+                if (cc == 0) px_rowacc_packed<1, 0>(pk, valid, lane, sacc);
+                else px_rowacc_packed<1, 1>(pk, valid, lane, sacc);
             }
         } else if (do_stats) {
             float v[32], s2[32];
@@ -339,14 +393,13 @@ __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile,
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {     // statistics of the values as stored (bf16-rounded)
-                    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
-                    const float lo = valid ? __low2float(b) : 0.f, hi = valid ? __high2float(b) : 0.f;
+                    const uint32_t wv = valid ? pk[j] : 0u;
+                    const float lo = __uint_as_float(wv << 16), hi = __uint_as_float(wv & 0xffff0000u);
                     v[2 * j] = lo; v[2 * j + 1] = hi;
                     s2[2 * j] = lo * lo; s2[2 * j + 1] = hi * hi;
                 }
             }
             if (RED) {      // BatchNorm-backward reduce of the previous layer: v = dz, s2 = dz * (y - mean) * invstd
-                const int grp = min((nt * p.TN) / p.group_images, 1);
                 const long long cbase = static_cast<long long>(grp) * p.cout_total + co0 + ch * 32;
                 const uint4* y4 = reinterpret_cast<const uint4*>(
                     p.red_y + ((static_cast<long long>(n) * p.H + h) * p.W + w) * p.cout_total + co0 + ch * 32);
@@ -389,16 +442,28 @@ __device__ __forceinline__ void px_store_epilogue(const PxParams& p, int m_tile,
                 s_part[(q * 2 + 1) * BN + ch * 32 + lane] = 0.f;
             }
         }
-    }
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) {
-        if (remote) mbar_arrive_cluster(arrive_bar);
-        else mbar_arrive(arrive_bar);
+    };
+    if constexpr (kEarlyRelease) {
+        uint32_t pk[kChunksPerWarp][16];
+#pragma unroll
+        for (int cc = 0; cc < kChunksPerWarp; ++cc) {
+            uint32_t r[32];
+            load_chunk(half + cc * (kPxEpiWarps / 4), r, pk[cc]);
+        }
+        release();
+#pragma unroll
+        for (int cc = 0; cc < kChunksPerWarp; ++cc) finish_chunk(half + cc * (kPxEpiWarps / 4), nullptr, pk[cc]);
+    } else {
+#pragma unroll 1
+        for (int ch = half; ch < BN / 32; ch += kPxEpiWarps / 4) {
+            uint32_t r[32], pk[16];
+            load_chunk(ch, r, pk);
+            finish_chunk(ch, r, pk);
+        }
+        release();
     }
     if (do_stats && !rowacc) {
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kPxEpiWarps) : "memory");
-        const int grp = min((nt * p.TN) / p.group_images, 1);     // at most two statistics groups (twin branches)
         if (sacc.n_tile != n_tile) {
             px_stat_flush<BN>(p, sacc, ew, lane, s_part);
             sacc.reset(n_tile);
@@ -468,9 +533,9 @@ tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
-                const int wt = m_tile % p.tiles_w, ht = (m_tile / p.tiles_w) % p.tiles_h,
-                          nt = m_tile / (p.tiles_w * p.tiles_h);
+                const int n_tile = fd_div(tile, p.fd_m), m_tile = tile - n_tile * p.num_m_tiles;
+                int wt, ht, nt;
+                px_tile_coord(p, m_tile, wt, ht, nt);
                 const int w0 = wt * p.TW, h0 = ht * p.TH, n0 = nt * p.TN, co0 = n_tile * BN;
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
                     for (int t = 0; t < p.ntaps; ++t) {
@@ -529,17 +594,19 @@ tapgemm_px_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
-            const int wt = m_tile % p.tiles_w, ht = (m_tile / p.tiles_w) % p.tiles_h,
-                      nt = m_tile / (p.tiles_w * p.tiles_h);
+            const int n_tile = fd_div(tile, p.fd_m), m_tile = tile - n_tile * p.num_m_tiles;
+            int wt, ht, nt;
+            px_tile_coord(p, m_tile, wt, ht, nt);
             const int w = wt * p.TW + w_l, h = ht * p.TH + h_l, n = nt * p.TN + n_l, co0 = n_tile * BN;
             const bool valid = (row < p.valid_rows) && (w < p.W) && (h < p.H) && (n < p.N);
+            PxRowCoord rc;
+            rc.n = n; rc.h = h; rc.w = w; rc.nt = nt; rc.valid = valid;
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 
             if (p.epi_mode == EPI_STORE) {
-                px_store_epilogue<BN, false, Op>(p, m_tile, n_tile, acc, tmem_base, q, ew, lane, s_part, bar_tempty + 8 * acc, false, sacc);
+                px_store_epilogue<BN, false, Op>(p, rc, n_tile, acc, tmem_base, q, ew, lane, s_part, bar_tempty + 8 * acc, false, sacc);
             } else {
                 // EPI_CONVT: column = (tap, co); scatter to the 2x upsampled grid, add bias.  A tile may span several
                 // taps (BN up to 4 * co_per_tap); every 32-column chunk lies inside one tap (co_per_tap % 32 == 0).

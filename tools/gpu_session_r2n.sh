@@ -1,9 +1,10 @@
 #!/bin/bash
-# why does the statistics epilogue of the 64-column tiles cost 14 %?  ncu --set full of the same layer with and without statistics
+# where do the epilogue instructions of the 64-column forward conv go?  source-level counts of one launch
 mkdir -p gpurun_out
-for k in fwd dgrad; do
-  ncu --set full --clock-control none -k regex:'halo_res_px' -s 2 -c 1 -o gpurun_out/r2n_$k -f python tools/profile_layer.py $k 128 256 256 64 64 3 > gpurun_out/r2n_ncu_$k.log 2>&1
-  python tools/ncu_stalls.py gpurun_out/r2n_$k.ncu-rep > gpurun_out/r2n_stalls_$k.txt
-  rm -f gpurun_out/r2n_$k.ncu-rep
-done
-wc -l gpurun_out/r2n_stalls_*.txt
+ncu --set full --clock-control none --import-source on -k regex:'halo_res_px' -s 2 -c 1 -o gpurun_out/r2n_fwd -f python tools/profile_layer.py fwd 128 256 256 64 64 3 > gpurun_out/r2n_ncu_fwd.log 2>&1
+ncu -i gpurun_out/r2n_fwd.ncu-rep --page source --csv > gpurun_out/r2n_source_raw.csv 2> gpurun_out/r2n_source_raw.err
+head -c 1500 gpurun_out/r2n_source_raw.csv
+python tools/ncu_source.py gpurun_out/r2n_fwd.ncu-rep 60 > gpurun_out/r2n_source_fwd.txt 2>&1
+head -30 gpurun_out/r2n_source_fwd.txt
+gzip -f gpurun_out/r2n_source_raw.csv
+rm -f gpurun_out/r2n_fwd.ncu-rep
