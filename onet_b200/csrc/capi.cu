@@ -1078,17 +1078,19 @@ int onet_bn_relu_apply(const void* y, int N, int H, int W, int C, const float* s
                        int group_images, void* out, int64_t ldo, int ooff, void* pool, void* pool_arg, int dtype, void* stream) {
     if (C % 8 || ldo % 8 || ooff % 8) return fail("bn_relu_apply: channel counts/offsets must be multiples of 8");
     const long long total = static_cast<long long>(N) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+    if (total >= (1LL << 30)) return fail("bn_relu_apply: %lld (window, channel octet) items exceed the 32-bit index range", total);
     const int gi = group_images > 0 ? group_images : N;
     constexpr int UNR = 2;
     const int grid = grid_for((total + UNR - 1) / UNR, 256, 148 * 24);
+    const FastDiv fd_oc = make_fastdiv(C / 8), fd_w2 = make_fastdiv((W + 1) / 2), fd_h2 = make_fastdiv((H + 1) / 2);
     if (dtype == ONET_F32)
         bn_relu_apply_kernel<float, UNR><<<grid, 256, 0, ST(stream)>>>(
             static_cast<const float*>(y), N, H, W, C, scale, shift, gi, static_cast<float*>(out), ldo, ooff, static_cast<float*>(pool),
-            static_cast<unsigned short*>(pool_arg));
+            static_cast<unsigned short*>(pool_arg), fd_oc, fd_w2, fd_h2);
     else
         bn_relu_apply_kernel<bf16, UNR><<<grid, 256, 0, ST(stream)>>>(
             static_cast<const bf16*>(y), N, H, W, C, scale, shift, gi, static_cast<bf16*>(out), ldo, ooff, static_cast<bf16*>(pool),
-            static_cast<unsigned short*>(pool_arg));
+            static_cast<unsigned short*>(pool_arg), fd_oc, fd_w2, fd_h2);
     return check_launch("bn_relu_apply");
 }
 
@@ -1140,6 +1142,8 @@ static int bn_bwd_impl(const void* y, int N, int H, int W, int C, const float* s
         if (OC > kBnWinThreads) return fail("bn_relu_bwd: the pooled variant supports C <= %d", 8 * kBnWinThreads);
         const int wlanes = kBnWinThreads / OC;
         const long long wins = static_cast<long long>(a.group_images) * ((H + 1) / 2) * ((W + 1) / 2);
+        if (static_cast<long long>(N) * ((H + 1) / 2) * ((W + 1) / 2) >= (1LL << 30)) return fail("bn_relu_bwd: too many windows for the 32-bit index range");
+        a.fd_w2 = make_fastdiv((W + 1) / 2); a.fd_h2 = make_fastdiv((H + 1) / 2);
         // 3 resident blocks of 128 threads per SM, two rounds
         const int wmax = (blocks_override > 0 ? blocks_override : 148 * 6) / G;
         const int gx = static_cast<int>(std::max(1LL, std::min<long long>((wins + wlanes - 1) / wlanes, wmax)));

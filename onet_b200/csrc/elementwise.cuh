@@ -4,6 +4,7 @@
 // weight packing and Adam.  All activations NHWC; 8 channels (16 B of bf16 / 32 B of fp32) per thread access.
 #pragma once
 #include "simt_conv.cuh"
+#include "fastdiv.cuh"
 
 namespace onet {
 
@@ -144,22 +145,27 @@ template <typename T, int UNR>
 __global__ void __launch_bounds__(256, 3)
 bn_relu_apply_kernel(const T* __restrict__ y, int N, int H, int W, int C, const float* __restrict__ scale,
                      const float* __restrict__ shift, int group_images, T* __restrict__ out, long long ldo, int ooff,
-                     T* __restrict__ pool, unsigned short* __restrict__ pool_arg) {
+                     T* __restrict__ pool, unsigned short* __restrict__ pool_arg, FastDiv fd_oc, FastDiv fd_w2, FastDiv fd_h2) {
+    // (window, channel octet) index < 2^31 (checked by the launcher): decomposed with multiply-high divisions - the three 64-bit
+    // div/mod pairs this loop used to do were ~300 instructions per window, twice the work on its 32 elements
     const int OC = C >> 3, H2 = (H + 1) >> 1, W2 = (W + 1) >> 1, HP = H >> 1, WP = W >> 1;
-    const long long total = static_cast<long long>(N) * H2 * W2 * OC;
-    const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
-    for (long long idx0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx0 < total; idx0 += nthreads * UNR) {
+    const int total = N * H2 * W2 * OC;
+    const int nthreads = static_cast<int>(gridDim.x * blockDim.x);
+    for (int idx0 = static_cast<int>(blockIdx.x * blockDim.x + threadIdx.x); idx0 < total; idx0 += nthreads * UNR) {
         Raw8<T> r[UNR][4];
         int oc_[UNR], n_[UNR], h2_[UNR], w2_[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-            const long long idx = idx0 + u * nthreads;
-            const bool live = idx < total;
-            long long q = live ? idx : 0;
-            oc_[u] = static_cast<int>(q % OC); q /= OC;
-            w2_[u] = static_cast<int>(q % W2); q /= W2;
-            h2_[u] = static_cast<int>(q % H2);
-            n_[u] = live ? static_cast<int>(q / H2) : -1;
+            const int idx = idx0 + u * nthreads;
+            const bool live = idx < total && idx >= 0;
+            const int q0 = live ? idx : 0;
+            const int q1 = fd_div(q0, fd_oc);
+            oc_[u] = q0 - q1 * OC;
+            const int q2 = fd_div(q1, fd_w2);
+            w2_[u] = q1 - q2 * W2;
+            const int q3 = fd_div(q2, fd_h2);
+            h2_[u] = q2 - q3 * H2;
+            n_[u] = live ? q3 : -1;
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
                 const int h = 2 * h2_[u] + (d >> 1), w = 2 * w2_[u] + (d & 1);
@@ -171,7 +177,7 @@ bn_relu_apply_kernel(const T* __restrict__ y, int N, int H, int W, int C, const 
         for (int u = 0; u < UNR; ++u) {
             if (n_[u] < 0) break;
             const int n = n_[u], oc = oc_[u];
-            const int g = min(n / group_images, 1);
+            const int g = n >= group_images ? 1 : 0;
             float sc[8], sh[8], mx[8];
             load8<float>(scale + g * C + oc * 8, sc);
             load8<float>(shift + g * C + oc * 8, sh);
@@ -231,6 +237,7 @@ struct BnBwdArgs {
     double* sums;                                // [G][2][C]
     double count;                                // elements per channel per group
     T* dy;                                       // [N,H,W,C]
+    FastDiv fd_w2, fd_h2;                        // window mapping: / ceil(W/2), / ceil(H/2)
 };
 
 // block-wide reduction of the per-thread (acc1, acc2) over the pixel lanes and one double atomic per channel
@@ -360,10 +367,9 @@ bn_bwd_win_kernel(const BnBwdArgs<T> a) {
     const int oc = threadIdx.x % OC, ln = threadIdx.x / OC;
     const int g = blockIdx.y;
     const int H = a.H, W = a.W, H2 = (H + 1) >> 1, W2 = (W + 1) >> 1, HP = H >> 1, WP = W >> 1;
-    const long long win_per_img = static_cast<long long>(H2) * W2;
     const int n_begin = g * a.group_images;
     const int n_end = (g == static_cast<int>(gridDim.y) - 1) ? a.N : (g + 1) * a.group_images;
-    const long long q_end = static_cast<long long>(n_end - n_begin) * win_per_img;
+    const int q_end = (n_end - n_begin) * H2 * W2;            // < 2^31 (checked by the launcher)
     float acc1[8] = {}, acc2[8] = {};
     if (ln < LANES) {
         float sc[8], sh[8], mu[8], k1[8], k2[8];
@@ -382,12 +388,13 @@ bn_bwd_win_kernel(const BnBwdArgs<T> a) {
                 k2[i] = sc[i] * is[i] * m2;
             }
         }
-        const long long stride = static_cast<long long>(gridDim.x) * LANES;
-        for (long long q = blockIdx.x * static_cast<long long>(LANES) + ln; q < q_end; q += stride) {
-            const int w2 = static_cast<int>(q % W2);
-            const long long t = q / W2;
-            const int h2 = static_cast<int>(t % H2);
-            const int n = n_begin + static_cast<int>(t / H2);
+        const int stride = static_cast<int>(gridDim.x) * LANES;
+        for (int q = static_cast<int>(blockIdx.x) * LANES + ln; q < q_end; q += stride) {
+            const int t = fd_div(q, a.fd_w2);
+            const int w2 = q - t * W2;
+            const int t2 = fd_div(t, a.fd_h2);
+            const int h2 = t - t2 * H2;
+            const int n = n_begin + t2;
             Raw8<T> ry[4], rg1[4], rg2[HAS_G2 ? 4 : 1], rp;
             bool ok[4];
 #pragma unroll

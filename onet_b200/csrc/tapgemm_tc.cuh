@@ -17,28 +17,11 @@
 // smem ring of STAGES operand stages, double-buffered TMEM accumulators (pixel-major kernel).
 #pragma once
 #include "tc_common.cuh"
+#include "fastdiv.cuh"
 
 namespace onet {
 
 constexpr int kMaxTaps = 9;
-
-// n / d for 0 <= n < 2^31 by multiply-high (the tile-index decompositions of the persistent kernels: a runtime integer division
-// is ~25 dependent instructions, and the epilogue warps did four of them per tile)
-struct FastDiv { uint32_t d, mul, shr; };
-inline FastDiv make_fastdiv(int d) {
-    FastDiv f;
-    f.d = static_cast<uint32_t>(d > 0 ? d : 1);
-    if (f.d == 1u) { f.mul = 0u; f.shr = 0u; return f; }
-    uint32_t lg = 0;
-    while ((1ull << lg) < f.d) ++lg;
-    const uint32_t pw = 31u + lg;
-    f.mul = static_cast<uint32_t>(((1ull << pw) + f.d - 1ull) / f.d);
-    f.shr = pw - 32u;
-    return f;
-}
-__device__ __forceinline__ int fd_div(int n, const FastDiv& f) {
-    return f.d == 1u ? n : static_cast<int>(__umulhi(static_cast<uint32_t>(n), f.mul) >> f.shr);
-}
 
 enum EpiMode : int { EPI_STORE = 0, EPI_CONVT = 1 };
 // (EPI_STORE with PxParams::scale != nullptr = inference: BatchNorm(eval) + ReLU folded into the store)
