@@ -344,7 +344,8 @@ def test_convT2x2(engine_name, n, h, w, cin, pad):
 
 
 @pytest.mark.parametrize("dt_name", ["fp32", "bf16"])
-@pytest.mark.parametrize("n,h,w,c,pool", [(4, 8, 8, 64, True), (2, 6, 10, 128, True), (2, 4, 4, 1024, False), (4, 16, 16, 64, False)])
+@pytest.mark.parametrize("n,h,w,c,pool", [(4, 8, 8, 64, True), (2, 6, 10, 128, True), (2, 4, 4, 1024, False), (4, 16, 16, 64, False),
+                                          (2, 7, 9, 64, True), (6, 12, 20, 256, True)])
 def test_bn_relu_fwd_bwd(dt_name, n, h, w, c, pool):
     """conv-output statistics -> finalize -> apply(+pool) and the fused backward, against torch autograd through
     batch_norm(training) -> relu -> (identity skip + max_pool2d)."""
