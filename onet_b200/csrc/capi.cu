@@ -12,6 +12,7 @@
 #include "elementwise.cuh"
 #include "first_layer.cuh"
 #include "first_layer_mma.cuh"
+#include "head_mma.cuh"
 #include "simt_conv.cuh"
 #include "synth.cuh"
 #include "tapgemm_tc.cuh"
@@ -1352,6 +1353,16 @@ int onet_convT2x2_wgrad(const void* x, int64_t ldx, int xoff, const void* go, in
 
 }  // extern "C"
 
+// bf16 head forward on warp-level MMAs (head_mma.cuh); ONET_NO_HEAD_MMA=1 = the CUDA-core kernel (A/B)
+static bool head_mma_ok(long long npx) {
+    static const bool off = getenv("ONET_NO_HEAD_MMA") != nullptr;
+    return !off && npx < (1LL << 30);
+}
+static int head_mma_grid(long long npx) {
+    const long long tiles = (npx + 15) / 16;
+    return static_cast<int>(std::max(1LL, std::min<long long>((tiles + 7) / 8, 148 * 2 * 4)));
+}
+
 template <typename T>
 static void fill_head(HeadArgs<T>& a, const void* L, int64_t ldl, int offl, const void* Hf, int64_t ldh, int offh, int B,
                       int H, int W) {
@@ -1377,7 +1388,8 @@ int onet_head_fwd(const void* L, int64_t ldl, int offl, const void* Hf, int64_t 
         HeadArgs<bf16> a;
         fill_head(a, L, ldl, offl, Hf, ldh, offh, B, H, W);
         a.Vt = Vt; a.Vd = Vd; a.S = S; a.a = a_out; a.b = b_out; a.loss_acc = loss_acc;
-        head_fwd_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(a);
+        if (head_mma_ok(npx)) head_fwd_mma_kernel<<<head_mma_grid(npx), 256, 0, ST(stream)>>>(a, make_fastdiv(H * W));
+        else head_fwd_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(a);
     }
     return check_launch("head_fwd");
 }
@@ -1400,7 +1412,8 @@ int onet_head_fwd_bn(const void* L, int64_t ldl, int offl, const void* Y, int64_
         fill_head(a, L, ldl, offl, Y, ldy, offy, B, H, W);
         a.Vt = Vt; a.Vd = Vd; a.S = S; a.a = a_out; a.b = b_out; a.loss_acc = loss_acc;
         a.hsc_t = hscale_t; a.hsh_t = hshift_t; a.hsc_d = hscale_d; a.hsh_d = hshift_d;
-        head_fwd_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(a);
+        if (head_mma_ok(npx)) head_fwd_mma_kernel<<<head_mma_grid(npx), 256, 0, ST(stream)>>>(a, make_fastdiv(H * W));
+        else head_fwd_kernel<bf16><<<grid, 256, 0, ST(stream)>>>(a);
     }
     return check_launch("head_fwd+bn");
 }
