@@ -696,7 +696,7 @@ class _Engine:
         dX = self._empty(n, h, w, cin)
         prev = rec.saved.get((si, li - 1)) if (li & 1) else None
         if (prev is not None and eng == ENGINE_TC and self.mode == "bf16" and colsum is None and prev["cout"] == cin and prev["h"] == h
-                and cin >= _BNRED_MIN_C and os.environ.get("ONET_NO_BNRED_FUSION") is None):
+                and prev.get("Y") is not None and cin >= _BNRED_MIN_C and os.environ.get("ONET_NO_BNRED_FUSION") is None):
             # second conv of a DoubleConv: its data gradient is the gradient w.r.t. the first conv's activation - reduce the
             # first conv's BatchNorm-backward sums in this launch's epilogue (saves one pass over (Y, g) in HBM)
             paff = prev["aff"]
