@@ -496,19 +496,19 @@ static int launch_wg(const CUtensorMap& tG, const CUtensorMap& tI, const WgParam
     return check_launch(Op::kTf32 ? "tapgemm_wg_kernel/tf32" : "tapgemm_wg_kernel", BNW);
 }
 
-template <int BNW>
+template <int BNW, int XS = 1>
 static int launch_wh(const CUtensorMap& tG, const CUtensorMap& tI, const WhParams& p, cudaStream_t st) {
-    using Cfg = WhCfg<BNW>;
+    using Cfg = WhCfg<BNW, XS>;
     static bool attr_set_[kMaxDevices] = {};
     bool& attr_set = attr_set_[cur_dev()];
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad3x3_halo_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-        if (e != cudaSuccess) return fail("cudaFuncSetAttribute(wh<%d>): %s", BNW, cudaGetErrorString(e));
+        cudaError_t e = cudaFuncSetAttribute(wgrad3x3_halo_kernel<BNW, XS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (e != cudaSuccess) return fail("cudaFuncSetAttribute(wh<%d,%d>): %s", BNW, XS, cudaGetErrorString(e));
         attr_set = true;
     }
     const int units = p.ntypes * p.num_m_tiles * p.num_n_tiles * p.ksplit;
-    wgrad3x3_halo_kernel<BNW><<<std::min(units, sm_count()), 192, Cfg::kSmemBytes, st>>>(tG, tI, p);
-    return check_launch("wgrad3x3_halo_kernel", BNW);
+    wgrad3x3_halo_kernel<BNW, XS><<<std::min(units, sm_count()), 192, Cfg::kSmemBytes, st>>>(tG, tI, p);
+    return check_launch(XS == 1 ? "wgrad3x3_halo_kernel" : "wgrad3x3_halo_kernel/xs", BNW);
 }
 
 // CTA-pair weight gradient (Mc, Nc multiples of 128)
@@ -584,7 +584,20 @@ static int wgrad3x3_halo_tc(const bf16* g, long long ldg, int goff, int Mc, cons
     p.tiles_w = (W + 7) / 8; p.tiles_h = (H + 7) / 8;
     p.num_px_tiles = p.tiles_w * p.tiles_h * N;
     int BNW;
-    if (Mc >= 128) {
+    static const bool no_xs = getenv("ONET_WG_NO_XSHIFT") != nullptr;       // A/B: the classic forms below
+    const bool xshift = !no_xs && (Mc == 64 || Nc == 64);
+    if (xshift) {
+        // 64-channel G blocks x 64-channel In blocks, filter column carried by three shifted In boxes (WhCfg, XS = 3)
+        BNW = 64;
+        p.m_tile_channels = 64; p.num_m_tiles = Mc / 64; p.ntypes = 1;
+        WhUnit& u = p.types[0];
+        u.nbox = 1; u.box_kw[0] = 1; u.box_ch[0] = 0;                       // one h-halo box, no shift in w
+        u.nacc = 2;
+        u.acc[0].start_off = 0; u.acc[0].lbo = 1024;                        // rows 0..63 = filter row 2, rows 64..127 = filter row 1
+        u.acc[0].tapA = 6; u.acc[0].tapB = 3; u.acc[0].chA = u.acc[0].chB = 0;
+        u.acc[1].start_off = 2048; u.acc[1].lbo = 1024;                     // rows 0..63 = filter row 0, rows 64..127 unused
+        u.acc[1].tapA = 0; u.acc[1].tapB = -1; u.acc[1].chA = u.acc[1].chB = 0;
+    } else if (Mc >= 128) {
         if (Mc % 128) return fail("tc wgrad: M channels %d not a multiple of 128", Mc);
         BNW = (Nc % 128 == 0) ? 128 : 64;
         p.m_tile_channels = 128; p.num_m_tiles = Mc / 128; p.ntypes = 3;
@@ -624,6 +637,7 @@ static int wgrad3x3_halo_tc(const bf16* g, long long ldg, int goff, int Mc, cons
     const uint32_t gbox[5] = {64, 8, 1, 10, 1}, ibox[5] = {64, 8, 1, 8, 1};
     if (make_act_map(&tG, g + goff, Mc, N, H, W, ldg, gbox)) return 1;
     if (make_act_map(&tI, in + ioff, Nc, N, H, W, ldi, ibox)) return 1;
+    if (xshift) return launch_wh<64, 3>(tG, tI, p, st);
     if (BNW == 128) return launch_wh<128>(tG, tI, p, st);
     return launch_wh<64>(tG, tI, p, st);
 }

@@ -490,20 +490,29 @@ struct WhParams {
     int m_total, n_total;
 };
 
-template <int BNW>
+// XS = 3 ("x-shifted" form, BNW = 64): the filter COLUMN kw is carried by the unshifted operand instead - its 64 channels are
+// loaded three times, shifted by kw - 1 pixels in w, and form N = 3 x 64 = 192 columns (column block = kw), while G is only
+// row-shifted (h-halo) and one accumulator holds two filter rows (M = 2 x 64):
+//     dW[co][ci][kh][kw] = sum_px G[px - (kh-1, 0)][co] * In[px + (0, kw-1)][ci]
+// A 64-channel G block then costs 8 MMAs of N = 192 per pixel slab (10 KB of operand reads per 96-clock MMA: tensor-bound)
+// instead of 20 MMAs of N = 64 (6 KB per 32-clock MMA: bound by the shared-memory pipe at 2/3 of the tensor rate).
+template <int BNW, int XS = 1>
 struct WhCfg {
-    static constexpr int kNBytes = (BNW / 64) * 8192;
-    static constexpr int kMBytes = kWhMaxBox * kWhBoxBytes;     // 40 KB
+    static constexpr int kNCols = BNW * XS;
+    static constexpr int kNBytes = (kNCols / 64) * 8192;
+    static constexpr int kMBytes = (XS == 1 ? kWhMaxBox : 2) * kWhBoxBytes;     // 40 KB / 20 KB
     static constexpr int kStageBytes = kNBytes + kMBytes;
-    static constexpr int kStages = 3;
+    static constexpr int kStages = XS == 1 ? 3 : 4;
     static constexpr int kTmemCols = 512;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 1024;
 };
 
-template <int BNW>
+template <int BNW, int XS = 1>
 __global__ void __launch_bounds__(192, 1)
 wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmI, const WhParams p) {
-    using Cfg = WhCfg<BNW>;
+    static_assert(XS == 1 || (XS == 3 && BNW == 64), "x-shifted form: three 64-channel column blocks");
+    using Cfg = WhCfg<BNW, XS>;
+    constexpr int NCOLS = Cfg::kNCols;
     constexpr int STAGES = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -553,8 +562,13 @@ wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_const
                     const uint32_t sN = base + stage * Cfg::kStageBytes, sM = sN + Cfg::kNBytes;
                     const uint32_t fb = bar_full + 8 * stage;
                     mbar_expect_tx(fb, tx);
+                    if constexpr (XS == 1) {
 #pragma unroll
-                    for (int b = 0; b < BNW / 64; ++b) tma_load_5d(sN + b * 8192, &tmI, fb, n0 + b * 64, w0, 0, h0, n);
+                        for (int b = 0; b < BNW / 64; ++b) tma_load_5d(sN + b * 8192, &tmI, fb, n0 + b * 64, w0, 0, h0, n);
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < XS; ++b) tma_load_5d(sN + b * 8192, &tmI, fb, n0, w0 + b - 1, 0, h0, n);   // column block = kw
+                    }
                     for (int b = 0; b < u.nbox; ++b)     // G shifted by -(kw-1) in w, one-row halo in h
                         tma_load_5d(sM + b * kWhBoxBytes, &tmG, fb, m0 + u.box_ch[b], w0 - (u.box_kw[b] - 1), 0, h0 - 1, n);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -563,7 +577,7 @@ wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_const
         }
     } else if (warp == 1) {
         if (elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(128, BNW, 1, 1);
+            constexpr uint32_t idesc = umma_idesc_bf16(128, NCOLS, 1, 1);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -584,7 +598,7 @@ wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_const
                         const uint64_t da = umma_smem_desc(sM + u.acc[a].start_off, u.acc[a].lbo, 1024);
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk)
-                            umma_bf16(tmem_base + a * BNW, da + 128 * kk, db + 128 * kk, idesc, (pt > px_begin) || kk);
+                            umma_bf16(tmem_base + a * NCOLS, da + 128 * kk, db + 128 * kk, idesc, (pt > px_begin) || kk);
                     }
                     umma_commit(bar_empty + 8 * stage);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -606,16 +620,18 @@ wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_const
             mbar_wait(bar_tfull, it & 1);
             tc_fence_after();
             for (int a = 0; a < u.nacc; ++a) {
-                const int tap = (row < 64) ? u.acc[a].tapA : u.acc[a].tapB;
+                const int tap = (row < 64) ? u.acc[a].tapA : u.acc[a].tapB;     // XS == 3: the tap of filter column 0 (kh * 3)
                 const int m = m0 + ((row < 64) ? u.acc[a].chA + row : u.acc[a].chB + row - 64);
-                const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BNW;
+                const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * NCOLS;
 #pragma unroll 1
-                for (int ch = 0; ch < BNW / 32; ++ch) {
+                for (int ch = 0; ch < NCOLS / 32; ++ch) {
                     uint32_t r[32];
                     tmem_ld_32x32(t_addr + ch * 32, r);
                     tmem_ld_wait();
                     if (tap >= 0) {
-                        float* dst = p.out + (static_cast<long long>(m) * p.n_total + n0 + ch * 32) * 9 + tap;
+                        const int col = XS == 1 ? ch * 32 : (ch & 1) * 32;      // channel inside the n-tile
+                        const int kw = XS == 1 ? 0 : (ch >> 1);                 // column block = filter column
+                        float* dst = p.out + (static_cast<long long>(m) * p.n_total + n0 + col) * 9 + tap + kw;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) atomicAdd(dst + j * 9, __uint_as_float(r[j]));
                     }
