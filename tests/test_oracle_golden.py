@@ -313,9 +313,13 @@ def test_reduced_precision_restatements_and_teacher_forcing():
     rel = lambda a, b: float((a - b).norm() / b.norm())
     # precision ladder against the FP32 run
     assert rel(outs["tf32"]["Vt"], outs[None]["Vt"]) < 5e-3 < 5 * rel(outs["bf16"]["Vt"], outs[None]["Vt"])
-    # bf16 policy: stored conv outputs and activations are bf16 values; tf32 policy: storage stays fp32
+    # bf16 policy: stored conv outputs and activations are bf16 values - except the first conv of a 1-channel network, whose
+    # output is never stored (closed-form statistics / recompute: onet_b200/csrc/first_layer.cuh) and therefore never rounded;
+    # tf32 policy: storage stays fp32
     for key, v in taps["bf16"]["top"].items():
-        if key.endswith(".raw") or key.endswith(".act") or key.endswith(".up.out"):
+        if key == "inc.double_conv.0.raw":
+            assert not torch.equal(bf(v.detach()), v.detach())
+        elif key.endswith(".raw") or key.endswith(".act") or key.endswith(".up.out"):
             assert torch.equal(bf(v.detach()), v.detach()), key
     raw = taps["tf32"]["top"]["down1.maxpool_conv.1.double_conv.0.raw"].detach()
     assert not torch.equal(bf(raw), raw)
