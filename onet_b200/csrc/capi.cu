@@ -1159,8 +1159,10 @@ static int bn_bwd_impl(const void* y, int N, int H, int W, int C, const float* s
         const long long wins = static_cast<long long>(a.group_images) * ((H + 1) / 2) * ((W + 1) / 2);
         if (static_cast<long long>(N) * ((H + 1) / 2) * ((W + 1) / 2) >= (1LL << 30)) return fail("bn_relu_bwd: too many windows for the 32-bit index range");
         a.fd_w2 = make_fastdiv((W + 1) / 2); a.fd_h2 = make_fastdiv((H + 1) / 2);
-        // 3 resident blocks of 128 threads per SM, two rounds
-        const int wmax = (blocks_override > 0 ? blocks_override : 148 * 6) / G;
+        // 3 resident blocks of 128 threads per SM; 8 blocks per SM in total: with exactly two full waves (148 * 6) every block of a
+        // wave reached its block reduction at the same time and the memory pipes idled twice - 148 * 8 staggers them
+        // (pooled C=64 @256x256 1.27 -> 1.13 ms, C=128 @128x128 0.66 -> 0.58 ms; tools/gpu_session_r2t.sh)
+        const int wmax = (blocks_override > 0 ? blocks_override : 148 * 8) / G;
         const int gx = static_cast<int>(std::max(1LL, std::min<long long>((wins + wlanes - 1) / wlanes, wmax)));
         if (g2 != nullptr) {
             bn_bwd_win_kernel<T, true, false><<<dim3(gx, G), kBnWinThreads, 0, st>>>(a);
