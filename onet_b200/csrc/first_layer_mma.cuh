@@ -178,8 +178,9 @@ first_mma_bwd_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* 
     const int tiles = gm.rows * gm.segs;
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
     for (int t = warp; t < tiles; t += 8) {
-        // [nt][j]: 8 channels (r*8..) of pixel 2q + j + 8nt.  (Prefetching the next segment's g one iteration ahead measured the
-        // same: 16 resident warps x 4 x 512 B in flight per SM already cover the HBM latency.)
+        // [nt][j]: 8 channels (r*8..) of pixel 2q + j + 8nt.  Neither prefetching the next segment's g one iteration ahead nor a
+        // 4-deep cp.async ring per warp made the kernel faster (0.33 -> 0.36 ms with the ring): it is bound by the rate of the
+        // legacy mma.sync path - 16 HMMAs per segment at ~32 clocks each per SM sub-partition account for 80 % of its cycles.
         uint4 gc[2][2];
         {
             const int row = t / gm.segs, seg = t - row * gm.segs;
