@@ -81,11 +81,12 @@ int onet_conv3x3_fwd(const void* in, int64_t ldi, int ci_off, int N, int H, int 
  *   onet_first_conv_bn_relu : out [N,H,W,64] = relu(conv(x) * scale + shift)   (training: batch statistics; eval: running)
  *   onet_first_conv_bwd     : g [N,H,W,64] = gradient w.r.t. out; reduces the BatchNorm-backward sums (sums: zeroed double
  *                             [G][2][64]), forms dY in registers and accumulates dw [64][Cin][3][3] (+ dgamma / dbeta).
- * in_chns = 1 with `gram` (zeroed double [G][90] = patch moments S[9], G[9][9] per statistics group): the conv output is linear
- * in the 3 x 3 patch, so the statistics are w.S and w^T G w (no pass over 64 channels), and the backward is ONE pass over g
- * (s1, s2 and A[c][k] = sum dz v[k] into `acc_a`, zeroed float [G][64][9]) followed by a closed-form assembly of dW from A, S, G;
- * y is then used unrounded everywhere (round_y = 0 in onet_first_conv_bn_relu).  gram = NULL (or in_chns = 3): the two-pass form
- * whose values are those of the stored path (round_y = 1). */
+ * With `gram` (zeroed double [G][K + K*K], K = 9 * in_chns: patch moments S[K], G[K][K] per statistics group, patch element
+ * k = tap * in_chns + channel): the conv output is linear in the 3 x 3 x in_chns patch, so the statistics are w.S and w^T G w (no
+ * pass over 64 channels), and the backward is ONE pass over g (s1 and A[c][k] = sum dz v[k] into `acc_a`, zeroed float [G][64][K])
+ * followed by a closed-form assembly of dW (and s2) from A, S, G; y is then used unrounded everywhere (round_y = 0 in
+ * onet_first_conv_bn_relu).  Available for in_chns = 1 (any dtype) and for in_chns = 3 with bf16 storage (moments and backward on
+ * warp-level MMAs).  gram = NULL: the two-pass form whose values are those of the stored path (round_y = 1). */
 int onet_first_conv_stats(const void* x, int N, int H, int W, int Cin, const void* wp, double* gram, double* stat_sum,
                           double* stat_sq, int group_images, int dtype, void* stream);
 int onet_first_conv_bn_relu(const void* x, int N, int H, int W, int Cin, const void* wp, const float* scale, const float* shift,

@@ -846,18 +846,26 @@ int onet_first_conv_stats(const void* x, int N, int H, int W, int Cin, const voi
     constexpr int ROWS = 32;
     const int gi = group_images > 0 ? group_images : N;
     const int chunks = (H + ROWS - 1) / ROWS;
-    if (Cin == 1 && gram != nullptr) {
+    if (gram != nullptr) {
         // closed form: patch moments S, G per statistics group, then sum y = w.S, sum y^2 = w^T G w (first_layer.cuh)
         const int G = std::min(2, (N + gi - 1) / gi);
-        const int WG = W / 4;
-        const int threads = WG <= 64 ? 64 : (WG <= 128 ? 128 : 256);
-        const int wgb = (WG + 255) / 256;
-        const unsigned fg = static_cast<unsigned>(N) * chunks * wgb;
-        if (dtype == ONET_F32) first_gram_kernel<float, ROWS><<<fg, threads, 0, ST(stream)>>>(static_cast<const float*>(x), N, H, W, gi, gram);
-        else first_gram_kernel<bf16, ROWS><<<fg, threads, 0, ST(stream)>>>(static_cast<const bf16*>(x), N, H, W, gi, gram);
+        const int K = 9 * Cin;
+        if (Cin == 1) {
+            const int WG = W / 4;
+            const int threads = WG <= 64 ? 64 : (WG <= 128 ? 128 : 256);
+            const int wgb = (WG + 255) / 256;
+            const unsigned fg = static_cast<unsigned>(N) * chunks * wgb;
+            if (dtype == ONET_F32) first_gram_kernel<float, ROWS><<<fg, threads, 0, ST(stream)>>>(static_cast<const float*>(x), N, H, W, gi, gram);
+            else first_gram_kernel<bf16, ROWS><<<fg, threads, 0, ST(stream)>>>(static_cast<const bf16*>(x), N, H, W, gi, gram);
+        } else {
+            // in_chns = 3: 27 + 27 x 27 moments on warp-level MMAs (first_layer_mma.cuh); bf16 storage only (exact operands)
+            if (dtype == ONET_F32 || first_mma_disabled()) return fail("first_conv_stats: patch moments for in_chns = 3 exist for bf16 storage only");
+            const unsigned mg = static_cast<unsigned>(N) * ((H + kFmRows - 1) / kFmRows) * ((W + kFmCols - 1) / kFmCols);
+            first_gram_mma_kernel<3><<<mg, 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), N, H, W, gi, gram);
+        }
         if (check_launch("first_gram")) return 1;
-        if (dtype == ONET_F32) first_stats_from_gram_kernel<float><<<G, 64, 0, ST(stream)>>>(static_cast<const float*>(wp), gram, G, stat_sum, stat_sq);
-        else first_stats_from_gram_kernel<bf16><<<G, 64, 0, ST(stream)>>>(static_cast<const bf16*>(wp), gram, G, stat_sum, stat_sq);
+        if (dtype == ONET_F32) first_stats_from_gram_kernel<float><<<G, 64, 0, ST(stream)>>>(static_cast<const float*>(wp), gram, G, K, stat_sum, stat_sq);
+        else first_stats_from_gram_kernel<bf16><<<G, 64, 0, ST(stream)>>>(static_cast<const bf16*>(wp), gram, G, K, stat_sum, stat_sq);
         return check_launch("first_stats_from_gram");
     }
     const int wgb = (W / 4 + 31) / 32;
@@ -888,11 +896,15 @@ int onet_first_conv_bn_relu(const void* x, int N, int H, int W, int Cin, const v
         if (Cin == 1) ONET_FIRST_FWD(float, 1, FIRST_APPLY, false, out); else ONET_FIRST_FWD(float, 3, FIRST_APPLY, false, out);
     } else if (round_y) {
         if (Cin == 1) ONET_FIRST_FWD(bf16, 1, FIRST_APPLY, true, out); else ONET_FIRST_FWD(bf16, 3, FIRST_APPLY, true, out);
-    } else if (Cin == 1 && !first_mma_disabled()) {
-        // unrounded y, one input channel: warp-level tensor-core form (first_layer_mma.cuh), any width
+    } else if (!first_mma_disabled()) {
+        // unrounded y: warp-level tensor-core form (first_layer_mma.cuh), any width
         const unsigned mg = static_cast<unsigned>(N) * ((H + kFmRows - 1) / kFmRows) * ((W + kFmCols - 1) / kFmCols);
-        first_mma_fwd_kernel<<<mg, 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), N, H, W, static_cast<const bf16*>(wp), scale, shift, gi,
-                                                         static_cast<bf16*>(out));
+        if (Cin == 1)
+            first_mma_fwd_kernel<1><<<mg, 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), N, H, W, static_cast<const bf16*>(wp), scale, shift, gi,
+                                                                static_cast<bf16*>(out));
+        else
+            first_mma_fwd_kernel<3><<<mg, 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), N, H, W, static_cast<const bf16*>(wp), scale, shift, gi,
+                                                                static_cast<bf16*>(out));
     } else {
         if (Cin == 1) ONET_FIRST_FWD(bf16, 1, FIRST_APPLY, false, out); else ONET_FIRST_FWD(bf16, 3, FIRST_APPLY, false, out);
     }
@@ -907,9 +919,10 @@ int onet_first_conv_bwd(const void* x, int N, int H, int W, int Cin, const void*
     if (first_layer_check("first_conv_bwd", N, H, W, Cin)) return 1;
     if (g == nullptr || sums == nullptr || dw == nullptr) return fail("first_conv_bwd: g, sums and dw are required");
     constexpr int ROWS = 32;
-    if (Cin == 1 && gram != nullptr) {
+    if (gram != nullptr) {
         // single pass over g + closed-form assembly from the patch moments of the forward pass (first_layer.cuh)
-        if (acc_a == nullptr) return fail("first_conv_bwd: acc_a (zeroed float [G][64][9]) is required with gram");
+        if (acc_a == nullptr) return fail("first_conv_bwd: acc_a (zeroed float [G][64][9 * in_chns]) is required with gram");
+        if (Cin == 3 && (dtype == ONET_F32 || first_mma_disabled())) return fail("first_conv_bwd: the closed form for in_chns = 3 exists for bf16 storage only");
         FirstFusedArgs fa;
         memset(&fa, 0, sizeof(fa));
         fa.N = N; fa.H = H; fa.W = W; fa.group_images = group_images > 0 ? group_images : N;
@@ -917,7 +930,7 @@ int onet_first_conv_bwd(const void* x, int N, int H, int W, int Cin, const void*
         const int G = std::min(2, (N + fa.group_images - 1) / fa.group_images);
         const int lanes = 16, wgb = (W / 4 + lanes - 1) / lanes, chunks = (H + ROWS - 1) / ROWS;
         const unsigned gx = static_cast<unsigned>(N) * chunks * wgb;
-        const long long numel = 64LL * 9;
+        const long long numel = 64LL * 9 * Cin;
         fa.partial = (dtype == ONET_F32) ? splitk_ws(static_cast<long long>(gx) * numel) : nullptr;
         const bool mma = dtype != ONET_F32 && !first_mma_disabled();
         if (dtype == ONET_F32) {
@@ -929,7 +942,8 @@ int onet_first_conv_bwd(const void* x, int N, int H, int W, int Cin, const void*
         } else {
             // bf16: A and s1 by warp-level MMAs, s2 derived from A in the assembly kernel (first_layer_mma.cuh)
             const unsigned mg = static_cast<unsigned>(N) * ((H + kFmRows - 1) / kFmRows) * ((W + kFmCols - 1) / kFmCols);
-            first_mma_bwd_kernel<<<mg, 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), static_cast<const bf16*>(wp), static_cast<const bf16*>(g), fa);
+            if (Cin == 1) first_mma_bwd_kernel<1><<<mg, 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), static_cast<const bf16*>(wp), static_cast<const bf16*>(g), fa);
+            else first_mma_bwd_kernel<3><<<mg, 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), static_cast<const bf16*>(wp), static_cast<const bf16*>(g), fa);
             if (check_launch("first_mma_bwd")) return 1;
         }
         if (fa.partial != nullptr) {       // deterministic: per-block partials added in block order, group by group
@@ -943,9 +957,9 @@ int onet_first_conv_bwd(const void* x, int N, int H, int W, int Cin, const void*
             }
         }
         if (dtype == ONET_F32)
-            first_bwd_assemble_kernel<float><<<(64 * 9 + 127) / 128, 128, 0, ST(stream)>>>(static_cast<const float*>(wp), gram, acc_a, sums, scale, mean, invstd, G, count, dw, 0);
+            first_bwd_assemble_kernel<float><<<(64 * 9 * Cin + 127) / 128, 128, 0, ST(stream)>>>(static_cast<const float*>(wp), gram, acc_a, sums, scale, mean, invstd, G, count, dw, 0, Cin);
         else
-            first_bwd_assemble_kernel<bf16><<<(64 * 9 + 127) / 128, 128, 0, ST(stream)>>>(static_cast<const bf16*>(wp), gram, acc_a, sums, scale, mean, invstd, G, count, dw, mma ? 1 : 0);
+            first_bwd_assemble_kernel<bf16><<<(64 * 9 * Cin + 127) / 128, 128, 0, ST(stream)>>>(static_cast<const bf16*>(wp), gram, acc_a, sums, scale, mean, invstd, G, count, dw, mma ? 1 : 0, Cin);
         if (check_launch("first_bwd_assemble")) return 1;
         if (dgamma0 != nullptr) {
             bn_param_grad_kernel<<<1, 64, 0, ST(stream)>>>(sums, G, 64, dgamma0, dbeta0, dgamma1 ? dgamma1 : dgamma0, dbeta1 ? dbeta1 : dbeta0);

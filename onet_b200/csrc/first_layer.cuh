@@ -419,25 +419,22 @@ first_gram_kernel(const T* __restrict__ in, int N, int H, int W, int group_image
     }
 }
 
-// stat_sum[g][c] = w_c . S_g,  stat_sq[g][c] = w_c^T G_g w_c   (the sums onet_bn_finalize expects); one thread per (g, c)
+// stat_sum[g][c] = w_c . S_g,  stat_sq[g][c] = w_c^T G_g w_c   (the sums onet_bn_finalize expects); one thread per (g, c).
+// K = 9 * in_chns patch elements (tap-major, channel fastest: the order of the packed weights); moments of group g: S[K] then G[K][K].
 template <typename T>
-__global__ void first_stats_from_gram_kernel(const T* __restrict__ wp, const double* __restrict__ gram, int G,
+__global__ void first_stats_from_gram_kernel(const T* __restrict__ wp, const double* __restrict__ gram, int G, int K,
                                              double* __restrict__ stat_sum, double* __restrict__ stat_sq) {
     const int c = threadIdx.x, g = blockIdx.x;
     if (c >= 64 || g >= G) return;
-    const double* S = gram + static_cast<long long>(g) * kGramSize;
-    const double* Gm = S + kGramK;
-    double w[kGramK];
-#pragma unroll
-    for (int k = 0; k < kGramK; ++k) w[k] = static_cast<double>(to_f<T>(wp[c * kGramK + k]));
+    const double* S = gram + static_cast<long long>(g) * (K + K * K);
+    const double* Gm = S + K;
     double s = 0.0, q = 0.0;
-#pragma unroll
-    for (int k = 0; k < kGramK; ++k) {
-        s += w[k] * S[k];
+    for (int k = 0; k < K; ++k) {
+        const double wk = static_cast<double>(to_f<T>(wp[c * K + k]));
+        s += wk * S[k];
         double r = 0.0;
-#pragma unroll
-        for (int k2 = 0; k2 < kGramK; ++k2) r += Gm[k * kGramK + k2] * w[k2];
-        q += w[k] * r;
+        for (int k2 = 0; k2 < K; ++k2) r += Gm[k * K + k2] * static_cast<double>(to_f<T>(wp[c * K + k2]));
+        q += wk * r;
     }
     stat_sum[g * 64 + c] = s;
     stat_sq[g * 64 + c] = q;
@@ -553,28 +550,29 @@ first_conv_bwd_fused_kernel(const T* __restrict__ in, const T* __restrict__ wp, 
     }
 }
 
-// dW[c][k] += sum_g [ sc A_g[c][k] - k1 S_g[k] - k2 ((G_g w_c)[k] - mu S_g[k]) ];  one thread per (c, k).
+// dW[c][k] += sum_g [ sc A_g[c][k] - k1 S_g[k] - k2 ((G_g w_c)[k] - mu S_g[k]) ];  one thread per (c, k), K = 9 * CIN.
 // derive_s2: sums[g][1][c] = sum dz (y - mu) invstd is not given but follows from A (y = w_c . v):  invstd (w_c . A_g[c][:] - mu s1);
 // every thread of channel c evaluates it for itself and the k == 0 thread stores it for bn_param_grad_kernel.
 template <typename T>
 __global__ void first_bwd_assemble_kernel(const T* __restrict__ wp, const double* __restrict__ gram, const float* __restrict__ acc_a,
                                           double* __restrict__ sums, const float* __restrict__ scale, const float* __restrict__ mean,
-                                          const float* __restrict__ invstd, int G, double count, float* __restrict__ dw, int derive_s2) {
+                                          const float* __restrict__ invstd, int G, double count, float* __restrict__ dw, int derive_s2,
+                                          int CIN) {
+    const int K = 9 * CIN;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 64 * kGramK) return;
-    const int c = i / kGramK, k = i % kGramK;
+    if (i >= 64 * K) return;
+    const int c = i / K, k = i % K;
     const double inv_n = 1.0 / count;            // 0 for eval-mode statistics (count = inf): the mean / projection terms vanish
     double t = 0.0;
     for (int g = 0; g < G; ++g) {
-        const double* S = gram + static_cast<long long>(g) * kGramSize;
-        const double* Gm = S + kGramK;
+        const double* S = gram + static_cast<long long>(g) * (K + K * K);
+        const double* Gm = S + K;
         const double sc = scale[g * 64 + c], mu = mean[g * 64 + c], is = invstd[g * 64 + c];
-        const float* Ac = acc_a + (static_cast<long long>(g) * 64 + c) * kGramK;
+        const float* Ac = acc_a + (static_cast<long long>(g) * 64 + c) * K;
         double s2;
         if (derive_s2) {
             double wa = 0.0;
-#pragma unroll
-            for (int k2i = 0; k2i < kGramK; ++k2i) wa += static_cast<double>(to_f<T>(wp[c * kGramK + k2i])) * static_cast<double>(Ac[k2i]);
+            for (int k2i = 0; k2i < K; ++k2i) wa += static_cast<double>(to_f<T>(wp[c * K + k2i])) * static_cast<double>(Ac[k2i]);
             s2 = is * (wa - mu * sums[(g * 2 + 0) * 64 + c]);
             if (k == 0) sums[(g * 2 + 1) * 64 + c] = s2;
         } else {
@@ -583,11 +581,11 @@ __global__ void first_bwd_assemble_kernel(const T* __restrict__ wp, const double
         const double k1 = sc * sums[(g * 2 + 0) * 64 + c] * inv_n;
         const double k2 = sc * is * s2 * inv_n;
         double gw = 0.0;
-#pragma unroll
-        for (int k2i = 0; k2i < kGramK; ++k2i) gw += Gm[k * kGramK + k2i] * static_cast<double>(to_f<T>(wp[c * kGramK + k2i]));
+        for (int k2i = 0; k2i < K; ++k2i) gw += Gm[k * K + k2i] * static_cast<double>(to_f<T>(wp[c * K + k2i]));
         t += sc * static_cast<double>(Ac[k]) - k1 * S[k] - k2 * (gw - mu * S[k]);
     }
-    dw[i] += static_cast<float>(t);       // dw is [64][1][3][3]: index c * 9 + tap
+    // k = tap * CIN + ci (packed order);  dw is [64][CIN][3][3]
+    dw[(static_cast<long long>(c) * CIN + k % CIN) * 9 + k / CIN] += static_cast<float>(t);
 }
 
 }  // namespace onet

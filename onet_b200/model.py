@@ -437,11 +437,14 @@ class _Engine:
         G, st = seg.groups, self.stream
         x = ptr(src, self._img_off(src, n0))
         aff = torch.empty(4, G, 64, dtype=torch.float32, device=self.dev)   # mean, invstd, scale, shift
-        # in_chns = 1: the conv output is linear in the 3 x 3 patch, so the patch moments (S[9], G[9][9] per statistics group) give
-        # the BatchNorm statistics in closed form and, in backward, the y-dependent part of the weight gradient
-        # (csrc/first_layer.cuh); y is then never rounded.  ONET_NO_FIRST_GRAM=1: the two-pass form (also used for in_chns = 3).
-        use_gram = cin == 1 and os.environ.get("ONET_NO_FIRST_GRAM") is None
-        gram = torch.zeros(G, 90, dtype=torch.float64, device=self.dev) if use_gram and (rec.training_stats or rec.save) else None
+        # The conv output is linear in the 3 x 3 x in_chns patch (K = 9 in_chns elements), so the patch moments (S[K], G[K][K] per
+        # statistics group) give the BatchNorm statistics in closed form and, in backward, the y-dependent part of the weight
+        # gradient (csrc/first_layer.cuh); y is then never rounded.  in_chns = 1: every storage type; in_chns = 3: bf16 storage
+        # (the moments come from warp-level MMAs, csrc/first_layer_mma.cuh).  ONET_NO_FIRST_GRAM=1: the two-pass form.
+        K = 9 * cin
+        use_gram = ((cin == 1 or (cin == 3 and self.mode == "bf16" and os.environ.get("ONET_NO_FIRST_MMA") is None))
+                    and os.environ.get("ONET_NO_FIRST_GRAM") is None)
+        gram = torch.zeros(G, K + K * K, dtype=torch.float64, device=self.dev) if use_gram and (rec.training_stats or rec.save) else None
         if rec.training_stats:
             stats = rec.stat_pool[rec.stat_off:rec.stat_off + 2 * G * 64].view(2, G, 64)
             rec.stat_off += 2 * G * 64
@@ -653,7 +656,7 @@ class _Engine:
             # the last call of a U-Net's backward: queued behind the deferred weight gradients on the same (side) stream - it
             # shares the deterministic split-K workspace of the FP32 mode with them, which must be used from ONE stream
             gram = sv.get("gram")
-            acc_a = torch.zeros(G, 64, 9, dtype=torch.float32, device=self.dev) if gram is not None else None
+            acc_a = torch.zeros(G, 64, 9 * cin, dtype=torch.float32, device=self.dev) if gram is not None else None
             self._wgrad((g1, src, sums, acc_a), "onet_first_conv_bwd", ptr(src, self._img_off(src, n0)), n, h, w, cin, ptr(sv["wf"]),
                         ptr(aff[2]), ptr(aff[3]), ptr(aff[0]), ptr(aff[1]), seg.group_images, ptr(g1), ptr(gram), ptr(acc_a),
                         ptr(sums), count,

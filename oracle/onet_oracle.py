@@ -47,7 +47,7 @@ DECODER = [("up1", 1024, 512), ("up2", 512, 256), ("up3", 256, 128), ("up4", 128
 # tolerances.  bf16 mode (onet_b200/csrc: conv epilogues, bn_relu_value, head_bwd_kernel, bn_bwd_*_kernel):
 #   forward : twin input, packed weights, every raw conv output Y, every post-ReLU activation and every up-conv output are
 #             stored as bf16; BatchNorm statistics are taken from the stored (rounded) Y; accumulation is fp32.  Exception: the
-#             first conv of a 1-channel network, whose Y (and dY) is never stored - recomputed in fp32 wherever it is needed.
+#             first conv of each U-Net, whose Y (and dY) is never stored - recomputed in fp32 wherever it is needed.
 #   backward: dL / dH from the head, every dY (BatchNorm backward) and every data gradient dX (conv / up-conv dgrad) are
 #             stored as bf16; weight / bias / BatchNorm parameter gradients stay fp32.
 # tf32 mode: storage is fp32 everywhere; only the tensor-core operands (activations, weights, output gradients of the 3x3
@@ -98,7 +98,7 @@ class _Policy:
 
     def conv_out(self, t, first=False, unstored=False):
         if self.mode == "bf16":
-            if unstored:      # first conv of a 1-channel network: y and dY are recomputed / kept in registers, never rounded
+            if unstored:      # first conv of a U-Net: y and dY are recomputed / kept in registers, never rounded
                 return t
             return _Ste.apply(t, _round_bf16, _round_bf16)       # Y stored as bf16, dY stored as bf16
         return t if first else _Ste.apply(t, None, _trunc_tf32)   # dY is a tensor-core operand of dgrad and wgrad
@@ -268,7 +268,7 @@ def double_conv(st, block, x, training, taps=None, q=None, force=None):
             x = F.conv2d(x, st[f"{p}.{conv_i}.weight"], None, padding=1)
         else:
             first = block == "inc" and conv_i == 0       # the 1 -> 64 / 3 -> 64 layer runs on CUDA cores in every mode
-            unstored = first and x.shape[1] == 1          # csrc/first_layer.cuh: in_chns = 1 never materialises this layer's Y / dY
+            unstored = first                              # csrc/first_layer.cuh: this layer's Y / dY is never materialised (closed form)
             x = q.conv_out(F.conv2d(q.conv_in(x, first), q.weight(st[f"{p}.{conv_i}.weight"], first), None, padding=1), first, unstored)
         x = _forced(x, force, f"{p}.{conv_i}.raw", taps)
         if taps is not None:

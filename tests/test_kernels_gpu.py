@@ -83,7 +83,8 @@ def test_conv3x3_tc_fwd(n, h, w, cin, cout):
 
 
 @pytest.mark.parametrize("dt_name", ["fp32", "bf16"])
-@pytest.mark.parametrize("n,h,w,cin", [(4, 32, 32, 1), (2, 40, 24, 3), (6, 16, 132, 1), (2, 67, 20, 1), (2, 35, 520, 1), (4, 16, 256, 1)])
+@pytest.mark.parametrize("n,h,w,cin", [(4, 32, 32, 1), (2, 40, 24, 3), (6, 16, 132, 1), (2, 67, 20, 1), (2, 35, 520, 1), (4, 16, 256, 1),
+                                       (2, 19, 276, 3), (4, 32, 32, 3)])
 def test_first_layer_recompute_matches_stored_path(dt_name, n, h, w, cin):
     """csrc/first_layer.cuh (the first convolution without materialising Y / dY) against the stored path of the same library:
     conv_first_fwd -> bn_finalize -> bn_relu_apply and bn_relu_bwd -> conv_first_wgrad.  Forward: bit-identical activations,
@@ -143,11 +144,12 @@ def test_first_layer_recompute_matches_stored_path(dt_name, n, h, w, cin):
     assert U.rel_l2(dgam, dgam_ref) < 1e-5 and U.rel_l2(dbet, dbet_ref) < 1e-5
     # bf16: a 1e-7 difference of a sum can flip the bf16 rounding of single dY elements
     assert U.rel_l2(dw, dw_ref) < (1e-5 if dt == U.F32 else 2e-3), U.rel_l2(dw, dw_ref)
-    if cin != 1:
+    if cin != 1 and dt != U.BF16:
         return
-    # in_chns = 1, closed form: statistics from the patch moments, ONE backward pass + assembly; y and dY unrounded, so against
-    # the stored bf16 path only up to the rounding it does (and exactly the same quantities in fp32)
-    gram = torch.zeros(2, 90, dtype=torch.float64, device="cuda")
+    # closed form (in_chns = 1: every dtype; in_chns = 3: bf16, warp-level MMAs): statistics from the patch moments, ONE backward
+    # pass + assembly; y and dY unrounded, so against the stored bf16 path only up to the rounding it does
+    K = 9 * cin
+    gram = torch.zeros(2, K + K * K, dtype=torch.float64, device="cuda")
     st2 = torch.zeros(2, 2, 64, dtype=torch.float64, device="cuda")
     call("onet_first_conv_stats", ptr(xn), n, h, w, cin, ptr(wf), ptr(gram), ptr(st2[0]), ptr(st2[1]), g, dt, U.stream())
     yf = F.conv2d(x, wt, padding=1).double()              # unrounded conv output (operands are exact in the storage type)
@@ -170,7 +172,7 @@ def test_first_layer_recompute_matches_stored_path(dt_name, n, h, w, cin):
         assert ((got - want).abs() <= want.abs() * 2.0 ** -7 + 1e-5).all()      # near zero: y * sc + sh cancels
     sums2 = torch.zeros_like(sums_ref)
     dw2 = torch.zeros(64, cin, 3, 3, device="cuda")
-    acc_a = torch.zeros(2, 64, 9, device="cuda")
+    acc_a = torch.zeros(2, 64, K, device="cuda")
     dgam2, dbet2 = torch.zeros(64, device="cuda"), torch.zeros(64, device="cuda")
     call("onet_first_conv_bwd", ptr(xn), n, h, w, cin, ptr(wf), ptr(aff2[2]), ptr(aff2[3]), ptr(aff2[0]), ptr(aff2[1]), g,
          ptr(gn), ptr(gram), ptr(acc_a), ptr(sums2), count, ptr(dw2), ptr(dgam2), ptr(dbet2), ptr(dgam2), ptr(dbet2), dt, U.stream())
