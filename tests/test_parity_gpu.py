@@ -341,3 +341,33 @@ def test_eval_between_graph_replays_sees_current_weights(mode):
         assert torch.equal(v, v_fresh)
         outs.append(v)
     assert not torch.equal(outs[0], outs[1]) and not torch.equal(outs[1], outs[2])
+
+
+def test_cached_eval_affine_follows_running_statistics_and_weights():
+    """The eval-mode BatchNorm affine (scale, shift) is cached per module between pure-inference forwards.  The cache must notice
+    what does not bump a tensor version: running statistics updated by a training-mode forward (raw-pointer kernel writes), and
+    must notice in-place parameter updates (torch optimizers) through the version counters."""
+    import onet_b200
+    from onet_b200 import model as M
+    from onet_b200.data import rayleigh_target_frames
+    torch.manual_seed(8)
+    net = onet_b200.Onet(1, True, True, mode="bf16").cuda()
+    x = rayleigh_target_frames(2, 1, 32, 32, seed=5).cuda()
+
+    def eval_vt(fresh=False):
+        if fresh:
+            M._EVAL_AFFINE.clear()
+        net.eval()
+        with torch.no_grad():
+            return net(x)[1].clone()
+    v0 = eval_vt()
+    assert torch.equal(v0, eval_vt()) and len(M._EVAL_AFFINE) > 0           # second call served from the cache
+    net.train()
+    with torch.no_grad():
+        net(x)                                                              # updates the running statistics only
+    v1 = eval_vt()
+    assert not torch.equal(v1, v0) and torch.equal(v1, eval_vt(fresh=True))
+    with torch.no_grad():
+        net.topu.inc.double_conv["1"].weight.mul_(1.5)                        # in-place parameter update: version counter
+    v2 = eval_vt()
+    assert not torch.equal(v2, v1) and torch.equal(v2, eval_vt(fresh=True))
