@@ -65,3 +65,41 @@ def test_snr_outside_the_reference_table_raises():
         with pytest.raises(ValueError):
             so.SNR_LIST.index(snr)
     assert synth.SNR_LIST == so.SNR_LIST
+
+
+def test_fastdiv_multiply_high_is_exact():
+    """onet_b200/csrc/fastdiv.cuh: n / d = umulhi(n, mul) >> shr with mul = ceil(2^(31 + ceil(log2 d)) / d), for every 0 <= n < 2^31.
+    The constants are parsed from the header's own formula (restated here) and checked on the divisors the kernels use (tile counts,
+    window counts, channel-octet counts, H * W) at the interval ends, around multiples of d, and on random dividends."""
+    import os
+    import random
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "onet_b200", "csrc", "fastdiv.cuh")).read()
+    assert re.search(r"pw = 31u \+ lg", src) and re.search(r"\(1ull << pw\) \+ f\.d - 1ull\) / f\.d", src) and "f.shr = pw - 32u" in src
+
+    def make(d):
+        if d == 1:
+            return None
+        lg = 0
+        while (1 << lg) < d:
+            lg += 1
+        pw = 31 + lg
+        mul = ((1 << pw) + d - 1) // d
+        assert mul < (1 << 32)
+        return mul, pw - 32
+
+    def div(n, d, f):
+        return n if f is None else ((n * f[0]) >> 32) >> f[1]
+    rng = random.Random(7)
+    divisors = set(range(1, 300)) | {2 ** k for k in range(0, 31)} | {2 ** k + 1 for k in range(1, 30)} | {2 ** k - 1 for k in range(2, 31)}
+    divisors |= {128 * 128, 256 * 256, 224 * 224, 1022, 1023, 1025, 2048 * 2048, 65535, 65537, 148, 8192 + 37, 2 ** 31 - 1}
+    top = 2 ** 31 - 1
+    for d in sorted(divisors):
+        f = make(d)
+        samples = {0, 1, d - 1, d, d + 1, top, top - 1, top - d, (top // d) * d, (top // d) * d - 1}
+        samples |= {rng.randrange(0, top + 1) for _ in range(200)}
+        samples |= {k * d + e for k in (1, 2, 3, 1000, top // d - 1) for e in (-1, 0, 1)}
+        for n in samples:
+            if 0 <= n <= top:
+                assert div(n, d, f) == n // d, (n, d)
