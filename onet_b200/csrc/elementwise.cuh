@@ -829,30 +829,35 @@ struct PackJobs {
     PackJob job[kPackMaxLayers];
 };
 
-template <typename T>
-__global__ void __launch_bounds__(256)
-pack_all_weights_kernel(const PackJobs jobs) {
-    __shared__ T s[9][32][34];
-    int li = 0;
-    while (li + 1 < jobs.n && static_cast<int>(blockIdx.x) >= jobs.job[li + 1].tile_begin) ++li;
-    const PackJob& j = jobs.job[li];
+// One 32 x 32 (outer x inner) tile of one layer, TAPS = 9 (conv) or 4 (up-conv) as a compile-time constant: the index
+// decompositions below are per ELEMENT, and with a runtime divisor they were most of the kernel's instructions.
+template <typename T, int TAPS>
+__device__ __forceinline__ void pack_tile(const PackJob& j, int t, T (*s)[32][34]) {
     const int tiles1 = (j.d1 + 31) / 32;
-    const int t = blockIdx.x - j.tile_begin;
     const int o0 = (t / tiles1) * 32, i0 = (t % tiles1) * 32;
-    const int n1 = min(32, j.d1 - i0), taps = j.taps;
-    const int row = n1 * taps;                       // contiguous floats per outer index inside this tile
-    for (int idx = threadIdx.x; idx < 32 * row; idx += 256) {
-        const int ol = idx / row, r = idx - ol * row;
-        const int il = r / taps, tap = r - il * taps;
-        if (o0 + ol < j.d0)
-            s[tap][ol][il] = from_f<T>(j.w[(static_cast<long long>(o0 + ol) * j.d1 + i0) * taps + r]);
+    const int n1 = min(32, j.d1 - i0);
+    const int row = n1 * TAPS;                       // contiguous floats per outer index inside this tile
+    if (n1 == 32) {
+        for (int idx = threadIdx.x; idx < 32 * 32 * TAPS; idx += 256) {
+            const int ol = idx / (32 * TAPS), r = idx - ol * (32 * TAPS);
+            const int il = r / TAPS, tap = r - il * TAPS;
+            if (o0 + ol < j.d0)
+                s[tap][ol][il] = from_f<T>(j.w[(static_cast<long long>(o0 + ol) * j.d1 + i0) * TAPS + r]);
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < 32 * row; idx += 256) {
+            const int ol = idx / row, r = idx - ol * row;
+            const int il = r / TAPS, tap = r - il * TAPS;
+            if (o0 + ol < j.d0)
+                s[tap][ol][il] = from_f<T>(j.w[(static_cast<long long>(o0 + ol) * j.d1 + i0) * TAPS + r]);
+        }
     }
     __syncthreads();
     T* wf = static_cast<T*>(j.wf);
     T* wd = static_cast<T*>(j.wd);
-    for (int idx = threadIdx.x; idx < taps * 32 * 32; idx += 256) {
+    for (int idx = threadIdx.x; idx < TAPS * 32 * 32; idx += 256) {
         const int fast = idx & 31, slow = (idx >> 5) & 31, tap = idx >> 10;
-        if (taps == 9) {
+        if (TAPS == 9) {
             // conv: outer = co, inner = ci.  wf[co][tap][ci] (ci fastest), wd[ci][8-tap][co] (co fastest)
             if (o0 + slow < j.d0 && fast < n1)
                 wf[(static_cast<long long>(o0 + slow) * 9 + tap) * j.d1 + i0 + fast] = s[tap][slow][fast];
@@ -866,6 +871,18 @@ pack_all_weights_kernel(const PackJobs jobs) {
                 wd[static_cast<long long>(o0 + slow) * 4 * j.d1 + tap * j.d1 + i0 + fast] = s[tap][slow][fast];
         }
     }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_all_weights_kernel(const PackJobs jobs) {
+    __shared__ T s[9][32][34];
+    int li = 0;
+    while (li + 1 < jobs.n && static_cast<int>(blockIdx.x) >= jobs.job[li + 1].tile_begin) ++li;
+    const PackJob& j = jobs.job[li];
+    const int t = blockIdx.x - j.tile_begin;
+    if (j.taps == 9) pack_tile<T, 9>(j, t, s);
+    else pack_tile<T, 4>(j, t, s);
 }
 
 // ------------------------------------------------------------------------------------------------
