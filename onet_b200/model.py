@@ -388,8 +388,9 @@ class _Engine:
             cache = _EVAL_AFFINE.setdefault(bn, {})
             hit = cache.get(key)
             if hit is not None and hit[0] == ver:
-                if hit[2] != st:                                 # computed on another stream: order this stream behind it
-                    torch.cuda.current_stream(self.dev).wait_event(hit[3])
+                if hit[2] != st:                                 # computed on another stream: order this stream behind it, and
+                    self._main.wait_event(hit[3])                # keep the allocator from recycling the buffer under this stream
+                    hit[1].record_stream(self._main)
                 return hit[1]
         aff = torch.empty(4, G, cout, dtype=torch.float32, device=self.dev)
         call("onet_bn_eval_prepare", G, cout, ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var),
@@ -401,7 +402,7 @@ class _Engine:
             aff[1] = torch.rsqrt(bn.running_var + 1e-5)
         if cacheable:
             ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(self.dev))
+            ev.record(self._main)
             cache[key] = (ver, aff, st, ev)
         return aff
 
